@@ -1,0 +1,224 @@
+/* stc_b200.h — C ABI of libstc_b200.so (sm_100a / B200 only).
+ *
+ * Drop-in boundary for the STC-UNet hot path.  The reference has no
+ * native code: every entry point below replaces a PyTorch call made by the reference's
+ * Python modules (file:line under /root/reference cited per function).  Conventions:
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch); the library never
+ *     allocates or frees caller tensors.  Scratch comes from `ws`/`ws_bytes` arguments.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*); no host sync.
+ *   - activations are NHWC ("channels_last"), element type given by `dtype`
+ *     (STC_F32 or STC_BF16); statistics / parameters / gradients of parameters are fp32,
+ *     BatchNorm sums are fp64.
+ *   - return value: 0 = ok, otherwise an STC_ERR_* code; stc_last_error() gives the text
+ *     (thread local).  There is NO CPU fallback: on a device that is not cc 10.x every
+ *     compute entry point returns STC_ERR_ARCH.
+ */
+#ifndef STC_B200_H_
+#define STC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STC_OK 0
+#define STC_ERR_INVALID 1
+#define STC_ERR_CUDA 2
+#define STC_ERR_ARCH 3
+#define STC_ERR_WORKSPACE 4
+
+#define STC_F32 0
+#define STC_BF16 1
+
+/* activation codes used by stc_bn_apply / stc_act_* */
+#define STC_ACT_NONE 0
+#define STC_ACT_RELU 1
+#define STC_ACT_HSWISH 2
+#define STC_ACT_SIGMOID 3
+
+/* conv engine selection (stc_conv_*): AUTO = tcgen05 when dtype is bf16 and the shape is
+ * eligible (Cin % 64 == 0, Cout % 16 == 0), else the fp32-accumulate SIMT kernel. */
+#define STC_ENGINE_AUTO 0
+#define STC_ENGINE_SIMT 1
+#define STC_ENGINE_TCGEN05 2
+
+const char* stc_last_error(void);
+int stc_version(void);
+/* 0 if the current device is cc 10.x, else STC_ERR_ARCH (also fills last error). */
+int stc_check_device(void);
+int stc_num_sms(void);
+
+/* ---------------------------------------------------------------- layout / packing */
+/* image (N,C,H,W) fp32 NCHW -> NHWC `dtype` with channels zero-padded to Cpad (input of
+ * UnetBackbone.forward, unet_backbone.py:36). */
+int stc_nchw_to_nhwc(const float* src, void* dst, int N, int C, int H, int W, int Cpad, int dtype, void* stream);
+/* Conv2d.weight (Cout,Cin,R,S) fp32 -> packed [R*S][Cout][CinPad] `dtype` (K-major per tap).
+ * transpose_flip != 0 packs the dgrad operand: [(R-1-r)*S+(S-1-s)][Cin][CoutPad] = W[co][ci][r][s]. */
+int stc_pack_conv_weight(const float* w, void* dst, int Cout, int Cin, int R, int S, int inner_pad,
+                         int transpose_flip, int dtype, void* stream);
+/* wgrad workspace [R*S][Cin][Cout] fp32 -> Conv2d.weight.grad (Cout,Cin,R,S) fp32
+ * (accumulate != 0 adds into dst). */
+int stc_unpack_conv_wgrad(const float* ws, float* dw, int Cout, int Cin, int R, int S, int accumulate, void* stream);
+
+/* ---------------------------------------------------------------- convolution (K1/K2/K3)
+ * Replaces nn.Conv2d(k, padding=k//2) in DoubleConv (unet_backbone.py:120,123; unet_head.py:67,70),
+ * KernelSelectAttention (unet_backbone.py:60-67), the 1x1 convs of CoordAtt (unet_head.py:123-129)
+ * and nn.Linear of TransformerLayer/KSA (unet_backbone.py:69-72,199-204) when R=S=1.
+ * x: NHWC (N,H,W,Cin), wp: packed [R*S][Cout][Cin], bias fp32[Cout] or NULL, y: NHWC (N,H,W,Cout).
+ * residual (same shape/dtype as y) may be NULL; act is an STC_ACT_* applied last.
+ * The same entry point computes dgrad when given dy and the transpose_flip-packed weight. */
+int stc_conv_fprop(const void* x, const void* wp, const float* bias, const void* residual, void* y,
+                   int N, int H, int W, int Cin, int Cout, int R, int S, int act, int dtype, int engine,
+                   void* stream);
+/* dW[(r,s)][ci][co] (fp32 workspace, must be zeroed by the caller when accumulate==0 is wanted)
+ * += sum_pixels x[p+(r,s)][ci] * dy[p][co].  Then stc_unpack_conv_wgrad -> OIHW. */
+int stc_conv_wgrad(const void* x, const void* dy, float* dw_ws, int N, int H, int W, int Cin, int Cout,
+                   int R, int S, int dtype, int engine, void* stream);
+/* column sums: out[c] (+)= sum_p x[p][c]  (Conv2d/Linear bias gradients). */
+int stc_colsum(const void* x, float* out, long long P, int C, int accumulate, int dtype, void* stream);
+
+/* ---------------------------------------------------------------- batched GEMM (K3/K4)
+ * C[b] = alpha * op(A[b]) * op(B[b]) (+ beta*C) ; op by element strides, so any of NN/NT/TN/TT.
+ * A(m,k) at A + b1*sA1 + b2*sA2 + m*sAm + k*sAk (elements), same for B(k,n), C(m,n) (C unit stride in n).
+ * Replaces the bmm/mm inside nn.MultiheadAttention (unet_backbone.py:202,207). */
+typedef struct {
+    int M, N, K;
+    int batch1, batch2;
+    long long sA1, sA2, sAm, sAk;
+    long long sB1, sB2, sBk, sBn;
+    long long sC1, sC2, sCm;
+    float alpha, beta;
+} stc_gemm_desc;
+int stc_gemm(const void* A, const void* B, void* C, const stc_gemm_desc* d, int dtype, int engine, void* stream);
+
+/* row softmax over the last dim: P = softmax(scale * S) ; rows x L (MHA, L = H*W tokens). */
+int stc_softmax_rows_fwd(const void* S, void* P, long long rows, int L, float scale, int dtype, void* stream);
+/* dS = scale * P * (dP - sum_j dP_j P_j) */
+int stc_softmax_rows_bwd(const void* P, const void* dP, void* dS, long long rows, int L, float scale, int dtype,
+                         void* stream);
+
+/* ---------------------------------------------------------------- BatchNorm (K5/K6, C1/C2)
+ * nn.SyncBatchNorm / BatchNorm2d train+eval (unet_backbone.py:64,121,124; unet_head.py:68,71,125). */
+/* sums[0:C] = sum_p y, sums[C:2C] = sum_p y^2 (fp64).  ws >= stc_bn_ws_bytes(P,C). */
+long long stc_bn_ws_bytes(long long P, int C);
+int stc_bn_reduce(const void* y, double* sums, long long P, int C, void* ws, long long ws_bytes, int dtype, void* stream);
+/* mean/invstd from (possibly all-reduced) sums over `count` samples; updates running stats
+ * (momentum, unbiased var) when running_mean != NULL. */
+int stc_bn_finalize(const double* sums, double count, float* mean, float* invstd, float* running_mean,
+                    float* running_var, int64_t* num_batches_tracked, float momentum, float eps, int C, void* stream);
+/* eval mode: mean = running_mean, invstd = rsqrt(running_var+eps) */
+int stc_bn_eval_stats(const float* running_mean, const float* running_var, float* mean, float* invstd, float eps,
+                      int C, void* stream);
+/* a = act(gamma*(y-mean)*invstd + beta) */
+int stc_bn_apply(const void* y, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                 void* a, long long P, int C, int act, int dtype, void* stream);
+/* g = dout * act'(z); sums[0:C] = sum g, sums[C:2C] = sum g*xhat (fp64) */
+int stc_bn_bwd_reduce(const void* y, const void* dout, const float* mean, const float* invstd, const float* gamma,
+                      const float* beta, double* sums, long long P, int C, int act, void* ws, long long ws_bytes,
+                      int dtype, void* stream);
+/* dgamma = sums[C:2C], dbeta = sums[0:C] (taken from the LOCAL sums, before any SyncBN all-reduce, as
+ * torch's SyncBatchNorm backward does). */
+int stc_bn_param_grads(const double* sums, float* dgamma, float* dbeta, int C, void* stream);
+/* dy = gamma*invstd*(g - sum_g/count - xhat*sum_gx/count) (train); eval != 0: dy = gamma*invstd*g. */
+int stc_bn_bwd_apply(const void* y, const void* dout, const float* mean, const float* invstd, const float* gamma,
+                     const float* beta, const double* sums, double count, void* dy,
+                     long long P, int C, int act, int eval, int dtype, void* stream);
+
+/* ---------------------------------------------------------------- pooling / upsampling (K7/K8/K9) */
+/* nn.MaxPool2d(2) (unet_backbone.py:107); H, W are the INPUT sizes (even). */
+int stc_maxpool2_fwd(const void* x, void* y, int N, int H, int W, int C, int dtype, void* stream);
+/* dx gets dy at the first arg-max of each 2x2 window (PyTorch tie rule), 0 elsewhere. */
+int stc_maxpool2_bwd(const void* x, const void* dy, void* dx, int N, int H, int W, int C, int dtype, void* stream);
+/* Up.forward's upsample+pad+cat (unet_head.py:51-55): out[...,0:Cs] = skip ;
+ * out[...,Cs:Cs+Cu] = pad(bilinear_x2(low, align_corners)) ; low is (N,h,w,Cu), out is (N,H,W,Cs+Cu). */
+int stc_upcat_fwd(const void* skip, const void* low, void* out, int N, int H, int W, int Cs, int h, int w, int Cu,
+                  int align_corners, int dtype, void* stream);
+int stc_upcat_bwd(const void* dout, void* dskip, void* dlow, int N, int H, int W, int Cs, int h, int w, int Cu,
+                  int align_corners, int dtype, void* stream);
+
+/* ---------------------------------------------------------------- CoordAtt (K10; unet_head.py:131-146,57) */
+/* y[n, 0:H, c] = mean_w x ; y[n, H:H+W, c] = mean_h x  ; y is (N, H+W, C) */
+int stc_rowcol_mean(const void* x, void* y, int N, int H, int W, int C, int dtype, void* stream);
+/* out = x + ah[n,h,c]*aw[n,w,c]; a is (N, H+W, C) with ah first. */
+int stc_coordatt_apply(const void* x, const void* a, void* out, int N, int H, int W, int C, int dtype, void* stream);
+/* da[n,h,c] = sum_w dout*aw ; da[n,H+w,c] = sum_h dout*ah */
+int stc_coordatt_apply_bwd(const void* dout, const void* a, void* da, int N, int H, int W, int C, int dtype, void* stream);
+/* dx = dout + dy[n,h,c]/W + dy[n,H+w,c]/H  (grad through x + the two mean-pools) */
+int stc_coordatt_dx(const void* dout, const void* dy, void* dx, int N, int H, int W, int C, int dtype, void* stream);
+
+/* ---------------------------------------------------------------- KernelSelectAttention fuse (K11; unet_backbone.py:80-99,46-48) */
+/* S[n,c] = mean_hw(f0+f1+f2) (fp32) */
+int stc_ksa_pool(const void* f0, const void* f1, const void* f2, float* S, int N, long long HW, int C, int dtype, void* stream);
+/* w = softmax over the 3 branches of a[3][N*C] (fp32) */
+int stc_softmax3_fwd(const float* a, float* w, long long NC, void* stream);
+int stc_softmax3_bwd(const float* w, const float* dw, float* da, long long NC, void* stream);
+/* out = x + sum_k w[k][n][c] * f_k */
+int stc_ksa_combine(const void* x, const void* f0, const void* f1, const void* f2, const float* w, void* out, int N,
+                    long long HW, int C, int dtype, void* stream);
+/* dw[k][n][c] = sum_hw dout * f_k (fp32) */
+int stc_ksa_dw(const void* dout, const void* f0, const void* f1, const void* f2, float* dw, int N, long long HW, int C,
+               int dtype, void* stream);
+/* df_k = w_k*dout + dS[n][c]/HW */
+int stc_ksa_df(const void* dout, const float* w, const float* dS, void* df0, void* df1, void* df2, int N, long long HW,
+               int C, int dtype, void* stream);
+
+/* ---------------------------------------------------------------- small fp32 dense layers (KSA fc/fcs; tiny)
+ * y[r][o] = act(sum_i x[r][i] W[o][i] + b[o]) ; fp32 row-major. */
+int stc_linear_f32_fwd(const float* x, const float* W, const float* b, float* y, int rows, int in, int out, void* stream);
+/* dx = dy W ; dW (+)= dy^T x ; db (+)= colsum dy  (any may be NULL) */
+int stc_linear_f32_bwd(const float* x, const float* W, const float* dy, float* dx, float* dW, float* db, int rows,
+                       int in, int out, void* stream);
+
+/* ---------------------------------------------------------------- elementwise */
+int stc_add(const void* a, const void* b, void* out, long long n, int dtype, void* stream);           /* out = a + b */
+int stc_axpy_f32(const float* x, float* y, float alpha, long long n, void* stream);                    /* y += alpha x */
+int stc_cast(const void* src, void* dst, long long n, int src_dtype, int dst_dtype, void* stream);
+int stc_act_bwd(const void* y_out, const void* dy, void* dx, long long n, int act, int dtype, void* stream); /* sigmoid: uses output */
+/* dst[n, dst_off + r, :] = src[n, src_off + r, :] for r < count, on (N, rows, C) tensors (CoordAtt split / cat). */
+int stc_copy_rows(const void* src, void* dst, int N, int src_rows, int dst_rows, int C, int src_off, int dst_off, int count,
+                  int dtype, void* stream);
+int stc_scale_channels(const void* x, const float* m, void* y, int N, long long HW, int C, int dtype, void* stream); /* Dropout2d mask: y = x*m[n][c] */
+
+/* ---------------------------------------------------------------- classifier + loss (K12-K15)
+ * BaseDecodeHead.cls_seg (decode_head.py:254-259): logits NCHW fp32 = conv1x1(x NHWC) + b. W is (Ccls,Cin) fp32. */
+int stc_cls_fwd(const void* x, const float* W, const float* b, float* logits, int N, long long HW, int Cin, int Ccls,
+                int dtype, void* stream);
+/* dx NHWC = dlogits^T W ; dW (+)= ..., db (+)= ... ; ws >= stc_cls_bwd_ws_bytes */
+long long stc_cls_bwd_ws_bytes(int N, long long HW, int Cin, int Ccls);
+int stc_cls_bwd(const float* dlogits, const void* x, const float* W, void* dx, float* dW, float* db, int N, long long HW,
+                int Cin, int Ccls, void* ws, long long ws_bytes, int dtype, void* stream);
+/* BaseDecodeHead.losses (decode_head.py:261-296) = CrossEntropyLoss(avg_non_ignore=False)
+ * (cross_entropy_loss.py:45-61) + DiceLoss (dice_loss.py:13-47,92-123) + accuracy (accuracy.py:6-61).
+ * logits NCHW fp32, label int64 (N,H,W).  stats (fp64, 3*N*C + 4): per (n,c) [sum p*t*m, sum p^2, sum t],
+ * then [ce_sum, n_correct, n_valid, 0].  out3 = {loss_bce, loss_dice, acc_seg} fp32. */
+long long stc_seg_loss_stats_len(int N, int C);
+int stc_seg_loss_fwd(const float* logits, const int64_t* label, double* stats, float* out3, int N, long long HW, int C,
+                     int ignore_index, float smooth, void* stream);
+/* dlogits = g_ce * dCE/dlogits + g_dice * dDice/dlogits */
+int stc_seg_loss_bwd(const float* logits, const int64_t* label, const double* stats, const float* g_ce, const float* g_dice,
+                     float* dlogits, int N, long long HW, int C, int ignore_index, float smooth, void* stream);
+
+/* ---------------------------------------------------------------- inference post-processing (K17; encoder_decoder.py:157-203,253,272) */
+/* preds[:, :, y1:y1+hc, x1:x1+wc] += crop ; count[:, y1.., x1..] += 1  (NCHW fp32; count (N,H,W)) */
+int stc_slide_accum(const float* crop, float* preds, float* count, int N, int C, int H, int W, int hc, int wc, int y1,
+                    int x1, void* stream);
+/* pred[n,h,w] = argmax_c softmax(preds/count) (first max wins); count may be NULL (whole mode) */
+int stc_argmax(const float* preds, const float* count, int64_t* pred, int N, int C, long long HW, void* stream);
+
+/* ---------------------------------------------------------------- integer confusion matrix (K18; metrics.py:75-87)
+ * cm[label*C + pred] += 1 for label != ignore, label,pred in [0,C).  pred int64, label uint8 or int64
+ * (label_is_u8).  areas (int64[4*C]: intersect, union, pred, label) follow metrics.py exactly
+ * (pred and label histogrammed independently).  Both are accumulated into (caller zeroes). */
+int stc_confusion_hist(const int64_t* pred, const void* label, int label_is_u8, long long n, int C, int ignore_index,
+                       int64_t* cm, int64_t* areas, void* stream);
+
+/* ---------------------------------------------------------------- optimizer (f-2; my_config/STC-UNet.py:87) */
+/* torch.optim.Adam semantics on a flat fp32 buffer; step is 1-based. */
+int stc_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STC_B200_H_ */

@@ -1,0 +1,311 @@
+// BatchNorm / SyncBatchNorm building blocks (K5/K6; C1/C2 exchange happens between reduce and finalize/apply).
+#include "reduce.cuh"
+
+namespace stc {
+
+__device__ __forceinline__ float act_fwd(float z, int act) {
+    if (act == STC_ACT_RELU) return fmaxf(z, 0.f);
+    if (act == STC_ACT_HSWISH) return z * fminf(fmaxf(z + 3.f, 0.f), 6.f) * (1.f / 6.f);
+    return z;
+}
+__device__ __forceinline__ float act_grad(float z, int act) {
+    if (act == STC_ACT_RELU) return z > 0.f ? 1.f : 0.f;
+    if (act == STC_ACT_HSWISH) {
+        // d/dz [ z * relu6(z+3)/6 ] with hardtanh's open-interval gradient
+        float r6 = fminf(fmaxf(z + 3.f, 0.f), 6.f);
+        float inside = (z + 3.f > 0.f && z + 3.f < 6.f) ? 1.f : 0.f;
+        return r6 * (1.f / 6.f) + z * inside * (1.f / 6.f);
+    }
+    return 1.f;
+}
+
+// ---------------------------------------------------------------- forward statistics
+template <typename T>
+__global__ void __launch_bounds__(256) bn_reduce_kernel(const T* __restrict__ y, float* __restrict__ partial, long long P, int C) {
+    __shared__ float smem[256 * 16];
+    const int lanes = C >> 3, lv = threadIdx.x % lanes, r0 = threadIdx.x / lanes, rstep = 256 / lanes;
+    float acc[2][8] = {};
+    for (long long p = (long long)blockIdx.x * rstep + r0; p < P; p += (long long)gridDim.x * rstep) {
+        Vec8<T> v;
+        v.load(y + p * C + lv * 8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            acc[0][k] += v.v[k];
+            acc[1][k] = fmaf(v.v[k], v.v[k], acc[1][k]);
+        }
+    }
+    block_reduce_lanes<2>(acc, lanes, lv, smem, partial, C);
+}
+
+// generic fallback (any C): one block column of 32 channels, fp64 atomics
+template <typename T>
+__global__ void bn_reduce_generic_kernel(const T* __restrict__ y, double* __restrict__ sums, long long P, int C) {
+    int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    int ry = threadIdx.x >> 5;
+    double s = 0, s2 = 0;
+    if (c < C)
+        for (long long p = (long long)blockIdx.y * 8 + ry; p < P; p += (long long)gridDim.y * 8) {
+            float v = ldf(y + p * C + c);
+            s += v;
+            s2 += (double)v * v;
+        }
+    if (c < C) {
+        atomicAdd(sums + c, s);
+        atomicAdd(sums + C + c, s2);
+    }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, float* __restrict__ mean,
+                                   float* __restrict__ invstd, float* __restrict__ rm, float* __restrict__ rv,
+                                   long long* __restrict__ nbt, float momentum, float eps, int C) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double m = sums[c] / count;
+    double var = sums[C + c] / count - m * m;
+    if (var < 0) var = 0;
+    mean[c] = (float)m;
+    invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (rm) {
+        double unb = count > 1 ? var * (count / (count - 1.0)) : var;
+        rm[c] = (1.f - momentum) * rm[c] + momentum * (float)m;
+        rv[c] = (1.f - momentum) * rv[c] + momentum * (float)unb;
+    }
+    if (nbt && c == 0) *nbt += 1;
+}
+
+__global__ void bn_eval_stats_kernel(const float* __restrict__ rm, const float* __restrict__ rv, float* __restrict__ mean,
+                                     float* __restrict__ invstd, float eps, int C) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    mean[c] = rm[c];
+    invstd[c] = rsqrtf(rv[c] + eps);
+}
+
+// ---------------------------------------------------------------- apply
+template <typename T>
+__global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ y, const float* __restrict__ mean,
+                                                       const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, T* __restrict__ a, long long nvec, int lanes,
+                                                       int act) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < nvec; i += stride) {
+        int c0 = (int)(i % lanes) * 8;
+        Vec8<T> v;
+        v.load(y + i * 8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float sc = gamma[c0 + k] * invstd[c0 + k];
+            float z = fmaf(v.v[k] - mean[c0 + k], sc, beta[c0 + k]);
+            v.v[k] = act_fwd(z, act);
+        }
+        v.store(a + i * 8);
+    }
+}
+
+template <typename T>
+__global__ void bn_apply_generic_kernel(const T* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                        const float* __restrict__ gamma, const float* __restrict__ beta, T* __restrict__ a,
+                                        long long total, int C, int act) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        int c = (int)(i % C);
+        float z = fmaf(ldf(y + i) - mean[c], gamma[c] * invstd[c], beta[c]);
+        stf(a + i, act_fwd(z, act));
+    }
+}
+
+// ---------------------------------------------------------------- backward
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* __restrict__ y, const T* __restrict__ dout,
+                                                            const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            float* __restrict__ partial, long long P, int C, int act) {
+    __shared__ float smem[256 * 16];
+    const int lanes = C >> 3, lv = threadIdx.x % lanes, r0 = threadIdx.x / lanes, rstep = 256 / lanes;
+    float mu[8], is[8], ga[8], be[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        mu[k] = mean[lv * 8 + k];
+        is[k] = invstd[lv * 8 + k];
+        ga[k] = gamma[lv * 8 + k];
+        be[k] = beta[lv * 8 + k];
+    }
+    float acc[2][8] = {};
+    for (long long p = (long long)blockIdx.x * rstep + r0; p < P; p += (long long)gridDim.x * rstep) {
+        Vec8<T> v, d;
+        v.load(y + p * C + lv * 8);
+        d.load(dout + p * C + lv * 8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float xh = (v.v[k] - mu[k]) * is[k];
+            float z = fmaf(xh, ga[k], be[k]);
+            float g = d.v[k] * act_grad(z, act);
+            acc[0][k] += g;
+            acc[1][k] = fmaf(g, xh, acc[1][k]);
+        }
+    }
+    block_reduce_lanes<2>(acc, lanes, lv, smem, partial, C);
+}
+
+template <typename T>
+__global__ void bn_bwd_reduce_generic_kernel(const T* __restrict__ y, const T* __restrict__ dout, const float* __restrict__ mean,
+                                             const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                             const float* __restrict__ beta, double* __restrict__ sums, long long P, int C,
+                                             int act) {
+    int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    int ry = threadIdx.x >> 5;
+    double s = 0, s2 = 0;
+    if (c < C)
+        for (long long p = (long long)blockIdx.y * 8 + ry; p < P; p += (long long)gridDim.y * 8) {
+            float xh = (ldf(y + p * C + c) - mean[c]) * invstd[c];
+            float g = ldf(dout + p * C + c) * act_grad(fmaf(xh, gamma[c], beta[c]), act);
+            s += g;
+            s2 += (double)g * xh;
+        }
+    if (c < C) {
+        atomicAdd(sums + c, s);
+        atomicAdd(sums + C + c, s2);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__ y, const T* __restrict__ dout,
+                                                           const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           const double* __restrict__ sums, float inv_count, T* __restrict__ dy,
+                                                           long long total, int C, int vec, int act, int eval) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    if (vec) {
+        const int lanes = C >> 3;
+        const long long nvec = total >> 3;
+        for (; i < nvec; i += stride) {
+            int c0 = (int)(i % lanes) * 8;
+            Vec8<T> v, d;
+            v.load(y + i * 8);
+            d.load(dout + i * 8);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                int c = c0 + k;
+                float xh = (v.v[k] - mean[c]) * invstd[c];
+                float g = d.v[k] * act_grad(fmaf(xh, gamma[c], beta[c]), act);
+                float r = eval ? g : g - (float)sums[c] * inv_count - xh * (float)sums[C + c] * inv_count;
+                v.v[k] = gamma[c] * invstd[c] * r;
+            }
+            v.store(dy + i * 8);
+        }
+    } else {
+        for (; i < total; i += stride) {
+            int c = (int)(i % C);
+            float xh = (ldf(y + i) - mean[c]) * invstd[c];
+            float g = ldf(dout + i) * act_grad(fmaf(xh, gamma[c], beta[c]), act);
+            float r = eval ? g : g - (float)sums[c] * inv_count - xh * (float)sums[C + c] * inv_count;
+            stf(dy + i, gamma[c] * invstd[c] * r);
+        }
+    }
+}
+
+__global__ void bn_param_grads_kernel(const double* __restrict__ sums, float* __restrict__ dgamma, float* __restrict__ dbeta, int C) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    if (dbeta) dbeta[c] = (float)sums[c];
+    if (dgamma) dgamma[c] = (float)sums[C + c];
+}
+
+}  // namespace stc
+
+using namespace stc;
+
+extern "C" long long stc_bn_ws_bytes(long long P, int C) {
+    (void)P;
+    return (long long)num_sms() * 4 * 3 * (long long)C * sizeof(float) + 256;
+}
+
+extern "C" int stc_bn_reduce(const void* y, double* sums, long long P, int C, void* ws, long long ws_bytes, int dtype, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    STC_REQUIRE(P > 0 && C > 0, "bn_reduce: bad shape");
+    if (vec_ok(C) && (((uintptr_t)y) & 15) == 0) {
+        int lanes = C / 8, G = reduce_blocks(P, lanes);
+        STC_REQUIRE(ws && ws_bytes >= (long long)G * 2 * C * (long long)sizeof(float), "bn_reduce: workspace too small");
+        STC_DISPATCH_DTYPE(dtype, (bn_reduce_kernel<T><<<G, 256, 0, st>>>((const T*)y, (float*)ws, P, C)));
+        reduce_partials_kernel<<<ceil_div(2 * C, 128), 128, 0, st>>>((const float*)ws, sums, G, 2 * C);
+    } else {
+        STC_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
+        dim3 grid(ceil_div(C, 32), (unsigned)max(1LL, min((long long)num_sms() * 2, (P + 63) / 64)));
+        STC_DISPATCH_DTYPE(dtype, (bn_reduce_generic_kernel<T><<<grid, 256, 0, st>>>((const T*)y, sums, P, C)));
+    }
+    return check_launch("bn_reduce");
+}
+
+extern "C" int stc_bn_finalize(const double* sums, double count, float* mean, float* invstd, float* running_mean,
+                               float* running_var, int64_t* num_batches_tracked, float momentum, float eps, int C, void* stream) {
+    STC_REQUIRE(count > 0 && C > 0, "bn_finalize: bad count");
+    bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, count, mean, invstd, running_mean, running_var,
+                                                                           (long long*)num_batches_tracked, momentum, eps, C);
+    return check_launch("bn_finalize");
+}
+
+extern "C" int stc_bn_eval_stats(const float* running_mean, const float* running_var, float* mean, float* invstd, float eps,
+                                 int C, void* stream) {
+    bn_eval_stats_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(running_mean, running_var, mean, invstd, eps, C);
+    return check_launch("bn_eval_stats");
+}
+
+extern "C" int stc_bn_apply(const void* y, const float* mean, const float* invstd, const float* gamma, const float* beta, void* a,
+                            long long P, int C, int act, int dtype, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    long long total = P * C;
+    if (total <= 0) return STC_OK;
+    bool vec = C % 8 == 0 && ((((uintptr_t)y) | ((uintptr_t)a)) & 15) == 0;
+    if (vec) {
+        long long nvec = total / 8;
+        int blocks = (int)min((long long)num_sms() * 8, (long long)ceil_div(nvec, 256));
+        STC_DISPATCH_DTYPE(dtype, (bn_apply_kernel<T><<<blocks, 256, 0, st>>>((const T*)y, mean, invstd, gamma, beta, (T*)a, nvec, C / 8, act)));
+    } else {
+        int blocks = (int)min((long long)num_sms() * 8, (long long)ceil_div(total, 256));
+        STC_DISPATCH_DTYPE(dtype, (bn_apply_generic_kernel<T><<<blocks, 256, 0, st>>>((const T*)y, mean, invstd, gamma, beta, (T*)a, total, C, act)));
+    }
+    return check_launch("bn_apply");
+}
+
+extern "C" int stc_bn_bwd_reduce(const void* y, const void* dout, const float* mean, const float* invstd, const float* gamma,
+                                 const float* beta, double* sums, long long P, int C, int act, void* ws, long long ws_bytes,
+                                 int dtype, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    STC_REQUIRE(P > 0 && C > 0, "bn_bwd_reduce: bad shape");
+    if (vec_ok(C) && ((((uintptr_t)y) | ((uintptr_t)dout)) & 15) == 0) {
+        int lanes = C / 8, G = reduce_blocks(P, lanes);
+        STC_REQUIRE(ws && ws_bytes >= (long long)G * 2 * C * (long long)sizeof(float), "bn_bwd_reduce: workspace too small");
+        STC_DISPATCH_DTYPE(dtype, (bn_bwd_reduce_kernel<T><<<G, 256, 0, st>>>((const T*)y, (const T*)dout, mean, invstd, gamma, beta,
+                                                                             (float*)ws, P, C, act)));
+        reduce_partials_kernel<<<ceil_div(2 * C, 128), 128, 0, st>>>((const float*)ws, sums, G, 2 * C);
+    } else {
+        STC_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
+        dim3 grid(ceil_div(C, 32), (unsigned)max(1LL, min((long long)num_sms() * 2, (P + 63) / 64)));
+        STC_DISPATCH_DTYPE(dtype, (bn_bwd_reduce_generic_kernel<T><<<grid, 256, 0, st>>>((const T*)y, (const T*)dout, mean, invstd,
+                                                                                        gamma, beta, sums, P, C, act)));
+    }
+    return check_launch("bn_bwd_reduce");
+}
+
+extern "C" int stc_bn_bwd_apply(const void* y, const void* dout, const float* mean, const float* invstd, const float* gamma,
+                                const float* beta, const double* sums, double count, void* dy,
+                                long long P, int C, int act, int eval, int dtype, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    long long total = P * C;
+    if (total <= 0) return STC_OK;
+    int vec = (C % 8 == 0 && ((((uintptr_t)y) | ((uintptr_t)dout) | ((uintptr_t)dy)) & 15) == 0) ? 1 : 0;
+    long long work = vec ? total / 8 : total;
+    int blocks = (int)min((long long)num_sms() * 8, (long long)ceil_div(work, 256));
+    STC_DISPATCH_DTYPE(dtype, (bn_bwd_apply_kernel<T><<<blocks, 256, 0, st>>>((const T*)y, (const T*)dout, mean, invstd, gamma, beta,
+                                                                            sums, (float)(1.0 / count), (T*)dy, total, C, vec, act,
+                                                                            eval)));
+    return check_launch("bn_bwd_apply");
+}
+
+extern "C" int stc_bn_param_grads(const double* sums, float* dgamma, float* dbeta, int C, void* stream) {
+    bn_param_grads_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, dgamma, dbeta, C);
+    return check_launch("bn_param_grads");
+}

@@ -1,0 +1,322 @@
+// Error plumbing, device checks, layout/packing and elementwise kernels.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace stc {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+        return STC_ERR_CUDA;
+    }
+    return STC_OK;
+}
+
+int num_sms() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+}  // namespace stc
+
+using namespace stc;
+
+extern "C" const char* stc_last_error(void) { return g_err; }
+extern "C" int stc_version(void) { return 100; }
+extern "C" int stc_num_sms(void) { return num_sms(); }
+
+extern "C" int stc_check_device(void) {
+    int dev = 0, major = 0;
+    STC_CUDA(cudaGetDevice(&dev));
+    STC_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10) {
+        set_error("libstc_b200 requires a compute-capability 10.x device (B200, sm_100a); got %d.x — no fallback path", major);
+        return STC_ERR_ARCH;
+    }
+    return STC_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// layout / packing
+// ------------------------------------------------------------------------------------
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, long long HW, int Cpad,
+                                    long long total) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;  // over N*HW*Cpad
+    if (i >= total) return;
+    int c = (int)(i % Cpad);
+    long long p = i / Cpad;
+    long long n = p / HW, hw = p % HW;
+    float v = c < C ? src[(n * C + c) * HW + hw] : 0.f;
+    stf(dst + i, v);
+}
+
+extern "C" int stc_nchw_to_nhwc(const float* src, void* dst, int N, int C, int H, int W, int Cpad, int dtype, void* stream) {
+    STC_REQUIRE(Cpad >= C && N > 0 && C > 0, "nchw_to_nhwc: bad shape");
+    long long HW = (long long)H * W, total = (long long)N * HW * Cpad;
+    STC_DISPATCH_DTYPE(dtype, (nchw_to_nhwc_kernel<T><<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                                   src, (T*)dst, C, HW, Cpad, total)));
+    return check_launch("nchw_to_nhwc");
+}
+
+template <typename T>
+__global__ void pack_w_kernel(const float* __restrict__ w, T* __restrict__ dst, int Cout, int Cin, int R, int S,
+                              int inner_pad, int tf, long long total) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int inner = (int)(i % inner_pad);
+    long long t = i / inner_pad;
+    int outer_n = tf ? Cin : Cout;
+    int outer = (int)(t % outer_n);
+    int tap = (int)(t / outer_n);
+    int r = tap / S, s = tap % S;
+    float v = 0.f;
+    if (!tf) {
+        // dst[tap][co][ci] = W[co][ci][r][s]
+        if (inner < Cin) v = w[(((long long)outer * Cin + inner) * R + r) * S + s];
+    } else {
+        // dst[(R-1-r)*S+(S-1-s)][ci][co] = W[co][ci][r][s]  <=> reading with flipped tap
+        int rr = R - 1 - r, ss = S - 1 - s;
+        if (inner < Cout) v = w[(((long long)inner * Cin + outer) * R + rr) * S + ss];
+    }
+    stf(dst + i, v);
+}
+
+extern "C" int stc_pack_conv_weight(const float* w, void* dst, int Cout, int Cin, int R, int S, int inner_pad,
+                                    int transpose_flip, int dtype, void* stream) {
+    int inner = transpose_flip ? Cout : Cin;
+    int outer = transpose_flip ? Cin : Cout;
+    STC_REQUIRE(inner_pad >= inner, "pack_conv_weight: inner_pad %d < inner %d", inner_pad, inner);
+    long long total = (long long)R * S * outer * inner_pad;
+    STC_DISPATCH_DTYPE(dtype, (pack_w_kernel<T><<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                                   w, (T*)dst, Cout, Cin, R, S, inner_pad, transpose_flip, total)));
+    return check_launch("pack_conv_weight");
+}
+
+__global__ void unpack_wgrad_kernel(const float* __restrict__ ws, float* __restrict__ dw, int Cout, int Cin, int RS,
+                                    int accumulate, long long total) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;  // over OIHW
+    if (i >= total) return;
+    int tap = (int)(i % RS);
+    long long t = i / RS;
+    int ci = (int)(t % Cin);
+    int co = (int)(t / Cin);
+    float v = ws[((long long)tap * Cin + ci) * Cout + co];
+    dw[i] = accumulate ? dw[i] + v : v;
+}
+
+extern "C" int stc_unpack_conv_wgrad(const float* ws, float* dw, int Cout, int Cin, int R, int S, int accumulate, void* stream) {
+    long long total = (long long)Cout * Cin * R * S;
+    unpack_wgrad_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(ws, dw, Cout, Cin, R * S, accumulate, total);
+    return check_launch("unpack_conv_wgrad");
+}
+
+// ------------------------------------------------------------------------------------
+// elementwise
+// ------------------------------------------------------------------------------------
+template <typename T>
+__global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, long long n8, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long j = i; j < n8; j += stride) {
+        Vec8<T> x, y;
+        x.load(a + j * 8);
+        y.load(b + j * 8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x.v[k] += y.v[k];
+        x.store(out + j * 8);
+    }
+    for (long long j = n8 * 8 + i; j < n; j += stride) stf(out + j, ldf(a + j) + ldf(b + j));
+}
+
+extern "C" int stc_add(const void* a, const void* b, void* out, long long n, int dtype, void* stream) {
+    if (n <= 0) return STC_OK;
+    bool aligned = (((uintptr_t)a | (uintptr_t)b | (uintptr_t)out) & 15) == 0;
+    long long n8 = aligned ? n / 8 : 0;
+    int blocks = (int)min((long long)num_sms() * 16, (long long)ceil_div(max(n8, 1LL), 256));
+    if (blocks < 1) blocks = 1;
+    STC_DISPATCH_DTYPE(dtype, (add_kernel<T><<<blocks, 256, 0, (cudaStream_t)stream>>>((const T*)a, (const T*)b, (T*)out, n8, n)));
+    return check_launch("add");
+}
+
+__global__ void axpy_kernel(const float* __restrict__ x, float* __restrict__ y, float alpha, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) y[i] += alpha * x[i];
+}
+
+extern "C" int stc_axpy_f32(const float* x, float* y, float alpha, long long n, void* stream) {
+    if (n <= 0) return STC_OK;
+    int blocks = (int)min((long long)num_sms() * 8, (long long)ceil_div(n, 256));
+    axpy_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, y, alpha, n);
+    return check_launch("axpy");
+}
+
+template <typename TS, typename TD>
+__global__ void cast_kernel(const TS* __restrict__ s, TD* __restrict__ d, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) stf(d + i, ldf(s + i));
+}
+
+extern "C" int stc_cast(const void* src, void* dst, long long n, int sd, int dd, void* stream) {
+    if (n <= 0) return STC_OK;
+    int blocks = (int)min((long long)num_sms() * 16, (long long)ceil_div(n, 256));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (sd == STC_F32 && dd == STC_BF16) cast_kernel<float, bf16><<<blocks, 256, 0, st>>>((const float*)src, (bf16*)dst, n);
+    else if (sd == STC_BF16 && dd == STC_F32) cast_kernel<bf16, float><<<blocks, 256, 0, st>>>((const bf16*)src, (float*)dst, n);
+    else if (sd == STC_F32 && dd == STC_F32) cast_kernel<float, float><<<blocks, 256, 0, st>>>((const float*)src, (float*)dst, n);
+    else if (sd == STC_BF16 && dd == STC_BF16) cast_kernel<bf16, bf16><<<blocks, 256, 0, st>>>((const bf16*)src, (bf16*)dst, n);
+    else { set_error("cast: bad dtypes"); return STC_ERR_INVALID; }
+    return check_launch("cast");
+}
+
+template <typename T>
+__global__ void act_bwd_kernel(const T* __restrict__ yo, const T* __restrict__ dy, T* __restrict__ dx, long long n, int act) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        float o = ldf(yo + i), g = ldf(dy + i), r;
+        if (act == STC_ACT_SIGMOID) r = g * o * (1.f - o);
+        else if (act == STC_ACT_RELU) r = o > 0.f ? g : 0.f;
+        else r = g;
+        stf(dx + i, r);
+    }
+}
+
+extern "C" int stc_act_bwd(const void* y_out, const void* dy, void* dx, long long n, int act, int dtype, void* stream) {
+    if (n <= 0) return STC_OK;
+    STC_REQUIRE(act == STC_ACT_SIGMOID || act == STC_ACT_RELU || act == STC_ACT_NONE, "act_bwd: unsupported act %d", act);
+    int blocks = (int)min((long long)num_sms() * 16, (long long)ceil_div(n, 256));
+    STC_DISPATCH_DTYPE(dtype, (act_bwd_kernel<T><<<blocks, 256, 0, (cudaStream_t)stream>>>((const T*)y_out, (const T*)dy, (T*)dx, n, act)));
+    return check_launch("act_bwd");
+}
+
+template <typename T>
+__global__ void scale_channels_kernel(const T* __restrict__ x, const float* __restrict__ m, T* __restrict__ y, long long HW,
+                                      int C, long long total) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        int c = (int)(i % C);
+        long long n = i / ((long long)C * HW);
+        stf(y + i, ldf(x + i) * m[n * C + c]);
+    }
+}
+
+extern "C" int stc_scale_channels(const void* x, const float* m, void* y, int N, long long HW, int C, int dtype, void* stream) {
+    long long total = (long long)N * HW * C;
+    if (total <= 0) return STC_OK;
+    int blocks = (int)min((long long)num_sms() * 16, (long long)ceil_div(total, 256));
+    STC_DISPATCH_DTYPE(dtype, (scale_channels_kernel<T><<<blocks, 256, 0, (cudaStream_t)stream>>>((const T*)x, m, (T*)y, HW, C, total)));
+    return check_launch("scale_channels");
+}
+
+// column sums out[c] = sum_p x[p][c]; block = 256 threads = 8 row-lanes x 32 channel lanes
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ x, float* __restrict__ out, long long P, int C) {
+    __shared__ float red[8][33];
+    int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    int c = blockIdx.x * 32 + cx;
+    float acc = 0.f;
+    if (c < C) {
+        long long rows_per = (P + gridDim.y - 1) / gridDim.y;
+        long long p0 = blockIdx.y * rows_per, p1 = min(P, p0 + rows_per);
+        for (long long p = p0 + ry; p < p1; p += 8) acc += ldf(x + p * C + c);
+    }
+    red[ry][cx] = acc;
+    __syncthreads();
+    if (ry == 0 && c < C) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += red[k][cx];
+        atomicAdd(out + c, s);
+    }
+}
+
+extern "C" int stc_colsum(const void* x, float* out, long long P, int C, int accumulate, int dtype, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!accumulate) STC_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * C, st));
+    if (P <= 0) return STC_OK;
+    int gx = ceil_div(C, 32);
+    int gy = (int)max(1LL, min((long long)ceil_div(P, 64), (long long)(num_sms() * 8 / gx + 1)));
+    dim3 grid(gx, gy);
+    STC_DISPATCH_DTYPE(dtype, (colsum_kernel<T><<<grid, 256, 0, st>>>((const T*)x, out, P, C)));
+    return check_launch("colsum");
+}
+
+// ------------------------------------------------------------------------------------
+// Adam (torch.optim.Adam, no amsgrad)
+// ------------------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        float gi = g[i], pi = p[i];
+        if (wd != 0.f) gi += wd * pi;
+        float mi = b1 * m[i] + (1.f - b1) * gi;
+        float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] = pi - (lr / bc1) * (mi / denom);
+    }
+}
+
+extern "C" int stc_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                             float eps, float weight_decay, int step, void* stream) {
+    if (n <= 0) return STC_OK;
+    STC_REQUIRE(step >= 1, "adam: step must be >= 1");
+    float bc1 = 1.f - powf(beta1, (float)step);
+    float bc2s = sqrtf(1.f - powf(beta2, (float)step));
+    int blocks = (int)min((long long)num_sms() * 16, (long long)ceil_div(n, 256));
+    adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2s);
+    return check_launch("adam");
+}
+
+// ------------------------------------------------------------------------------------
+// row-block copy between (N, rows, C) tensors: dst[n, dst_off + r, :] = src[n, src_off + r, :], r < count
+// ------------------------------------------------------------------------------------
+template <typename T>
+__global__ void copy_rows_kernel(const T* __restrict__ src, T* __restrict__ dst, int src_rows, int dst_rows, int C, int src_off,
+                                 int dst_off, int count, long long total) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        int c = (int)(i % C);
+        long long t = i / C;
+        int r = (int)(t % count);
+        long long n = t / count;
+        dst[(n * dst_rows + dst_off + r) * C + c] = src[(n * src_rows + src_off + r) * C + c];
+    }
+}
+
+extern "C" int stc_copy_rows(const void* src, void* dst, int N, int src_rows, int dst_rows, int C, int src_off, int dst_off,
+                             int count, int dtype, void* stream) {
+    STC_REQUIRE(src_off >= 0 && dst_off >= 0 && src_off + count <= src_rows && dst_off + count <= dst_rows, "copy_rows: range");
+    long long total = (long long)N * count * C;
+    if (total <= 0) return STC_OK;
+    int blocks = (int)min((long long)num_sms() * 8, (long long)ceil_div(total, 256));
+    STC_DISPATCH_DTYPE(dtype, (copy_rows_kernel<T><<<blocks, 256, 0, (cudaStream_t)stream>>>((const T*)src, (T*)dst, src_rows, dst_rows, C,
+                                                                                           src_off, dst_off, count, total)));
+    return check_launch("copy_rows");
+}

@@ -1,0 +1,398 @@
+// Classifier (1x1 conv to NCHW fp32 logits), fused CE + Dice + accuracy, inference post-processing
+// and the integer confusion-matrix histogram.
+#include "reduce.cuh"
+
+namespace stc {
+
+constexpr int kMaxCls = 32;
+
+// ---------------------------------------------------------------- cls_seg
+template <typename T>
+__global__ void __launch_bounds__(256) cls_fwd_kernel(const T* __restrict__ x, const float* __restrict__ Wt, const float* __restrict__ b,
+                                                      float* __restrict__ logits, long long HW, int Cin, int Ccls, long long P) {
+    extern __shared__ float sw[];  // [Ccls][Cin] + [Ccls]
+    for (int i = threadIdx.x; i < Ccls * Cin; i += blockDim.x) sw[i] = Wt[i];
+    for (int i = threadIdx.x; i < Ccls; i += blockDim.x) sw[Ccls * Cin + i] = b ? b[i] : 0.f;
+    __syncthreads();
+    long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    long long n = p / HW, hw = p - n * HW;
+    const T* xr = x + p * Cin;
+    for (int k0 = 0; k0 < Ccls; k0 += 4) {
+        float acc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = (k0 + j < Ccls) ? sw[Ccls * Cin + k0 + j] : 0.f;
+        for (int c = 0; c < Cin; c += 8) {
+            Vec8<T> v;
+            v.load(xr + c);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (k0 + j < Ccls) {
+                    const float* wr = sw + (k0 + j) * Cin + c;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[j] = fmaf(v.v[e], wr[e], acc[j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (k0 + j < Ccls) logits[(n * Ccls + k0 + j) * HW + hw] = acc[j];
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) cls_bwd_dx_kernel(const float* __restrict__ dl, const float* __restrict__ Wt, T* __restrict__ dx,
+                                                         long long HW, int Cin, int Ccls, long long P) {
+    extern __shared__ float sw[];  // [Ccls][Cin]
+    for (int i = threadIdx.x; i < Ccls * Cin; i += blockDim.x) sw[i] = Wt[i];
+    __syncthreads();
+    long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    long long n = p / HW, hw = p - n * HW;
+    float g[kMaxCls];
+    for (int k = 0; k < Ccls; ++k) g[k] = dl[(n * Ccls + k) * HW + hw];
+    for (int c = 0; c < Cin; c += 8) {
+        Vec8<T> v;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v.v[e] = 0.f;
+        for (int k = 0; k < Ccls; ++k) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v.v[e] = fmaf(g[k], sw[k * Cin + c + e], v.v[e]);
+        }
+        v.store(dx + p * Cin + c);
+    }
+}
+
+// dW[k][c] += sum_p dl[k][p] x[p][c] for 4 classes starting at k0; db likewise
+template <typename T>
+__global__ void __launch_bounds__(256) cls_bwd_dw_kernel(const float* __restrict__ dl, const T* __restrict__ x, float* __restrict__ dW,
+                                                         float* __restrict__ db, long long HW, int Cin, int Ccls, long long P, int k0) {
+    __shared__ float smem[256 * 8 * 4];
+    const int lanes = Cin >> 3, lv = threadIdx.x % lanes, r0 = threadIdx.x / lanes, rstep = 256 / lanes;
+    float acc[4][8] = {};
+    float bs[4] = {};
+    for (long long p = (long long)blockIdx.x * rstep + r0; p < P; p += (long long)gridDim.x * rstep) {
+        long long n = p / HW, hw = p - n * HW;
+        Vec8<T> v;
+        v.load(x + p * Cin + lv * 8);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (k0 + j < Ccls) {
+                float g = dl[(n * Ccls + k0 + j) * HW + hw];
+                if (lv == 0) bs[j] += g;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[j][e] = fmaf(g, v.v[e], acc[j][e]);
+            }
+        }
+    }
+    block_reduce_lanes_emit<4>(acc, lanes, smem, Cin, [&](int q, int c, float s) {
+        if (k0 + q < Ccls) atomicAdd(dW + (long long)(k0 + q) * Cin + c, s);
+    });
+    if (db && lv == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (k0 + j < Ccls && bs[j] != 0.f) atomicAdd(db + k0 + j, bs[j]);
+    }
+}
+
+// ---------------------------------------------------------------- CE + Dice + accuracy
+// stats layout (fp64): [n][c][3] = {sum p*t*m, sum p^2, sum t}; tail [4] = {ce_sum, n_correct, n_valid, unused}
+template <int CM>
+__global__ void __launch_bounds__(256) seg_loss_fwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__ label,
+                                                           double* __restrict__ stats, long long HW, int C, int N, int ignore) {
+    const long long n = blockIdx.y;
+    const float* lg = logits + n * C * HW;
+    const int64_t* lb = label + n * HW;
+    float spt[CM], sp2[CM], st[CM];
+#pragma unroll
+    for (int k = 0; k < CM; ++k) spt[k] = sp2[k] = st[k] = 0.f;
+    float ce = 0.f, correct = 0.f, nvalid = 0.f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x) {
+        const long long y = lb[i];
+        const bool valid = y != ignore;
+        const int yc = (int)(y < 0 ? 0 : (y > C - 1 ? C - 1 : y));
+        float z[CM];
+        float m = -INFINITY, zy = 0.f;
+        int arg = 0;
+#pragma unroll
+        for (int k = 0; k < CM; ++k) {
+            if (k < C) {
+                z[k] = lg[k * HW + i];
+                if (z[k] > m) { m = z[k]; arg = k; }
+                if (k == yc) zy = z[k];
+            }
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < CM; ++k)
+            if (k < C) { z[k] = expf(z[k] - m); sum += z[k]; }
+        const float inv = 1.f / sum;
+#pragma unroll
+        for (int k = 0; k < CM; ++k) {
+            if (k < C) {
+                float p = z[k] * inv;
+                sp2[k] = fmaf(p, p, sp2[k]);
+                if (k == yc) {
+                    st[k] += 1.f;
+                    if (valid) spt[k] += p;
+                }
+            }
+        }
+        if (valid) {
+            nvalid += 1.f;
+            if (arg == (int)y) correct += 1.f;
+            ce += logf(sum) + (m - zy);  // -log softmax[y]
+        }
+    }
+    // block reduction of 3*C + 3 values
+    __shared__ float red[8][3 * CM + 3];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < CM; ++k) {
+        float a = warp_sum(spt[k]), b = warp_sum(sp2[k]), c = warp_sum(st[k]);
+        if (lane == 0) { red[warp][3 * k] = a; red[warp][3 * k + 1] = b; red[warp][3 * k + 2] = c; }
+    }
+    {
+        float a = warp_sum(ce), b = warp_sum(correct), c = warp_sum(nvalid);
+        if (lane == 0) { red[warp][3 * CM] = a; red[warp][3 * CM + 1] = b; red[warp][3 * CM + 2] = c; }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < 3 * CM + 3; j += blockDim.x) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[w][j];
+        if (j < 3 * CM) {
+            int k = j / 3;
+            if (k < C) atomicAdd(stats + (n * C + k) * 3 + (j - 3 * k), (double)s);
+        } else {
+            atomicAdd(stats + (long long)N * C * 3 + (j - 3 * CM), (double)s);
+        }
+    }
+}
+
+__global__ void seg_loss_finalize_kernel(const double* __restrict__ stats, float* __restrict__ out3, int N, int C, long long HW, float smooth) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double* tail = stats + (long long)N * C * 3;
+    out3[0] = (float)(tail[0] / ((double)N * (double)HW));
+    double total = 0.0;
+    for (int k = 0; k < C; ++k) {
+        double acc = 0.0;
+        for (int n = 0; n < N; ++n) {
+            const double* s = stats + ((long long)n * C + k) * 3;
+            // reference arithmetic is fp32 per image: 1 - (2*spt + smooth) / (sp2 + st + smooth)
+            float num = (float)s[0] * 2.f + smooth;
+            float den = (float)(s[1] + s[2]) + smooth;
+            acc += (double)(1.f - num / den);
+        }
+        total += acc / N;
+    }
+    out3[1] = (float)(total / C);
+    const float eps = 1.1920928955078125e-07f;
+    out3[2] = ((float)tail[1] + eps) * (100.0f / ((float)tail[2] + eps));
+}
+
+template <int CM>
+__global__ void __launch_bounds__(256) seg_loss_bwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__ label,
+                                                           const double* __restrict__ stats, const float* __restrict__ g_ce,
+                                                           const float* __restrict__ g_dice, float* __restrict__ dlogits, long long HW,
+                                                           int C, int N, int ignore, float smooth) {
+    const long long n = blockIdx.y;
+    const float* lg = logits + n * C * HW;
+    float* dl = dlogits + n * C * HW;
+    const int64_t* lb = label + n * HW;
+    __shared__ float sA[CM], sB[CM];
+    if (threadIdx.x < C) {
+        const double* s = stats + (n * C + threadIdx.x) * 3;
+        sA[threadIdx.x] = (float)s[0] * 2.f + smooth;
+        sB[threadIdx.x] = (float)(s[1] + s[2]) + smooth;
+    }
+    __syncthreads();
+    const float gce = (g_ce ? *g_ce : 0.f) / ((float)N * (float)HW);
+    const float gd = (g_dice ? *g_dice : 0.f) / ((float)C * (float)N);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x) {
+        float p[CM];
+        float m = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < CM; ++k)
+            if (k < C) { p[k] = lg[k * HW + i]; m = fmaxf(m, p[k]); }
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < CM; ++k)
+            if (k < C) { p[k] = expf(p[k] - m); sum += p[k]; }
+        const float inv = 1.f / sum;
+        const long long y = lb[i];
+        const bool valid = y != ignore;
+        const int yc = (int)(y < 0 ? 0 : (y > C - 1 ? C - 1 : y));
+        // dDice/dp_k = -gd * ( 2 t_k m / B_k - A_k * 2 p_k / B_k^2 )
+        float gp[CM];
+        float dot = 0.f;
+#pragma unroll
+        for (int k = 0; k < CM; ++k) {
+            if (k < C) {
+                p[k] *= inv;
+                float t = (k == yc) ? 1.f : 0.f;
+                float tm = (valid && k == yc) ? 1.f : 0.f;
+                float B = sB[k];
+                gp[k] = -gd * (2.f * tm / B - sA[k] * 2.f * p[k] / (B * B));
+                (void)t;
+                dot = fmaf(gp[k], p[k], dot);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < CM; ++k) {
+            if (k < C) {
+                float d = p[k] * (gp[k] - dot);
+                if (valid) d += gce * (p[k] - (k == yc ? 1.f : 0.f));
+                dl[k * HW + i] = d;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- inference post-processing
+__global__ void slide_accum_kernel(const float* __restrict__ crop, float* __restrict__ preds, float* __restrict__ count, int C, int H, int W,
+                                   int hc, int wc, int y1, int x1, long long total) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int x = (int)(i % wc), y = (int)((i / wc) % hc);
+    long long n = i / ((long long)wc * hc);
+    long long o = ((long long)(y1 + y)) * W + (x1 + x);
+    for (int k = 0; k < C; ++k) preds[(n * C + k) * (long long)H * W + o] += crop[(n * C + k) * (long long)hc * wc + (long long)y * wc + x];
+    count[n * (long long)H * W + o] += 1.f;
+}
+
+__global__ void argmax_kernel(const float* __restrict__ preds, const float* __restrict__ count, int64_t* __restrict__ pred, int C, long long HW,
+                              long long total) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    long long n = i / HW, hw = i - n * HW;
+    // softmax is monotone: argmax of softmax(preds / count) == argmax of preds / count (first max wins)
+    float inv = count ? 1.f / count[i] : 1.f;
+    float best = -INFINITY;
+    int arg = 0;
+    for (int k = 0; k < C; ++k) {
+        float v = preds[(n * C + k) * HW + hw] * inv;
+        if (v > best) { best = v; arg = k; }
+    }
+    pred[i] = arg;
+}
+
+// ---------------------------------------------------------------- confusion matrix / area histograms
+__global__ void __launch_bounds__(256) confusion_hist_kernel(const int64_t* __restrict__ pred, const void* __restrict__ label, int label_u8,
+                                                             long long n, int C, int ignore, unsigned long long* __restrict__ cm,
+                                                             unsigned long long* __restrict__ areas) {
+    __shared__ unsigned int s_cm[kMaxCls * kMaxCls];
+    __shared__ unsigned int s_ar[3 * kMaxCls];
+    for (int i = threadIdx.x; i < C * C; i += blockDim.x) s_cm[i] = 0;
+    for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) s_ar[i] = 0;
+    __syncthreads();
+    const uint8_t* l8 = reinterpret_cast<const uint8_t*>(label);
+    const int64_t* l64 = reinterpret_cast<const int64_t*>(label);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        long long y = label_u8 ? (long long)l8[i] : l64[i];
+        if (y == ignore) continue;
+        long long p = pred[i];
+        bool yin = y >= 0 && y < C, pin = p >= 0 && p < C;
+        if (yin) atomicAdd(&s_ar[2 * C + (int)y], 1u);            // area_label
+        if (pin) atomicAdd(&s_ar[C + (int)p], 1u);                // area_pred_label
+        if (pin && p == y) atomicAdd(&s_ar[(int)p], 1u);          // area_intersect
+        if (yin && pin) atomicAdd(&s_cm[(int)y * C + (int)p], 1u);
+    }
+    __syncthreads();
+    if (cm)
+        for (int i = threadIdx.x; i < C * C; i += blockDim.x)
+            if (s_cm[i]) atomicAdd(cm + i, (unsigned long long)s_cm[i]);
+    if (areas)
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            // global layout int64[4][C] = intersect, union, pred, label; union is linear in the other three
+            unsigned long long I = s_ar[c], Pp = s_ar[C + c], Ll = s_ar[2 * C + c];
+            if (I) atomicAdd(areas + c, I);
+            if (Pp + Ll - I) atomicAdd(areas + C + c, Pp + Ll - I);
+            if (Pp) atomicAdd(areas + 2 * C + c, Pp);
+            if (Ll) atomicAdd(areas + 3 * C + c, Ll);
+        }
+}
+
+}  // namespace stc
+
+using namespace stc;
+
+extern "C" int stc_cls_fwd(const void* x, const float* W, const float* b, float* logits, int N, long long HW, int Cin, int Ccls,
+                           int dtype, void* stream) {
+    STC_REQUIRE(Cin % 8 == 0 && Ccls >= 1 && Ccls <= kMaxCls, "cls_fwd: Cin=%d (mult of 8) Ccls=%d (<=%d)", Cin, Ccls, kMaxCls);
+    long long P = (long long)N * HW;
+    size_t smem = sizeof(float) * ((size_t)Ccls * Cin + Ccls);
+    STC_DISPATCH_DTYPE(dtype, (cls_fwd_kernel<T><<<ceil_div(P, 256), 256, smem, (cudaStream_t)stream>>>((const T*)x, W, b, logits, HW, Cin, Ccls, P)));
+    return check_launch("cls_fwd");
+}
+
+extern "C" long long stc_cls_bwd_ws_bytes(int, long long, int, int) { return 0; }
+
+extern "C" int stc_cls_bwd(const float* dlogits, const void* x, const float* W, void* dx, float* dW, float* db, int N, long long HW,
+                           int Cin, int Ccls, void* ws, long long ws_bytes, int dtype, void* stream) {
+    (void)ws; (void)ws_bytes;
+    STC_REQUIRE(vec_ok(Cin) && Ccls >= 1 && Ccls <= kMaxCls, "cls_bwd: Cin=%d must be 8*2^k, Ccls=%d (<=%d)", Cin, Ccls, kMaxCls);
+    cudaStream_t st = (cudaStream_t)stream;
+    long long P = (long long)N * HW;
+    if (dx) {
+        size_t smem = sizeof(float) * (size_t)Ccls * Cin;
+        STC_DISPATCH_DTYPE(dtype, (cls_bwd_dx_kernel<T><<<ceil_div(P, 256), 256, smem, st>>>(dlogits, W, (T*)dx, HW, Cin, Ccls, P)));
+    }
+    if (dW) {
+        int G = reduce_blocks(P, Cin / 8);
+        for (int k0 = 0; k0 < Ccls; k0 += 4)
+            STC_DISPATCH_DTYPE(dtype, (cls_bwd_dw_kernel<T><<<G, 256, 0, st>>>(dlogits, (const T*)x, dW, db, HW, Cin, Ccls, P, k0)));
+    }
+    return check_launch("cls_bwd");
+}
+
+extern "C" long long stc_seg_loss_stats_len(int N, int C) { return (long long)N * C * 3 + 4; }
+
+extern "C" int stc_seg_loss_fwd(const float* logits, const int64_t* label, double* stats, float* out3, int N, long long HW, int C,
+                                int ignore_index, float smooth, void* stream) {
+    STC_REQUIRE(C >= 1 && C <= kMaxCls && N >= 1, "seg_loss_fwd: C=%d must be in [1,%d]", C, kMaxCls);
+    cudaStream_t st = (cudaStream_t)stream;
+    STC_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * stc_seg_loss_stats_len(N, C), st));
+    dim3 grid((unsigned)max(1LL, min((long long)ceil_div(HW, 256 * 4), (long long)num_sms() * 4 / N + 1)), N);
+    if (C <= 4) seg_loss_fwd_kernel<4><<<grid, 256, 0, st>>>(logits, label, stats, HW, C, N, ignore_index);
+    else if (C <= 8) seg_loss_fwd_kernel<8><<<grid, 256, 0, st>>>(logits, label, stats, HW, C, N, ignore_index);
+    else seg_loss_fwd_kernel<kMaxCls><<<grid, 256, 0, st>>>(logits, label, stats, HW, C, N, ignore_index);
+    seg_loss_finalize_kernel<<<1, 32, 0, st>>>(stats, out3, N, C, HW, smooth);
+    return check_launch("seg_loss_fwd");
+}
+
+extern "C" int stc_seg_loss_bwd(const float* logits, const int64_t* label, const double* stats, const float* g_ce, const float* g_dice,
+                                float* dlogits, int N, long long HW, int C, int ignore_index, float smooth, void* stream) {
+    STC_REQUIRE(C >= 1 && C <= kMaxCls && N >= 1, "seg_loss_bwd: C=%d must be in [1,%d]", C, kMaxCls);
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid((unsigned)max(1LL, min((long long)ceil_div(HW, 256 * 2), (long long)num_sms() * 8 / N + 1)), N);
+    if (C <= 4) seg_loss_bwd_kernel<4><<<grid, 256, 0, st>>>(logits, label, stats, g_ce, g_dice, dlogits, HW, C, N, ignore_index, smooth);
+    else if (C <= 8) seg_loss_bwd_kernel<8><<<grid, 256, 0, st>>>(logits, label, stats, g_ce, g_dice, dlogits, HW, C, N, ignore_index, smooth);
+    else seg_loss_bwd_kernel<kMaxCls><<<grid, 256, 0, st>>>(logits, label, stats, g_ce, g_dice, dlogits, HW, C, N, ignore_index, smooth);
+    return check_launch("seg_loss_bwd");
+}
+
+extern "C" int stc_slide_accum(const float* crop, float* preds, float* count, int N, int C, int H, int W, int hc, int wc, int y1, int x1,
+                               void* stream) {
+    STC_REQUIRE(y1 >= 0 && x1 >= 0 && y1 + hc <= H && x1 + wc <= W, "slide_accum: window out of range");
+    long long total = (long long)N * hc * wc;
+    slide_accum_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(crop, preds, count, C, H, W, hc, wc, y1, x1, total);
+    return check_launch("slide_accum");
+}
+
+extern "C" int stc_argmax(const float* preds, const float* count, int64_t* pred, int N, int C, long long HW, void* stream) {
+    long long total = (long long)N * HW;
+    argmax_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(preds, count, pred, C, HW, total);
+    return check_launch("argmax");
+}
+
+extern "C" int stc_confusion_hist(const int64_t* pred, const void* label, int label_is_u8, long long n, int C, int ignore_index,
+                                  int64_t* cm, int64_t* areas, void* stream) {
+    STC_REQUIRE(C >= 1 && C <= kMaxCls, "confusion_hist: C=%d must be in [1,%d]", C, kMaxCls);
+    if (n <= 0) return STC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int blocks = (int)max(1LL, min((long long)num_sms() * 4, (long long)ceil_div(n, 256 * 8)));
+    confusion_hist_kernel<<<blocks, 256, 0, st>>>(pred, label, label_is_u8, n, C, ignore_index, (unsigned long long*)cm,
+                                                   (unsigned long long*)areas);
+    return check_launch("confusion_hist");
+}

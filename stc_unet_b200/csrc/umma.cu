@@ -1,0 +1,581 @@
+// tcgen05 / TMEM / TMA implicit-GEMM engine (sm_100a).
+//
+// One persistent, warp-specialised kernel serves the three dense contractions of the path:
+//   MODE_CONV  : y[pixel][co] = sum_{tap,ci} x[pixel+tap][ci] * w[tap][co][ci]   (fprop, and dgrad with the
+//                flipped/transposed weight pack).  A = NHWC activations fetched per tap by a 4-D TMA box whose
+//                out-of-bounds rows/cols are zero-filled (this IS the conv zero padding), B = packed weights.
+//   MODE_GEMM  : batched C = alpha * A * B with K-major or MN-major operands (attention QK^T, PV and their grads).
+//   MODE_WGRAD : dW[(tap,ci)][co] += sum_pixels x[pixel+tap][ci] * dy[pixel][co]; both operands MN-major,
+//                split-K over pixel tiles, fp32 red.add into the workspace.
+// Roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer,
+// warps 2..5 = epilogue (TMEM -> registers -> global).  smem ring of `stages` A/B slots (128B-swizzled),
+// two TMEM accumulator stages of 256 columns so the epilogue of tile i overlaps the main loop of tile i+1.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace stc {
+
+enum { MODE_CONV = 0, MODE_GEMM = 1, MODE_WGRAD = 2 };
+
+struct alignas(64) UmmaParams {
+    CUtensorMap tmA;
+    CUtensorMap tmB;
+    int mode;
+    int num_tiles, num_n_tiles, num_m_tiles;
+    int num_k_iters;  // conv/gemm: k iterations per tile; wgrad: total pixel tiles
+    int BN, stages, ksteps;
+    uint32_t a_stage_bytes, b_stage_bytes;
+    int a_boxes, b_boxes;
+    uint32_t a_box_bytes, b_box_bytes;
+    uint32_t a_lbo, a_sbo, a_kstep_bytes;
+    uint32_t b_lbo, b_sbo, b_kstep_bytes;
+    int a_mn_major, b_mn_major;
+    uint32_t idesc;
+    // conv / wgrad geometry
+    int H, W, BW, BH, bw_shift, tiles_w, tiles_h, cin_chunks, R, S;
+    int num_atoms, k_per_split;
+    // gemm
+    int M, batch2;
+    // epilogue
+    void* out;
+    const float* bias;
+    const void* residual;
+    int act, out_dtype, Cout;
+    long long ldc, sC1, sC2;
+    float alpha;
+};
+
+struct TileInfo {
+    int nt, mt;
+    int n_img, h0, w0;  // conv
+    int b1, b2;         // gemm
+    int k0, k1;         // k-iteration range
+};
+
+__device__ __forceinline__ void pixel_tile_origin(const UmmaParams& p, int pt, int& n_img, int& h0, int& w0) {
+    int per_img = p.tiles_h * p.tiles_w;
+    n_img = pt / per_img;
+    int rem = pt - n_img * per_img;
+    int th = rem / p.tiles_w;
+    h0 = th * p.BH;
+    w0 = (rem - th * p.tiles_w) * p.BW;
+}
+
+__device__ __forceinline__ TileInfo decode_tile(const UmmaParams& p, int tile) {
+    TileInfo t;
+    t.nt = tile % p.num_n_tiles;
+    int t2 = tile / p.num_n_tiles;
+    t.n_img = t.h0 = t.w0 = t.b1 = t.b2 = 0;
+    t.k0 = 0;
+    t.k1 = p.num_k_iters;
+    if (p.mode == MODE_CONV) {
+        t.mt = t2;
+        pixel_tile_origin(p, t2, t.n_img, t.h0, t.w0);
+    } else if (p.mode == MODE_GEMM) {
+        t.mt = t2 % p.num_m_tiles;
+        int b = t2 / p.num_m_tiles;
+        t.b1 = b / p.batch2;
+        t.b2 = b - t.b1 * p.batch2;
+    } else {
+        t.mt = t2 % p.num_m_tiles;
+        int split = t2 / p.num_m_tiles;
+        t.k0 = split * p.k_per_split;
+        t.k1 = min(p.num_k_iters, t.k0 + p.k_per_split);
+    }
+    return t;
+}
+
+__device__ __forceinline__ float epi_act(float v, int act) {
+    if (act == STC_ACT_RELU) return fmaxf(v, 0.f);
+    if (act == STC_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
+    if (act == STC_ACT_HSWISH) return v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
+    return v;
+}
+
+constexpr int kUmmaThreads = 192;
+constexpr int kAccCols = 256;
+
+__global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_constant__ UmmaParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    // 1024B alignment for the 128B swizzle atoms
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    // bars: [0,stages) full, [stages,2*stages) empty, then tmem_full[2], tmem_empty[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = ptx::smem_u32(smem);
+    const uint32_t bar_base = ptx::smem_u32(bars);
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * p.stages + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * p.stages + 2 + s); };
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&p.tmA);
+        ptx::prefetch_tensormap(&p.tmB);
+        for (int s = 0; s < p.stages; ++s) {
+            ptx::mbar_init(full_bar(s), 1);
+            ptx::mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(tfull_bar(s), 1);
+            ptx::mbar_init(tempty_bar(s), 4);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                TileInfo t = decode_tile(p, tile);
+                for (int kt = t.k0; kt < t.k1; ++kt) {
+                    ptx::mbar_wait(empty_bar(stage), phase ^ 1);
+                    const uint32_t a_dst = smem_base + stage * stage_bytes;
+                    const uint32_t b_dst = a_dst + p.a_stage_bytes;
+                    const uint32_t fb = full_bar(stage);
+                    ptx::mbar_arrive_expect_tx(fb, stage_bytes);
+                    if (p.mode == MODE_CONV) {
+                        int tap = kt / p.cin_chunks, cc = kt - tap * p.cin_chunks;
+                        int r = tap / p.S, s = tap - r * p.S;
+                        ptx::tma_load_4d(a_dst, &p.tmA, fb, cc * 64, t.w0 + s - p.S / 2, t.h0 + r - p.R / 2, t.n_img);
+                        ptx::tma_load_3d(b_dst, &p.tmB, fb, cc * 64, t.nt * p.BN, tap);
+                    } else if (p.mode == MODE_GEMM) {
+                        if (!p.a_mn_major) {
+                            ptx::tma_load_4d(a_dst, &p.tmA, fb, kt * 64, t.mt * 128, t.b2, t.b1);
+                        } else {
+                            for (int j = 0; j < p.a_boxes; ++j)
+                                ptx::tma_load_4d(a_dst + j * p.a_box_bytes, &p.tmA, fb, t.mt * 128 + j * 64, kt * 64, t.b2, t.b1);
+                        }
+                        if (!p.b_mn_major) {
+                            ptx::tma_load_4d(b_dst, &p.tmB, fb, kt * 64, t.nt * p.BN, t.b2, t.b1);
+                        } else {
+                            for (int j = 0; j < p.b_boxes; ++j)
+                                ptx::tma_load_4d(b_dst + j * p.b_box_bytes, &p.tmB, fb, t.nt * p.BN + j * 64, kt * 64, t.b2, t.b1);
+                        }
+                    } else {
+                        int n_img, h0, w0;
+                        pixel_tile_origin(p, kt, n_img, h0, w0);
+                        for (int j = 0; j < 2; ++j) {
+                            int atom = 2 * t.mt + j;
+                            if (atom >= p.num_atoms) atom = 0;  // dummy rows, dropped by the epilogue
+                            int tap = atom / p.cin_chunks, cc = atom - tap * p.cin_chunks;
+                            int r = tap / p.S, s = tap - r * p.S;
+                            ptx::tma_load_4d(a_dst + j * p.a_box_bytes, &p.tmA, fb, cc * 64, w0 + s - p.S / 2, h0 + r - p.R / 2, n_img);
+                        }
+                        for (int j = 0; j < p.b_boxes; ++j)
+                            ptx::tma_load_4d(b_dst + j * p.b_box_bytes, &p.tmB, fb, t.nt * p.BN + j * 64, w0, h0, n_img);
+                    }
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase[2] = {0, 0};
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                TileInfo t = decode_tile(p, tile);
+                if (t.k1 <= t.k0) continue;
+                ptx::mbar_wait(tempty_bar(acc), acc_phase[acc] ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * kAccCols;
+                for (int kt = t.k0; kt < t.k1; ++kt) {
+                    ptx::mbar_wait(full_bar(stage), phase);
+                    ptx::tc_fence_after();
+                    const uint32_t a_addr = smem_base + stage * stage_bytes;
+                    const uint32_t b_addr = a_addr + p.a_stage_bytes;
+                    const uint64_t a_desc0 = ptx::make_smem_desc_sw128(a_addr, p.a_lbo, p.a_sbo);
+                    const uint64_t b_desc0 = ptx::make_smem_desc_sw128(b_addr, p.b_lbo, p.b_sbo);
+                    for (int ks = 0; ks < p.ksteps; ++ks) {
+                        // advancing the 14-bit start-address field (16B units); never carries out of it (smem < 256 KB)
+                        uint64_t a_desc = a_desc0 + (uint64_t)((ks * p.a_kstep_bytes) >> 4);
+                        uint64_t b_desc = b_desc0 + (uint64_t)((ks * p.b_kstep_bytes) >> 4);
+                        ptx::mma_bf16_ss(d_tmem, a_desc, b_desc, p.idesc, (kt > t.k0 || ks > 0) ? 1u : 0u);
+                    }
+                    ptx::tc_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                ptx::tc_commit(tfull_bar(acc));  // accumulator ready for the epilogue
+                acc_phase[acc] ^= 1;
+                acc ^= 1;
+            }
+        }
+    } else {
+        // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;
+        int acc = 0;
+        uint32_t acc_phase[2] = {0, 0};
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            TileInfo t = decode_tile(p, tile);
+            if (t.k1 <= t.k0) continue;
+            bool valid;
+            long long off;
+            if (p.mode == MODE_CONV) {
+                int hl = row >> p.bw_shift, wl = row & (p.BW - 1);
+                int h = t.h0 + hl, w = t.w0 + wl;
+                valid = (h < p.H) && (w < p.W);
+                off = (((long long)t.n_img * p.H + h) * p.W + w) * p.Cout + (long long)t.nt * p.BN;
+            } else if (p.mode == MODE_GEMM) {
+                int m = t.mt * 128 + row;
+                valid = m < p.M;
+                off = t.b1 * p.sC1 + t.b2 * p.sC2 + (long long)m * p.ldc + (long long)t.nt * p.BN;
+            } else {
+                int atom = 2 * t.mt + (row >> 6);
+                valid = atom < p.num_atoms;
+                off = ((long long)atom * 64 + (row & 63)) * p.Cout + (long long)t.nt * p.BN;
+            }
+            ptx::mbar_wait(tfull_bar(acc), acc_phase[acc]);
+            ptx::tc_fence_after();
+            const uint32_t t_addr = tmem_base + acc * kAccCols + ((uint32_t)(q * 32) << 16);
+            for (int c = 0; c < p.BN; c += 32) {
+                uint32_t v[32];
+                ptx::tmem_ld_32x32(t_addr + c, v);
+                ptx::tmem_ld_wait();
+                if (!valid) continue;
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+                if (p.mode == MODE_WGRAD) {
+                    float* o = reinterpret_cast<float*>(p.out) + off + c;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) atomicAdd(o + j, f[j]);
+                    continue;
+                }
+                if (p.bias) {
+                    const float* b = p.bias + t.nt * p.BN + c;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] += __ldg(b + j);
+                }
+                if (p.residual) {
+                    if (p.out_dtype == STC_BF16) {
+                        const uint4* r = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.residual) + off + c);
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            uint4 rv = __ldg(r + g);
+                            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                float2 x = __bfloat1622float2(h[e]);
+                                f[g * 8 + 2 * e] += x.x;
+                                f[g * 8 + 2 * e + 1] += x.y;
+                            }
+                        }
+                    } else {
+                        const float* r = reinterpret_cast<const float*>(p.residual) + off + c;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] += __ldg(r + j);
+                    }
+                }
+                if (p.act != STC_ACT_NONE) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = epi_act(f[j], p.act);
+                }
+                if (p.out_dtype == STC_BF16) {
+                    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + off + c);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        uint4 ov;
+                        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(f[g * 8 + 2 * e], f[g * 8 + 2 * e + 1]);
+                        o[g] = ov;
+                    }
+                } else {
+                    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off + c);
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) o[g] = make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+            acc_phase[acc] ^= 1;
+            acc ^= 1;
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// rank-`rank` bf16 tensor map with 128B swizzle; dims/strides innermost first; strides[0] is implicit (2 bytes)
+static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled entry point unavailable");
+        return STC_ERR_CUDA;
+    }
+    cuuint64_t gdims[5], gstr[4];
+    cuuint32_t gbox[5], estr[5];
+    for (int i = 0; i < rank; ++i) {
+        gdims[i] = dims[i];
+        gbox[i] = box[i];
+        estr[i] = 1;
+        if (i > 0) gstr[i - 1] = strides_bytes[i];
+    }
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr, gbox, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu] box [%u %u %u %u] base %p", (int)r, rank,
+                  (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0),
+                  (unsigned long long)(rank > 3 ? dims[3] : 0), box[0], box[1], rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0, base);
+        return STC_ERR_CUDA;
+    }
+    return STC_OK;
+}
+
+static int pick_bn(int n) {
+    const int cands[] = {256, 192, 128, 96, 64, 32};
+    for (int c : cands)
+        if (n % c == 0) return c;
+    return 0;
+}
+
+static int launch(UmmaParams& p, cudaStream_t st) {
+    size_t smem = (size_t)p.stages * (p.a_stage_bytes + p.b_stage_bytes) + (2 * p.stages + 4) * 8 + 16 + 1024;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        STC_CUDA(cudaFuncSetAttribute(umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set[dev] = true;
+    }
+    if (smem > 227 * 1024) {
+        set_error("umma: smem %zu too large", smem);
+        return STC_ERR_INVALID;
+    }
+    int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+    if (grid <= 0) return STC_OK;
+    umma_kernel<<<grid, kUmmaThreads, smem, st>>>(p);
+    return check_launch("umma_kernel");
+}
+
+static void conv_geometry(UmmaParams& p, int H, int W, int R, int S, int Cin) {
+    int bw = 1;
+    while (bw * 2 <= W && bw * 2 <= 128) bw *= 2;
+    p.BW = bw;
+    p.BH = 128 / bw;
+    p.bw_shift = 0;
+    while ((1 << p.bw_shift) < bw) ++p.bw_shift;
+    p.tiles_w = (W + p.BW - 1) / p.BW;
+    p.tiles_h = (H + p.BH - 1) / p.BH;
+    p.H = H;
+    p.W = W;
+    p.R = R;
+    p.S = S;
+    p.cin_chunks = Cin / 64;
+}
+
+static int pick_stages(uint32_t stage_bytes) {
+    int s = (int)((200 * 1024) / stage_bytes);
+    if (s > 8) s = 8;
+    return s;
+}
+
+bool conv_umma_eligible(int Cin, int Cout, int dtype) { return dtype == STC_BF16 && Cin % 64 == 0 && pick_bn(Cout) != 0; }
+
+int conv_fprop_umma(const void* x, const void* wp, const float* bias, const void* residual, void* y, int N, int H, int W,
+                    int Cin, int Cout, int R, int S, int act, cudaStream_t st) {
+    STC_REQUIRE(conv_umma_eligible(Cin, Cout, STC_BF16), "conv_fprop_umma: shape Cin=%d Cout=%d not eligible", Cin, Cout);
+    STC_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)wp & 15) == 0 && ((uintptr_t)y & 15) == 0, "conv_fprop_umma: unaligned pointer");
+    UmmaParams p;
+    memset(&p, 0, sizeof(p));
+    p.mode = MODE_CONV;
+    conv_geometry(p, H, W, R, S, Cin);
+    p.BN = pick_bn(Cout);
+    {
+        uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+        uint64_t str[4] = {2, (uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+        uint32_t box[4] = {64, (uint32_t)p.BW, (uint32_t)p.BH, 1};
+        int rc = encode_map(&p.tmA, x, 4, dims, str, box);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)(R * S)};
+        uint64_t str[3] = {2, (uint64_t)Cin * 2, (uint64_t)Cout * Cin * 2};
+        uint32_t box[3] = {64, (uint32_t)p.BN, 1};
+        int rc = encode_map(&p.tmB, wp, 3, dims, str, box);
+        if (rc) return rc;
+    }
+    p.num_n_tiles = Cout / p.BN;
+    p.num_m_tiles = N * p.tiles_h * p.tiles_w;
+    p.num_tiles = p.num_m_tiles * p.num_n_tiles;
+    p.num_k_iters = R * S * p.cin_chunks;
+    p.ksteps = 4;
+    p.a_boxes = p.b_boxes = 1;
+    p.a_stage_bytes = p.a_box_bytes = 128 * 128;
+    p.b_stage_bytes = p.b_box_bytes = (uint32_t)p.BN * 128;
+    p.a_lbo = 0; p.a_sbo = 1024; p.a_kstep_bytes = 32;
+    p.b_lbo = 0; p.b_sbo = 1024; p.b_kstep_bytes = 32;
+    p.idesc = make_idesc_bf16(128, p.BN, 0, 0);
+    p.stages = pick_stages(p.a_stage_bytes + p.b_stage_bytes);
+    p.out = y; p.bias = bias; p.residual = residual; p.act = act; p.out_dtype = STC_BF16; p.Cout = Cout;
+    p.alpha = 1.f;
+    return launch(p, st);
+}
+
+int conv_wgrad_umma(const void* x, const void* dy, float* ws, int N, int H, int W, int Cin, int Cout, int R, int S,
+                    cudaStream_t st) {
+    STC_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "conv_wgrad_umma: Cin=%d Cout=%d must be multiples of 64", Cin, Cout);
+    UmmaParams p;
+    memset(&p, 0, sizeof(p));
+    p.mode = MODE_WGRAD;
+    conv_geometry(p, H, W, R, S, Cin);
+    p.BN = Cout % 128 == 0 ? 128 : 64;
+    {
+        uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+        uint64_t str[4] = {2, (uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+        uint32_t box[4] = {64, (uint32_t)p.BW, (uint32_t)p.BH, 1};
+        int rc = encode_map(&p.tmA, x, 4, dims, str, box);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+        uint64_t str[4] = {2, (uint64_t)Cout * 2, (uint64_t)W * Cout * 2, (uint64_t)H * W * Cout * 2};
+        uint32_t box[4] = {64, (uint32_t)p.BW, (uint32_t)p.BH, 1};
+        int rc = encode_map(&p.tmB, dy, 4, dims, str, box);
+        if (rc) return rc;
+    }
+    p.num_atoms = R * S * p.cin_chunks;
+    p.num_m_tiles = (p.num_atoms + 1) / 2;
+    p.num_n_tiles = Cout / p.BN;
+    p.num_k_iters = N * p.tiles_h * p.tiles_w;  // pixel tiles of 128
+    int base_tiles = p.num_m_tiles * p.num_n_tiles;
+    int splits = (num_sms() * 2 + base_tiles - 1) / base_tiles;
+    if (splits > p.num_k_iters) splits = p.num_k_iters;
+    if (splits < 1) splits = 1;
+    p.k_per_split = (p.num_k_iters + splits - 1) / splits;
+    splits = (p.num_k_iters + p.k_per_split - 1) / p.k_per_split;
+    p.num_tiles = base_tiles * splits;
+    p.ksteps = 8;  // 128 pixels per stage / UMMA_K 16
+    p.a_boxes = 2;
+    p.a_box_bytes = 128 * 128;
+    p.a_stage_bytes = 2 * p.a_box_bytes;
+    p.b_boxes = p.BN / 64;
+    p.b_box_bytes = 128 * 128;
+    p.b_stage_bytes = p.b_boxes * p.b_box_bytes;
+    // MN-major, 128B swizzle: SBO = 8 k-rows * 128 B, LBO = bytes between 64-wide MN atoms, k-step = 16 rows
+    p.a_lbo = p.a_box_bytes; p.a_sbo = 1024; p.a_kstep_bytes = 16 * 128;
+    p.b_lbo = p.b_box_bytes; p.b_sbo = 1024; p.b_kstep_bytes = 16 * 128;
+    p.a_mn_major = p.b_mn_major = 1;
+    p.idesc = make_idesc_bf16(128, p.BN, 1, 1);
+    p.stages = pick_stages(p.a_stage_bytes + p.b_stage_bytes);
+    p.out = ws; p.out_dtype = STC_F32; p.Cout = Cout; p.alpha = 1.f;
+    return launch(p, st);
+}
+
+// Batched GEMM on the tensor cores.  Supported operand layouts (element strides):
+//   A: K-major (sAk == 1) or M-major (sAm == 1);  B: K-major (sBk == 1) or N-major (sBn == 1).
+bool gemm_umma_eligible(const stc_gemm_desc* d, int dtype) {
+    if (dtype != STC_BF16 || d->beta != 0.f) return false;
+    if (!(d->sAk == 1 || d->sAm == 1) || !(d->sBk == 1 || d->sBn == 1)) return false;
+    int bn = pick_bn(d->N);
+    if (bn == 0) return false;
+    if (d->sBn == 1 && d->sBk != 1 && bn % 64 != 0) return false;
+    auto ok8 = [](long long s) { return s % 8 == 0; };
+    long long lda = d->sAk == 1 ? d->sAm : d->sAk, ldb = d->sBk == 1 ? d->sBn : d->sBk;
+    if (!ok8(lda) || !ok8(ldb) || !ok8(d->sA1) || !ok8(d->sA2) || !ok8(d->sB1) || !ok8(d->sB2)) return false;
+    if (!ok8(d->sCm) || !ok8(d->sC1) || !ok8(d->sC2)) return false;
+    if (d->sAm == 1 && d->sAk != 1 && d->M % 64 != 0) return false;
+    return true;
+}
+
+int gemm_umma(const void* A, const void* B, void* C, const stc_gemm_desc* d, int out_dtype, cudaStream_t st) {
+    STC_REQUIRE(gemm_umma_eligible(d, STC_BF16), "gemm_umma: descriptor not eligible");
+    UmmaParams p;
+    memset(&p, 0, sizeof(p));
+    p.mode = MODE_GEMM;
+    p.BN = pick_bn(d->N);
+    p.a_mn_major = (d->sAk != 1);
+    p.b_mn_major = (d->sBk != 1);
+    uint64_t b1 = (uint64_t)d->batch1, b2 = (uint64_t)d->batch2;
+    {
+        // inner dim is the unit-stride one
+        uint64_t inner = p.a_mn_major ? d->M : d->K, outer = p.a_mn_major ? d->K : d->M;
+        uint64_t ld = p.a_mn_major ? d->sAk : d->sAm;
+        uint64_t dims[4] = {inner, outer, b2, b1};
+        uint64_t str[4] = {2, ld * 2, (uint64_t)(d->sA2 ? d->sA2 : 8) * 2, (uint64_t)(d->sA1 ? d->sA1 : 8) * 2};
+        uint32_t box[4] = {64, (uint32_t)(p.a_mn_major ? 64 : 128), 1, 1};
+        int rc = encode_map(&p.tmA, A, 4, dims, str, box);
+        if (rc) return rc;
+    }
+    {
+        uint64_t inner = p.b_mn_major ? d->N : d->K, outer = p.b_mn_major ? d->K : d->N;
+        uint64_t ld = p.b_mn_major ? d->sBk : d->sBn;
+        uint64_t dims[4] = {inner, outer, b2, b1};
+        uint64_t str[4] = {2, ld * 2, (uint64_t)(d->sB2 ? d->sB2 : 8) * 2, (uint64_t)(d->sB1 ? d->sB1 : 8) * 2};
+        uint32_t box[4] = {64, (uint32_t)(p.b_mn_major ? 64 : p.BN), 1, 1};
+        int rc = encode_map(&p.tmB, B, 4, dims, str, box);
+        if (rc) return rc;
+    }
+    p.M = d->M;
+    p.batch2 = d->batch2;
+    p.num_m_tiles = (d->M + 127) / 128;
+    p.num_n_tiles = d->N / p.BN;
+    p.num_tiles = p.num_m_tiles * p.num_n_tiles * d->batch1 * d->batch2;
+    p.num_k_iters = (d->K + 63) / 64;
+    p.ksteps = 4;
+    if (!p.a_mn_major) {
+        p.a_boxes = 1; p.a_box_bytes = 128 * 128; p.a_lbo = 0; p.a_sbo = 1024; p.a_kstep_bytes = 32;
+    } else {
+        p.a_boxes = 2; p.a_box_bytes = 64 * 128; p.a_lbo = p.a_box_bytes; p.a_sbo = 1024; p.a_kstep_bytes = 16 * 128;
+    }
+    p.a_stage_bytes = 128 * 128;
+    if (!p.b_mn_major) {
+        p.b_boxes = 1; p.b_box_bytes = (uint32_t)p.BN * 128; p.b_lbo = 0; p.b_sbo = 1024; p.b_kstep_bytes = 32;
+    } else {
+        p.b_boxes = p.BN / 64; p.b_box_bytes = 64 * 128; p.b_lbo = p.b_box_bytes; p.b_sbo = 1024; p.b_kstep_bytes = 16 * 128;
+    }
+    p.b_stage_bytes = (uint32_t)p.BN * 128;
+    p.idesc = make_idesc_bf16(128, p.BN, p.a_mn_major, p.b_mn_major);
+    p.stages = pick_stages(p.a_stage_bytes + p.b_stage_bytes);
+    p.out = C; p.out_dtype = out_dtype; p.Cout = d->N;
+    p.ldc = d->sCm; p.sC1 = d->sC1; p.sC2 = d->sC2; p.alpha = d->alpha;
+    return launch(p, st);
+}
+
+}  // namespace stc

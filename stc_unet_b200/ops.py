@@ -1,0 +1,795 @@
+"""autograd.Function wrappers over the C ABI (libstc_b200.so).
+
+PyTorch is plumbing here: it owns the device memory, the autograd tape and the streams; every
+arithmetic step is one of our CUDA kernels, called with raw device pointers.  Activations are
+NHWC tensors of shape (N, H, W, C) in `float32` or `bfloat16`; parameters are fp32 in the
+reference's layouts (Conv2d OIHW, Linear (out,in)).
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Sequence
+
+import torch
+import torch.distributed as dist
+from torch.autograd import Function
+
+from . import _lib
+from ._lib import GemmDesc, dtype_code, lib, stream_ptr
+
+# ---------------------------------------------------------------------------------------------
+# global knobs
+# ---------------------------------------------------------------------------------------------
+class _Config:
+    engine = _lib.ENGINE_AUTO       # dense engine selection passed to stc_conv_* / stc_gemm
+
+
+config = _Config()
+
+
+def _sync_world(bn) -> int:
+    """World size over which BN statistics are exchanged (1 = plain BatchNorm)."""
+    if bn.sync and dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(bn.group)
+    return 1
+
+
+_WS = {}
+
+
+def _workspace(device, nbytes: int) -> torch.Tensor:
+    key = (device.type, device.index)
+    buf = _WS.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _WS[key] = buf
+    return buf
+
+
+def _chk(t: torch.Tensor) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError("stc_unet_b200 ops need CUDA tensors (B200); there is no CPU fallback")
+    lib.ensure_device(t.device.index if t.device.index is not None else torch.cuda.current_device())
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ---------------------------------------------------------------------------------------------
+# flat gradient arena: parameter gradients are written straight into one flat fp32 buffer
+# (single bucketed NCCL all-reduce + single fused Adam kernel, no per-tensor copies)
+# ---------------------------------------------------------------------------------------------
+class GradArena:
+    def __init__(self, params: Sequence[torch.nn.Parameter]):
+        self.params = [p for p in params if p.requires_grad]
+        total = 0
+        self.offsets = {}
+        for p in self.params:
+            self.offsets[id(p)] = (total, p.numel())
+            total += (p.numel() + 3) // 4 * 4  # keep every slice 16-byte aligned
+        dev = self.params[0].device
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.total = total
+
+    def view(self, p: torch.nn.Parameter) -> Optional[torch.Tensor]:
+        ent = self.offsets.get(id(p))
+        if ent is None:
+            return None
+        off, n = ent
+        return self.flat[off:off + n].view(p.shape)
+
+
+_ARENA: Optional[GradArena] = None
+
+
+def set_grad_arena(arena: Optional[GradArena]):
+    global _ARENA
+    _ARENA = arena
+
+
+def _grad_buf(param, shape, device, zero=False) -> torch.Tensor:
+    """fp32 buffer that will become param.grad: a fresh view into the arena when one is active."""
+    if _ARENA is not None and param is not None:
+        v = _ARENA.view(param)
+        if v is not None:
+            if zero:
+                v.zero_()
+            return v.view(shape)
+    return (torch.zeros if zero else torch.empty)(shape, dtype=torch.float32, device=device)
+
+
+# ---------------------------------------------------------------------------------------------
+# dense helpers
+# ---------------------------------------------------------------------------------------------
+def pack_weight(w: torch.Tensor, dtype: torch.dtype, transpose_flip: bool = False) -> torch.Tensor:
+    Cout, Cin, R, S = w.shape
+    inner, outer = (Cout, Cin) if transpose_flip else (Cin, Cout)
+    out = torch.empty((R * S, outer, inner), dtype=dtype, device=w.device)
+    lib.call("stc_pack_conv_weight", w, out, Cout, Cin, R, S, inner, int(transpose_flip), dtype_code(dtype), stream_ptr())
+    return out
+
+
+def conv_fprop(x, wp, bias, residual, Cout: int, R: int, S: int, act: int = 0) -> torch.Tensor:
+    N, H, W, Cin = x.shape
+    y = torch.empty((N, H, W, Cout), dtype=x.dtype, device=x.device)
+    lib.call("stc_conv_fprop", x, wp, bias, residual, y, N, H, W, Cin, Cout, R, S, act, dtype_code(x.dtype),
+             config.engine, stream_ptr())
+    return y
+
+
+def conv_wgrad(x, dy, R: int, S: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    N, H, W, Cin = x.shape
+    Cout = dy.shape[-1]
+    ws = torch.zeros(R * S * Cin * Cout, dtype=torch.float32, device=x.device)
+    lib.call("stc_conv_wgrad", x, dy, ws, N, H, W, Cin, Cout, R, S, dtype_code(x.dtype), config.engine, stream_ptr())
+    if out is None:
+        out = torch.empty((Cout, Cin, R, S), dtype=torch.float32, device=x.device)
+    lib.call("stc_unpack_conv_wgrad", ws, out, Cout, Cin, R, S, 0, stream_ptr())
+    return out
+
+
+def colsum(x2d_rows: int, C: int, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if out is None:
+        out = torch.empty(C, dtype=torch.float32, device=x.device)
+    lib.call("stc_colsum", x, out, x2d_rows, C, 0, dtype_code(x.dtype), stream_ptr())
+    return out
+
+
+def add(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    out = torch.empty_like(a)
+    lib.call("stc_add", a, b, out, a.numel(), dtype_code(a.dtype), stream_ptr())
+    return out
+
+
+def gemm(A, B, C, M, N, K, batch1, batch2, sA, sB, sC, alpha=1.0):
+    d = GemmDesc(M, N, K, batch1, batch2, sA[0], sA[1], sA[2], sA[3], sB[0], sB[1], sB[2], sB[3], sC[0], sC[1], sC[2],
+                 alpha, 0.0)
+    lib.call("stc_gemm", A, B, C, d, dtype_code(A.dtype), config.engine, stream_ptr())
+
+
+# ---------------------------------------------------------------------------------------------
+# fan-out: explicit gradient summation with our add kernel (instead of autograd's implicit add)
+# ---------------------------------------------------------------------------------------------
+class _Fanout(Function):
+    @staticmethod
+    def forward(ctx, x, n):
+        ctx.n = n
+        return tuple(x.view_as(x) for _ in range(n))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        acc = None
+        for g in grads:
+            if g is None:
+                continue
+            g = _chk(g)
+            acc = g if acc is None else add(acc, g)
+        return acc, None
+
+
+def fanout(x: torch.Tensor, n: int):
+    if n == 1 or not (torch.is_grad_enabled() and x.requires_grad):
+        return tuple(x for _ in range(n))
+    return _Fanout.apply(x, n)
+
+
+# ---------------------------------------------------------------------------------------------
+# Conv + BatchNorm + activation  (DoubleConv halves, KSA branches, CoordAtt conv1+bn1+h_swish)
+# ---------------------------------------------------------------------------------------------
+class BNState:
+    """Non-tensor side inputs of the BN part (buffers are updated in place by the kernels)."""
+
+    def __init__(self, running_mean, running_var, num_batches_tracked, momentum, eps, training, sync=False, group=None):
+        self.running_mean, self.running_var, self.nbt = running_mean, running_var, num_batches_tracked
+        self.momentum, self.eps, self.training = momentum, eps, training
+        self.sync, self.group = sync, group
+
+
+def _bn_forward_stats(y, P, C, bn: BNState):
+    dev = y.device
+    mean = torch.empty(C, dtype=torch.float32, device=dev)
+    invstd = torch.empty(C, dtype=torch.float32, device=dev)
+    count = float(P)
+    if bn.training:
+        sums = torch.empty(2 * C, dtype=torch.float64, device=dev)
+        nb = lib.raw("stc_bn_ws_bytes")(P, C)
+        ws = _workspace(dev, nb)
+        lib.call("stc_bn_reduce", y, sums, P, C, ws, ws.numel(), dtype_code(y.dtype), stream_ptr())
+        world = _sync_world(bn)
+        if world > 1:
+            # C1: one all-reduce of [sum, sumsq]; every rank holds the same per-GPU batch (count = P * world)
+            dist.all_reduce(sums, group=bn.group)
+            count = float(P) * world
+        lib.call("stc_bn_finalize", sums, count, mean, invstd, bn.running_mean, bn.running_var, bn.nbt,
+                 float(bn.momentum), float(bn.eps), C, stream_ptr())
+    else:
+        lib.call("stc_bn_eval_stats", bn.running_mean, bn.running_var, mean, invstd, float(bn.eps), C, stream_ptr())
+    return mean, invstd, count
+
+
+def _bn_backward(y, dout, mean, invstd, gamma, beta, P, C, act, bn, count, pg, pb):
+    training = bn.training
+    dev = y.device
+    sums = torch.empty(2 * C, dtype=torch.float64, device=dev)
+    nb = lib.raw("stc_bn_ws_bytes")(P, C)
+    ws = _workspace(dev, nb)
+    code = dtype_code(y.dtype)
+    lib.call("stc_bn_bwd_reduce", y, dout, mean, invstd, gamma, beta, sums, P, C, act, ws, ws.numel(), code, stream_ptr())
+    dgamma = _grad_buf(pg, (C,), dev)
+    dbeta = _grad_buf(pb, (C,), dev)
+    lib.call("stc_bn_param_grads", sums, dgamma, dbeta, C, stream_ptr())
+    if training and _sync_world(bn) > 1:
+        dist.all_reduce(sums, group=bn.group)  # C2
+    dy = torch.empty_like(y)
+    lib.call("stc_bn_bwd_apply", y, dout, mean, invstd, gamma, beta, sums, float(count), dy, P, C, act,
+             0 if training else 1, code, stream_ptr())
+    return dy, dgamma, dbeta
+
+
+class _ConvBnAct(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, gamma, beta, bn: BNState, act: int, pobjs):
+        x = _chk(x)
+        Cout, Cin, R, S = weight.shape
+        N, H, W, _ = x.shape
+        P = N * H * W
+        wp = pack_weight(weight, x.dtype)
+        y = conv_fprop(x, wp, bias, None, Cout, R, S)
+        mean, invstd, count = _bn_forward_stats(y, P, Cout, bn)
+        a = torch.empty_like(y)
+        lib.call("stc_bn_apply", y, mean, invstd, gamma, beta, a, P, Cout, act, dtype_code(y.dtype), stream_ptr())
+        ctx.save_for_backward(x, y, weight, gamma, beta, mean, invstd)
+        ctx.meta = (act, bn, count, R, S, pobjs, bias is not None)
+        return a
+
+    @staticmethod
+    def backward(ctx, da):
+        x, y, weight, gamma, beta, mean, invstd = ctx.saved_tensors
+        act, bn, count, R, S, pobjs, has_bias = ctx.meta
+        pw, pbias, pg, pb = pobjs
+        da = _chk(da)
+        N, H, W, Cout = y.shape
+        P = N * H * W
+        dy, dgamma, dbeta = _bn_backward(y, da, mean, invstd, gamma, beta, P, Cout, act, bn, count, pg, pb)
+        dbias = colsum(P, Cout, dy, _grad_buf(pbias, (Cout,), dy.device)) if has_bias else None
+        dw = conv_wgrad(x, dy, R, S, _grad_buf(pw, weight.shape, dy.device))
+        dx = None
+        if ctx.needs_input_grad[0]:
+            wpt = pack_weight(weight, dy.dtype, transpose_flip=True)
+            dx = conv_fprop(dy, wpt, None, None, weight.shape[1], R, S)
+        return dx, dw, dbias, dgamma, dbeta, None, None, None
+
+
+def conv_bn_act(x, conv: torch.nn.Conv2d, bn: torch.nn.modules.batchnorm._BatchNorm, act: int, training: bool):
+    sync = isinstance(bn, torch.nn.SyncBatchNorm)
+    state = BNState(bn.running_mean, bn.running_var, bn.num_batches_tracked,
+                    0.1 if bn.momentum is None else bn.momentum, bn.eps, training or not bn.track_running_stats,
+                    sync=sync, group=getattr(bn, "process_group", None) if sync else None)
+    return _ConvBnAct.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, state, act,
+                            (conv.weight, conv.bias, bn.weight, bn.bias))
+
+
+# ---------------------------------------------------------------------------------------------
+# Conv / Linear without norm: y = act(conv(x) + bias + residual)
+# ---------------------------------------------------------------------------------------------
+class _Conv(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, act: int, pobjs):
+        x = _chk(x)
+        if residual is not None:
+            residual = _chk(residual)
+        Cout, Cin, R, S = weight.shape
+        wp = pack_weight(weight, x.dtype)
+        y = conv_fprop(x, wp, bias, residual, Cout, R, S, act)
+        ctx.save_for_backward(x, weight, y if act != 0 else None)
+        ctx.meta = (act, R, S, pobjs, bias is not None, residual is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y = ctx.saved_tensors
+        act, R, S, pobjs, has_bias, has_res = ctx.meta
+        pw, pbias = pobjs
+        dy = _chk(dy)
+        if act != 0:
+            dz = torch.empty_like(dy)
+            lib.call("stc_act_bwd", y, dy, dz, dy.numel(), act, dtype_code(dy.dtype), stream_ptr())
+        else:
+            dz = dy
+        Cout = weight.shape[0]
+        P = dz.numel() // Cout
+        dbias = colsum(P, Cout, dz, _grad_buf(pbias, (Cout,), dz.device)) if has_bias else None
+        dw = conv_wgrad(x, dz, R, S, _grad_buf(pw, weight.shape, dz.device)) if ctx.needs_input_grad[1] else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            wpt = pack_weight(weight, dz.dtype, transpose_flip=True)
+            dx = conv_fprop(dz, wpt, None, None, weight.shape[1], R, S)
+        dres = dz if (has_res and ctx.needs_input_grad[3]) else None
+        return dx, dw, dbias, dres, None, None
+
+
+def conv2d(x, weight, bias=None, residual=None, act: int = 0, pobjs=None):
+    """x NHWC; weight OIHW (odd kernel, padding k//2)."""
+    return _Conv.apply(x, weight, bias, residual, act, pobjs or (weight, bias))
+
+
+def linear_tokens(x, weight, bias=None, residual=None, act: int = 0, pobjs=None):
+    """x (..., in) -> (..., out) with weight (out, in): a 1x1 conv over a (1,1,rows,in) image."""
+    shp = x.shape
+    rows = x.numel() // shp[-1]
+    y = _Conv.apply(x.reshape(1, 1, rows, shp[-1]), weight.view(weight.shape[0], weight.shape[1], 1, 1), bias,
+                    None if residual is None else residual.reshape(1, 1, rows, weight.shape[0]), act,
+                    pobjs or (weight, bias))
+    return y.view(*shp[:-1], weight.shape[0])
+
+
+# ---------------------------------------------------------------------------------------------
+# MaxPool2d(2)
+# ---------------------------------------------------------------------------------------------
+class _MaxPool2(Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _chk(x)
+        N, H, W, C = x.shape
+        y = torch.empty((N, H // 2, W // 2, C), dtype=x.dtype, device=x.device)
+        lib.call("stc_maxpool2_fwd", x, y, N, H, W, C, dtype_code(x.dtype), stream_ptr())
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dy = _chk(dy)
+        N, H, W, C = x.shape
+        dx = torch.empty_like(x)
+        lib.call("stc_maxpool2_bwd", x, dy, dx, N, H, W, C, dtype_code(x.dtype), stream_ptr())
+        return dx
+
+
+def maxpool2(x):
+    return _MaxPool2.apply(x)
+
+
+# ---------------------------------------------------------------------------------------------
+# bilinear x2 upsample + pad + concat
+# ---------------------------------------------------------------------------------------------
+class _UpCat(Function):
+    @staticmethod
+    def forward(ctx, skip, low, align_corners: bool):
+        skip, low = _chk(skip), _chk(low)
+        N, H, W, Cs = skip.shape
+        _, h, w, Cu = low.shape
+        out = torch.empty((N, H, W, Cs + Cu), dtype=skip.dtype, device=skip.device)
+        lib.call("stc_upcat_fwd", skip, low, out, N, H, W, Cs, h, w, Cu, int(align_corners), dtype_code(skip.dtype), stream_ptr())
+        ctx.meta = (N, H, W, Cs, h, w, Cu, int(align_corners))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        N, H, W, Cs, h, w, Cu, ac = ctx.meta
+        dout = _chk(dout)
+        dskip = torch.empty((N, H, W, Cs), dtype=dout.dtype, device=dout.device) if ctx.needs_input_grad[0] else None
+        dlow = torch.empty((N, h, w, Cu), dtype=dout.dtype, device=dout.device) if ctx.needs_input_grad[1] else None
+        lib.call("stc_upcat_bwd", dout, dskip, dlow, N, H, W, Cs, h, w, Cu, ac, dtype_code(dout.dtype), stream_ptr())
+        return dskip, dlow, None
+
+
+def upcat(skip, low, align_corners=True):
+    return _UpCat.apply(skip, low, align_corners)
+
+
+# ---------------------------------------------------------------------------------------------
+# CoordAtt: pooled descriptors and the additive attention map
+# ---------------------------------------------------------------------------------------------
+class _RowColMean(Function):
+    """(N,H,W,C) -> (N,H+W,C): rows 0..H-1 = mean over W, rows H.. = mean over H.  Its backward is folded
+    into _CoordAttApply (which owns the only other use of x), so this node returns no grad for x."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _chk(x)
+        N, H, W, C = x.shape
+        y = torch.empty((N, H + W, C), dtype=x.dtype, device=x.device)
+        lib.call("stc_rowcol_mean", x, y, N, H, W, C, dtype_code(x.dtype), stream_ptr())
+        ctx.shape = (N, H, W, C)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        N, H, W, C = ctx.shape
+        dy = _chk(dy)
+        dx = torch.zeros((N, H, W, C), dtype=dy.dtype, device=dy.device)
+        lib.call("stc_coordatt_dx", dx, dy, dx, N, H, W, C, dtype_code(dy.dtype), stream_ptr())
+        return dx
+
+
+class _CoordAttApply(Function):
+    """out = x + a_h * a_w with a = (N,H+W,C)."""
+
+    @staticmethod
+    def forward(ctx, x, a):
+        x, a = _chk(x), _chk(a)
+        N, H, W, C = x.shape
+        out = torch.empty_like(x)
+        lib.call("stc_coordatt_apply", x, a, out, N, H, W, C, dtype_code(x.dtype), stream_ptr())
+        ctx.save_for_backward(a)
+        ctx.shape = (N, H, W, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (a,) = ctx.saved_tensors
+        N, H, W, C = ctx.shape
+        dout = _chk(dout)
+        da = torch.empty_like(a)
+        lib.call("stc_coordatt_apply_bwd", dout, a, da, N, H, W, C, dtype_code(dout.dtype), stream_ptr())
+        return dout, da
+
+
+def rowcol_mean(x):
+    return _RowColMean.apply(x)
+
+
+def coordatt_apply(x, a):
+    return _CoordAttApply.apply(x, a)
+
+
+# ---------------------------------------------------------------------------------------------
+# KernelSelectAttention fuse: out = x + sum_k softmax_k(fcs_k(fc(GAP(f0+f1+f2)))) * f_k
+# ---------------------------------------------------------------------------------------------
+class _KSAFuse(Function):
+    @staticmethod
+    def forward(ctx, x, f0, f1, f2, fc_w, fc_b, w0, b0, w1, b1, w2, b2, pobjs):
+        x, f0, f1, f2 = _chk(x), _chk(f0), _chk(f1), _chk(f2)
+        N, H, W, C = x.shape
+        HW = H * W
+        dev = x.device
+        d = fc_w.shape[0]
+        code = dtype_code(x.dtype)
+        S = torch.empty((N, C), dtype=torch.float32, device=dev)
+        lib.call("stc_ksa_pool", f0, f1, f2, S, N, HW, C, code, stream_ptr())
+        Z = torch.empty((N, d), dtype=torch.float32, device=dev)
+        lib.call("stc_linear_f32_fwd", S, fc_w, fc_b, Z, N, C, d, stream_ptr())
+        a = torch.empty((3, N, C), dtype=torch.float32, device=dev)
+        for k, (wk, bk) in enumerate(((w0, b0), (w1, b1), (w2, b2))):
+            lib.call("stc_linear_f32_fwd", Z, wk, bk, a[k], N, d, C, stream_ptr())
+        wts = torch.empty_like(a)
+        lib.call("stc_softmax3_fwd", a, wts, N * C, stream_ptr())
+        out = torch.empty_like(x)
+        lib.call("stc_ksa_combine", x, f0, f1, f2, wts, out, N, HW, C, code, stream_ptr())
+        ctx.save_for_backward(f0, f1, f2, wts, S, Z, fc_w, w0, w1, w2)
+        ctx.pobjs = pobjs
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        f0, f1, f2, wts, S, Z, fc_w, w0, w1, w2 = ctx.saved_tensors
+        pobjs = ctx.pobjs
+        dout = _chk(dout)
+        N, H, W, C = dout.shape
+        HW = H * W
+        dev = dout.device
+        d = fc_w.shape[0]
+        code = dtype_code(dout.dtype)
+        dw = torch.empty((3, N, C), dtype=torch.float32, device=dev)
+        lib.call("stc_ksa_dw", dout, f0, f1, f2, dw, N, HW, C, code, stream_ptr())
+        da = torch.empty_like(dw)
+        lib.call("stc_softmax3_bwd", wts, dw, da, N * C, stream_ptr())
+        dZ = torch.zeros((N, d), dtype=torch.float32, device=dev)
+        dZk = torch.empty_like(dZ)
+        grads = []
+        for k, wk in enumerate((w0, w1, w2)):
+            gW = _grad_buf(pobjs[2 + 2 * k], wk.shape, dev, zero=True)
+            gb = _grad_buf(pobjs[3 + 2 * k], (C,), dev, zero=True)
+            lib.call("stc_linear_f32_bwd", Z, wk, da[k], dZk, gW, gb, N, d, C, stream_ptr())
+            lib.call("stc_axpy_f32", dZk, dZ, 1.0, dZ.numel(), stream_ptr())
+            grads += [gW, gb]
+        dS = torch.empty((N, C), dtype=torch.float32, device=dev)
+        gfcW = _grad_buf(pobjs[0], fc_w.shape, dev, zero=True)
+        gfcb = _grad_buf(pobjs[1], (d,), dev, zero=True)
+        lib.call("stc_linear_f32_bwd", S, fc_w, dZ, dS, gfcW, gfcb, N, C, d, stream_ptr())
+        df0, df1, df2 = torch.empty_like(f0), torch.empty_like(f1), torch.empty_like(f2)
+        lib.call("stc_ksa_df", dout, wts, dS, df0, df1, df2, N, HW, C, code, stream_ptr())
+        return (dout, df0, df1, df2, gfcW, gfcb, *grads, None)
+
+
+def ksa_fuse(x, f0, f1, f2, fc, fcs):
+    ps = (fc.weight, fc.bias, fcs[0].weight, fcs[0].bias, fcs[1].weight, fcs[1].bias, fcs[2].weight, fcs[2].bias)
+    return _KSAFuse.apply(x, f0, f1, f2, *ps, ps)
+
+
+# ---------------------------------------------------------------------------------------------
+# Multi-head attention core: softmax(Q K^T / sqrt(hd)) V on (N, L, E) token tensors
+# ---------------------------------------------------------------------------------------------
+class _Attention(Function):
+    @staticmethod
+    def forward(ctx, q, k, v, heads: int):
+        q, k, v = _chk(q), _chk(k), _chk(v)
+        N, L, E = q.shape
+        hd = E // heads
+        dev = q.device
+        P = torch.empty((N, heads, L, L), dtype=q.dtype, device=dev)
+        tok = (L * E, hd)  # batch strides of a (N, L, E) tensor split into heads
+        gemm(q, k, P, L, L, hd, N, heads, (*tok, E, 1), (*tok, 1, E), (heads * L * L, L * L, L))
+        scale = 1.0 / math.sqrt(hd)
+        lib.call("stc_softmax_rows_fwd", P, P, N * heads * L, L, scale, dtype_code(q.dtype), stream_ptr())
+        o = torch.empty_like(q)
+        gemm(P, v, o, L, hd, L, N, heads, (heads * L * L, L * L, L, 1), (*tok, E, 1), (L * E, hd, E))
+        ctx.save_for_backward(q, k, v, P)
+        ctx.heads = heads
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q, k, v, P = ctx.saved_tensors
+        heads = ctx.heads
+        do = _chk(do)
+        N, L, E = q.shape
+        hd = E // heads
+        tok = (L * E, hd)
+        pb = (heads * L * L, L * L)
+        scale = 1.0 / math.sqrt(hd)
+        dv = torch.empty_like(v)
+        gemm(P, do, dv, L, hd, L, N, heads, (*pb, 1, L), (*tok, E, 1), (L * E, hd, E))            # dV = P^T dO
+        dP = torch.empty_like(P)
+        gemm(do, v, dP, L, L, hd, N, heads, (*tok, E, 1), (*tok, 1, E), (*pb, L))                  # dP = dO V^T
+        lib.call("stc_softmax_rows_bwd", P, dP, dP, N * heads * L, L, scale, dtype_code(q.dtype), stream_ptr())
+        dq = torch.empty_like(q)
+        gemm(dP, k, dq, L, hd, L, N, heads, (*pb, L, 1), (*tok, E, 1), (L * E, hd, E))             # dQ = dS K
+        dk = torch.empty_like(k)
+        gemm(dP, q, dk, L, hd, L, N, heads, (*pb, 1, L), (*tok, E, 1), (L * E, hd, E))             # dK = dS^T Q
+        return dq, dk, dv, None
+
+
+def attention(q, k, v, heads: int):
+    return _Attention.apply(q, k, v, heads)
+
+
+class _InProj(Function):
+    """nn.MultiheadAttention's packed in-projection: (q,k,v) -> (q W_q^T + b_q, k W_k^T + b_k, v W_v^T + b_v)
+    with in_proj_weight (3E, E) / in_proj_bias (3E); the parameter gradients are produced whole."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, W, b, pobjs):
+        q, k, v = _chk(q), _chk(k), _chk(v)
+        N, L, E = q.shape
+        rows = N * L
+        outs = []
+        for i, t in enumerate((q, k, v)):
+            wp = pack_weight(W[i * E:(i + 1) * E].view(E, E, 1, 1), t.dtype)
+            outs.append(conv_fprop(t.view(1, 1, rows, E), wp, b[i * E:(i + 1) * E], None, E, 1, 1).view(N, L, E))
+        ctx.save_for_backward(q, k, v, W)
+        ctx.pobjs = pobjs
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, dq, dk, dv):
+        q, k, v, W = ctx.saved_tensors
+        N, L, E = q.shape
+        rows = N * L
+        dev = q.device
+        dW = _grad_buf(ctx.pobjs[0], W.shape, dev)
+        db = _grad_buf(ctx.pobjs[1], (3 * E,), dev)
+        dins = []
+        for i, (t, g) in enumerate(((q, dq), (k, dk), (v, dv))):
+            g = _chk(g)
+            colsum(rows, E, g, db[i * E:(i + 1) * E])
+            conv_wgrad(t.view(1, 1, rows, E), g.view(1, 1, rows, E), 1, 1, dW[i * E:(i + 1) * E].view(E, E, 1, 1))
+            wpt = pack_weight(W[i * E:(i + 1) * E].view(E, E, 1, 1), g.dtype, transpose_flip=True)
+            dins.append(conv_fprop(g.view(1, 1, rows, E), wpt, None, None, E, 1, 1).view(N, L, E))
+        return dins[0], dins[1], dins[2], dW, db, None
+
+
+def in_proj(q, k, v, mha: torch.nn.MultiheadAttention):
+    return _InProj.apply(q, k, v, mha.in_proj_weight, mha.in_proj_bias, (mha.in_proj_weight, mha.in_proj_bias))
+
+
+# ---------------------------------------------------------------------------------------------
+# classifier + loss
+# ---------------------------------------------------------------------------------------------
+class _ClsSeg(Function):
+    """Dropout2d mask (optional, (N,Cin) fp32 already scaled) + Conv2d(Cin, Ccls, 1): NHWC -> NCHW fp32 logits."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, mask, pobjs):
+        x = _chk(x)
+        N, H, W, Cin = x.shape
+        Ccls = weight.shape[0]
+        code = dtype_code(x.dtype)
+        if mask is not None:
+            xm = torch.empty_like(x)
+            lib.call("stc_scale_channels", x, mask, xm, N, H * W, Cin, code, stream_ptr())
+        else:
+            xm = x
+        logits = torch.empty((N, Ccls, H, W), dtype=torch.float32, device=x.device)
+        lib.call("stc_cls_fwd", xm, weight.view(Ccls, Cin), bias, logits, N, H * W, Cin, Ccls, code, stream_ptr())
+        ctx.save_for_backward(xm, weight, mask)
+        ctx.pobjs = pobjs
+        return logits
+
+    @staticmethod
+    def backward(ctx, dl):
+        xm, weight, mask = ctx.saved_tensors
+        dl = _chk(dl)
+        N, H, W, Cin = xm.shape
+        Ccls = weight.shape[0]
+        code = dtype_code(xm.dtype)
+        dev = xm.device
+        dx = torch.empty_like(xm) if ctx.needs_input_grad[0] else None
+        dW = _grad_buf(ctx.pobjs[0], weight.shape, dev, zero=True)
+        db = _grad_buf(ctx.pobjs[1], (Ccls,), dev, zero=True)
+        lib.call("stc_cls_bwd", dl, xm, weight.view(Ccls, Cin), dx, dW, db, N, H * W, Cin, Ccls, None, 0, code, stream_ptr())
+        if mask is not None and dx is not None:
+            lib.call("stc_scale_channels", dx, mask, dx, N, H * W, Cin, code, stream_ptr())
+        return dx, dW, db, None, None
+
+
+def cls_seg(x, conv_seg: torch.nn.Conv2d, mask=None):
+    return _ClsSeg.apply(x, conv_seg.weight, conv_seg.bias, mask, (conv_seg.weight, conv_seg.bias))
+
+
+class _SegLoss(Function):
+    """(loss_ce_mean_over_all_pixels, loss_dice, acc_seg) from NCHW fp32 logits and (N,H,W) int64 labels."""
+
+    @staticmethod
+    def forward(ctx, logits, label, ignore_index: int, smooth: float):
+        logits = _chk(logits)
+        label = _chk(label)
+        N, C, H, W = logits.shape
+        n = lib.raw("stc_seg_loss_stats_len")(N, C)
+        stats = torch.empty(n, dtype=torch.float64, device=logits.device)
+        out3 = torch.empty(3, dtype=torch.float32, device=logits.device)
+        lib.call("stc_seg_loss_fwd", logits, label, stats, out3, N, H * W, C, ignore_index, float(smooth), stream_ptr())
+        ctx.save_for_backward(logits, label, stats)
+        ctx.meta = (ignore_index, float(smooth))
+        return out3[0], out3[1], out3[2]
+
+    @staticmethod
+    def backward(ctx, g_ce, g_dice, _g_acc):
+        logits, label, stats = ctx.saved_tensors
+        ignore_index, smooth = ctx.meta
+        N, C, H, W = logits.shape
+        dl = torch.empty_like(logits)
+        g_ce = None if g_ce is None else _chk(g_ce.float())
+        g_dice = None if g_dice is None else _chk(g_dice.float())
+        lib.call("stc_seg_loss_bwd", logits, label, stats, g_ce, g_dice, dl, N, H * W, C, ignore_index, smooth, stream_ptr())
+        return dl, None, None, None
+
+
+def seg_loss(logits, label, ignore_index=255, smooth=1.0):
+    return _SegLoss.apply(logits, label, ignore_index, smooth)
+
+
+# ---------------------------------------------------------------------------------------------
+# layout conversion and inference / metric helpers (no autograd)
+# ---------------------------------------------------------------------------------------------
+def image_to_nhwc(img: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    img = _chk(img.float())
+    N, C, H, W = img.shape
+    out = torch.empty((N, H, W, C), dtype=dtype, device=img.device)
+    lib.call("stc_nchw_to_nhwc", img, out, N, C, H, W, C, dtype_code(dtype), stream_ptr())
+    return out
+
+
+def argmax_nchw(preds: torch.Tensor, count: Optional[torch.Tensor] = None) -> torch.Tensor:
+    preds = _chk(preds)
+    N, C, H, W = preds.shape
+    out = torch.empty((N, H, W), dtype=torch.int64, device=preds.device)
+    lib.call("stc_argmax", preds, count, out, N, C, H * W, stream_ptr())
+    return out
+
+
+def slide_accum(crop, preds, count, y1, x1):
+    crop = _chk(crop)
+    N, C, H, W = preds.shape
+    lib.call("stc_slide_accum", crop, preds, count, N, C, H, W, crop.shape[2], crop.shape[3], y1, x1, stream_ptr())
+
+
+def confusion_hist(pred: torch.Tensor, label: torch.Tensor, num_classes: int, ignore_index: int = 255,
+                   cm: Optional[torch.Tensor] = None, areas: Optional[torch.Tensor] = None):
+    """Accumulates the int64 confusion matrix CM[label, pred] and the four area vectors of
+    intersect_and_union (metrics.py:75-87) on the device."""
+    pred = _chk(pred.to(torch.int64))
+    if label.dtype not in (torch.uint8, torch.int64):
+        label = label.to(torch.int64)
+    label = _chk(label)
+    dev = pred.device
+    if cm is None:
+        cm = torch.zeros((num_classes, num_classes), dtype=torch.int64, device=dev)
+    if areas is None:
+        areas = torch.zeros((4, num_classes), dtype=torch.int64, device=dev)
+    lib.call("stc_confusion_hist", pred, label, int(label.dtype == torch.uint8), pred.numel(), num_classes, ignore_index,
+             cm, areas, stream_ptr())
+    return cm, areas
+
+
+# ---------------------------------------------------------------------------------------------
+# small differentiable helpers
+# ---------------------------------------------------------------------------------------------
+class _Add(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        return add(_chk(a), _chk(b))
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+def add_autograd(a, b):
+    return _Add.apply(a, b)
+
+
+def _copy_rows(src, dst, src_off, dst_off, count):
+    N, rs, C = src.shape[0], src.shape[1], src.shape[-1]
+    lib.call("stc_copy_rows", src, dst, N, rs, dst.shape[1], C, src_off, dst_off, count, dtype_code(src.dtype), stream_ptr())
+
+
+class _SliceRows(Function):
+    """(N, R, 1, C) -> (N, count, 1, C) starting at row `off`."""
+
+    @staticmethod
+    def forward(ctx, x, off, count):
+        x = _chk(x)
+        out = torch.empty((x.shape[0], count, 1, x.shape[-1]), dtype=x.dtype, device=x.device)
+        _copy_rows(x, out, off, 0, count)
+        ctx.meta = (x.shape, off, count)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        shape, off, count = ctx.meta
+        g = _chk(g)
+        dx = torch.zeros(shape, dtype=g.dtype, device=g.device)
+        _copy_rows(g, dx, 0, off, count)
+        return dx, None, None
+
+
+def slice_rows(x, off, count):
+    return _SliceRows.apply(x, off, count)
+
+
+class _CatRows(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = _chk(a), _chk(b)
+        ra, rb = a.shape[1], b.shape[1]
+        out = torch.empty((a.shape[0], ra + rb, 1, a.shape[-1]), dtype=a.dtype, device=a.device)
+        _copy_rows(a, out, 0, 0, ra)
+        _copy_rows(b, out, 0, ra, rb)
+        ctx.meta = (ra, rb)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        ra, rb = ctx.meta
+        g = _chk(g)
+        N, C = g.shape[0], g.shape[-1]
+        ga = torch.empty((N, ra, 1, C), dtype=g.dtype, device=g.device)
+        gb = torch.empty((N, rb, 1, C), dtype=g.dtype, device=g.device)
+        _copy_rows(g, ga, 0, 0, ra)
+        _copy_rows(g, gb, ra, 0, rb)
+        return ga, gb
+
+
+def cat_rows(a, b):
+    return _CatRows.apply(a, b)
+
+
+class _Scale(Function):
+    @staticmethod
+    def forward(ctx, x, alpha):
+        ctx.alpha = alpha
+        x = _chk(x.float())
+        out = torch.zeros_like(x)
+        lib.call("stc_axpy_f32", x, out, float(alpha), x.numel(), stream_ptr())
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _chk(g.float())
+        out = torch.zeros_like(g)
+        lib.call("stc_axpy_f32", g, out, float(ctx.alpha), g.numel(), stream_ptr())
+        return out, None
+
+
+def scale(x, alpha):
+    return x if float(alpha) == 1.0 else _Scale.apply(x, alpha)

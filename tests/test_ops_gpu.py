@@ -1,0 +1,373 @@
+"""Kernel-level parity (GPU): every C-ABI op against a plain PyTorch fp32 reference of the same op.
+Tolerances: fp32 path 1e-5 (1e-4 is the north-star bound for whole-model fp32); bf16 path 2e-2."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.util import bf16_round, nchw, nhwc, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def S():
+    import stc_unet_b200 as S
+    from stc_unet_b200 import ops
+    ops.config.engine = S._lib.ENGINE_AUTO
+    return S
+
+
+DT = [torch.float32, torch.bfloat16]
+
+
+def tol(dt):
+    return 2e-5 if dt == torch.float32 else 2e-2
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("shape", [(2, 3, 8, 16, 16, 3), (1, 16, 24, 9, 13, 5), (2, 8, 8, 12, 12, 7), (3, 40, 24, 5, 7, 1)])
+def test_conv_simt_fwd_bwd(S, dt, shape):
+    from stc_unet_b200 import ops
+    ops.config.engine = S._lib.ENGINE_SIMT
+    N, Cin, Cout, H, W, k = shape
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(N, Cin, H, W, device=dev(), generator=g)
+    w = torch.randn(Cout, Cin, k, k, device=dev(), generator=g) * 0.2
+    b = torch.randn(Cout, device=dev(), generator=g)
+    xr = (bf16_round(x) if dt == torch.bfloat16 else x).clone().requires_grad_(True)
+    wr = (bf16_round(w) if dt == torch.bfloat16 else w).clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    ref = F.conv2d(xr, wr, br, padding=k // 2)
+    xo = nhwc(x).to(dt).requires_grad_(True)
+    wo, bo = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    out = ops.conv2d(xo, wo, bo)
+    assert rel_l2(nchw(out.float()), ref) < tol(dt)
+    go = torch.randn_like(ref)
+    ref.backward(go)
+    out.backward(nhwc(go).to(dt))
+    assert rel_l2(nchw(xo.grad.float()), xr.grad) < tol(dt)
+    assert rel_l2(wo.grad, wr.grad) < tol(dt)
+    assert rel_l2(bo.grad, br.grad) < tol(dt)
+    ops.config.engine = S._lib.ENGINE_AUTO
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("C", [8, 16, 64, 24, 5])
+def test_conv_bn_relu(S, dt, C):
+    from stc_unet_b200 import ops
+    ops.config.engine = S._lib.ENGINE_SIMT
+    torch.manual_seed(0)
+    N, Cin, H, W = 2, 8, 10, 12
+    conv = torch.nn.Conv2d(Cin, C, 3, padding=1).to(dev())
+    bn = torch.nn.BatchNorm2d(C).to(dev())
+    bn.weight.data.uniform_(0.5, 1.5)
+    bn.bias.data.uniform_(-0.5, 0.5)
+    conv_r, bn_r = torch.nn.Conv2d(Cin, C, 3, padding=1).to(dev()), torch.nn.BatchNorm2d(C).to(dev())
+    conv_r.load_state_dict(conv.state_dict())
+    bn_r.load_state_dict(bn.state_dict())
+    x = torch.randn(N, Cin, H, W, device=dev())
+    if dt == torch.bfloat16:
+        x = bf16_round(x)
+        conv_r.weight.data = bf16_round(conv_r.weight.data)
+    xr = x.clone().requires_grad_(True)
+    ref = F.relu(bn_r(conv_r(xr)))
+    xo = nhwc(x).to(dt).requires_grad_(True)
+    out = ops.conv_bn_act(xo, conv, bn, S._lib.ACT_RELU, True)
+    assert rel_l2(nchw(out.float()), ref) < tol(dt)
+    go = torch.randn_like(ref)
+    ref.backward(go)
+    out.backward(nhwc(go).to(dt))
+    t = tol(dt) * 5
+    assert rel_l2(nchw(xo.grad.float()), xr.grad) < t
+    assert rel_l2(conv.weight.grad, conv_r.weight.grad) < t
+    assert rel_l2(bn.weight.grad, bn_r.weight.grad) < t
+    assert rel_l2(bn.bias.grad, bn_r.bias.grad) < t
+    assert rel_l2(bn.running_mean, bn_r.running_mean) < tol(dt)
+    assert rel_l2(bn.running_var, bn_r.running_var) < tol(dt)
+    assert int(bn.num_batches_tracked) == 1
+    # conv bias feeding a train-mode BN has a ~0 gradient: compare with an absolute floor
+    assert float((conv.bias.grad - conv_r.bias.grad).abs().max()) < 1e-3 * (1 + float(go.abs().sum()) * 1e-4)
+    # eval mode
+    bn.eval(); bn_r.eval()
+    out_e = ops.conv_bn_act(nhwc(x).to(dt), conv, bn, S._lib.ACT_RELU, False)
+    assert rel_l2(nchw(out_e.float()), F.relu(bn_r(conv_r(x)))) < tol(dt)
+    ops.config.engine = S._lib.ENGINE_AUTO
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_maxpool_ties_and_grad(S, dt):
+    from stc_unet_b200 import ops
+    torch.manual_seed(0)
+    x = torch.relu(torch.randn(2, 16, 12, 20, device=dev()))  # many exact-zero ties, like post-ReLU maps
+    if dt == torch.bfloat16:
+        x = bf16_round(x)
+    xr = x.clone().requires_grad_(True)
+    ref = F.max_pool2d(xr, 2)
+    xo = nhwc(x).to(dt).requires_grad_(True)
+    out = ops.maxpool2(xo)
+    assert torch.equal(nchw(out.float()), ref)
+    go = torch.randn_like(ref)
+    if dt == torch.bfloat16:
+        go = bf16_round(go)
+    ref.backward(go)
+    out.backward(nhwc(go).to(dt))
+    assert torch.equal(nchw(xo.grad.float()), xr.grad)
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("shape", [(2, 8, 16, 5, 7, 10, 14), (1, 16, 8, 4, 4, 9, 11), (2, 8, 8, 1, 3, 2, 6)])
+def test_upcat(S, dt, shape):
+    from stc_unet_b200 import ops
+    N, Cs, Cu, h, w, H, W = shape
+    torch.manual_seed(0)
+    skip = torch.randn(N, Cs, H, W, device=dev())
+    low = torch.randn(N, Cu, h, w, device=dev())
+    if dt == torch.bfloat16:
+        skip, low = bf16_round(skip), bf16_round(low)
+    sr, lr = skip.clone().requires_grad_(True), low.clone().requires_grad_(True)
+    up = F.interpolate(lr, scale_factor=2, mode="bilinear", align_corners=True)
+    dy, dx = H - up.shape[2], W - up.shape[3]
+    ref = torch.cat([sr, F.pad(up, (dx // 2, dx - dx // 2, dy // 2, dy - dy // 2))], dim=1)
+    so, lo = nhwc(skip).to(dt).requires_grad_(True), nhwc(low).to(dt).requires_grad_(True)
+    out = ops.upcat(so, lo, True)
+    assert rel_l2(nchw(out.float()), ref) < (1e-6 if dt == torch.float32 else 1e-2)
+    go = torch.randn_like(ref)
+    ref.backward(go)
+    out.backward(nhwc(go).to(dt))
+    assert rel_l2(nchw(so.grad.float()), sr.grad) < tol(dt)
+    assert rel_l2(nchw(lo.grad.float()), lr.grad) < tol(dt)
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_upcat_align_false(S, dt):
+    from stc_unet_b200 import ops
+    torch.manual_seed(0)
+    skip, low = torch.randn(1, 8, 12, 10, device=dev()), torch.randn(1, 8, 6, 5, device=dev())
+    if dt == torch.bfloat16:
+        skip, low = bf16_round(skip), bf16_round(low)
+    lr = low.clone().requires_grad_(True)
+    ref = torch.cat([skip, F.interpolate(lr, scale_factor=2, mode="bilinear", align_corners=False)], dim=1)
+    lo = nhwc(low).to(dt).requires_grad_(True)
+    out = ops.upcat(nhwc(skip).to(dt), lo, False)
+    assert rel_l2(nchw(out.float()), ref) < (1e-6 if dt == torch.float32 else 1e-2)
+    go = torch.randn_like(ref)
+    ref.backward(go)
+    out.backward(nhwc(go).to(dt))
+    assert rel_l2(nchw(lo.grad.float()), lr.grad) < tol(dt)
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_coordatt_block(S, dt):
+    """CoordAtt(x) + x against the oracle restatement, through the module."""
+    from oracle import stc_oracle as O
+    from stc_unet_b200 import ops
+    ops.config.engine = S._lib.ENGINE_SIMT
+    torch.manual_seed(0)
+    C, N, H, W = 32, 2, 6, 10
+    ca = S.CoordAtt(C, C).to(dev())
+    ca.bn1.weight.data.uniform_(0.5, 1.5)
+    sd = {"ca." + k: v.detach().clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in ca.state_dict().items()}
+    x = torch.randn(N, C, H, W, device=dev())
+    if dt == torch.bfloat16:
+        x = bf16_round(x)
+    xr = x.clone().requires_grad_(True)
+    ref = O.coord_att(sd, "ca", xr, True, None) + xr
+    xo = nhwc(x).to(dt).requires_grad_(True)
+    out = ca.forward_add(xo)
+    assert rel_l2(nchw(out.float()), ref) < tol(dt)
+    go = torch.randn_like(ref)
+    ref.backward(go)
+    out.backward(nhwc(go).to(dt))
+    t = tol(dt) * 5
+    assert rel_l2(nchw(xo.grad.float()), xr.grad) < t
+    for name, p in ca.named_parameters():
+        g_ref = sd["ca." + name].grad
+        if name == "conv1.bias":  # feeds a train-mode BN: true gradient is 0
+            assert float((p.grad - g_ref).abs().max()) < 1e-3
+        else:
+            assert rel_l2(p.grad, g_ref) < (t if dt == torch.float32 else 5e-2), name
+    ops.config.engine = S._lib.ENGINE_AUTO
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_ksa_block(S, dt):
+    from oracle import stc_oracle as O
+    from stc_unet_b200 import ops
+    ops.config.engine = S._lib.ENGINE_SIMT
+    torch.manual_seed(0)
+    C, N, H, W = 16, 2, 9, 8
+    ksa = S.KernelSelectAttention(channel=C).to(dev())
+    sd = {"k." + k: v.detach().clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in ksa.state_dict().items()}
+    x = torch.randn(N, C, H, W, device=dev())
+    if dt == torch.bfloat16:
+        x = bf16_round(x)
+    xr = x.clone().requires_grad_(True)
+    ref = O.kernel_select_attention(sd, "k", xr, True, None) + xr
+    xo = nhwc(x).to(dt).requires_grad_(True)
+    out = ksa.forward_residual(xo)
+    assert rel_l2(nchw(out.float()), ref) < tol(dt)
+    go = torch.randn_like(ref)
+    ref.backward(go)
+    out.backward(nhwc(go).to(dt))
+    t = tol(dt) * 5
+    assert rel_l2(nchw(xo.grad.float()), xr.grad) < t
+    for name, p in ksa.named_parameters():
+        g_ref = sd["k." + name].grad
+        if name.startswith("convs") and name.endswith("0.bias"):
+            assert float((p.grad - g_ref).abs().max()) < 1e-3
+        else:
+            assert rel_l2(p.grad, g_ref) < (t if dt == torch.float32 else 5e-2), name
+    ops.config.engine = S._lib.ENGINE_AUTO
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_transformer_block(S, dt):
+    from oracle import stc_oracle as O
+    from stc_unet_b200 import ops
+    ops.config.engine = S._lib.ENGINE_SIMT
+    torch.manual_seed(0)
+    N, H, W = 2, 4, 6
+    tb = S.TransformerBlock(512, 512, 2, 2).to(dev())
+    sd = {"t." + k: v.detach().clone().requires_grad_(True) for k, v in tb.state_dict().items()}
+    x = torch.randn(N, 512, H, W, device=dev()) * 0.5
+    if dt == torch.bfloat16:
+        x = bf16_round(x)
+    xr = x.clone().requires_grad_(True)
+    ref = O.transformer_block(sd, "t", xr, heads=2, layers=2) + xr
+    xo = nhwc(x).to(dt).requires_grad_(True)
+    out = tb.forward_residual(xo)
+    assert rel_l2(nchw(out.float()), ref) < tol(dt)
+    go = torch.randn_like(ref)
+    ref.backward(go)
+    out.backward(nhwc(go).to(dt))
+    t = tol(dt) * 5
+    assert rel_l2(nchw(xo.grad.float()), xr.grad) < t
+    for name, p in tb.named_parameters():
+        assert rel_l2(p.grad, sd["t." + name].grad) < (t if dt == torch.float32 else 6e-2), name
+    ops.config.engine = S._lib.ENGINE_AUTO
+
+
+@pytest.mark.parametrize("C", [2, 3, 5, 19])
+def test_cls_and_loss(S, C):
+    from oracle import stc_oracle as O
+    from stc_unet_b200 import ops
+    torch.manual_seed(0)
+    N, H, W = 3, 17, 23
+    conv_seg = torch.nn.Conv2d(64, C, 1).to(dev())
+    x = torch.randn(N, 64, H, W, device=dev())
+    label = torch.randint(0, C, (N, H, W), device=dev())
+    label[:, :3] = 255
+    xr = x.clone().requires_grad_(True)
+    wr, br = conv_seg.weight.detach().clone().requires_grad_(True), conv_seg.bias.detach().clone().requires_grad_(True)
+    logits_r = F.conv2d(xr, wr, br)
+    lr = O.losses(logits_r, label.unsqueeze(1))
+    xo = nhwc(x).requires_grad_(True)
+    logits = ops.cls_seg(xo, conv_seg)
+    assert rel_l2(logits, logits_r) < 1e-5
+    ce, dice, acc = ops.seg_loss(logits, label, 255, 1.0)
+    assert abs(float(ce) - float(lr["loss_bce"])) < 1e-5 * max(1, abs(float(ce)))
+    assert abs(float(dice) - float(lr["loss_dice"])) < 1e-5
+    assert abs(float(acc) - float(lr["acc_seg"])) < 1e-3
+    (lr["loss_bce"] + 0.7 * lr["loss_dice"]).backward()
+    total = ops.add_autograd(ce.reshape(1), ops.scale(dice, 0.7).reshape(1))
+    total.backward(torch.ones(1, device=dev()))
+    assert rel_l2(nchw(xo.grad), xr.grad) < 1e-4
+    assert rel_l2(conv_seg.weight.grad, wr.grad) < 1e-4
+    assert rel_l2(conv_seg.bias.grad, br.grad) < 1e-4
+
+
+def test_ce_known_answers(S):
+    """tests/test_models/test_losses/test_ce_loss.py:25-39 ([[100,-100]], label 1 -> 200) and :43-86
+    (full(0.5) logits 2x21x8x8 with an ignore stripe: mean over ALL pixels)."""
+    from stc_unet_b200 import ops
+    logits = torch.tensor([[100.0, -100.0]], device=dev()).view(1, 2, 1, 1)
+    label = torch.tensor([1], device=dev()).view(1, 1, 1)
+    ce, _, _ = ops.seg_loss(logits, label, 255, 1.0)
+    assert abs(float(ce) - 200.0) < 1e-4
+    logits = torch.full((2, 21, 8, 8), 0.5, device=dev())
+    label = torch.ones(2, 8, 8, device=dev()).long()
+    label[:, 0, 0] = 255
+    ce, _, _ = ops.seg_loss(logits, label, 255, 1.0)
+    want = F.cross_entropy(logits, label, reduction="none", ignore_index=255).sum() / label.numel()
+    assert abs(float(ce) - float(want)) < 1e-5
+
+
+@pytest.mark.parametrize("C", [2, 3, 19])
+def test_confusion_hist_bit_exact(S, C):
+    """tests/test_metrics.py:9-26 (np.bincount confusion matrix) and metrics.py:75-87 (area vectors)."""
+    import numpy as np
+    from oracle import stc_oracle as O
+    from stc_unet_b200 import ops
+    rng = np.random.RandomState(0)
+    pred = rng.randint(0, C, size=(10, 30, 30))
+    label = rng.randint(0, C, size=(10, 30, 30))
+    label[:, 2, 5:10] = 255
+    cm, areas = ops.confusion_hist(torch.from_numpy(pred).cuda(), torch.from_numpy(label.astype(np.uint8)).cuda(), C, 255)
+    assert np.array_equal(cm.cpu().numpy(), O.confusion_matrix(pred, label, C, 255))
+    a_i, a_u, a_p, a_l = O.intersect_and_union(pred, label, C, 255)
+    got = areas.cpu().numpy()
+    assert np.array_equal(got[0], a_i) and np.array_equal(got[1], a_u) and np.array_equal(got[2], a_p) and np.array_equal(got[3], a_l)
+    # int64 labels, out-of-range predictions are dropped like histc does
+    pred2 = pred.copy(); pred2[0, 0, :5] = C + 3
+    cm2, areas2 = ops.confusion_hist(torch.from_numpy(pred2).cuda(), torch.from_numpy(label).cuda(), C, 255)
+    assert np.array_equal(cm2.cpu().numpy(), O.confusion_matrix(pred2, label, C, 255))
+    b = O.intersect_and_union(pred2, label, C, 255)
+    assert all(np.array_equal(areas2.cpu().numpy()[i], b[i]) for i in range(4))
+
+
+def test_argmax_and_slide(S):
+    from oracle import stc_oracle as O
+    from stc_unet_b200 import ops
+    torch.manual_seed(0)
+    N, C, H, W = 2, 3, 20, 28
+    crop, stride = (8, 12), (5, 7)
+    img = torch.randn(N, C, H, W, device=dev())
+    fn = lambda t: t * 1.5 + 0.25  # stand-in "network": pointwise, so windows are consistent
+    ref = O.slide_inference(fn, img, C, crop, stride)
+    preds = torch.zeros(N, C, H, W, device=dev()); cnt = torch.zeros(N, H, W, device=dev())
+    for (y1, x1, y2, x2) in S.slide_windows(H, W, crop, stride):
+        ops.slide_accum(fn(img[:, :, y1:y2, x1:x2]).contiguous(), preds, cnt, y1, x1)
+    assert torch.equal(ops.argmax_nchw(preds, cnt), O.simple_test(ref))
+    assert rel_l2(preds / cnt.unsqueeze(1), ref) < 1e-6
+    tie = torch.zeros(1, 4, 3, 3, device=dev())
+    assert torch.equal(ops.argmax_nchw(tie), torch.zeros(1, 3, 3, dtype=torch.int64, device=dev()))
+
+
+def test_adam(S):
+    from stc_unet_b200._lib import lib, stream_ptr
+    torch.manual_seed(0)
+    p = torch.randn(1000, device=dev()); ref = torch.nn.Parameter(p.clone())
+    opt = torch.optim.Adam([ref], lr=1e-2, betas=(0.9, 0.999))
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 4):
+        g = torch.randn(1000, device=dev())
+        ref.grad = g.clone(); opt.step()
+        lib.call("stc_adam_step", p, g, m, v, p.numel(), 1e-2, 0.9, 0.999, 1e-8, 0.0, step, stream_ptr())
+    assert rel_l2(p, ref.data) < 1e-6
+
+
+def test_gemm_layouts_simt(S):
+    from stc_unet_b200 import ops
+    ops.config.engine = S._lib.ENGINE_SIMT
+    torch.manual_seed(0)
+    N, Hh, L, hd = 2, 2, 24, 16
+    E = Hh * hd
+    q, k, v = (torch.randn(N, L, E, device=dev()) for _ in range(3))
+    qr, kr, vr = (t.clone().requires_grad_(True) for t in (q, k, v))
+    def heads(t): return t.view(N, L, Hh, hd).transpose(1, 2)
+    att = torch.softmax(heads(qr) @ heads(kr).transpose(-1, -2) / math.sqrt(hd), -1)
+    ref = (att @ heads(vr)).transpose(1, 2).reshape(N, L, E)
+    qo, ko, vo = (t.clone().requires_grad_(True) for t in (q, k, v))
+    out = ops.attention(qo, ko, vo, Hh)
+    assert rel_l2(out, ref) < 1e-5
+    go = torch.randn_like(ref)
+    ref.backward(go); out.backward(go)
+    for a, b in ((qo, qr), (ko, kr), (vo, vr)):
+        assert rel_l2(a.grad, b.grad) < 1e-4
+    ops.config.engine = S._lib.ENGINE_AUTO

@@ -1,0 +1,125 @@
+"""tcgen05 / TMEM / TMA engine (bf16) against PyTorch fp32 on bf16-rounded operands.  The engine is forced
+(ENGINE_TCGEN05) so a silent SIMT fallback would raise instead of passing."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.util import bf16_round, nchw, nhwc, rel_l2
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+@pytest.fixture()
+def tc():
+    import stc_unet_b200 as S
+    from stc_unet_b200 import ops
+    ops.config.engine = S._lib.ENGINE_TCGEN05
+    yield ops
+    ops.config.engine = S._lib.ENGINE_AUTO
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+CONV_SHAPES = [
+    # N, Cin, Cout, H, W, k
+    (1, 64, 64, 8, 128, 1),
+    (2, 64, 64, 32, 32, 3),
+    (1, 128, 256, 16, 16, 3),
+    (1, 64, 128, 20, 24, 5),     # ragged: W not a power of two, tiles hang over the image
+    (2, 64, 64, 12, 40, 7),
+    (1, 192, 96, 9, 9, 3),       # BN = 96, 3 K-chunks per tap
+    (1, 512, 512, 8, 8, 3),      # two N tiles of 256
+    (3, 64, 32, 5, 300, 3),      # wide rows, several tiles per row
+]
+
+
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+def test_conv_fprop_tcgen05(tc, shape):
+    N, Cin, Cout, H, W, k = shape
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = bf16_round(torch.randn(N, Cin, H, W, device=dev(), generator=g))
+    w = bf16_round(torch.randn(Cout, Cin, k, k, device=dev(), generator=g) / math.sqrt(Cin * k * k))
+    b = torch.randn(Cout, device=dev(), generator=g)
+    ref = F.conv2d(x, w, b, padding=k // 2)
+    wp = tc.pack_weight(w, BF)
+    y = tc.conv_fprop(nhwc(x).to(BF), wp, b, None, Cout, k, k)
+    assert rel_l2(nchw(y.float()), ref) < 6e-3
+    # epilogue: residual + relu
+    res = bf16_round(torch.randn_like(ref))
+    y2 = tc.conv_fprop(nhwc(x).to(BF), wp, b, nhwc(res).to(BF), Cout, k, k, act=1)
+    assert rel_l2(nchw(y2.float()), torch.relu(ref + res)) < 6e-3
+
+
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+def test_conv_dgrad_wgrad_tcgen05(tc, shape):
+    N, Cin, Cout, H, W, k = shape
+    if Cout % 64 != 0:
+        pytest.skip("tcgen05 wgrad/dgrad need Cout % 64 == 0 (SIMT handles the rest)")
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = bf16_round(torch.randn(N, Cin, H, W, device=dev(), generator=g)).requires_grad_(True)
+    w = bf16_round(torch.randn(Cout, Cin, k, k, device=dev(), generator=g) / math.sqrt(Cin * k * k)).requires_grad_(True)
+    dy = bf16_round(torch.randn(N, Cout, H, W, device=dev(), generator=g))
+    F.conv2d(x, w, None, padding=k // 2).backward(dy)
+    wpt = tc.pack_weight(w.detach(), BF, transpose_flip=True)
+    dx = tc.conv_fprop(nhwc(dy).to(BF), wpt, None, None, Cin, k, k)
+    assert rel_l2(nchw(dx.float()), x.grad) < 6e-3
+    dw = tc.conv_wgrad(nhwc(x.detach()).to(BF), nhwc(dy).to(BF), k, k)
+    assert rel_l2(dw, w.grad) < 2e-3
+
+
+@pytest.mark.parametrize("L,heads", [(128, 2), (320, 2), (64, 2)])
+def test_attention_tcgen05(tc, L, heads):
+    """All four GEMM operand layouts (K-major / MN-major A and B) through attention fwd + bwd, head_dim 256."""
+    N, E = 2, 512
+    hd = E // heads
+    g = torch.Generator(device="cuda").manual_seed(4)
+    q, k, v = (bf16_round(torch.randn(N, L, E, device=dev(), generator=g) * 0.5) for _ in range(3))
+    qr, kr, vr = (t.clone().requires_grad_(True) for t in (q, k, v))
+    def hsplit(t): return t.view(N, L, heads, hd).transpose(1, 2)
+    att = torch.softmax(hsplit(qr) @ hsplit(kr).transpose(-1, -2) / math.sqrt(hd), -1)
+    ref = (att @ hsplit(vr)).transpose(1, 2).reshape(N, L, E)
+    qo, ko, vo = (t.to(BF).requires_grad_(True) for t in (q, k, v))
+    out = tc.attention(qo, ko, vo, heads)
+    assert rel_l2(out.float(), ref) < 2e-2
+    go = bf16_round(torch.randn_like(ref))
+    ref.backward(go)
+    out.backward(go.to(BF))
+    for a, b_ in ((qo, qr), (ko, kr), (vo, vr)):
+        assert rel_l2(a.grad.float(), b_.grad) < 3e-2
+
+
+def test_linear_tokens_tcgen05(tc):
+    g = torch.Generator(device="cuda").manual_seed(5)
+    rows, E, O = 300, 512, 1536
+    x = bf16_round(torch.randn(2, rows // 2, E, device=dev(), generator=g))
+    W = bf16_round(torch.randn(O, E, device=dev(), generator=g) / math.sqrt(E))
+    b = torch.randn(O, device=dev(), generator=g)
+    xr, Wr, br = x.clone().requires_grad_(True), W.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = xr @ Wr.t() + br
+    xo, Wo, bo = x.to(BF).requires_grad_(True), W.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    out = tc.linear_tokens(xo, Wo, bo)
+    assert rel_l2(out.float(), ref) < 6e-3
+    go = bf16_round(torch.randn_like(ref))
+    ref.backward(go)
+    out.backward(go.to(BF))
+    assert rel_l2(xo.grad.float(), xr.grad) < 6e-3
+    assert rel_l2(Wo.grad, Wr.grad) < 3e-3
+    assert rel_l2(bo.grad, br.grad) < 3e-3
+
+
+def test_tcgen05_matches_simt_large(tc):
+    """Full-size L1 layer (64->64 3x3 at 512x512): tensor-core result vs the fp32-accumulate SIMT engine."""
+    import stc_unet_b200 as S
+    g = torch.Generator(device="cuda").manual_seed(6)
+    x = torch.randn(1, 512, 512, 64, device=dev(), generator=g).to(BF)
+    w = torch.randn(64, 64, 3, 3, device=dev(), generator=g) / 24.0
+    wp = tc.pack_weight(w, BF)
+    y_tc = tc.conv_fprop(x, wp, None, None, 64, 3, 3)
+    tc.config.engine = S._lib.ENGINE_SIMT
+    y_simt = tc.conv_fprop(x, wp, None, None, 64, 3, 3)
+    assert rel_l2(y_tc.float(), y_simt.float()) < 4e-3
