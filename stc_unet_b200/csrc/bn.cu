@@ -24,17 +24,39 @@ template <typename T>
 __global__ void __launch_bounds__(256) bn_reduce_kernel(const T* __restrict__ y, float* __restrict__ partial, long long P, int C) {
     __shared__ float smem[256 * 16];
     const int lanes = C >> 3, lv = threadIdx.x % lanes, r0 = threadIdx.x / lanes, rstep = 256 / lanes;
+    // Shifted sums: accumulate (y - s) and (y - s)^2 with s = y[0][c] (the same shift in every block), so the fp32
+    // partials do not suffer the E[y^2] - mean^2 cancellation when |mean| >> std; bn_unshift_kernel undoes the
+    // shift in fp64.
+    Vec8<T> sh;
+    sh.load(y + lv * 8);
     float acc[2][8] = {};
     for (long long p = (long long)blockIdx.x * rstep + r0; p < P; p += (long long)gridDim.x * rstep) {
         Vec8<T> v;
         v.load(y + p * C + lv * 8);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            acc[0][k] += v.v[k];
-            acc[1][k] = fmaf(v.v[k], v.v[k], acc[1][k]);
+            float d = v.v[k] - sh.v[k];
+            acc[0][k] += d;
+            acc[1][k] = fmaf(d, d, acc[1][k]);
         }
     }
     block_reduce_lanes<2>(acc, lanes, lv, smem, partial, C);
+}
+
+// sums[c] = sum y, sums[C+c] = sum y^2 in fp64 from the shifted fp32 block partials
+template <typename T>
+__global__ void bn_unshift_kernel(const float* __restrict__ partial, const T* __restrict__ y, double* __restrict__ sums, int G,
+                                  long long P, int C) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s1 = 0.0, s2 = 0.0;
+    for (int g = 0; g < G; ++g) {
+        s1 += (double)partial[(size_t)g * 2 * C + c];
+        s2 += (double)partial[(size_t)g * 2 * C + C + c];
+    }
+    const double s = (double)ldf(y + c), n = (double)P;
+    sums[c] = s1 + n * s;
+    sums[C + c] = s2 + 2.0 * s * s1 + n * s * s;
 }
 
 // generic fallback (any C): one block column of 32 channels, fp64 atomics
@@ -230,7 +252,7 @@ extern "C" int stc_bn_reduce(const void* y, double* sums, long long P, int C, vo
         int lanes = C / 8, G = reduce_blocks(P, lanes);
         STC_REQUIRE(ws && ws_bytes >= (long long)G * 2 * C * (long long)sizeof(float), "bn_reduce: workspace too small");
         STC_DISPATCH_DTYPE(dtype, (bn_reduce_kernel<T><<<G, 256, 0, st>>>((const T*)y, (float*)ws, P, C)));
-        reduce_partials_kernel<<<ceil_div(2 * C, 128), 128, 0, st>>>((const float*)ws, sums, G, 2 * C);
+        STC_DISPATCH_DTYPE(dtype, (bn_unshift_kernel<T><<<ceil_div(C, 128), 128, 0, st>>>((const float*)ws, (const T*)y, sums, G, P, C)));
     } else {
         STC_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
         dim3 grid(ceil_div(C, 32), (unsigned)max(1LL, min((long long)num_sms() * 2, (P + 63) / 64)));

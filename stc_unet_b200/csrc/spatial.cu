@@ -394,14 +394,23 @@ __global__ void __launch_bounds__(256) softmax_rows_bwd_kernel(const T* __restri
     const T* g = dP + (long long)blockIdx.x * L;
     T* o = dS + (long long)blockIdx.x * L;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    float dot = 0.f;
-    for (int j = tid; j < L; j += 256) dot = fmaf(ldf(p + j), ldf(g + j), dot);
+    // dot = sum(dP * P) / sum(P): dividing by the ACTUAL row sum of the (possibly bf16-rounded) probabilities keeps
+    // sum_j dS_j == 0, so a large common component of K/Q cannot leak into dQ/dK.
+    float dot = 0.f, psum = 0.f;
+    for (int j = tid; j < L; j += 256) {
+        float pj = ldf(p + j);
+        dot = fmaf(pj, ldf(g + j), dot);
+        psum += pj;
+    }
     dot = warp_sum(dot);
-    if (lane == 0) red[warp] = dot;
+    psum = warp_sum(psum);
+    __shared__ float red2[8];
+    if (lane == 0) { red[warp] = dot; red2[warp] = psum; }
     __syncthreads();
-    dot = 0.f;
+    dot = 0.f; psum = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) dot += red[k];
+    for (int k = 0; k < 8; ++k) { dot += red[k]; psum += red2[k]; }
+    dot /= psum;
     for (int j = tid; j < L; j += 256) stf(o + j, scale * ldf(p + j) * (ldf(g + j) - dot));
 }
 
