@@ -91,6 +91,9 @@ typedef struct {
     float alpha, beta;
 } stc_gemm_desc;
 int stc_gemm(const void* A, const void* B, void* C, const stc_gemm_desc* d, int dtype, int engine, void* stream);
+/* STC_ENGINE_SIMT or STC_ENGINE_TCGEN05: the engine the last stc_conv_fprop / stc_conv_wgrad / stc_gemm call on this
+ * thread actually ran (bench.py attributes FLOPs and launch counts with it). */
+int stc_dense_last_engine(void);
 
 /* row softmax over the last dim: P = softmax(scale * S) ; rows x L (MHA, L = H*W tokens). */
 int stc_softmax_rows_fwd(const void* S, void* P, long long rows, int L, float scale, int dtype, void* stream);

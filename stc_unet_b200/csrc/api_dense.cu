@@ -17,6 +17,10 @@ int gemm_umma(const void*, const void*, void*, const stc_gemm_desc*, int, cudaSt
 
 using namespace stc;
 
+static thread_local int g_last_engine = 0;
+/* engine actually used by the last stc_conv_fprop / stc_conv_wgrad / stc_gemm call on this thread */
+extern "C" int stc_dense_last_engine(void) { return g_last_engine; }
+
 extern "C" int stc_conv_fprop(const void* x, const void* wp, const float* bias, const void* residual, void* y, int N, int H,
                               int W, int Cin, int Cout, int R, int S, int act, int dtype, int engine, void* stream) {
     STC_REQUIRE(N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && (R & 1) && (S & 1), "conv_fprop: bad shape N=%d H=%d W=%d Cin=%d Cout=%d R=%d S=%d",
@@ -25,9 +29,14 @@ extern "C" int stc_conv_fprop(const void* x, const void* wp, const float* bias, 
     bool elig = conv_umma_eligible(Cin, Cout, dtype);
     if (engine == STC_ENGINE_TCGEN05) {
         STC_REQUIRE(elig, "conv_fprop: tcgen05 engine requested but shape/dtype not eligible (Cin=%d Cout=%d dtype=%d)", Cin, Cout, dtype);
+        g_last_engine = STC_ENGINE_TCGEN05;
         return conv_fprop_umma(x, wp, bias, residual, y, N, H, W, Cin, Cout, R, S, act, st);
     }
-    if (engine == STC_ENGINE_AUTO && elig) return conv_fprop_umma(x, wp, bias, residual, y, N, H, W, Cin, Cout, R, S, act, st);
+    if (engine == STC_ENGINE_AUTO && elig) {
+        g_last_engine = STC_ENGINE_TCGEN05;
+        return conv_fprop_umma(x, wp, bias, residual, y, N, H, W, Cin, Cout, R, S, act, st);
+    }
+    g_last_engine = STC_ENGINE_SIMT;
     return conv_fprop_simt(x, wp, bias, residual, y, N, H, W, Cin, Cout, R, S, act, dtype, st);
 }
 
@@ -38,9 +47,14 @@ extern "C" int stc_conv_wgrad(const void* x, const void* dy, float* dw_ws, int N
     bool elig = dtype == STC_BF16 && Cin % 64 == 0 && Cout % 64 == 0;
     if (engine == STC_ENGINE_TCGEN05) {
         STC_REQUIRE(elig, "conv_wgrad: tcgen05 engine requested but shape/dtype not eligible");
+        g_last_engine = STC_ENGINE_TCGEN05;
         return conv_wgrad_umma(x, dy, dw_ws, N, H, W, Cin, Cout, R, S, st);
     }
-    if (engine == STC_ENGINE_AUTO && elig) return conv_wgrad_umma(x, dy, dw_ws, N, H, W, Cin, Cout, R, S, st);
+    if (engine == STC_ENGINE_AUTO && elig) {
+        g_last_engine = STC_ENGINE_TCGEN05;
+        return conv_wgrad_umma(x, dy, dw_ws, N, H, W, Cin, Cout, R, S, st);
+    }
+    g_last_engine = STC_ENGINE_SIMT;
     return conv_wgrad_simt(x, dy, dw_ws, N, H, W, Cin, Cout, R, S, dtype, st);
 }
 
@@ -50,8 +64,13 @@ extern "C" int stc_gemm(const void* A, const void* B, void* C, const stc_gemm_de
     bool elig = gemm_umma_eligible(d, dtype);
     if (engine == STC_ENGINE_TCGEN05) {
         STC_REQUIRE(elig, "gemm: tcgen05 engine requested but descriptor/dtype not eligible");
+        g_last_engine = STC_ENGINE_TCGEN05;
         return gemm_umma(A, B, C, d, dtype, st);
     }
-    if (engine == STC_ENGINE_AUTO && elig) return gemm_umma(A, B, C, d, dtype, st);
+    if (engine == STC_ENGINE_AUTO && elig) {
+        g_last_engine = STC_ENGINE_TCGEN05;
+        return gemm_umma(A, B, C, d, dtype, st);
+    }
+    g_last_engine = STC_ENGINE_SIMT;
     return gemm_simt(A, B, C, d, dtype, st);
 }

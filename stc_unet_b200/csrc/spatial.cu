@@ -358,6 +358,9 @@ __global__ void softmax3_bwd_kernel(const float* __restrict__ w, const float* __
 }
 
 // ---------------------------------------------------------------- row softmax (MHA)
+template <typename T> __device__ __forceinline__ float row_exp(float x);
+template <> __device__ __forceinline__ float row_exp<float>(float x) { return expf(x); }     // fp32 parity path: full precision
+template <> __device__ __forceinline__ float row_exp<bf16>(float x) { return __expf(x); }    // bf16 path: SFU ex2
 template <typename T>
 __global__ void __launch_bounds__(256) softmax_rows_fwd_kernel(const T* __restrict__ S, T* __restrict__ P, int L, float scale) {
     __shared__ float red[8];
@@ -375,7 +378,7 @@ __global__ void __launch_bounds__(256) softmax_rows_fwd_kernel(const T* __restri
     for (int k = 1; k < 8; ++k) m = fmaxf(m, red[k]);
     __syncthreads();
     float sum = 0.f;
-    for (int j = tid; j < L; j += 256) sum += __expf(ldf(s + j) * scale - m);
+    for (int j = tid; j < L; j += 256) sum += row_exp<T>(ldf(s + j) * scale - m);
     sum = warp_sum(sum);
     if (lane == 0) red[warp] = sum;
     __syncthreads();
@@ -383,7 +386,7 @@ __global__ void __launch_bounds__(256) softmax_rows_fwd_kernel(const T* __restri
 #pragma unroll
     for (int k = 0; k < 8; ++k) sum += red[k];
     const float inv = 1.f / sum;
-    for (int j = tid; j < L; j += 256) stf(p + j, __expf(ldf(s + j) * scale - m) * inv);
+    for (int j = tid; j < L; j += 256) stf(p + j, row_exp<T>(ldf(s + j) * scale - m) * inv);
 }
 
 template <typename T>

@@ -97,6 +97,60 @@ def _grad_buf(param, shape, device, zero=False) -> torch.Tensor:
 
 
 # ---------------------------------------------------------------------------------------------
+# optional per-launch profiler (bench.py): CUDA events on the launching stream around every dense call,
+# with the call's algorithmic FLOPs, plus a count of every kernel-launching C-ABI call
+# ---------------------------------------------------------------------------------------------
+class LaunchProfiler:
+    def __init__(self, time_dense: bool = False):
+        self.time_dense = time_dense
+        self.records = []       # (kind, engine, flops, start_event, end_event)
+        self.calls = 0
+
+    def dense(self, kind, flops, fn):
+        if self.time_dense:
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn()
+            e.record()
+            self.records.append((kind, lib.raw("stc_dense_last_engine")(), flops, s, e))
+        else:
+            fn()
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for kind, engine, flops, s, e in self.records:
+            d = out.setdefault((kind, engine), dict(launches=0, flops=0.0, ms=0.0))
+            d["launches"] += 1
+            d["flops"] += flops
+            d["ms"] += s.elapsed_time(e)
+        return out
+
+
+_PROF: Optional[LaunchProfiler] = None
+
+
+def set_profiler(p: Optional[LaunchProfiler]):
+    global _PROF
+    _PROF = p
+    _orig = _lib._Lib.call
+    if p is not None:
+        def counting_call(self_, name, *args, _o=_orig):
+            p.calls += 1
+            return _o(self_, name, *args)
+        lib.call = counting_call.__get__(lib, type(lib))
+    elif "call" in lib.__dict__:
+        del lib.__dict__["call"]
+
+
+def _dense(kind, flops, fn):
+    if _PROF is not None:
+        _PROF.dense(kind, flops, fn)
+    else:
+        fn()
+
+
+# ---------------------------------------------------------------------------------------------
 # dense helpers
 # ---------------------------------------------------------------------------------------------
 def pack_weight(w: torch.Tensor, dtype: torch.dtype, transpose_flip: bool = False) -> torch.Tensor:
@@ -110,8 +164,9 @@ def pack_weight(w: torch.Tensor, dtype: torch.dtype, transpose_flip: bool = Fals
 def conv_fprop(x, wp, bias, residual, Cout: int, R: int, S: int, act: int = 0) -> torch.Tensor:
     N, H, W, Cin = x.shape
     y = torch.empty((N, H, W, Cout), dtype=x.dtype, device=x.device)
-    lib.call("stc_conv_fprop", x, wp, bias, residual, y, N, H, W, Cin, Cout, R, S, act, dtype_code(x.dtype),
-             config.engine, stream_ptr())
+    _dense("conv_fprop", 2.0 * N * H * W * Cin * Cout * R * S,
+           lambda: lib.call("stc_conv_fprop", x, wp, bias, residual, y, N, H, W, Cin, Cout, R, S, act, dtype_code(x.dtype),
+                            config.engine, stream_ptr()))
     return y
 
 
@@ -119,7 +174,8 @@ def conv_wgrad(x, dy, R: int, S: int, out: Optional[torch.Tensor] = None) -> tor
     N, H, W, Cin = x.shape
     Cout = dy.shape[-1]
     ws = torch.zeros(R * S * Cin * Cout, dtype=torch.float32, device=x.device)
-    lib.call("stc_conv_wgrad", x, dy, ws, N, H, W, Cin, Cout, R, S, dtype_code(x.dtype), config.engine, stream_ptr())
+    _dense("conv_wgrad", 2.0 * N * H * W * Cin * Cout * R * S,
+           lambda: lib.call("stc_conv_wgrad", x, dy, ws, N, H, W, Cin, Cout, R, S, dtype_code(x.dtype), config.engine, stream_ptr()))
     if out is None:
         out = torch.empty((Cout, Cin, R, S), dtype=torch.float32, device=x.device)
     lib.call("stc_unpack_conv_wgrad", ws, out, Cout, Cin, R, S, 0, stream_ptr())
@@ -142,7 +198,8 @@ def add(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 def gemm(A, B, C, M, N, K, batch1, batch2, sA, sB, sC, alpha=1.0):
     d = GemmDesc(M, N, K, batch1, batch2, sA[0], sA[1], sA[2], sA[3], sB[0], sB[1], sB[2], sB[3], sC[0], sC[1], sC[2],
                  alpha, 0.0)
-    lib.call("stc_gemm", A, B, C, d, dtype_code(A.dtype), config.engine, stream_ptr())
+    _dense("gemm", 2.0 * M * N * K * batch1 * batch2,
+           lambda: lib.call("stc_gemm", A, B, C, d, dtype_code(A.dtype), config.engine, stream_ptr()))
 
 
 # ---------------------------------------------------------------------------------------------

@@ -1,0 +1,156 @@
+"""Training-step plumbing around the hot path:
+
+  * FlatParams   — every parameter becomes a view into ONE fp32 buffer (one rank-0 broadcast, one fused Adam kernel)
+  * GradArena    — (ops.py) every parameter gradient is written by our kernels straight into ONE fp32 buffer
+  * GradReducer  — bucketed NCCL all-reduce(AVG) of that buffer on a side stream, launched from post-accumulate
+                   hooks while backward is still running (replaces MMDistributedDataParallel's reducer,
+                   mmseg/apis/train.py:104-113, broadcast_buffers=False)
+  * FusedAdam    — torch.optim.Adam semantics (my_config/STC-UNet.py:87: lr 1e-5, betas (0.9, 0.999)) as one
+                   stc_adam_step launch over the flat buffers
+  * Trainer      — zero_grad -> forward_train -> backward -> (all-reduce) -> Adam, i.e. what mmcv's
+                   EpochBasedRunner + OptimizerHook do per iteration around BaseSegmentor.train_step.
+
+SyncBN statistics are exchanged inside the BN ops themselves (ops._bn_forward_stats / _bn_backward) whenever the BN
+containers are nn.SyncBatchNorm and torch.distributed is initialised.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from ._lib import lib, stream_ptr
+
+
+def _dist_on() -> bool:
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+class FlatParams:
+    def __init__(self, params: List[torch.nn.Parameter]):
+        self.params = [p for p in params if p.requires_grad]
+        dev = self.params[0].device
+        total, self.offsets = 0, []
+        for p in self.params:
+            self.offsets.append(total)
+            total += (p.numel() + 3) // 4 * 4
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        for p, off in zip(self.params, self.offsets):
+            view = self.flat[off:off + p.numel()].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+        self.total = total
+
+    def broadcast(self, src: int = 0):
+        if _dist_on():
+            dist.broadcast(self.flat, src)
+
+
+class GradReducer:
+    """Buckets are contiguous ranges of the arena taken from its END (backward produces the last parameters
+    first); a bucket's all-reduce starts on the comm stream as soon as all of its gradients have been written."""
+
+    def __init__(self, arena: ops.GradArena, bucket_mb: float = 25.0):
+        self.arena = arena
+        self.comm = torch.cuda.Stream()
+        cap = int(bucket_mb * (1 << 20) // 4)
+        self.buckets = []          # (start, end, n_params)
+        self.bucket_of: Dict[int, int] = {}
+        cur_end, cur_start, cnt = arena.total, arena.total, 0
+        for p in reversed(arena.params):
+            off, n = arena.offsets[id(p)]
+            cur_start = off
+            self.bucket_of[id(p)] = len(self.buckets)
+            cnt += 1
+            if cur_end - cur_start >= cap:
+                self.buckets.append((cur_start, cur_end, cnt))
+                cur_end, cnt = cur_start, 0
+        if cnt:
+            self.buckets.append((cur_start, cur_end, cnt))
+        self.pending = [0] * len(self.buckets)
+        self.handles = []
+        self.enabled = _dist_on()
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in arena.params]
+
+    def reset(self):
+        self.pending = [b[2] for b in self.buckets]
+        self.handles = []
+
+    def _on_grad(self, p):
+        if not self.enabled:
+            return
+        b = self.bucket_of[id(p)]
+        self.pending[b] -= 1
+        if self.pending[b] == 0:
+            start, end, _ = self.buckets[b]
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self.comm.wait_event(ev)
+            with torch.cuda.stream(self.comm):
+                self.handles.append(dist.all_reduce(self.arena.flat[start:end], op=dist.ReduceOp.AVG, async_op=True))
+
+    def finish(self):
+        if not self.enabled:
+            return
+        for h in self.handles:
+            h.wait()
+        torch.cuda.current_stream().wait_stream(self.comm)
+        self.handles = []
+
+
+class FusedAdam:
+    """Adam over the flat parameter / gradient buffers (one kernel).  Exposes `param_groups` so LR schedulers
+    written against torch.optim (mmcv's PolyLrUpdaterHook sets group['lr']) keep working."""
+
+    def __init__(self, flat_params: FlatParams, arena: ops.GradArena, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        assert flat_params.total == arena.total
+        self.fp, self.arena = flat_params, arena
+        self.param_groups = [dict(params=flat_params.params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, initial_lr=lr)]
+        self.m = torch.zeros_like(flat_params.flat)
+        self.v = torch.zeros_like(flat_params.flat)
+        self.t = 0
+
+    def zero_grad(self, set_to_none: bool = True):
+        for p in self.fp.params:
+            p.grad = None
+
+    def step(self):
+        g = self.param_groups[0]
+        self.t += 1
+        lib.call("stc_adam_step", self.fp.flat, self.arena.flat, self.m, self.v, self.fp.total, float(g["lr"]),
+                 float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]), self.t, stream_ptr())
+
+    def state_dict(self):
+        return dict(step=self.t, exp_avg=self.m, exp_avg_sq=self.v, param_groups=[{k: v for k, v in self.param_groups[0].items() if k != "params"}])
+
+    def load_state_dict(self, sd):
+        self.t = int(sd["step"])
+        self.m.copy_(sd["exp_avg"]); self.v.copy_(sd["exp_avg_sq"])
+        self.param_groups[0].update(sd["param_groups"][0])
+
+
+class Trainer:
+    def __init__(self, segmentor: torch.nn.Module, lr=1e-5, betas=(0.9, 0.999), bucket_mb=25.0):
+        self.model = segmentor
+        params = [p for p in segmentor.parameters() if p.requires_grad]
+        self.flat = FlatParams(params)
+        self.flat.broadcast(0)
+        self.arena = ops.GradArena(self.flat.params)
+        self.reducer = GradReducer(self.arena, bucket_mb)
+        self.optim = FusedAdam(self.flat, self.arena, lr=lr, betas=betas)
+
+    def step(self, img: torch.Tensor, gt_semantic_seg: torch.Tensor):
+        """One training iteration; returns the (device) log-var tensors, no host sync."""
+        ops.set_grad_arena(self.arena)
+        try:
+            self.optim.zero_grad()
+            self.reducer.reset()
+            out = self.model.train_step(dict(img=img, img_metas=None, gt_semantic_seg=gt_semantic_seg))
+            out["loss"].backward()
+            self.reducer.finish()
+            self.optim.step()
+        finally:
+            ops.set_grad_arena(None)
+        return out["log_vars"]

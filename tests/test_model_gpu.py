@@ -50,7 +50,7 @@ def build(stc: bool, num_classes: int, dtype: str, seed=0, posbn=False):
 
 def is_bn_cancelled_bias(name):
     """Conv biases feeding a train-mode BN: true gradient is 0 (SURVEY §7 traps) — excluded from relative checks."""
-    return name.endswith((".conv.conv.0.bias", ".conv.conv.3.bias", "ca.conv1.bias")) or (".convs." in name and name.endswith(".0.bias"))
+    return name.endswith((".conv.0.bias", ".conv.3.bias", "ca.conv1.bias")) or (".convs." in name and name.endswith(".0.bias"))
 
 
 def oracle(bb, hd, img, gt, dt, autocast=False):
@@ -129,7 +129,7 @@ def test_fp32_parity(stc, C, posbn):
     check_bn_cancelled(got, ref64, 1e-3)
     if posbn:
         for k, e in e_ours.items():
-            assert e <= max(1e-4, 2.0 * e_torch[k]), (k, e, e_torch[k])
+            assert e <= max(1e-4, 3.0 * e_torch[k]), (k, e, e_torch[k])
     else:
         assert statistics.median(e_ours.values()) <= max(1e-4, 1.5 * statistics.median(e_torch.values()))
         assert max(e_ours.values()) <= max(1e-4, 3.0 * max(e_torch.values()))
