@@ -185,12 +185,13 @@ int stc_scale_channels(const void* x, const float* m, void* y, int N, long long 
 
 /* ---------------------------------------------------------------- classifier + loss (K12-K15)
  * BaseDecodeHead.cls_seg (decode_head.py:254-259): logits NCHW fp32 = conv1x1(x NHWC) + b. W is (Ccls,Cin) fp32. */
-int stc_cls_fwd(const void* x, const float* W, const float* b, float* logits, int N, long long HW, int Cin, int Ccls,
-                int dtype, void* stream);
+/* mask: optional Dropout2d factors, fp32 (N, Cin), already scaled by 1/(1-p); NULL = no dropout. */
+int stc_cls_fwd(const void* x, const float* W, const float* b, const float* mask, float* logits, int N, long long HW, int Cin,
+                int Ccls, int dtype, void* stream);
 /* dx NHWC = dlogits^T W ; dW (+)= ..., db (+)= ... ; ws >= stc_cls_bwd_ws_bytes */
 long long stc_cls_bwd_ws_bytes(int N, long long HW, int Cin, int Ccls);
-int stc_cls_bwd(const float* dlogits, const void* x, const float* W, void* dx, float* dW, float* db, int N, long long HW,
-                int Cin, int Ccls, void* ws, long long ws_bytes, int dtype, void* stream);
+int stc_cls_bwd(const float* dlogits, const void* x, const float* W, const float* mask, void* dx, float* dW, float* db, int N,
+                long long HW, int Cin, int Ccls, void* ws, long long ws_bytes, int dtype, void* stream);
 /* BaseDecodeHead.losses (decode_head.py:261-296) = CrossEntropyLoss(avg_non_ignore=False)
  * (cross_entropy_loss.py:45-61) + DiceLoss (dice_loss.py:13-47,92-123) + accuracy (accuracy.py:6-61).
  * logits NCHW fp32, label int64 (N,H,W).  stats (fp64, 3*N*C + 4): per (n,c) [sum p*t*m, sum p^2, sum t],

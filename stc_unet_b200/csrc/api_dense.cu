@@ -12,6 +12,8 @@ int conv_fprop_umma(const void*, const void*, const float*, const void*, void*, 
                     cudaStream_t);
 int conv_wgrad_umma(const void*, const void*, float*, int, int, int, int, int, int, int, cudaStream_t);
 bool gemm_umma_eligible(const stc_gemm_desc*, int dtype);
+bool conv_convh_eligible(int W, int Cin, int Cout, int R, int S, int dtype);
+int conv_fprop_convh(const void*, const void*, const float*, const void*, void*, int, int, int, int, int, int, int, int, cudaStream_t);
 int gemm_umma(const void*, const void*, void*, const stc_gemm_desc*, int, cudaStream_t);
 }  // namespace stc
 
@@ -27,6 +29,10 @@ extern "C" int stc_conv_fprop(const void* x, const void* wp, const float* bias, 
                 N, H, W, Cin, Cout, R, S);
     cudaStream_t st = (cudaStream_t)stream;
     bool elig = conv_umma_eligible(Cin, Cout, dtype);
+    if (engine != STC_ENGINE_SIMT && elig && conv_convh_eligible(W, Cin, Cout, R, S, dtype)) {
+        g_last_engine = STC_ENGINE_TCGEN05;  // halo-reuse variant of the tcgen05 engine
+        return conv_fprop_convh(x, wp, bias, residual, y, N, H, W, Cin, Cout, R, S, act, st);
+    }
     if (engine == STC_ENGINE_TCGEN05) {
         STC_REQUIRE(elig, "conv_fprop: tcgen05 engine requested but shape/dtype not eligible (Cin=%d Cout=%d dtype=%d)", Cin, Cout, dtype);
         g_last_engine = STC_ENGINE_TCGEN05;

@@ -47,13 +47,17 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const T* __restrict__ y,
 template <typename T>
 __global__ void bn_unshift_kernel(const float* __restrict__ partial, const T* __restrict__ y, double* __restrict__ sums, int G,
                                   long long P, int C) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per channel: lanes stride over the G block partials
+    int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= C) return;
     double s1 = 0.0, s2 = 0.0;
-    for (int g = 0; g < G; ++g) {
+    for (int g = lane; g < G; g += 32) {
         s1 += (double)partial[(size_t)g * 2 * C + c];
         s2 += (double)partial[(size_t)g * 2 * C + C + c];
     }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane) return;
     const double s = (double)ldf(y + c), n = (double)P;
     sums[c] = s1 + n * s;
     sums[C + c] = s2 + 2.0 * s * s1 + n * s * s;
@@ -236,6 +240,74 @@ __global__ void bn_param_grads_kernel(const double* __restrict__ sums, float* __
     if (dgamma) dgamma[c] = (float)sums[C + c];
 }
 
+
+// ---------------------------------------------------------------- row-strided fast paths (C/8 a power of two <= 256)
+// Each thread owns one 8-channel lane for the whole launch, so the per-channel constants live in registers and the
+// inner loop is load -> fma -> store with no index arithmetic beyond a pointer bump.
+template <typename T>
+__global__ void __launch_bounds__(256) bn_apply_rows_kernel(const T* __restrict__ y, const float* __restrict__ mean,
+                                                            const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, T* __restrict__ a, long long P, int C,
+                                                            int act) {
+    const int lanes = C >> 3, lv = threadIdx.x % lanes, r0 = threadIdx.x / lanes, rstep = 256 / lanes;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        int c = lv * 8 + k;
+        sc[k] = gamma[c] * invstd[c];
+        sh[k] = beta[c] - mean[c] * sc[k];
+    }
+    const long long step = (long long)gridDim.x * rstep;
+    for (long long p = (long long)blockIdx.x * rstep + r0; p < P; p += step) {
+        Vec8<T> v;
+        v.load(y + p * C + lv * 8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v.v[k] = act_fwd(fmaf(v.v[k], sc[k], sh[k]), act);
+        v.store(a + p * C + lv * 8);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_apply_rows_kernel(const T* __restrict__ y, const T* __restrict__ dout,
+                                                                const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                const double* __restrict__ sums, float inv_count, T* __restrict__ dy,
+                                                                long long P, int C, int act, int eval) {
+    const int lanes = C >> 3, lv = threadIdx.x % lanes, r0 = threadIdx.x / lanes, rstep = 256 / lanes;
+    float sc[8], sh[8], mu[8], is[8], c1[8], c2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        int c = lv * 8 + k;
+        mu[k] = mean[c];
+        is[k] = invstd[c];
+        sc[k] = gamma[c] * is[k];
+        sh[k] = beta[c] - mu[k] * sc[k];
+        c1[k] = eval ? 0.f : (float)sums[c] * inv_count;
+        c2[k] = eval ? 0.f : (float)sums[C + c] * inv_count;
+    }
+    const long long step = (long long)gridDim.x * rstep;
+    for (long long p = (long long)blockIdx.x * rstep + r0; p < P; p += step) {
+        Vec8<T> v, d;
+        v.load(y + p * C + lv * 8);
+        d.load(dout + p * C + lv * 8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float g = d.v[k] * act_grad(fmaf(v.v[k], sc[k], sh[k]), act);
+            float xh = (v.v[k] - mu[k]) * is[k];
+            v.v[k] = sc[k] * (g - c1[k] - xh * c2[k]);
+        }
+        v.store(dy + p * C + lv * 8);
+    }
+}
+
+inline int rows_blocks(long long P, int lanes) {
+    long long rstep = 256 / lanes;
+    long long want = (P + rstep * 4 - 1) / (rstep * 4);
+    long long cap = (long long)num_sms() * 8;
+    long long g = want < cap ? want : cap;
+    return (int)(g < 1 ? 1 : g);
+}
+
 }  // namespace stc
 
 using namespace stc;
@@ -252,7 +324,7 @@ extern "C" int stc_bn_reduce(const void* y, double* sums, long long P, int C, vo
         int lanes = C / 8, G = reduce_blocks(P, lanes);
         STC_REQUIRE(ws && ws_bytes >= (long long)G * 2 * C * (long long)sizeof(float), "bn_reduce: workspace too small");
         STC_DISPATCH_DTYPE(dtype, (bn_reduce_kernel<T><<<G, 256, 0, st>>>((const T*)y, (float*)ws, P, C)));
-        STC_DISPATCH_DTYPE(dtype, (bn_unshift_kernel<T><<<ceil_div(C, 128), 128, 0, st>>>((const float*)ws, (const T*)y, sums, G, P, C)));
+        STC_DISPATCH_DTYPE(dtype, (bn_unshift_kernel<T><<<ceil_div((long long)C * 32, 128), 128, 0, st>>>((const float*)ws, (const T*)y, sums, G, P, C)));
     } else {
         STC_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
         dim3 grid(ceil_div(C, 32), (unsigned)max(1LL, min((long long)num_sms() * 2, (P + 63) / 64)));
@@ -281,7 +353,10 @@ extern "C" int stc_bn_apply(const void* y, const float* mean, const float* invst
     long long total = P * C;
     if (total <= 0) return STC_OK;
     bool vec = C % 8 == 0 && ((((uintptr_t)y) | ((uintptr_t)a)) & 15) == 0;
-    if (vec) {
+    if (vec && vec_ok(C)) {
+        STC_DISPATCH_DTYPE(dtype, (bn_apply_rows_kernel<T><<<rows_blocks(P, C / 8), 256, 0, st>>>((const T*)y, mean, invstd, gamma, beta,
+                                                                                                (T*)a, P, C, act)));
+    } else if (vec) {
         long long nvec = total / 8;
         int blocks = (int)min((long long)num_sms() * 8, (long long)ceil_div(nvec, 256));
         STC_DISPATCH_DTYPE(dtype, (bn_apply_kernel<T><<<blocks, 256, 0, st>>>((const T*)y, mean, invstd, gamma, beta, (T*)a, nvec, C / 8, act)));
@@ -302,7 +377,7 @@ extern "C" int stc_bn_bwd_reduce(const void* y, const void* dout, const float* m
         STC_REQUIRE(ws && ws_bytes >= (long long)G * 2 * C * (long long)sizeof(float), "bn_bwd_reduce: workspace too small");
         STC_DISPATCH_DTYPE(dtype, (bn_bwd_reduce_kernel<T><<<G, 256, 0, st>>>((const T*)y, (const T*)dout, mean, invstd, gamma, beta,
                                                                              (float*)ws, P, C, act)));
-        reduce_partials_kernel<<<ceil_div(2 * C, 128), 128, 0, st>>>((const float*)ws, sums, G, 2 * C);
+        reduce_partials_kernel<<<ceil_div((long long)2 * C * 32, 128), 128, 0, st>>>((const float*)ws, sums, G, 2 * C);
     } else {
         STC_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
         dim3 grid(ceil_div(C, 32), (unsigned)max(1LL, min((long long)num_sms() * 2, (P + 63) / 64)));
@@ -319,6 +394,11 @@ extern "C" int stc_bn_bwd_apply(const void* y, const void* dout, const float* me
     long long total = P * C;
     if (total <= 0) return STC_OK;
     int vec = (C % 8 == 0 && ((((uintptr_t)y) | ((uintptr_t)dout) | ((uintptr_t)dy)) & 15) == 0) ? 1 : 0;
+    if (vec && vec_ok(C)) {
+        STC_DISPATCH_DTYPE(dtype, (bn_bwd_apply_rows_kernel<T><<<rows_blocks(P, C / 8), 256, 0, st>>>(
+                                      (const T*)y, (const T*)dout, mean, invstd, gamma, beta, sums, (float)(1.0 / count), (T*)dy, P, C, act, eval)));
+        return check_launch("bn_bwd_apply");
+    }
     long long work = vec ? total / 8 : total;
     int blocks = (int)min((long long)num_sms() * 8, (long long)ceil_div(work, 256));
     STC_DISPATCH_DTYPE(dtype, (bn_bwd_apply_kernel<T><<<blocks, 256, 0, st>>>((const T*)y, (const T*)dout, mean, invstd, gamma, beta,

@@ -9,7 +9,8 @@ constexpr int kMaxCls = 32;
 // ---------------------------------------------------------------- cls_seg
 template <typename T>
 __global__ void __launch_bounds__(256) cls_fwd_kernel(const T* __restrict__ x, const float* __restrict__ Wt, const float* __restrict__ b,
-                                                      float* __restrict__ logits, long long HW, int Cin, int Ccls, long long P) {
+                                                      const float* __restrict__ mask, float* __restrict__ logits, long long HW, int Cin,
+                                                      int Ccls, long long P) {
     extern __shared__ float sw[];  // [Ccls][Cin] + [Ccls]
     for (int i = threadIdx.x; i < Ccls * Cin; i += blockDim.x) sw[i] = Wt[i];
     for (int i = threadIdx.x; i < Ccls; i += blockDim.x) sw[Ccls * Cin + i] = b ? b[i] : 0.f;
@@ -25,6 +26,10 @@ __global__ void __launch_bounds__(256) cls_fwd_kernel(const T* __restrict__ x, c
         for (int c = 0; c < Cin; c += 8) {
             Vec8<T> v;
             v.load(xr + c);
+            if (mask) {  // Dropout2d: one factor per (image, channel)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v.v[e] *= mask[n * Cin + c + e];
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 if (k0 + j < Ccls) {
@@ -41,8 +46,9 @@ __global__ void __launch_bounds__(256) cls_fwd_kernel(const T* __restrict__ x, c
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) cls_bwd_dx_kernel(const float* __restrict__ dl, const float* __restrict__ Wt, T* __restrict__ dx,
-                                                         long long HW, int Cin, int Ccls, long long P) {
+__global__ void __launch_bounds__(256) cls_bwd_dx_kernel(const float* __restrict__ dl, const float* __restrict__ Wt,
+                                                         const float* __restrict__ mask, T* __restrict__ dx, long long HW, int Cin,
+                                                         int Ccls, long long P) {
     extern __shared__ float sw[];  // [Ccls][Cin]
     for (int i = threadIdx.x; i < Ccls * Cin; i += blockDim.x) sw[i] = Wt[i];
     __syncthreads();
@@ -59,14 +65,19 @@ __global__ void __launch_bounds__(256) cls_bwd_dx_kernel(const float* __restrict
 #pragma unroll
             for (int e = 0; e < 8; ++e) v.v[e] = fmaf(g[k], sw[k * Cin + c + e], v.v[e]);
         }
+        if (mask) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v.v[e] *= mask[n * Cin + c + e];
+        }
         v.store(dx + p * Cin + c);
     }
 }
 
 // dW[k][c] += sum_p dl[k][p] x[p][c] for 4 classes starting at k0; db likewise
 template <typename T>
-__global__ void __launch_bounds__(256) cls_bwd_dw_kernel(const float* __restrict__ dl, const T* __restrict__ x, float* __restrict__ dW,
-                                                         float* __restrict__ db, long long HW, int Cin, int Ccls, long long P, int k0) {
+__global__ void __launch_bounds__(256) cls_bwd_dw_kernel(const float* __restrict__ dl, const T* __restrict__ x, const float* __restrict__ mask,
+                                                         float* __restrict__ dW, float* __restrict__ db, long long HW, int Cin, int Ccls,
+                                                         long long P, int k0) {
     __shared__ float smem[256 * 8 * 4];
     const int lanes = Cin >> 3, lv = threadIdx.x % lanes, r0 = threadIdx.x / lanes, rstep = 256 / lanes;
     float acc[4][8] = {};
@@ -75,6 +86,10 @@ __global__ void __launch_bounds__(256) cls_bwd_dw_kernel(const float* __restrict
         long long n = p / HW, hw = p - n * HW;
         Vec8<T> v;
         v.load(x + p * Cin + lv * 8);
+        if (mask) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v.v[e] *= mask[n * Cin + lv * 8 + e];
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             if (k0 + j < Ccls) {
@@ -317,31 +332,31 @@ __global__ void __launch_bounds__(256) confusion_hist_kernel(const int64_t* __re
 
 using namespace stc;
 
-extern "C" int stc_cls_fwd(const void* x, const float* W, const float* b, float* logits, int N, long long HW, int Cin, int Ccls,
-                           int dtype, void* stream) {
+extern "C" int stc_cls_fwd(const void* x, const float* W, const float* b, const float* mask, float* logits, int N, long long HW,
+                           int Cin, int Ccls, int dtype, void* stream) {
     STC_REQUIRE(Cin % 8 == 0 && Ccls >= 1 && Ccls <= kMaxCls, "cls_fwd: Cin=%d (mult of 8) Ccls=%d (<=%d)", Cin, Ccls, kMaxCls);
     long long P = (long long)N * HW;
     size_t smem = sizeof(float) * ((size_t)Ccls * Cin + Ccls);
-    STC_DISPATCH_DTYPE(dtype, (cls_fwd_kernel<T><<<ceil_div(P, 256), 256, smem, (cudaStream_t)stream>>>((const T*)x, W, b, logits, HW, Cin, Ccls, P)));
+    STC_DISPATCH_DTYPE(dtype, (cls_fwd_kernel<T><<<ceil_div(P, 256), 256, smem, (cudaStream_t)stream>>>((const T*)x, W, b, mask, logits, HW, Cin, Ccls, P)));
     return check_launch("cls_fwd");
 }
 
 extern "C" long long stc_cls_bwd_ws_bytes(int, long long, int, int) { return 0; }
 
-extern "C" int stc_cls_bwd(const float* dlogits, const void* x, const float* W, void* dx, float* dW, float* db, int N, long long HW,
-                           int Cin, int Ccls, void* ws, long long ws_bytes, int dtype, void* stream) {
+extern "C" int stc_cls_bwd(const float* dlogits, const void* x, const float* W, const float* mask, void* dx, float* dW, float* db, int N,
+                           long long HW, int Cin, int Ccls, void* ws, long long ws_bytes, int dtype, void* stream) {
     (void)ws; (void)ws_bytes;
     STC_REQUIRE(vec_ok(Cin) && Ccls >= 1 && Ccls <= kMaxCls, "cls_bwd: Cin=%d must be 8*2^k, Ccls=%d (<=%d)", Cin, Ccls, kMaxCls);
     cudaStream_t st = (cudaStream_t)stream;
     long long P = (long long)N * HW;
     if (dx) {
         size_t smem = sizeof(float) * (size_t)Ccls * Cin;
-        STC_DISPATCH_DTYPE(dtype, (cls_bwd_dx_kernel<T><<<ceil_div(P, 256), 256, smem, st>>>(dlogits, W, (T*)dx, HW, Cin, Ccls, P)));
+        STC_DISPATCH_DTYPE(dtype, (cls_bwd_dx_kernel<T><<<ceil_div(P, 256), 256, smem, st>>>(dlogits, W, mask, (T*)dx, HW, Cin, Ccls, P)));
     }
     if (dW) {
         int G = reduce_blocks(P, Cin / 8);
         for (int k0 = 0; k0 < Ccls; k0 += 4)
-            STC_DISPATCH_DTYPE(dtype, (cls_bwd_dw_kernel<T><<<G, 256, 0, st>>>(dlogits, (const T*)x, dW, db, HW, Cin, Ccls, P, k0)));
+            STC_DISPATCH_DTYPE(dtype, (cls_bwd_dw_kernel<T><<<G, 256, 0, st>>>(dlogits, (const T*)x, mask, dW, db, HW, Cin, Ccls, P, k0)));
     }
     return check_launch("cls_bwd");
 }

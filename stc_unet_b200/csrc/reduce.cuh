@@ -40,11 +40,13 @@ __device__ __forceinline__ void block_reduce_lanes(float (&acc)[NV][8], int lane
 
 // sums partial[g][j] over g in fp64
 static __global__ void reduce_partials_kernel(const float* __restrict__ partial, double* __restrict__ out, int G, int len) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    // launched with 32 threads per output element (ceil_div(len * 32, blockDim))
+    int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (j >= len) return;
     double s = 0.0;
-    for (int g = 0; g < G; ++g) s += (double)partial[(size_t)g * len + j];
-    out[j] = s;
+    for (int g = lane; g < G; g += 32) s += (double)partial[(size_t)g * len + j];
+    s = warp_sum(s);
+    if (lane == 0) out[j] = s;
 }
 
 inline int reduce_blocks(long long P, int lanes) {

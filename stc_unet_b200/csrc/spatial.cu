@@ -417,6 +417,104 @@ __global__ void __launch_bounds__(256) softmax_rows_bwd_kernel(const T* __restri
     for (int j = tid; j < L; j += 256) stf(o + j, scale * ldf(p + j) * (ldf(g + j) - dot));
 }
 
+
+// single-pass variants: the row (L <= 256*8*NV elements, L % 8 == 0) is held in registers, one global read per element
+__device__ __forceinline__ float block_max_256(float v, float* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = red[0];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) r = fmaxf(r, red[k]);
+    __syncthreads();
+    return r;
+}
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r += red[k];
+    __syncthreads();
+    return r;
+}
+
+template <typename T, int NV>
+__global__ void __launch_bounds__(256) softmax_rows_fwd_fast_kernel(const T* __restrict__ S, T* __restrict__ P, int L, float scale) {
+    __shared__ float red[8];
+    const T* s = S + (long long)blockIdx.x * L;
+    T* p = P + (long long)blockIdx.x * L;
+    const int nvec = L >> 3;
+    Vec8<T> v[NV];
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        int j = threadIdx.x + 256 * i;
+        if (j < nvec) {
+            v[i].load(s + j * 8);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { v[i].v[k] *= scale; m = fmaxf(m, v[i].v[k]); }
+        }
+    }
+    m = block_max_256(m, red);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        int j = threadIdx.x + 256 * i;
+        if (j < nvec) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { v[i].v[k] = row_exp<T>(v[i].v[k] - m); sum += v[i].v[k]; }
+        }
+    }
+    sum = block_sum_256(sum, red);
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        int j = threadIdx.x + 256 * i;
+        if (j < nvec) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[i].v[k] *= inv;
+            v[i].store(p + j * 8);
+        }
+    }
+}
+
+template <typename T, int NV>
+__global__ void __launch_bounds__(256) softmax_rows_bwd_fast_kernel(const T* __restrict__ P, const T* __restrict__ dP, T* __restrict__ dS,
+                                                                    int L, float scale) {
+    __shared__ float red[8];
+    const T* p = P + (long long)blockIdx.x * L;
+    const T* g = dP + (long long)blockIdx.x * L;
+    T* o = dS + (long long)blockIdx.x * L;
+    const int nvec = L >> 3;
+    Vec8<T> pv[NV], gv[NV];
+    float dot = 0.f, psum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        int j = threadIdx.x + 256 * i;
+        if (j < nvec) {
+            pv[i].load(p + j * 8);
+            gv[i].load(g + j * 8);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { dot = fmaf(pv[i].v[k], gv[i].v[k], dot); psum += pv[i].v[k]; }
+        }
+    }
+    dot = block_sum_256(dot, red);
+    psum = block_sum_256(psum, red);
+    dot /= psum;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        int j = threadIdx.x + 256 * i;
+        if (j < nvec) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) gv[i].v[k] = scale * pv[i].v[k] * (gv[i].v[k] - dot);
+            gv[i].store(o + j * 8);
+        }
+    }
+}
+
 // ---------------------------------------------------------------- tiny fp32 dense layers
 __global__ void linear_f32_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ b,
                                       float* __restrict__ y, int rows, int in, int out) {
@@ -587,13 +685,31 @@ extern "C" int stc_softmax3_bwd(const float* w, const float* dw, float* da, long
 extern "C" int stc_softmax_rows_fwd(const void* S, void* P, long long rows, int L, float scale, int dtype, void* stream) {
     if (rows <= 0) return STC_OK;
     STC_REQUIRE(rows < (1LL << 31), "softmax_rows: too many rows");
-    STC_DISPATCH_DTYPE(dtype, (softmax_rows_fwd_kernel<T><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((const T*)S, (T*)P, L, scale)));
+    cudaStream_t st = (cudaStream_t)stream;
+    bool al = ((((uintptr_t)S) | ((uintptr_t)P)) & 15) == 0 && L % 8 == 0;
+    if (al && L <= 2048) {
+        STC_DISPATCH_DTYPE(dtype, (softmax_rows_fwd_fast_kernel<T, 1><<<(unsigned)rows, 256, 0, st>>>((const T*)S, (T*)P, L, scale)));
+    } else if (al && L <= 4096) {
+        STC_DISPATCH_DTYPE(dtype, (softmax_rows_fwd_fast_kernel<T, 2><<<(unsigned)rows, 256, 0, st>>>((const T*)S, (T*)P, L, scale)));
+    } else if (al && L <= 8192) {
+        STC_DISPATCH_DTYPE(dtype, (softmax_rows_fwd_fast_kernel<T, 4><<<(unsigned)rows, 256, 0, st>>>((const T*)S, (T*)P, L, scale)));
+    } else {
+        STC_DISPATCH_DTYPE(dtype, (softmax_rows_fwd_kernel<T><<<(unsigned)rows, 256, 0, st>>>((const T*)S, (T*)P, L, scale)));
+    }
     return check_launch("softmax_rows_fwd");
 }
 extern "C" int stc_softmax_rows_bwd(const void* P, const void* dP, void* dS, long long rows, int L, float scale, int dtype, void* stream) {
     if (rows <= 0) return STC_OK;
     STC_REQUIRE(rows < (1LL << 31), "softmax_rows: too many rows");
-    STC_DISPATCH_DTYPE(dtype, (softmax_rows_bwd_kernel<T><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((const T*)P, (const T*)dP, (T*)dS, L, scale)));
+    cudaStream_t st = (cudaStream_t)stream;
+    bool al = ((((uintptr_t)P) | ((uintptr_t)dP) | ((uintptr_t)dS)) & 15) == 0 && L % 8 == 0;
+    if (al && L <= 2048) {
+        STC_DISPATCH_DTYPE(dtype, (softmax_rows_bwd_fast_kernel<T, 1><<<(unsigned)rows, 256, 0, st>>>((const T*)P, (const T*)dP, (T*)dS, L, scale)));
+    } else if (al && L <= 4096) {
+        STC_DISPATCH_DTYPE(dtype, (softmax_rows_bwd_fast_kernel<T, 2><<<(unsigned)rows, 256, 0, st>>>((const T*)P, (const T*)dP, (T*)dS, L, scale)));
+    } else {
+        STC_DISPATCH_DTYPE(dtype, (softmax_rows_bwd_kernel<T><<<(unsigned)rows, 256, 0, st>>>((const T*)P, (const T*)dP, (T*)dS, L, scale)));
+    }
     return check_launch("softmax_rows_bwd");
 }
 

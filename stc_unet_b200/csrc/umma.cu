@@ -375,6 +375,11 @@ static int pick_bn(int n) {
     return 0;
 }
 
+int encode_map_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+    return encode_map(m, base, rank, dims, strides_bytes, box);
+}
+int umma_pick_bn(int n) { return pick_bn(n); }
+
 static int launch(UmmaParams& p, cudaStream_t st) {
     size_t smem = (size_t)p.stages * (p.a_stage_bytes + p.b_stage_bytes) + (2 * p.stages + 4) * 8 + 16 + 1024;
     static bool attr_set[64] = {false};

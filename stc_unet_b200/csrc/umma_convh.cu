@@ -1,0 +1,347 @@
+// tcgen05 implicit-GEMM convolution with shared-memory HALO reuse (fprop, and dgrad with the flipped weight pack).
+//
+// The per-tap kernel in umma.cu re-fetches a 128-pixel x 64-channel A tile from L2 for every filter tap; on B200
+// that fetch stream (~5.5 TB/s of distinct lines chip-wide) is what bounds it: every k-iteration costs the same
+// ~0.4 us whatever the N tile is (profiles/r1_conv_sweep_v1.txt: 375 / 745 / 1300 TFLOP/s at Cout = 64 / 128 / 256).
+// Here an input ROW SEGMENT of (128 + S - 1) pixels x 64 channels is loaded ONCE into a 128B-swizzled smem slot and
+// every tap (r, s) that needs it reads it in place: the UMMA descriptor's start address is simply advanced by
+// s * 128 bytes (one pixel row of the K-major tile), with the descriptor's base-offset field carrying the swizzle
+// phase.  A work item is a strip of T vertically adjacent output rows x 128 pixels x one N tile with T accumulators
+// in TMEM, so a segment is also shared by the R output rows that touch it:
+//     A traffic per output tile:  R*S*16 KB  ->  (T+R-1)/T * 17 KB   (3x3, T=4: 144 KB -> 26 KB)
+// Loop order inside a strip: for cin-chunk { for r { for s { B(r,s,chunk) once; for t: acc[t] += seg[t+r](+s) * B } } }.
+// Warps: 0 = A (segment) producer, 1 = MMA issuer + TMEM owner, 2..5 = epilogue, 6 = B (weight) producer.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace stc {
+
+struct alignas(64) ConvHParams {
+    CUtensorMap tmA;  // NHWC activations {C, W, H, N}, box {64, 128+S-1, 1, 1}
+    CUtensorMap tmB;  // packed weights {Cin, Cout, taps}, box {64, BN, 1}
+    int H, W, R, S, cin_chunks, T, BN, num_n_tiles;
+    int strips_h, strips_w, num_strips;
+    int a_slots, b_stages;
+    uint32_t a_slot_bytes, a_box_bytes, b_stage_bytes;
+    uint32_t idesc;
+    int bo_mode;  // 0: base_offset = (start >> 7) & 7 ; 1: base_offset = 0
+    void* out;
+    const float* bias;
+    const void* residual;
+    int act, Cout;
+};
+
+constexpr int kConvHThreads = 224;
+
+__device__ __forceinline__ float convh_act(float v, int act) {
+    if (act == STC_ACT_RELU) return fmaxf(v, 0.f);
+    if (act == STC_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
+    if (act == STC_ACT_HSWISH) return v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
+    return v;
+}
+
+struct Strip {
+    int nt, n_img, h0, w0;
+};
+__device__ __forceinline__ Strip decode_strip(const ConvHParams& p, int idx) {
+    Strip s;
+    s.nt = idx % p.num_n_tiles;
+    int r = idx / p.num_n_tiles;
+    int sw = r % p.strips_w;
+    r /= p.strips_w;
+    int sh = r % p.strips_h;
+    s.n_img = r / p.strips_h;
+    s.h0 = sh * p.T;
+    s.w0 = sw * 128;
+    return s;
+}
+
+__global__ void __launch_bounds__(kConvHThreads, 1) umma_convh_kernel(const __grid_constant__ ConvHParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t a_bytes = (uint32_t)p.a_slots * p.a_slot_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a_bytes + (size_t)p.b_stages * p.b_stage_bytes);
+    // bars: a_full[a_slots], a_empty[a_slots], b_full[b_stages], b_empty[b_stages], tmem_full[2], tmem_empty[2]
+    const int nb = 2 * p.a_slots + 2 * p.b_stages + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + nb);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = ptx::smem_u32(smem);
+    const uint32_t b_base = smem_base + a_bytes;
+    const uint32_t bar_base = ptx::smem_u32(bars);
+    auto a_full = [&](int s) { return bar_base + 8u * s; };
+    auto a_empty = [&](int s) { return bar_base + 8u * (p.a_slots + s); };
+    auto b_full = [&](int s) { return bar_base + 8u * (2 * p.a_slots + s); };
+    auto b_empty = [&](int s) { return bar_base + 8u * (2 * p.a_slots + p.b_stages + s); };
+    auto tfull = [&](int s) { return bar_base + 8u * (2 * p.a_slots + 2 * p.b_stages + s); };
+    auto tempty = [&](int s) { return bar_base + 8u * (2 * p.a_slots + 2 * p.b_stages + 2 + s); };
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&p.tmA);
+        ptx::prefetch_tensormap(&p.tmB);
+        for (int s = 0; s < p.a_slots; ++s) { ptx::mbar_init(a_full(s), 1); ptx::mbar_init(a_empty(s), 1); }
+        for (int s = 0; s < p.b_stages; ++s) { ptx::mbar_init(b_full(s), 1); ptx::mbar_init(b_empty(s), 1); }
+        for (int s = 0; s < 2; ++s) { ptx::mbar_init(tfull(s), 1); ptx::mbar_init(tempty(s), 4); }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int segs_per_chunk = p.T + p.R - 1;
+    const int pr = p.R / 2, ps = p.S / 2;
+
+    if (warp == 0) {
+        // ===================== A producer: input row segments =====================
+        if (lane == 0) {
+            uint32_t idx = 0;  // running segment counter -> ring slot / phase
+            for (int st = blockIdx.x; st < p.num_strips; st += gridDim.x) {
+                Strip s = decode_strip(p, st);
+                for (int cc = 0; cc < p.cin_chunks; ++cc) {
+                    for (int i = 0; i < segs_per_chunk; ++i, ++idx) {
+                        const int slot = idx % p.a_slots;
+                        const uint32_t phase = (idx / p.a_slots) & 1;
+                        ptx::mbar_wait(a_empty(slot), phase ^ 1);
+                        ptx::mbar_arrive_expect_tx(a_full(slot), p.a_box_bytes);
+                        ptx::tma_load_4d(smem_base + slot * p.a_slot_bytes, &p.tmA, a_full(slot), cc * 64, s.w0 - ps, s.h0 + i - pr, s.n_img);
+                    }
+                }
+            }
+        }
+    } else if (warp == 6) {
+        // ===================== B producer: one weight tile per (chunk, tap) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int st = blockIdx.x; st < p.num_strips; st += gridDim.x) {
+                Strip s = decode_strip(p, st);
+                for (int cc = 0; cc < p.cin_chunks; ++cc) {
+                    for (int tap = 0; tap < p.R * p.S; ++tap) {
+                        ptx::mbar_wait(b_empty(stage), phase ^ 1);
+                        ptx::mbar_arrive_expect_tx(b_full(stage), p.b_stage_bytes);
+                        ptx::tma_load_3d(b_base + stage * p.b_stage_bytes, &p.tmB, b_full(stage), cc * 64, s.nt * p.BN, tap);
+                        if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            uint32_t a_idx = 0;  // segment counter at the start of the current chunk
+            int bstage = 0;
+            uint32_t bphase = 0;
+            int acc = 0;
+            uint32_t acc_phase[2] = {0, 0};
+            for (int st = blockIdx.x; st < p.num_strips; st += gridDim.x) {
+                ptx::mbar_wait(tempty(acc), acc_phase[acc] ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_base = tmem_base + acc * 256;
+                for (int cc = 0; cc < p.cin_chunks; ++cc) {
+                    int ready = 0;  // segments of this chunk whose full barrier has been observed
+                    for (int r = 0; r < p.R; ++r) {
+                        for (int s = 0; s < p.S; ++s) {
+                            ptx::mbar_wait(b_full(bstage), bphase);
+                            ptx::tc_fence_after();
+                            const uint32_t b_addr = b_base + bstage * p.b_stage_bytes;
+                            const uint64_t b_desc0 = ptx::make_smem_desc_sw128(b_addr, 0, 1024);
+                            for (int t = 0; t < p.T; ++t) {
+                                const int i = t + r;
+                                while (ready <= i) {
+                                    const uint32_t id = a_idx + ready;
+                                    ptx::mbar_wait(a_full(id % p.a_slots), (id / p.a_slots) & 1);
+                                    ++ready;
+                                }
+                                ptx::tc_fence_after();
+                                const uint32_t id = a_idx + i;
+                                const uint32_t a_addr = smem_base + (id % p.a_slots) * p.a_slot_bytes + (uint32_t)s * 128u;
+                                uint64_t a_desc0 = ptx::make_smem_desc_sw128(a_addr, 0, 1024);
+                                if (p.bo_mode == 0) a_desc0 |= (uint64_t)((a_addr >> 7) & 7) << 49;
+                                const uint32_t first = (cc == 0 && r == 0 && s == 0) ? 1u : 0u;
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks)
+                                    ptx::mma_bf16_ss(d_base + t * p.BN, a_desc0 + (uint64_t)(ks * 2), b_desc0 + (uint64_t)(ks * 2), p.idesc,
+                                                     (first && ks == 0) ? 0u : 1u);
+                            }
+                            ptx::tc_commit(b_empty(bstage));
+                            if (++bstage == p.b_stages) { bstage = 0; bphase ^= 1; }
+                        }
+                        // segments whose last reader was this filter row can be recycled
+                        if (r < p.R - 1) {
+                            ptx::tc_commit(a_empty((a_idx + r) % p.a_slots));
+                        } else {
+                            for (int i = p.R - 1; i < segs_per_chunk; ++i) ptx::tc_commit(a_empty((a_idx + i) % p.a_slots));
+                        }
+                    }
+                    a_idx += segs_per_chunk;
+                }
+                ptx::tc_commit(tfull(acc));
+                acc_phase[acc] ^= 1;
+                acc ^= 1;
+            }
+        }
+    } else if (warp >= 2 && warp <= 5) {
+        // ===================== epilogue =====================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        int acc = 0;
+        uint32_t acc_phase[2] = {0, 0};
+        for (int st = blockIdx.x; st < p.num_strips; st += gridDim.x) {
+            Strip s = decode_strip(p, st);
+            const int w = s.w0 + row;
+            ptx::mbar_wait(tfull(acc), acc_phase[acc]);
+            ptx::tc_fence_after();
+            for (int t = 0; t < p.T; ++t) {
+                const int h = s.h0 + t;
+                if (h >= p.H) break;  // uniform across the CTA
+                const bool valid = w < p.W;
+                const long long off = (((long long)s.n_img * p.H + h) * p.W + w) * p.Cout + (long long)s.nt * p.BN;
+                const uint32_t t_addr = tmem_base + acc * 256 + t * p.BN + ((uint32_t)(q * 32) << 16);
+                for (int c = 0; c < p.BN; c += 32) {
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32(t_addr + c, v);
+                    ptx::tmem_ld_wait();
+                    if (!valid) continue;
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                    if (p.bias) {
+                        const float* b = p.bias + s.nt * p.BN + c;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] += __ldg(b + j);
+                    }
+                    if (p.residual) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.residual) + off + c);
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            uint4 rv = __ldg(rp + g);
+                            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                float2 x = __bfloat1622float2(h2[e]);
+                                f[g * 8 + 2 * e] += x.x;
+                                f[g * 8 + 2 * e + 1] += x.y;
+                            }
+                        }
+                    }
+                    if (p.act != STC_ACT_NONE) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = convh_act(f[j], p.act);
+                    }
+                    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + off + c);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        uint4 ov;
+                        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(f[g * 8 + 2 * e], f[g * 8 + 2 * e + 1]);
+                        o[g] = ov;
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tempty(acc));
+            acc_phase[acc] ^= 1;
+            acc ^= 1;
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+int encode_map_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
+int umma_pick_bn(int n);
+
+static int convh_plan(int Cout, int R, int& BN, int& T, int& a_slots, int& b_stages) {
+    BN = umma_pick_bn(Cout);
+    if (BN == 0 || BN > 256) return 0;
+    const int tmax = 256 / BN;  // two accumulator stages of 256 TMEM columns
+    const int cands[] = {4, 2, 1};
+    for (int t : cands) {
+        if (t > tmax) continue;
+        for (int extra = 3; extra >= 1; --extra) {
+            for (int bs = 4; bs >= 2; --bs) {
+                int slots = t + R - 1 + extra;
+                size_t smem = (size_t)slots * 17408 + (size_t)bs * BN * 128 + (2 * slots + 2 * bs + 4) * 8 + 16 + 1024;
+                if (smem <= 225 * 1024) {
+                    T = t; a_slots = slots; b_stages = bs;
+                    return 1;
+                }
+            }
+        }
+    }
+    return 0;
+}
+
+bool conv_convh_eligible(int W, int Cin, int Cout, int R, int S, int dtype) {
+    static int disabled = -1;
+    if (disabled < 0) { const char* e = getenv("STC_CONVH"); disabled = (e && e[0] == '0') ? 1 : 0; }
+    if (disabled) return false;
+    int BN, T, a, b;
+    return dtype == STC_BF16 && W >= 128 && Cin % 64 == 0 && R == S && (R == 3 || R == 5 || R == 7) && convh_plan(Cout, R, BN, T, a, b);
+}
+
+int conv_fprop_convh(const void* x, const void* wp, const float* bias, const void* residual, void* y, int N, int H, int W, int Cin,
+                     int Cout, int R, int S, int act, cudaStream_t st) {
+    ConvHParams p;
+    memset(&p, 0, sizeof(p));
+    STC_REQUIRE(convh_plan(Cout, R, p.BN, p.T, p.a_slots, p.b_stages), "conv_fprop_convh: no plan for Cout=%d R=%d", Cout, R);
+    STC_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)wp & 15) == 0 && ((uintptr_t)y & 15) == 0, "conv_fprop_convh: unaligned pointer");
+    const int bwh = 128 + S - 1;
+    {
+        uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+        uint64_t str[4] = {2, (uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+        uint32_t box[4] = {64, (uint32_t)bwh, 1, 1};
+        int rc = encode_map_bf16(&p.tmA, x, 4, dims, str, box);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)(R * S)};
+        uint64_t str[3] = {2, (uint64_t)Cin * 2, (uint64_t)Cout * Cin * 2};
+        uint32_t box[3] = {64, (uint32_t)p.BN, 1};
+        int rc = encode_map_bf16(&p.tmB, wp, 3, dims, str, box);
+        if (rc) return rc;
+    }
+    p.H = H; p.W = W; p.R = R; p.S = S; p.cin_chunks = Cin / 64;
+    p.num_n_tiles = Cout / p.BN;
+    p.strips_h = (H + p.T - 1) / p.T;
+    p.strips_w = (W + 127) / 128;
+    p.num_strips = N * p.strips_h * p.strips_w * p.num_n_tiles;
+    p.a_slot_bytes = 17408;
+    p.a_box_bytes = (uint32_t)bwh * 128;
+    p.b_stage_bytes = (uint32_t)p.BN * 128;
+    p.idesc = make_idesc_bf16(128, p.BN, 0, 0);
+    {
+        static int bo = -1;
+        if (bo < 0) { const char* e = getenv("STC_CONVH_BO"); bo = e ? atoi(e) : 0; }
+        p.bo_mode = bo;
+    }
+    p.out = y; p.bias = bias; p.residual = residual; p.act = act; p.Cout = Cout;
+    size_t smem = (size_t)p.a_slots * p.a_slot_bytes + (size_t)p.b_stages * p.b_stage_bytes + (2 * p.a_slots + 2 * p.b_stages + 4) * 8 + 16 + 1024;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        STC_CUDA(cudaFuncSetAttribute(umma_convh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set[dev] = true;
+    }
+    int grid = p.num_strips < num_sms() ? p.num_strips : num_sms();
+    umma_convh_kernel<<<grid, kConvHThreads, smem, st>>>(p);
+    return check_launch("umma_convh_kernel");
+}
+
+}  // namespace stc

@@ -306,7 +306,14 @@ class _ConvBnAct(Function):
         N, H, W, Cout = y.shape
         P = N * H * W
         dy, dgamma, dbeta = _bn_backward(y, da, mean, invstd, gamma, beta, P, Cout, act, bn, count, pg, pb)
-        dbias = colsum(P, Cout, dy, _grad_buf(pbias, (Cout,), dy.device)) if has_bias else None
+        dbias = None
+        if has_bias:
+            if bn.training:
+                # sum_p dy == gamma*invstd*(sum g - n*mean(g) - sum(xhat)*mean(g*xhat)) == 0 exactly: a conv bias feeding a
+                # train-mode BN has no gradient (the reference's autograd returns fp32 rounding noise here)
+                dbias = _grad_buf(pbias, (Cout,), dy.device, zero=True)
+            else:
+                dbias = colsum(P, Cout, dy, _grad_buf(pbias, (Cout,), dy.device))
         dw = conv_wgrad(x, dy, R, S, _grad_buf(pw, weight.shape, dy.device))
         dx = None
         if ctx.needs_input_grad[0]:
@@ -652,13 +659,10 @@ class _ClsSeg(Function):
         Ccls = weight.shape[0]
         code = dtype_code(x.dtype)
         if mask is not None:
-            xm = torch.empty_like(x)
-            lib.call("stc_scale_channels", x, mask, xm, N, H * W, Cin, code, stream_ptr())
-        else:
-            xm = x
+            mask = _chk(mask.float())
         logits = torch.empty((N, Ccls, H, W), dtype=torch.float32, device=x.device)
-        lib.call("stc_cls_fwd", xm, weight.view(Ccls, Cin), bias, logits, N, H * W, Cin, Ccls, code, stream_ptr())
-        ctx.save_for_backward(xm, weight, mask)
+        lib.call("stc_cls_fwd", x, weight.view(Ccls, Cin), bias, mask, logits, N, H * W, Cin, Ccls, code, stream_ptr())
+        ctx.save_for_backward(x, weight, mask)
         ctx.pobjs = pobjs
         return logits
 
@@ -673,9 +677,7 @@ class _ClsSeg(Function):
         dx = torch.empty_like(xm) if ctx.needs_input_grad[0] else None
         dW = _grad_buf(ctx.pobjs[0], weight.shape, dev, zero=True)
         db = _grad_buf(ctx.pobjs[1], (Ccls,), dev, zero=True)
-        lib.call("stc_cls_bwd", dl, xm, weight.view(Ccls, Cin), dx, dW, db, N, H * W, Cin, Ccls, None, 0, code, stream_ptr())
-        if mask is not None and dx is not None:
-            lib.call("stc_scale_channels", dx, mask, dx, N, H * W, Cin, code, stream_ptr())
+        lib.call("stc_cls_bwd", dl, xm, weight.view(Ccls, Cin), mask, dx, dW, db, N, H * W, Cin, Ccls, None, 0, code, stream_ptr())
         return dx, dW, db, None, None
 
 
