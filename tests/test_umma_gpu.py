@@ -123,3 +123,34 @@ def test_tcgen05_matches_simt_large(tc):
     tc.config.engine = S._lib.ENGINE_SIMT
     y_simt = tc.conv_fprop(x, wp, None, None, 64, 3, 3)
     assert rel_l2(y_tc.float(), y_simt.float()) < 4e-3
+
+
+HALO_SHAPES = [
+    # N, Cin, Cout, H, W, k      (W >= 128 -> halo-reuse kernel umma_convh_kernel)
+    (1, 64, 64, 9, 128, 3),       # T=4 strips, H not a multiple of T
+    (2, 64, 64, 16, 256, 5),
+    (1, 64, 64, 11, 200, 7),      # ragged W (two column blocks, second partly outside), T=2
+    (1, 128, 128, 8, 128, 3),     # two cin chunks, BN=128 -> T=2
+    (1, 192, 256, 5, 128, 5),     # BN=256 -> T=1
+    (1, 128, 512, 6, 160, 7),     # two N tiles
+    (2, 64, 32, 7, 384, 3),
+]
+
+
+@pytest.mark.parametrize("shape", HALO_SHAPES)
+def test_conv_halo_tcgen05(tc, shape):
+    N, Cin, Cout, H, W, k = shape
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = bf16_round(torch.randn(N, Cin, H, W, device=dev(), generator=g))
+    w = bf16_round(torch.randn(Cout, Cin, k, k, device=dev(), generator=g) / math.sqrt(Cin * k * k))
+    b = torch.randn(Cout, device=dev(), generator=g)
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=k // 2)
+    wp = tc.pack_weight(w, BF)
+    y = tc.conv_fprop(nhwc(x).to(BF), wp, b, None, Cout, k, k)
+    assert rel_l2(nchw(y.float()), ref) < 6e-3
+    res = bf16_round(torch.randn(N, Cout, H, W, device=dev(), generator=g))
+    y2 = tc.conv_fprop(nhwc(x).to(BF), wp, b, nhwc(res).to(BF), Cout, k, k, act=1)
+    assert rel_l2(nchw(y2.float()), torch.relu(ref + res.double())) < 6e-3
+    # back-to-back launches reuse the rings / TMEM cleanly
+    y3 = tc.conv_fprop(nhwc(x).to(BF), wp, b, None, Cout, k, k)
+    assert torch.equal(y, y3)
