@@ -135,10 +135,14 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_cons
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (tmem_base != 0) {  // we allocate all 512 columns, so the base must be column 0 / lane 0
+        if (threadIdx.x == 0) printf("stc_b200: unexpected TMEM base 0x%x\n", tmem_base);
+        __trap();
+    }
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
+        // ===================== TMA producer (warp-uniform; one elected lane issues) =====================
+        {
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -148,6 +152,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_cons
                     const uint32_t a_dst = smem_base + stage * stage_bytes;
                     const uint32_t b_dst = a_dst + p.a_stage_bytes;
                     const uint32_t fb = full_bar(stage);
+                    if (ptx::elect_one_sync()) {
                     ptx::mbar_arrive_expect_tx(fb, stage_bytes);
                     if (p.mode == MODE_CONV) {
                         int tap = kt / p.cin_chunks, cc = kt - tap * p.cin_chunks;
@@ -180,13 +185,15 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_cons
                         for (int j = 0; j < p.b_boxes; ++j)
                             ptx::tma_load_4d(b_dst + j * p.b_box_bytes, &p.tmB, fb, t.nt * p.BN + j * 64, w0, h0, n_img);
                     }
+                    }
+                    __syncwarp();
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (warp-uniform; one elected lane issues) =====================
+        {
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -196,7 +203,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_cons
                 if (t.k1 <= t.k0) continue;
                 ptx::mbar_wait(tempty_bar(acc), acc_phase[acc] ^ 1);
                 ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * kAccCols;
+                const uint32_t d_tmem = acc * kAccCols;  // TMEM base is 0: the CTA owns all 512 columns (checked above)
                 for (int kt = t.k0; kt < t.k1; ++kt) {
                     ptx::mbar_wait(full_bar(stage), phase);
                     ptx::tc_fence_after();
@@ -204,16 +211,20 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_cons
                     const uint32_t b_addr = a_addr + p.a_stage_bytes;
                     const uint64_t a_desc0 = ptx::make_smem_desc_sw128(a_addr, p.a_lbo, p.a_sbo);
                     const uint64_t b_desc0 = ptx::make_smem_desc_sw128(b_addr, p.b_lbo, p.b_sbo);
-                    for (int ks = 0; ks < p.ksteps; ++ks) {
-                        // advancing the 14-bit start-address field (16B units); never carries out of it (smem < 256 KB)
-                        uint64_t a_desc = a_desc0 + (uint64_t)((ks * p.a_kstep_bytes) >> 4);
-                        uint64_t b_desc = b_desc0 + (uint64_t)((ks * p.b_kstep_bytes) >> 4);
-                        ptx::mma_bf16_ss(d_tmem, a_desc, b_desc, p.idesc, (kt > t.k0 || ks > 0) ? 1u : 0u);
+                    if (ptx::elect_one_sync()) {
+                        for (int ks = 0; ks < p.ksteps; ++ks) {
+                            // advancing the 14-bit start-address field (16B units); never carries out of it (smem < 256 KB)
+                            uint64_t a_desc = a_desc0 + (uint64_t)((ks * p.a_kstep_bytes) >> 4);
+                            uint64_t b_desc = b_desc0 + (uint64_t)((ks * p.b_kstep_bytes) >> 4);
+                            ptx::mma_bf16_ss(d_tmem, a_desc, b_desc, p.idesc, (kt > t.k0 || ks > 0) ? 1u : 0u);
+                        }
+                        ptx::tc_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
                     }
-                    ptx::tc_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+                    __syncwarp();
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
-                ptx::tc_commit(tfull_bar(acc));  // accumulator ready for the epilogue
+                if (ptx::elect_one_sync()) ptx::tc_commit(tfull_bar(acc));  // accumulator ready for the epilogue
+                __syncwarp();
                 acc_phase[acc] ^= 1;
                 acc ^= 1;
             }

@@ -5,8 +5,9 @@
 // ~0.4 us whatever the N tile is (profiles/r1_conv_sweep_v1.txt: 375 / 745 / 1300 TFLOP/s at Cout = 64 / 128 / 256).
 // Here an input ROW SEGMENT of (128 + S - 1) pixels x 64 channels is loaded ONCE into a 128B-swizzled smem slot and
 // every tap (r, s) that needs it reads it in place: the UMMA descriptor's start address is simply advanced by
-// s * 128 bytes (one pixel row of the K-major tile), with the descriptor's base-offset field carrying the swizzle
-// phase.  A work item is a strip of T vertically adjacent output rows x 128 pixels x one N tile with T accumulators
+// s * 128 bytes (one pixel row of the K-major tile).  Measured on B200: the 128B swizzle XOR is taken from the
+// absolute shared-memory address bits [7,10), exactly as TMA wrote it, so the shifted descriptor needs NO base-offset
+// correction (base_offset = (start >> 7) & 7 gives garbage; base_offset = 0 is bit-exact; tests/test_umma_gpu.py).  A work item is a strip of T vertically adjacent output rows x 128 pixels x one N tile with T accumulators
 // in TMEM, so a segment is also shared by the R output rows that touch it:
 //     A traffic per output tile:  R*S*16 KB  ->  (T+R-1)/T * 17 KB   (3x3, T=4: 144 KB -> 26 KB)
 // Loop order inside a strip: for cin-chunk { for r { for s { B(r,s,chunk) once; for t: acc[t] += seg[t+r](+s) * B } } }.
@@ -27,7 +28,7 @@ struct alignas(64) ConvHParams {
     int a_slots, b_stages;
     uint32_t a_slot_bytes, a_box_bytes, b_stage_bytes;
     uint32_t idesc;
-    int bo_mode;  // 0: base_offset = (start >> 7) & 7 ; 1: base_offset = 0
+    int bo_mode;  // debugging only (STC_CONVH_BO=0 sets base_offset = (start >> 7) & 7, which is WRONG on B200)
     void* out;
     const float* bias;
     const void* residual;
@@ -95,29 +96,36 @@ __global__ void __launch_bounds__(kConvHThreads, 1) umma_convh_kernel(const __gr
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (tmem_base != 0) {
+        if (threadIdx.x == 0) printf("stc_b200: unexpected TMEM base 0x%x\n", tmem_base);
+        __trap();
+    }
     const int segs_per_chunk = p.T + p.R - 1;
     const int pr = p.R / 2, ps = p.S / 2;
 
     if (warp == 0) {
-        // ===================== A producer: input row segments =====================
-        if (lane == 0) {
-            uint32_t idx = 0;  // running segment counter -> ring slot / phase
+        // ===================== A producer: input row segments (warp-uniform; elected lane issues) =====================
+        {
+            int slot = 0;          // ring position of the next segment
+            uint32_t phase = 0;    // flips every time the ring wraps
             for (int st = blockIdx.x; st < p.num_strips; st += gridDim.x) {
                 Strip s = decode_strip(p, st);
                 for (int cc = 0; cc < p.cin_chunks; ++cc) {
-                    for (int i = 0; i < segs_per_chunk; ++i, ++idx) {
-                        const int slot = idx % p.a_slots;
-                        const uint32_t phase = (idx / p.a_slots) & 1;
+                    for (int i = 0; i < segs_per_chunk; ++i) {
                         ptx::mbar_wait(a_empty(slot), phase ^ 1);
-                        ptx::mbar_arrive_expect_tx(a_full(slot), p.a_box_bytes);
-                        ptx::tma_load_4d(smem_base + slot * p.a_slot_bytes, &p.tmA, a_full(slot), cc * 64, s.w0 - ps, s.h0 + i - pr, s.n_img);
+                        if (ptx::elect_one_sync()) {
+                            ptx::mbar_arrive_expect_tx(a_full(slot), p.a_box_bytes);
+                            ptx::tma_load_4d(smem_base + slot * p.a_slot_bytes, &p.tmA, a_full(slot), cc * 64, s.w0 - ps, s.h0 + i - pr, s.n_img);
+                        }
+                        __syncwarp();
+                        if (++slot == p.a_slots) { slot = 0; phase ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 6) {
         // ===================== B producer: one weight tile per (chunk, tap) =====================
-        if (lane == 0) {
+        {
             int stage = 0;
             uint32_t phase = 0;
             for (int st = blockIdx.x; st < p.num_strips; st += gridDim.x) {
@@ -125,65 +133,88 @@ __global__ void __launch_bounds__(kConvHThreads, 1) umma_convh_kernel(const __gr
                 for (int cc = 0; cc < p.cin_chunks; ++cc) {
                     for (int tap = 0; tap < p.R * p.S; ++tap) {
                         ptx::mbar_wait(b_empty(stage), phase ^ 1);
-                        ptx::mbar_arrive_expect_tx(b_full(stage), p.b_stage_bytes);
-                        ptx::tma_load_3d(b_base + stage * p.b_stage_bytes, &p.tmB, b_full(stage), cc * 64, s.nt * p.BN, tap);
+                        if (ptx::elect_one_sync()) {
+                            ptx::mbar_arrive_expect_tx(b_full(stage), p.b_stage_bytes);
+                            ptx::tma_load_3d(b_base + stage * p.b_stage_bytes, &p.tmB, b_full(stage), cc * 64, s.nt * p.BN, tap);
+                        }
+                        __syncwarp();
                         if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            uint32_t a_idx = 0;  // segment counter at the start of the current chunk
+        // ===================== MMA issuer (warp-uniform; elected lane issues) =====================
+        {
+            int a_head = 0;            // ring slot of segment 0 of the current chunk
+            uint32_t a_phase = 0;      // parity of the ring pass that a_head belongs to
             int bstage = 0;
             uint32_t bphase = 0;
             int acc = 0;
-            uint32_t acc_phase[2] = {0, 0};
+            uint32_t acc_phase0 = 0, acc_phase1 = 0;
+            // descriptor constants (16-byte units): SBO = 1024 B, version 1, SWIZZLE_128B; base_offset stays 0 (see header)
+            const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+            const uint32_t a_slot16 = p.a_slot_bytes >> 4, b_stage16 = p.b_stage_bytes >> 4;
+            const uint32_t a_base16 = (smem_base >> 4) & 0x3FFF, b_base16 = (b_base >> 4) & 0x3FFF;
             for (int st = blockIdx.x; st < p.num_strips; st += gridDim.x) {
-                ptx::mbar_wait(tempty(acc), acc_phase[acc] ^ 1);
+                ptx::mbar_wait(tempty(acc), (acc ? acc_phase1 : acc_phase0) ^ 1);
                 ptx::tc_fence_after();
-                const uint32_t d_base = tmem_base + acc * 256;
+                const uint32_t d_base = acc * 256;  // TMEM base is 0 (all 512 columns are ours; checked after the allocation)
                 for (int cc = 0; cc < p.cin_chunks; ++cc) {
                     int ready = 0;  // segments of this chunk whose full barrier has been observed
                     for (int r = 0; r < p.R; ++r) {
                         for (int s = 0; s < p.S; ++s) {
                             ptx::mbar_wait(b_full(bstage), bphase);
-                            ptx::tc_fence_after();
-                            const uint32_t b_addr = b_base + bstage * p.b_stage_bytes;
-                            const uint64_t b_desc0 = ptx::make_smem_desc_sw128(b_addr, 0, 1024);
+                            const uint64_t b_desc0 = desc_hi | (uint64_t)(b_base16 + bstage * b_stage16);
                             for (int t = 0; t < p.T; ++t) {
                                 const int i = t + r;
                                 while (ready <= i) {
-                                    const uint32_t id = a_idx + ready;
-                                    ptx::mbar_wait(a_full(id % p.a_slots), (id / p.a_slots) & 1);
+                                    int sl = a_head + ready;
+                                    uint32_t ph = a_phase;
+                                    if (sl >= p.a_slots) { sl -= p.a_slots; ph ^= 1; }
+                                    ptx::mbar_wait(a_full(sl), ph);
                                     ++ready;
                                 }
                                 ptx::tc_fence_after();
-                                const uint32_t id = a_idx + i;
-                                const uint32_t a_addr = smem_base + (id % p.a_slots) * p.a_slot_bytes + (uint32_t)s * 128u;
-                                uint64_t a_desc0 = ptx::make_smem_desc_sw128(a_addr, 0, 1024);
-                                if (p.bo_mode == 0) a_desc0 |= (uint64_t)((a_addr >> 7) & 7) << 49;
-                                const uint32_t first = (cc == 0 && r == 0 && s == 0) ? 1u : 0u;
-#pragma unroll
-                                for (int ks = 0; ks < 4; ++ks)
-                                    ptx::mma_bf16_ss(d_base + t * p.BN, a_desc0 + (uint64_t)(ks * 2), b_desc0 + (uint64_t)(ks * 2), p.idesc,
-                                                     (first && ks == 0) ? 0u : 1u);
+                                int sl = a_head + i;
+                                if (sl >= p.a_slots) sl -= p.a_slots;
+                                const uint64_t a_desc0 = desc_hi | (uint64_t)(a_base16 + sl * a_slot16 + s * 8);
+                                const uint32_t acc_flag = (cc | r | s) ? 1u : 0u;
+                                const uint32_t d_addr = d_base + t * p.BN;
+                                if (ptx::elect_one_sync()) {
+                                    ptx::mma_bf16_ss(d_addr, a_desc0, b_desc0, p.idesc, acc_flag);
+                                    ptx::mma_bf16_ss(d_addr, a_desc0 + 2, b_desc0 + 2, p.idesc, 1u);
+                                    ptx::mma_bf16_ss(d_addr, a_desc0 + 4, b_desc0 + 4, p.idesc, 1u);
+                                    ptx::mma_bf16_ss(d_addr, a_desc0 + 6, b_desc0 + 6, p.idesc, 1u);
+                                }
+                                __syncwarp();
                             }
-                            ptx::tc_commit(b_empty(bstage));
+                            if (ptx::elect_one_sync()) ptx::tc_commit(b_empty(bstage));
+                            __syncwarp();
                             if (++bstage == p.b_stages) { bstage = 0; bphase ^= 1; }
                         }
                         // segments whose last reader was this filter row can be recycled
-                        if (r < p.R - 1) {
-                            ptx::tc_commit(a_empty((a_idx + r) % p.a_slots));
-                        } else {
-                            for (int i = p.R - 1; i < segs_per_chunk; ++i) ptx::tc_commit(a_empty((a_idx + i) % p.a_slots));
+                        if (ptx::elect_one_sync()) {
+                            if (r < p.R - 1) {
+                                int sl = a_head + r;
+                                if (sl >= p.a_slots) sl -= p.a_slots;
+                                ptx::tc_commit(a_empty(sl));
+                            } else {
+                                for (int i = p.R - 1; i < segs_per_chunk; ++i) {
+                                    int sl = a_head + i;
+                                    if (sl >= p.a_slots) sl -= p.a_slots;
+                                    ptx::tc_commit(a_empty(sl));
+                                }
+                            }
                         }
+                        __syncwarp();
                     }
-                    a_idx += segs_per_chunk;
+                    a_head += segs_per_chunk;
+                    if (a_head >= p.a_slots) { a_head -= p.a_slots; a_phase ^= 1; }
                 }
-                ptx::tc_commit(tfull(acc));
-                acc_phase[acc] ^= 1;
+                if (ptx::elect_one_sync()) ptx::tc_commit(tfull(acc));
+                __syncwarp();
+                if (acc) acc_phase1 ^= 1; else acc_phase0 ^= 1;
                 acc ^= 1;
             }
         }
@@ -327,7 +358,7 @@ int conv_fprop_convh(const void* x, const void* wp, const float* bias, const voi
     p.idesc = make_idesc_bf16(128, p.BN, 0, 0);
     {
         static int bo = -1;
-        if (bo < 0) { const char* e = getenv("STC_CONVH_BO"); bo = e ? atoi(e) : 0; }
+        if (bo < 0) { const char* e = getenv("STC_CONVH_BO"); bo = e ? atoi(e) : 1; }
         p.bo_mode = bo;
     }
     p.out = y; p.bias = bias; p.residual = residual; p.act = act; p.Cout = Cout;

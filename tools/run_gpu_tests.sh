@@ -15,7 +15,6 @@ case $g in
   umma_grad) run umma_grad tests/test_umma_gpu.py -k "test_conv_dgrad_wgrad_tcgen05" ;;
   umma_attn) run umma_attn tests/test_umma_gpu.py -k "test_attention_tcgen05" ;;
   umma_halo) run umma_halo tests/test_umma_gpu.py -k "test_conv_halo_tcgen05" ;;
-  umma_halo_bo1) STC_CONVH_BO=1 run umma_halo_bo1 tests/test_umma_gpu.py -k "test_conv_halo_tcgen05" ;;
   umma_misc) run umma_misc tests/test_umma_gpu.py -k "test_linear_tokens_tcgen05 or test_tcgen05_matches_simt_large" ;;
   model_fp32) run model_fp32 tests/test_model_gpu.py -k "fp32" ;;
   model_bf16) run model_bf16 tests/test_model_gpu.py -k "bf16" ;;
