@@ -60,6 +60,7 @@ __device__ __forceinline__ Strip decode_strip(const ConvHParams& p, int idx) {
     return s;
 }
 
+template <int T>
 __global__ void __launch_bounds__(kConvHThreads, 1) umma_convh_kernel(const __grid_constant__ ConvHParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(kConvHThreads, 1) umma_convh_kernel(const __gr
         if (threadIdx.x == 0) printf("stc_b200: unexpected TMEM base 0x%x\n", tmem_base);
         __trap();
     }
-    const int segs_per_chunk = p.T + p.R - 1;
+    const int segs_per_chunk = T + p.R - 1;
     const int pr = p.R / 2, ps = p.S / 2;
 
     if (warp == 0) {
@@ -163,33 +164,38 @@ __global__ void __launch_bounds__(kConvHThreads, 1) umma_convh_kernel(const __gr
                 for (int cc = 0; cc < p.cin_chunks; ++cc) {
                     int ready = 0;  // segments of this chunk whose full barrier has been observed
                     for (int r = 0; r < p.R; ++r) {
+                        // filter row r reads segments r .. r+T-1: at most one new segment per row (all T at r == 0)
+                        while (ready < r + T) {
+                            int sl = a_head + ready;
+                            uint32_t ph = a_phase;
+                            if (sl >= p.a_slots) { sl -= p.a_slots; ph ^= 1; }
+                            ptx::mbar_wait(a_full(sl), ph);
+                            ++ready;
+                        }
+                        uint32_t a16[T];  // start-address fields (16 B units) of the T segments this row reads
+#pragma unroll
+                        for (int t = 0; t < T; ++t) {
+                            int sl = a_head + r + t;
+                            if (sl >= p.a_slots) sl -= p.a_slots;
+                            a16[t] = a_base16 + sl * a_slot16;
+                        }
                         for (int s = 0; s < p.S; ++s) {
                             ptx::mbar_wait(b_full(bstage), bphase);
+                            ptx::tc_fence_after();
                             const uint64_t b_desc0 = desc_hi | (uint64_t)(b_base16 + bstage * b_stage16);
-                            for (int t = 0; t < p.T; ++t) {
-                                const int i = t + r;
-                                while (ready <= i) {
-                                    int sl = a_head + ready;
-                                    uint32_t ph = a_phase;
-                                    if (sl >= p.a_slots) { sl -= p.a_slots; ph ^= 1; }
-                                    ptx::mbar_wait(a_full(sl), ph);
-                                    ++ready;
-                                }
-                                ptx::tc_fence_after();
-                                int sl = a_head + i;
-                                if (sl >= p.a_slots) sl -= p.a_slots;
-                                const uint64_t a_desc0 = desc_hi | (uint64_t)(a_base16 + sl * a_slot16 + s * 8);
-                                const uint32_t acc_flag = (cc | r | s) ? 1u : 0u;
-                                const uint32_t d_addr = d_base + t * p.BN;
-                                if (ptx::elect_one_sync()) {
+                            const uint32_t acc_flag = (cc | r | s) ? 1u : 0u;
+                            if (ptx::elect_one_sync()) {
+#pragma unroll
+                                for (int t = 0; t < T; ++t) {
+                                    const uint64_t a_desc0 = desc_hi | (uint64_t)(a16[t] + s * 8);
+                                    const uint32_t d_addr = d_base + t * p.BN;
                                     ptx::mma_bf16_ss(d_addr, a_desc0, b_desc0, p.idesc, acc_flag);
                                     ptx::mma_bf16_ss(d_addr, a_desc0 + 2, b_desc0 + 2, p.idesc, 1u);
                                     ptx::mma_bf16_ss(d_addr, a_desc0 + 4, b_desc0 + 4, p.idesc, 1u);
                                     ptx::mma_bf16_ss(d_addr, a_desc0 + 6, b_desc0 + 6, p.idesc, 1u);
                                 }
-                                __syncwarp();
+                                ptx::tc_commit(b_empty(bstage));
                             }
-                            if (ptx::elect_one_sync()) ptx::tc_commit(b_empty(bstage));
                             __syncwarp();
                             if (++bstage == p.b_stages) { bstage = 0; bphase ^= 1; }
                         }
@@ -229,7 +235,7 @@ __global__ void __launch_bounds__(kConvHThreads, 1) umma_convh_kernel(const __gr
             const int w = s.w0 + row;
             ptx::mbar_wait(tfull(acc), acc_phase[acc]);
             ptx::tc_fence_after();
-            for (int t = 0; t < p.T; ++t) {
+            for (int t = 0; t < T; ++t) {
                 const int h = s.h0 + t;
                 if (h >= p.H) break;  // uniform across the CTA
                 const bool valid = w < p.W;
@@ -367,11 +373,15 @@ int conv_fprop_convh(const void* x, const void* wp, const float* bias, const voi
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        STC_CUDA(cudaFuncSetAttribute(umma_convh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        STC_CUDA(cudaFuncSetAttribute(umma_convh_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        STC_CUDA(cudaFuncSetAttribute(umma_convh_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        STC_CUDA(cudaFuncSetAttribute(umma_convh_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set[dev] = true;
     }
     int grid = p.num_strips < num_sms() ? p.num_strips : num_sms();
-    umma_convh_kernel<<<grid, kConvHThreads, smem, st>>>(p);
+    if (p.T == 4) umma_convh_kernel<4><<<grid, kConvHThreads, smem, st>>>(p);
+    else if (p.T == 2) umma_convh_kernel<2><<<grid, kConvHThreads, smem, st>>>(p);
+    else umma_convh_kernel<1><<<grid, kConvHThreads, smem, st>>>(p);
     return check_launch("umma_convh_kernel");
 }
 
