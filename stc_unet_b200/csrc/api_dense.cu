@@ -13,6 +13,8 @@ int conv_fprop_umma(const void*, const void*, const float*, const void*, void*, 
 int conv_wgrad_umma(const void*, const void*, float*, int, int, int, int, int, int, int, cudaStream_t);
 bool gemm_umma_eligible(const stc_gemm_desc*, int dtype);
 bool conv_convh_eligible(int W, int Cin, int Cout, int R, int S, int dtype);
+bool conv_wgradh_eligible(int W, int Cin, int Cout, int R, int S, int dtype);
+int conv_wgrad_wgradh(const void*, const void*, float*, int, int, int, int, int, int, int, cudaStream_t);
 int conv_fprop_convh(const void*, const void*, const float*, const void*, void*, int, int, int, int, int, int, int, int, cudaStream_t);
 int gemm_umma(const void*, const void*, void*, const stc_gemm_desc*, int, cudaStream_t);
 }  // namespace stc
@@ -51,6 +53,10 @@ extern "C" int stc_conv_wgrad(const void* x, const void* dy, float* dw_ws, int N
     STC_REQUIRE(N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && (R & 1) && (S & 1), "conv_wgrad: bad shape");
     cudaStream_t st = (cudaStream_t)stream;
     bool elig = dtype == STC_BF16 && Cin % 64 == 0 && Cout % 64 == 0;
+    if (engine != STC_ENGINE_SIMT && elig && conv_wgradh_eligible(W, Cin, Cout, R, S, dtype)) {
+        g_last_engine = STC_ENGINE_TCGEN05;  // halo-reuse variant
+        return conv_wgrad_wgradh(x, dy, dw_ws, N, H, W, Cin, Cout, R, S, st);
+    }
     if (engine == STC_ENGINE_TCGEN05) {
         STC_REQUIRE(elig, "conv_wgrad: tcgen05 engine requested but shape/dtype not eligible");
         g_last_engine = STC_ENGINE_TCGEN05;

@@ -1,0 +1,313 @@
+// tcgen05 weight-gradient kernel with shared-memory HALO reuse.
+//
+//   dW[(r,s)][ci][co] += sum_{n,h,w} x[n, h+r-pr, w+s-ps, ci] * dy[n, h, w, co]
+//
+// GEMM view per output row h and 128-pixel block: D[(tap, ci)][co] += A[(tap, ci)][px] * B[px][co], K = 128 pixels.
+// Both operands are MN-major in smem exactly as TMA delivers NHWC rows ([pixel][64 channels], 128B swizzle):
+//   B = dy tile  : BN/64 atoms of [128 px][64 co]               (LBO = 16 KB between co atoms)
+//   A = x segment: one input row, [(128 + S - 1) px][64 ci].  The M = 128 rows of one MMA are TWO TAPS (r, s) and
+//       (r, s+1) of the same 64-channel chunk: the second 64-row atom is the same segment shifted by one pixel, i.e.
+//       LBO = 128 bytes (overlapping atoms), and tap s starts s * 128 bytes into the segment.  A segment therefore feeds
+//       all S taps of its filter row, and — rolling down the image — the R-1 following output rows as well.
+//   (for odd S the last pair's second atom is a dummy "tap S"; its rows are dropped by the epilogue)
+// Accumulators (all taps of the CTA's filter-row group x 64 ci x BN co, fp32) stay in TMEM over the CTA's whole pixel
+// range and are red.add-ed into the [tap][ci][co] workspace once at the end.
+// A work item = (filter-row group, ci chunk, co tile, image n, column block, row range).
+// Traffic per output row and CTA: one new x segment (17 KB) + one dy tile (BN*256 B) for rg*ceil(S/2)*8 MMAs.
+// Warps: 0 = x-segment producer, 1 = MMA issuer + TMEM owner, 2..5 = epilogue, 6 = dy producer.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace stc {
+
+struct alignas(64) WgradHParams {
+    CUtensorMap tmX;   // x  {Cin,  W, H, N}, box {64, 128+S-1, 1, 1}
+    CUtensorMap tmDY;  // dy {Cout, W, H, N}, box {64, 128, 1, 1}
+    int H, W, R, S, SP, cin_chunks, BN, num_n_tiles;
+    int RG, num_groups;          // filter rows per group, number of groups
+    int blocks_w, row_splits, rows_per_split;
+    int num_items;
+    int a_slots, b_stages;
+    uint32_t a_slot_bytes, a_box_bytes, b_stage_bytes;
+    uint32_t idesc;
+    float* ws;
+    int Cin, Cout;
+};
+
+constexpr int kWgradHThreads = 224;
+
+struct WItem {
+    int g, cc, nt, n_img, w0, h_a, h_b, r0, rg;
+};
+__device__ __forceinline__ WItem decode_item(const WgradHParams& p, int idx) {
+    WItem it;
+    it.nt = idx % p.num_n_tiles; idx /= p.num_n_tiles;
+    it.cc = idx % p.cin_chunks; idx /= p.cin_chunks;
+    it.g = idx % p.num_groups; idx /= p.num_groups;
+    int sp = idx % p.row_splits; idx /= p.row_splits;
+    int wb = idx % p.blocks_w;
+    it.n_img = idx / p.blocks_w;
+    it.w0 = wb * 128;
+    it.h_a = sp * p.rows_per_split;
+    it.h_b = min(p.H, it.h_a + p.rows_per_split);
+    it.r0 = it.g * p.RG;
+    it.rg = min(p.RG, p.R - it.r0);
+    return it;
+}
+
+__global__ void __launch_bounds__(kWgradHThreads, 1) umma_wgradh_kernel(const __grid_constant__ WgradHParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t a_bytes = (uint32_t)p.a_slots * p.a_slot_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a_bytes + (size_t)p.b_stages * p.b_stage_bytes);
+    // bars: a_full[a_slots], a_empty[a_slots], b_full[b_stages], b_empty[b_stages], acc_full, acc_empty
+    const int nb = 2 * p.a_slots + 2 * p.b_stages + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + nb);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = ptx::smem_u32(smem);
+    const uint32_t b_base = smem_base + a_bytes;
+    const uint32_t bar_base = ptx::smem_u32(bars);
+    auto a_full = [&](int s) { return bar_base + 8u * s; };
+    auto a_empty = [&](int s) { return bar_base + 8u * (p.a_slots + s); };
+    auto b_full = [&](int s) { return bar_base + 8u * (2 * p.a_slots + s); };
+    auto b_empty = [&](int s) { return bar_base + 8u * (2 * p.a_slots + p.b_stages + s); };
+    const uint32_t acc_full = bar_base + 8u * (2 * p.a_slots + 2 * p.b_stages);
+    const uint32_t acc_empty = acc_full + 8u;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&p.tmX);
+        ptx::prefetch_tensormap(&p.tmDY);
+        for (int s = 0; s < p.a_slots; ++s) { ptx::mbar_init(a_full(s), 1); ptx::mbar_init(a_empty(s), 1); }
+        for (int s = 0; s < p.b_stages; ++s) { ptx::mbar_init(b_full(s), 1); ptx::mbar_init(b_empty(s), 1); }
+        ptx::mbar_init(acc_full, 1);
+        ptx::mbar_init(acc_empty, 4);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (tmem_base != 0) {
+        if (threadIdx.x == 0) printf("stc_b200: unexpected TMEM base 0x%x\n", tmem_base);
+        __trap();
+    }
+    const int pr = p.R / 2, ps = p.S / 2;
+
+    if (warp == 0) {
+        // ===================== x-segment producer: input rows h_a + r0 - pr ... h_b - 1 + r0 + rg - 1 - pr =====================
+        int slot = 0;
+        uint32_t phase = 0;
+        for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+            WItem it = decode_item(p, item);
+            const int first = it.h_a + it.r0 - pr, count = (it.h_b - it.h_a) + it.rg - 1;
+            for (int e = 0; e < count; ++e) {
+                ptx::mbar_wait(a_empty(slot), phase ^ 1);
+                if (ptx::elect_one_sync()) {
+                    ptx::mbar_arrive_expect_tx(a_full(slot), p.a_box_bytes);
+                    ptx::tma_load_4d(smem_base + slot * p.a_slot_bytes, &p.tmX, a_full(slot), it.cc * 64, it.w0 - ps, first + e, it.n_img);
+                }
+                __syncwarp();
+                if (++slot == p.a_slots) { slot = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 6) {
+        // ===================== dy producer: one [128 px][BN] tile per output row =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        const int nbox = p.BN / 64;
+        for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+            WItem it = decode_item(p, item);
+            for (int h = it.h_a; h < it.h_b; ++h) {
+                ptx::mbar_wait(b_empty(stage), phase ^ 1);
+                if (ptx::elect_one_sync()) {
+                    ptx::mbar_arrive_expect_tx(b_full(stage), p.b_stage_bytes);
+                    for (int j = 0; j < nbox; ++j)
+                        ptx::tma_load_4d(b_base + stage * p.b_stage_bytes + j * 16384, &p.tmDY, b_full(stage), it.nt * p.BN + j * 64, it.w0, h, it.n_img);
+                }
+                __syncwarp();
+                if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (warp-uniform; elected lane issues) =====================
+        int a_head = 0;          // ring slot of the oldest live segment (x row h + r0 - pr)
+        uint32_t a_phase = 0;
+        int bstage = 0;
+        uint32_t bphase = 0;
+        uint32_t acc_phase = 0;
+        // MN-major SW128 descriptors (16 B units): SBO = 1024 B between 8-pixel groups, version 1, layout 2
+        const uint64_t desc_common = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+        const uint64_t a_hi = desc_common | ((uint64_t)(128 >> 4) << 16);     // LBO = 128 B: second atom = next tap (one pixel on)
+        const uint64_t b_hi = desc_common | ((uint64_t)(16384 >> 4) << 16);   // LBO = 16 KB between 64-wide co atoms
+        const uint32_t a_slot16 = p.a_slot_bytes >> 4, b_stage16 = p.b_stage_bytes >> 4;
+        const uint32_t a_base16 = (smem_base >> 4) & 0x3FFF, b_base16 = (b_base >> 4) & 0x3FFF;
+        for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+            WItem it = decode_item(p, item);
+            ptx::mbar_wait(acc_empty, acc_phase ^ 1);
+            ptx::tc_fence_after();
+            int ready = 0;  // segments of this item observed full (relative to a_head at item start -> tracked via `seen`)
+            int seen_slot = a_head;
+            uint32_t seen_phase = a_phase;
+            for (int h = it.h_a; h < it.h_b; ++h) {
+                // output row h reads segments (h - h_a) .. (h - h_a) + rg - 1
+                const int need = (h - it.h_a) + it.rg;
+                while (ready < need) {
+                    ptx::mbar_wait(a_full(seen_slot), seen_phase);
+                    if (++seen_slot == p.a_slots) { seen_slot = 0; seen_phase ^= 1; }
+                    ++ready;
+                }
+                ptx::mbar_wait(b_full(bstage), bphase);
+                ptx::tc_fence_after();
+                const uint64_t b_desc0 = b_hi | (uint64_t)(b_base16 + bstage * b_stage16);
+                const uint32_t acc_flag = (h > it.h_a) ? 1u : 0u;
+                if (ptx::elect_one_sync()) {
+                    for (int rr = 0; rr < it.rg; ++rr) {
+                        int sl = a_head + rr;
+                        if (sl >= p.a_slots) sl -= p.a_slots;
+                        const uint32_t seg16 = a_base16 + sl * a_slot16;
+                        for (int sp = 0; sp < p.SP; ++sp) {
+                            const uint64_t a_desc0 = a_hi | (uint64_t)(seg16 + sp * 16);   // tap s = 2*sp starts 2*sp*128 B in
+                            const uint32_t d_addr = (uint32_t)((rr * p.SP + sp) * p.BN);
+                            ptx::mma_bf16_ss(d_addr, a_desc0, b_desc0, p.idesc, acc_flag);
+#pragma unroll
+                            for (int ks = 1; ks < 8; ++ks)   // K step = 16 pixels = 2048 B = 128 units
+                                ptx::mma_bf16_ss(d_addr, a_desc0 + (uint64_t)(ks * 128), b_desc0 + (uint64_t)(ks * 128), p.idesc, 1u);
+                        }
+                    }
+                    ptx::tc_commit(b_empty(bstage));
+                    ptx::tc_commit(a_empty(a_head));   // x row h + r0 - pr is not read by later output rows
+                }
+                __syncwarp();
+                if (++bstage == p.b_stages) { bstage = 0; bphase ^= 1; }
+                if (++a_head == p.a_slots) { a_head = 0; a_phase ^= 1; }
+            }
+            // the last rg-1 segments of the item are still held: release them and move the ring head past them
+            if (ptx::elect_one_sync()) {
+                for (int k = 0; k < it.rg - 1; ++k) {
+                    int sl = a_head + k;
+                    if (sl >= p.a_slots) sl -= p.a_slots;
+                    ptx::tc_commit(a_empty(sl));
+                }
+                ptx::tc_commit(acc_full);
+            }
+            __syncwarp();
+            a_head += it.rg - 1;
+            if (a_head >= p.a_slots) { a_head -= p.a_slots; a_phase ^= 1; }
+            acc_phase ^= 1;
+        }
+    } else if (warp >= 2 && warp <= 5) {
+        // ===================== epilogue: TMEM -> red.add into ws[tap][ci][co] =====================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        uint32_t acc_phase = 0;
+        for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+            WItem it = decode_item(p, item);
+            ptx::mbar_wait(acc_full, acc_phase);
+            ptx::tc_fence_after();
+            for (int rr = 0; rr < it.rg; ++rr) {
+                for (int sp = 0; sp < p.SP; ++sp) {
+                    const int s = 2 * sp + (row >> 6);
+                    const bool valid = s < p.S;
+                    const int tap = (it.r0 + rr) * p.S + s;
+                    float* o = p.ws + ((long long)tap * p.Cin + it.cc * 64 + (row & 63)) * p.Cout + it.nt * p.BN;
+                    const uint32_t t_addr = (uint32_t)((rr * p.SP + sp) * p.BN) + ((uint32_t)(q * 32) << 16);
+                    for (int c = 0; c < p.BN; c += 32) {
+                        uint32_t v[32];
+                        ptx::tmem_ld_32x32(t_addr + c, v);
+                        ptx::tmem_ld_wait();
+                        if (!valid) continue;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) atomicAdd(o + c + j, __uint_as_float(v[j]));
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(acc_empty);
+            acc_phase ^= 1;
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+int encode_map_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
+
+bool conv_wgradh_eligible(int W, int Cin, int Cout, int R, int S, int dtype) {
+    static int disabled = -1;
+    if (disabled < 0) { const char* e = getenv("STC_WGRADH"); disabled = (e && e[0] == '0') ? 1 : 0; }
+    if (disabled) return false;
+    return dtype == STC_BF16 && W >= 128 && Cin % 64 == 0 && Cout % 64 == 0 && R == S && (R == 3 || R == 5 || R == 7);
+}
+
+int conv_wgrad_wgradh(const void* x, const void* dy, float* ws, int N, int H, int W, int Cin, int Cout, int R, int S, cudaStream_t st) {
+    WgradHParams p;
+    memset(&p, 0, sizeof(p));
+    p.BN = Cout % 128 == 0 ? 128 : 64;
+    p.SP = (S + 1) / 2;
+    p.RG = 512 / (p.SP * p.BN);
+    if (p.RG > R) p.RG = R;
+    STC_REQUIRE(p.RG >= 1, "conv_wgrad_wgradh: no plan");
+    p.num_groups = (R + p.RG - 1) / p.RG;
+    const int bwh = 128 + S - 1;
+    {
+        uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+        uint64_t str[4] = {2, (uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+        uint32_t box[4] = {64, (uint32_t)bwh, 1, 1};
+        int rc = encode_map_bf16(&p.tmX, x, 4, dims, str, box);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+        uint64_t str[4] = {2, (uint64_t)Cout * 2, (uint64_t)W * Cout * 2, (uint64_t)H * W * Cout * 2};
+        uint32_t box[4] = {64, 128, 1, 1};
+        int rc = encode_map_bf16(&p.tmDY, dy, 4, dims, str, box);
+        if (rc) return rc;
+    }
+    p.H = H; p.W = W; p.R = R; p.S = S; p.Cin = Cin; p.Cout = Cout;
+    p.cin_chunks = Cin / 64;
+    p.num_n_tiles = Cout / p.BN;
+    p.blocks_w = (W + 127) / 128;
+    // row splits: enough work items for ~2 per SM, at least 16 rows each so the R-1 warm-up segments amortise
+    long long base = (long long)p.num_n_tiles * p.cin_chunks * p.num_groups * p.blocks_w * N;
+    int want = (int)((2LL * num_sms() + base - 1) / base);
+    int max_splits = H / 16 > 0 ? H / 16 : 1;
+    p.row_splits = want < 1 ? 1 : (want > max_splits ? max_splits : want);
+    p.rows_per_split = (H + p.row_splits - 1) / p.row_splits;
+    p.row_splits = (H + p.rows_per_split - 1) / p.rows_per_split;
+    p.num_items = (int)(base * p.row_splits);
+    p.a_slot_bytes = 17408;
+    p.a_box_bytes = (uint32_t)bwh * 128;
+    p.b_stage_bytes = (uint32_t)p.BN * 256;
+    p.a_slots = p.RG + 3;
+    p.b_stages = p.BN == 64 ? 4 : 3;
+    p.idesc = make_idesc_bf16(128, p.BN, 1, 1);
+    p.ws = ws;
+    size_t smem = (size_t)p.a_slots * p.a_slot_bytes + (size_t)p.b_stages * p.b_stage_bytes + (2 * p.a_slots + 2 * p.b_stages + 2) * 8 + 16 + 1024;
+    STC_REQUIRE(smem <= 227 * 1024, "conv_wgrad_wgradh: smem %zu", smem);
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        STC_CUDA(cudaFuncSetAttribute(umma_wgradh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set[dev] = true;
+    }
+    int grid = p.num_items < num_sms() ? p.num_items : num_sms();
+    umma_wgradh_kernel<<<grid, kWgradHThreads, smem, st>>>(p);
+    return check_launch("umma_wgradh_kernel");
+}
+
+}  // namespace stc

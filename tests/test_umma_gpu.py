@@ -154,3 +154,18 @@ def test_conv_halo_tcgen05(tc, shape):
     # back-to-back launches reuse the rings / TMEM cleanly
     y3 = tc.conv_fprop(nhwc(x).to(BF), wp, b, None, Cout, k, k)
     assert torch.equal(y, y3)
+
+
+@pytest.mark.parametrize("shape", [s for s in HALO_SHAPES if s[2] % 64 == 0] + [(2, 64, 64, 40, 128, 3), (1, 128, 64, 33, 256, 5)])
+def test_wgrad_halo_tcgen05(tc, shape):
+    """umma_wgradh_kernel: two taps per MMA via overlapping MN-major atoms, rolling x-row reuse, several row splits."""
+    N, Cin, Cout, H, W, k = shape
+    g = torch.Generator(device="cuda").manual_seed(8)
+    x = bf16_round(torch.randn(N, Cin, H, W, device=dev(), generator=g)).double().requires_grad_(False)
+    w = torch.zeros(Cout, Cin, k, k, device=dev(), dtype=torch.float64, requires_grad=True)
+    dy = bf16_round(torch.randn(N, Cout, H, W, device=dev(), generator=g)).double()
+    F.conv2d(x, w, None, padding=k // 2).backward(dy)
+    dw = tc.conv_wgrad(nhwc(x.float()).to(BF), nhwc(dy.float()).to(BF), k, k)
+    assert rel_l2(dw, w.grad) < 2e-3
+    dw2 = tc.conv_wgrad(nhwc(x.float()).to(BF), nhwc(dy.float()).to(BF), k, k)
+    assert rel_l2(dw2, w.grad) < 2e-3

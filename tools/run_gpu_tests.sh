@@ -12,7 +12,7 @@ case $g in
   ops) run ops tests/test_ops_gpu.py ;;
   umma_first) run umma_first "tests/test_umma_gpu.py::test_conv_fprop_tcgen05[shape0]" "tests/test_umma_gpu.py::test_conv_fprop_tcgen05[shape1]" ;;
   umma_fprop) run umma_fprop tests/test_umma_gpu.py -k "test_conv_fprop_tcgen05" ;;
-  umma_grad) run umma_grad tests/test_umma_gpu.py -k "test_conv_dgrad_wgrad_tcgen05" ;;
+  umma_grad) run umma_grad tests/test_umma_gpu.py -k "test_conv_dgrad_wgrad_tcgen05 or test_wgrad_halo_tcgen05" ;;
   umma_attn) run umma_attn tests/test_umma_gpu.py -k "test_attention_tcgen05" ;;
   umma_halo) run umma_halo tests/test_umma_gpu.py -k "test_conv_halo_tcgen05" ;;
   umma_misc) run umma_misc tests/test_umma_gpu.py -k "test_linear_tokens_tcgen05 or test_tcgen05_matches_simt_large" ;;
