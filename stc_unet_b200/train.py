@@ -48,6 +48,25 @@ class FlatParams:
             dist.broadcast(self.flat, src)
 
 
+def plan_buckets(spans, total: int, cap_elems: int):
+    """spans: [(offset, numel)] of the parameters in arena (= forward) order.  Returns (buckets, owner): buckets are
+    contiguous [start, end) ranges taken from the END of the arena (backward produces the last parameters first), each
+    at least `cap_elems` long (except possibly the last one), with the number of parameters inside; owner[i] is the
+    bucket index of parameter i."""
+    buckets, owner = [], [0] * len(spans)
+    cur_end, cur_start, cnt = total, total, 0
+    for i in range(len(spans) - 1, -1, -1):
+        cur_start = spans[i][0]
+        owner[i] = len(buckets)
+        cnt += 1
+        if cur_end - cur_start >= cap_elems:
+            buckets.append((cur_start, cur_end, cnt))
+            cur_end, cnt = cur_start, 0
+    if cnt:
+        buckets.append((cur_start, cur_end, cnt))
+    return buckets, owner
+
+
 class GradReducer:
     """Buckets are contiguous ranges of the arena taken from its END (backward produces the last parameters
     first); a bucket's all-reduce starts on the comm stream as soon as all of its gradients have been written."""
@@ -56,19 +75,9 @@ class GradReducer:
         self.arena = arena
         self.comm = torch.cuda.Stream()
         cap = int(bucket_mb * (1 << 20) // 4)
-        self.buckets = []          # (start, end, n_params)
-        self.bucket_of: Dict[int, int] = {}
-        cur_end, cur_start, cnt = arena.total, arena.total, 0
-        for p in reversed(arena.params):
-            off, n = arena.offsets[id(p)]
-            cur_start = off
-            self.bucket_of[id(p)] = len(self.buckets)
-            cnt += 1
-            if cur_end - cur_start >= cap:
-                self.buckets.append((cur_start, cur_end, cnt))
-                cur_end, cnt = cur_start, 0
-        if cnt:
-            self.buckets.append((cur_start, cur_end, cnt))
+        spans = [arena.offsets[id(p)] for p in arena.params]
+        self.buckets, owner = plan_buckets(spans, arena.total, cap)   # (start, end, n_params)
+        self.bucket_of: Dict[int, int] = {id(p): owner[i] for i, p in enumerate(arena.params)}
         self.pending = [0] * len(self.buckets)
         self.handles = []
         self.enabled = _dist_on()

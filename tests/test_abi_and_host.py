@@ -1,0 +1,77 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library builds/loads and exports every declared symbol, the
+module mirror has the reference's constructor surface and state_dict layout, and nothing silently runs on the CPU."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from stc_unet_b200 import build
+    from stc_unet_b200._lib import HEADER_PATH, lib, parse_header
+    path = build.build()
+    assert os.path.exists(path)
+    protos = parse_header(HEADER_PATH)
+    declared = set(re.findall(r"\b(stc_\w+)\s*\(", re.sub(r"/\*.*?\*/", " ", open(HEADER_PATH).read(), flags=re.S)))
+    assert declared == set(protos), declared ^ set(protos)
+    dll = ctypes.CDLL(path)
+    for name in protos:
+        assert hasattr(dll, name), f"{name} declared in include/stc_b200.h but not exported"
+    assert lib.raw("stc_version")() >= 100
+    assert len(protos) >= 50
+
+
+def test_no_cpu_fallback():
+    import stc_unet_b200 as S
+    bb = S.build_backbone(dict(type="UnetBackbone", in_channels=3, channel_list=[64, 128, 256, 512]))
+    with pytest.raises(RuntimeError, match="no CPU"):
+        bb(torch.rand(1, 3, 32, 32))
+    with pytest.raises(RuntimeError, match="no CPU"):
+        S.ops.seg_loss(torch.zeros(1, 2, 4, 4), torch.zeros(1, 4, 4, dtype=torch.long))
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            S._lib.lib.ensure_device(0)
+
+
+def test_registry_contract_and_constructor_surface():
+    import stc_unet_b200 as S
+    for name in ("UnetBackbone", "UnetHead", "CrossEntropyLoss", "DiceLoss", "EncoderDecoder"):
+        assert S.MODELS.get(name) is not None or S.MODELS.get(name + "B200") is not None
+    with pytest.raises(KeyError):
+        S.build_backbone(dict(type="NoSuchBackbone"))
+    with pytest.raises(ValueError):
+        S.build_head(dict(type="UnetHead", num_classes=3, out_channels=2))
+    with pytest.warns(UserWarning, match="binary segmentation"):
+        hd = S.build_head(dict(type="UnetHead", num_classes=2, loss_decode=dict(type="CrossEntropyLoss", loss_name="loss_ce")))
+    assert hd.out_channels == 2 and hd.num_classes == 2 and hd.align_corners is False and hd.ignore_index == 255
+    assert hd.dropout is not None and hd.conv_seg.weight.shape == (2, 64, 1, 1)
+    hd.init_weights()
+    assert float(hd.conv_seg.weight.std()) < 0.05 and float(hd.conv_seg.bias.abs().max()) == 0.0
+    with pytest.warns(UserWarning):
+        hd1 = S.build_head(dict(type="UnetHead", num_classes=2, out_channels=1))
+    assert hd1.threshold == 0.3
+    seg = S.build_segmentor(dict(type="EncoderDecoder", backbone=dict(type="UnetBackbone"), decode_head=dict(type="UnetHead", num_classes=3)),
+                            test_cfg=dict(mode="whole"))
+    keys = list(seg.state_dict())
+    assert keys[0] == "backbone.inc.conv.conv.0.weight" and "decode_head.conv_seg.weight" in keys
+    assert isinstance(seg.backbone.inc.conv.conv[1], torch.nn.SyncBatchNorm)
+
+
+def test_grad_arena_layout_and_bucket_plan():
+    from stc_unet_b200.ops import GradArena
+    from stc_unet_b200.train import plan_buckets
+    ps = [torch.nn.Parameter(torch.zeros(n)) for n in (5, 64, 3, 1000, 7)]
+    arena = GradArena(ps)
+    offs = [arena.offsets[id(p)][0] for p in ps]
+    assert offs == [0, 8, 72, 76, 1076] and arena.total == 1084 and all(o % 4 == 0 for o in offs)
+    v = arena.view(ps[3])
+    assert v.shape == (1000,) and v.data_ptr() == arena.flat.data_ptr() + 76 * 4
+    buckets, owner = plan_buckets([(o, p.numel()) for o, p in zip(offs, ps)], arena.total, cap_elems=1000)
+    # buckets are contiguous, cover the arena, and are ordered from the END (backward order)
+    assert buckets[0][1] == arena.total and buckets[-1][0] == 0
+    assert all(buckets[i][0] == buckets[i + 1][1] for i in range(len(buckets) - 1))
+    assert sum(b[2] for b in buckets) == len(ps) and owner[4] == 0 and owner[0] == len(buckets) - 1
