@@ -60,6 +60,12 @@ int stc_pack_conv_weight(const float* w, void* dst, int Cout, int Cin, int R, in
 /* wgrad workspace [R*S][Cin][Cout] fp32 -> Conv2d.weight.grad (Cout,Cin,R,S) fp32
  * (accumulate != 0 adds into dst). */
 int stc_unpack_conv_wgrad(const float* ws, float* dw, int Cout, int Cin, int R, int S, int accumulate, void* stream);
+/* Small-Cin convolutions (the 3-channel image conv, unet_backbone.py:120 via InConv) run as a K = Kpad 1x1 conv on the tensor
+ * cores: out[p][k] = x[p + tap][ci] with k = tap*Cin + ci (zero padded to Kpad, a multiple of 64 for the tcgen05 engine).
+ * The matching weight pack is stc_pack_conv_weight(..., inner_pad = Kpad, transpose_flip = 2) -> [Cout][Kpad], and
+ * stc_unpack_im2col_wgrad maps the wgrad workspace [Kpad][Cout] back to Conv2d.weight.grad (Cout,Cin,R,S). */
+int stc_im2col(const void* x, void* out, int N, int H, int W, int Cin, int R, int S, int Kpad, int dtype, void* stream);
+int stc_unpack_im2col_wgrad(const float* ws, float* dw, int Cout, int Cin, int R, int S, void* stream);
 
 /* ---------------------------------------------------------------- convolution (K1/K2/K3)
  * Replaces nn.Conv2d(k, padding=k//2) in DoubleConv (unet_backbone.py:120,123; unet_head.py:67,70),

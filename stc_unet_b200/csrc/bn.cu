@@ -159,15 +159,32 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* __restrict_
         be[k] = beta[lv * 8 + k];
     }
     float acc[2][8] = {};
-    for (long long p = (long long)blockIdx.x * rstep + r0; p < P; p += (long long)gridDim.x * rstep) {
+    // two rows per iteration: four independent 16/32-byte loads in flight per thread
+    const long long step = (long long)gridDim.x * rstep;
+    long long p = (long long)blockIdx.x * rstep + r0;
+    for (; p + step < P; p += 2 * step) {
+        Vec8<T> v0, d0, v1, d1;
+        v0.load(y + p * C + lv * 8);
+        d0.load(dout + p * C + lv * 8);
+        v1.load(y + (p + step) * C + lv * 8);
+        d1.load(dout + (p + step) * C + lv * 8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float xh0 = (v0.v[k] - mu[k]) * is[k], xh1 = (v1.v[k] - mu[k]) * is[k];
+            float g0 = d0.v[k] * act_grad(fmaf(xh0, ga[k], be[k]), act);
+            float g1 = d1.v[k] * act_grad(fmaf(xh1, ga[k], be[k]), act);
+            acc[0][k] += g0 + g1;
+            acc[1][k] = fmaf(g0, xh0, fmaf(g1, xh1, acc[1][k]));
+        }
+    }
+    for (; p < P; p += step) {
         Vec8<T> v, d;
         v.load(y + p * C + lv * 8);
         d.load(dout + p * C + lv * 8);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             float xh = (v.v[k] - mu[k]) * is[k];
-            float z = fmaf(xh, ga[k], be[k]);
-            float g = d.v[k] * act_grad(z, act);
+            float g = d.v[k] * act_grad(fmaf(xh, ga[k], be[k]), act);
             acc[0][k] += g;
             acc[1][k] = fmaf(g, xh, acc[1][k]);
         }

@@ -89,6 +89,18 @@ __global__ void pack_w_kernel(const float* __restrict__ w, T* __restrict__ dst, 
     int tap = (int)(t / outer_n);
     int r = tap / S, s = tap % S;
     float v = 0.f;
+    if (tf == 2) {
+        // im2col pack: dst[co][k], k = tap*Cin + ci  (one "tap" of K = inner_pad >= R*S*Cin channels)
+        int RS = R * S;
+        long long co = i / inner_pad;
+        int k = inner;
+        if (k < RS * Cin) {
+            int tp = k / Cin, ci = k - tp * Cin;
+            v = w[((co * Cin + ci) * RS) + tp];
+        }
+        stf(dst + i, v);
+        return;
+    }
     if (!tf) {
         // dst[tap][co][ci] = W[co][ci][r][s]
         if (inner < Cin) v = w[(((long long)outer * Cin + inner) * R + r) * S + s];
@@ -102,10 +114,10 @@ __global__ void pack_w_kernel(const float* __restrict__ w, T* __restrict__ dst, 
 
 extern "C" int stc_pack_conv_weight(const float* w, void* dst, int Cout, int Cin, int R, int S, int inner_pad,
                                     int transpose_flip, int dtype, void* stream) {
-    int inner = transpose_flip ? Cout : Cin;
-    int outer = transpose_flip ? Cin : Cout;
+    int inner = transpose_flip == 1 ? Cout : (transpose_flip == 2 ? R * S * Cin : Cin);
+    int outer = transpose_flip == 1 ? Cin : Cout;
     STC_REQUIRE(inner_pad >= inner, "pack_conv_weight: inner_pad %d < inner %d", inner_pad, inner);
-    long long total = (long long)R * S * outer * inner_pad;
+    long long total = transpose_flip == 2 ? (long long)Cout * inner_pad : (long long)R * S * outer * inner_pad;
     STC_DISPATCH_DTYPE(dtype, (pack_w_kernel<T><<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
                                    w, (T*)dst, Cout, Cin, R, S, inner_pad, transpose_flip, total)));
     return check_launch("pack_conv_weight");
@@ -319,4 +331,60 @@ extern "C" int stc_copy_rows(const void* src, void* dst, int N, int src_rows, in
     STC_DISPATCH_DTYPE(dtype, (copy_rows_kernel<T><<<blocks, 256, 0, (cudaStream_t)stream>>>((const T*)src, (T*)dst, src_rows, dst_rows, C,
                                                                                            src_off, dst_off, count, total)));
     return check_launch("copy_rows");
+}
+
+
+// ------------------------------------------------------------------------------------
+// im2col for small-Cin convolutions (the 3-channel image conv): out[p][k], k = tap*Cin + ci, zero padded to Kpad,
+// so the layer runs as a K = Kpad 1x1 convolution on the tensor cores.
+// ------------------------------------------------------------------------------------
+template <typename T>
+__global__ void im2col_kernel(const T* __restrict__ x, T* __restrict__ out, int H, int W, int Cin, int R, int S, int Kpad, long long total) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;  // over P * Kpad/8
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const int kv = Kpad >> 3, K = R * S * Cin, pr = R / 2, ps = S / 2;
+    for (; i < total; i += stride) {
+        int v8 = (int)(i % kv);
+        long long p = i / kv;
+        int w_ = (int)(p % W), h_ = (int)((p / W) % H);
+        long long n = p / ((long long)W * H);
+        Vec8<T> o;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            int k = v8 * 8 + e;
+            float v = 0.f;
+            if (k < K) {
+                int tp = k / Cin, ci = k - tp * Cin;
+                int hh = h_ + tp / S - pr, ww = w_ + tp % S - ps;
+                if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = ldf(x + ((n * H + hh) * W + ww) * Cin + ci);
+            }
+            o.v[e] = v;
+        }
+        o.store(out + i * 8);
+    }
+}
+
+extern "C" int stc_im2col(const void* x, void* out, int N, int H, int W, int Cin, int R, int S, int Kpad, int dtype, void* stream) {
+    STC_REQUIRE(Kpad % 8 == 0 && Kpad >= R * S * Cin, "im2col: Kpad=%d must be a multiple of 8 and >= R*S*Cin=%d", Kpad, R * S * Cin);
+    long long total = (long long)N * H * W * (Kpad / 8);
+    if (total <= 0) return STC_OK;
+    int blocks = (int)min((long long)num_sms() * 16, (long long)ceil_div(total, 256));
+    STC_DISPATCH_DTYPE(dtype, (im2col_kernel<T><<<blocks, 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)out, H, W, Cin, R, S, Kpad, total)));
+    return check_launch("im2col");
+}
+
+__global__ void unpack_im2col_wgrad_kernel(const float* __restrict__ ws, float* __restrict__ dw, int Cout, int Cin, int RS, long long total) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;  // over OIHW
+    if (i >= total) return;
+    int tp = (int)(i % RS);
+    long long t = i / RS;
+    int ci = (int)(t % Cin);
+    int co = (int)(t / Cin);
+    dw[i] = ws[((long long)tp * Cin + ci) * Cout + co];   // ws is [Kpad][Cout], k = tap*Cin + ci
+}
+
+extern "C" int stc_unpack_im2col_wgrad(const float* ws, float* dw, int Cout, int Cin, int R, int S, void* stream) {
+    long long total = (long long)Cout * Cin * R * S;
+    unpack_im2col_wgrad_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(ws, dw, Cout, Cin, R * S, total);
+    return check_launch("unpack_im2col_wgrad");
 }

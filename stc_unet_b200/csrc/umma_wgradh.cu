@@ -225,7 +225,10 @@ __global__ void __launch_bounds__(kWgradHThreads, 1) umma_wgradh_kernel(const __
                         ptx::tmem_ld_wait();
                         if (!valid) continue;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) atomicAdd(o + c + j, __uint_as_float(v[j]));
+                        for (int j = 0; j < 32; j += 4)   // 16-byte vector reductions: 4x fewer L2 atomic instructions
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + c + j), "f"(__uint_as_float(v[j])),
+                                         "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                                         : "memory");
                     }
                 }
             }
@@ -256,7 +259,8 @@ bool conv_wgradh_eligible(int W, int Cin, int Cout, int R, int S, int dtype) {
 int conv_wgrad_wgradh(const void* x, const void* dy, float* ws, int N, int H, int W, int Cin, int Cout, int R, int S, cudaStream_t st) {
     WgradHParams p;
     memset(&p, 0, sizeof(p));
-    p.BN = Cout % 128 == 0 ? 128 : 64;
+    // BN = 128 when possible (measured 5-40 % faster than 64 on the Cout >= 128 layers: fewer, longer MMAs per dy tile)
+    { const char* e = getenv("STC_WGRADH_BN"); p.BN = (Cout % 128 == 0 && !(e && atoi(e) == 64)) ? 128 : 64; }
     p.SP = (S + 1) / 2;
     p.RG = 512 / (p.SP * p.BN);
     if (p.RG > R) p.RG = R;

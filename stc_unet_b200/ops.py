@@ -281,6 +281,19 @@ def _bn_backward(y, dout, mean, invstd, gamma, beta, P, C, act, bn, count, pg, p
     return dy, dgamma, dbeta
 
 
+def _use_im2col(x, weight) -> bool:
+    """Small-Cin convs (the image conv) go through im2col + a K=64 1x1 conv so they run on the tensor cores."""
+    Cout, Cin, R, S = weight.shape
+    return x.dtype == torch.bfloat16 and Cin < 8 and R * S * Cin <= 64 and Cout % 32 == 0 and config.engine != _lib.ENGINE_SIMT
+
+
+def _im2col(x, R, S, Kpad=64):
+    N, H, W, Cin = x.shape
+    out = torch.empty((N, H, W, Kpad), dtype=x.dtype, device=x.device)
+    lib.call("stc_im2col", x, out, N, H, W, Cin, R, S, Kpad, dtype_code(x.dtype), stream_ptr())
+    return out
+
+
 class _ConvBnAct(Function):
     @staticmethod
     def forward(ctx, x, weight, bias, gamma, beta, bn: BNState, act: int, pobjs):
@@ -288,8 +301,15 @@ class _ConvBnAct(Function):
         Cout, Cin, R, S = weight.shape
         N, H, W, _ = x.shape
         P = N * H * W
-        wp = pack_weight(weight, x.dtype)
-        y = conv_fprop(x, wp, bias, None, Cout, R, S)
+        ctx.im2col = _use_im2col(x, weight)
+        if ctx.im2col:
+            x = _im2col(x, R, S)          # (N,H,W,64): saved instead of the 3-channel image for the wgrad GEMM
+            wp = torch.empty((1, Cout, 64), dtype=x.dtype, device=x.device)
+            lib.call("stc_pack_conv_weight", weight, wp, Cout, Cin, R, S, 64, 2, dtype_code(x.dtype), stream_ptr())
+            y = conv_fprop(x, wp, bias, None, Cout, 1, 1)
+        else:
+            wp = pack_weight(weight, x.dtype)
+            y = conv_fprop(x, wp, bias, None, Cout, R, S)
         mean, invstd, count = _bn_forward_stats(y, P, Cout, bn)
         a = torch.empty_like(y)
         lib.call("stc_bn_apply", y, mean, invstd, gamma, beta, a, P, Cout, act, dtype_code(y.dtype), stream_ptr())
@@ -314,6 +334,15 @@ class _ConvBnAct(Function):
                 dbias = _grad_buf(pbias, (Cout,), dy.device, zero=True)
             else:
                 dbias = colsum(P, Cout, dy, _grad_buf(pbias, (Cout,), dy.device))
+        if ctx.im2col:
+            if ctx.needs_input_grad[0]:
+                raise RuntimeError("im2col conv path does not provide an input gradient (it is only used for the image conv)")
+            ws = torch.zeros(64 * Cout, dtype=torch.float32, device=dy.device)
+            _dense("conv_wgrad", 2.0 * P * 64 * Cout,
+                   lambda: lib.call("stc_conv_wgrad", x, dy, ws, N, H, W, 64, Cout, 1, 1, dtype_code(x.dtype), config.engine, stream_ptr()))
+            dw = _grad_buf(pw, weight.shape, dy.device)
+            lib.call("stc_unpack_im2col_wgrad", ws, dw, Cout, weight.shape[1], R, S, stream_ptr())
+            return None, dw, dbias, dgamma, dbeta, None, None, None
         dw = conv_wgrad(x, dy, R, S, _grad_buf(pw, weight.shape, dy.device))
         dx = None
         if ctx.needs_input_grad[0]:
