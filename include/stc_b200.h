@@ -57,6 +57,10 @@ int stc_nchw_to_nhwc(const float* src, void* dst, int N, int C, int H, int W, in
  * transpose_flip != 0 packs the dgrad operand: [(R-1-r)*S+(S-1-s)][Cin][CoutPad] = W[co][ci][r][s]. */
 int stc_pack_conv_weight(const float* w, void* dst, int Cout, int Cin, int R, int S, int inner_pad,
                          int transpose_flip, int dtype, void* stream);
+/* Every weight pack of a step in one launch.  table: n rows of 8 int64 {src device pointer (fp32 OIHW), dst element offset,
+ * Cout, Cin, R, S, inner_pad, mode (0 fprop, 1 dgrad, 2 im2col)}; prefix: n+1 cumulative packed element counts. */
+int stc_pack_conv_weights_batched(const int64_t* table, const int64_t* prefix, int n, void* dst, long long total, int dtype,
+                                  void* stream);
 /* wgrad workspace [R*S][Cin][Cout] fp32 -> Conv2d.weight.grad (Cout,Cin,R,S) fp32
  * (accumulate != 0 adds into dst). */
 int stc_unpack_conv_wgrad(const float* ws, float* dw, int Cout, int Cin, int R, int S, int accumulate, void* stream);
@@ -181,6 +185,7 @@ int stc_linear_f32_bwd(const float* x, const float* W, const float* dy, float* d
 
 /* ---------------------------------------------------------------- elementwise */
 int stc_add(const void* a, const void* b, void* out, long long n, int dtype, void* stream);           /* out = a + b */
+int stc_add_n(const void* a, const void* b, const void* c, const void* d, void* out, long long n, int dtype, void* stream); /* out = a+b(+c)(+d); c, d may be NULL */
 int stc_axpy_f32(const float* x, float* y, float alpha, long long n, void* stream);                    /* y += alpha x */
 int stc_cast(const void* src, void* dst, long long n, int src_dtype, int dst_dtype, void* stream);
 int stc_act_bwd(const void* y_out, const void* dy, void* dx, long long n, int act, int dtype, void* stream); /* sigmoid: uses output */

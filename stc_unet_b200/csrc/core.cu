@@ -388,3 +388,102 @@ extern "C" int stc_unpack_im2col_wgrad(const float* ws, float* dw, int Cout, int
     unpack_im2col_wgrad_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(ws, dw, Cout, Cin, R * S, total);
     return check_launch("unpack_im2col_wgrad");
 }
+
+
+// out = a + b (+ c (+ d)) in one pass: fan-out gradient sums (KSA input: 4 consumers, transformer tokens: 4)
+template <typename T>
+__global__ void add_n_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ c, const T* __restrict__ d,
+                             T* __restrict__ out, long long n8, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long j = i; j < n8; j += stride) {
+        Vec8<T> x, y;
+        x.load(a + j * 8);
+        y.load(b + j * 8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x.v[k] += y.v[k];
+        if (c) {
+            y.load(c + j * 8);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x.v[k] += y.v[k];
+        }
+        if (d) {
+            y.load(d + j * 8);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x.v[k] += y.v[k];
+        }
+        x.store(out + j * 8);
+    }
+    for (long long j = n8 * 8 + i; j < n; j += stride) {
+        float v = ldf(a + j) + ldf(b + j);
+        if (c) v += ldf(c + j);
+        if (d) v += ldf(d + j);
+        stf(out + j, v);
+    }
+}
+
+extern "C" int stc_add_n(const void* a, const void* b, const void* c, const void* d, void* out, long long n, int dtype, void* stream) {
+    if (n <= 0) return STC_OK;
+    STC_REQUIRE(a && b, "add_n: the first two inputs are mandatory");
+    bool aligned = (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d | (uintptr_t)out) & 15) == 0;
+    long long n8 = aligned ? n / 8 : 0;
+    int blocks = (int)min((long long)num_sms() * 16, (long long)ceil_div(max(n8, 1LL), 256));
+    if (blocks < 1) blocks = 1;
+    STC_DISPATCH_DTYPE(dtype, (add_n_kernel<T><<<blocks, 256, 0, (cudaStream_t)stream>>>((const T*)a, (const T*)b, (const T*)c, (const T*)d,
+                                                                                     (T*)out, n8, n)));
+    return check_launch("add_n");
+}
+
+
+// ------------------------------------------------------------------------------------
+// all weight packs of a training step in ONE launch.  table: n rows of 8 int64
+// {src ptr, dst element offset, Cout, Cin, R, S, inner_pad, mode}; prefix: n+1 cumulative element counts.
+// ------------------------------------------------------------------------------------
+template <typename T>
+__global__ void pack_batched_kernel(const long long* __restrict__ table, const long long* __restrict__ prefix, int n,
+                                    T* __restrict__ dst_base, long long total) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        int lo = 0, hi = n;  // prefix[lo] <= i < prefix[hi]
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (prefix[mid] <= i) lo = mid; else hi = mid;
+        }
+        const long long* e = table + (long long)lo * 8;
+        const float* w = reinterpret_cast<const float*>(e[0]);
+        const int Cout = (int)e[2], Cin = (int)e[3], R = (int)e[4], S = (int)e[5], inner_pad = (int)e[6], tf = (int)e[7];
+        const long long j = i - prefix[lo];
+        const int inner = (int)(j % inner_pad);
+        float v = 0.f;
+        if (tf == 2) {
+            const int RS = R * S;
+            const long long co = j / inner_pad;
+            if (inner < RS * Cin) {
+                int tp = inner / Cin, ci = inner - tp * Cin;
+                v = w[((co * Cin + ci) * RS) + tp];
+            }
+        } else {
+            long long t = j / inner_pad;
+            const int outer_n = tf ? Cin : Cout;
+            const int outer = (int)(t % outer_n);
+            const int tap = (int)(t / outer_n);
+            const int r = tap / S, sx = tap % S;
+            if (!tf) {
+                if (inner < Cin) v = w[(((long long)outer * Cin + inner) * R + r) * S + sx];
+            } else {
+                if (inner < Cout) v = w[(((long long)inner * Cin + outer) * R + (R - 1 - r)) * S + (S - 1 - sx)];
+            }
+        }
+        stf(dst_base + e[1] + j, v);
+    }
+}
+
+extern "C" int stc_pack_conv_weights_batched(const int64_t* table, const int64_t* prefix, int n, void* dst, long long total, int dtype,
+                                             void* stream) {
+    if (n <= 0 || total <= 0) return STC_OK;
+    int blocks = (int)min((long long)num_sms() * 16, (long long)ceil_div(total, 256));
+    STC_DISPATCH_DTYPE(dtype, (pack_batched_kernel<T><<<blocks, 256, 0, (cudaStream_t)stream>>>((const long long*)table, (const long long*)prefix,
+                                                                                            n, (T*)dst, total)));
+    return check_launch("pack_conv_weights_batched");
+}

@@ -220,8 +220,7 @@ class CoordAtt(nn.Module):
 
     def forward_add(self, x):  # x NHWC
         N, H, W, C = x.shape
-        xa, xb = ops.fanout(x, 2)
-        y = ops.rowcol_mean(xa)                                   # (N, H+W, C)
+        y, xb = ops.coordatt_pool(x)                              # (N, H+W, C) descriptors + pass-through of x
         # conv1 + bn1 + h_swish over the N*(H+W) descriptors, as a (N, H+W, 1, C) image
         y = ops.conv_bn_act(y.view(N, H + W, 1, C), self.conv1, self.bn1, ACT_HSWISH, self.training)
         mip = y.shape[-1]

@@ -68,6 +68,7 @@ class GradArena:
         dev = self.params[0].device
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
         self.total = total
+        self.prezeroed = False     # Trainer zeroes the whole arena once per step (one memset) and sets this
 
     def view(self, p: torch.nn.Parameter) -> Optional[torch.Tensor]:
         ent = self.offsets.get(id(p))
@@ -90,7 +91,7 @@ def _grad_buf(param, shape, device, zero=False) -> torch.Tensor:
     if _ARENA is not None and param is not None:
         v = _ARENA.view(param)
         if v is not None:
-            if zero:
+            if zero and not _ARENA.prezeroed:
                 v.zero_()
             return v.view(shape)
     return (torch.zeros if zero else torch.empty)(shape, dtype=torch.float32, device=device)
@@ -153,12 +154,112 @@ def _dense(kind, flops, fn):
 # ---------------------------------------------------------------------------------------------
 # dense helpers
 # ---------------------------------------------------------------------------------------------
-def pack_weight(w: torch.Tensor, dtype: torch.dtype, transpose_flip: bool = False) -> torch.Tensor:
+class StepCache:
+    """Record / replay of a training step's weight packs and wgrad workspaces (used by train.Trainer).
+
+    The first step records which (weight, orientation) packs and which wgrad workspaces the model asks for; from the second
+    step on ONE stc_pack_conv_weights_batched launch refreshes every packed copy right after the optimizer step and ONE memset
+    zeroes all wgrad workspaces, instead of ~200 small pack launches and ~100 fills per step."""
+
+    def __init__(self):
+        self.mode = "off"            # off | record | replay
+        self.packs = {}              # key -> (dst_off, shape)
+        self.order = []              # keys in first-use order
+        self.ws_sizes, self.ws_cursor = [], 0
+        self.arena = self.table = self.prefix = self.ws_arena = None
+        self.dtype = None
+        self.total = 0
+
+    def begin_step(self):
+        if self.mode == "off":
+            self.mode = "record"
+        elif self.mode == "record":
+            self._finalize()
+            self.mode = "replay"
+        if self.mode == "replay":
+            lib.call("stc_pack_conv_weights_batched", self.table, self.prefix, len(self.order), self.arena, self.total,
+                     dtype_code(self.dtype), stream_ptr())
+            self.ws_arena.zero_()
+            self.ws_cursor = 0
+
+    def _finalize(self):
+        rows, prefix, off = [], [0], 0
+        dev = None
+        for key in self.order:
+            ptr, shape, mode, dt, inner_pad, n, dev = self.packs[key]
+            Cout, Cin, R, S = shape
+            rows.append([ptr, off, Cout, Cin, R, S, inner_pad, mode])
+            self.packs[key] = (off, n)
+            off += (n + 7) // 8 * 8            # keep every packed tensor 16-byte aligned (TMA base alignment)
+            prefix.append(prefix[-1] + n)
+            self.dtype = dt
+        self.total = prefix[-1]
+        # dst offsets are padded, the work index space (prefix) is dense
+        self.arena = torch.empty(max(off, 8), dtype=self.dtype, device=dev)
+        self.table = torch.tensor(rows, dtype=torch.int64, device=dev)
+        self.prefix = torch.tensor(prefix, dtype=torch.int64, device=dev)
+        self.ws_off = [0]
+        for n in self.ws_sizes:
+            self.ws_off.append(self.ws_off[-1] + (n + 3) // 4 * 4)
+        self.ws_arena = torch.empty(max(self.ws_off[-1], 4), dtype=torch.float32, device=dev)
+
+    def pack(self, w, dtype, mode, inner_pad, shape_out):
+        key = (w.data_ptr(), tuple(w.shape), mode, dtype, inner_pad)
+        if self.mode == "replay":
+            ent = self.packs.get(key)
+            if ent is not None:
+                off, n = ent
+                return self.arena[off:off + n].view(shape_out)
+            return None
+        if self.mode == "record" and key not in self.packs:
+            n = 1
+            for d in shape_out:
+                n *= d
+            self.packs[key] = (w.data_ptr(), tuple(w.shape), mode, dtype, inner_pad, n, w.device)
+            self.order.append(key)
+        return None
+
+    def workspace(self, n, device):
+        if self.mode == "replay" and self.ws_cursor < len(self.ws_sizes) and self.ws_sizes[self.ws_cursor] == n:
+            off = self.ws_off[self.ws_cursor]
+            self.ws_cursor += 1
+            return self.ws_arena[off:off + n]
+        if self.mode == "record":
+            self.ws_sizes.append(n)
+        return torch.zeros(n, dtype=torch.float32, device=device)
+
+
+_STEP_CACHE: Optional[StepCache] = None
+
+
+def set_step_cache(c: Optional[StepCache]):
+    global _STEP_CACHE
+    _STEP_CACHE = c
+
+
+def pack_weight(w: torch.Tensor, dtype: torch.dtype, transpose_flip: bool = False, im2col_pad: int = 0) -> torch.Tensor:
+    """Conv2d.weight (Cout,Cin,R,S) fp32 -> packed `dtype` operand: [R*S][Cout][Cin] (fprop), [R*S][Cin][Cout] with flipped
+    taps (dgrad, transpose_flip) or [1][Cout][im2col_pad] with k = tap*Cin + ci (im2col)."""
     Cout, Cin, R, S = w.shape
-    inner, outer = (Cout, Cin) if transpose_flip else (Cin, Cout)
-    out = torch.empty((R * S, outer, inner), dtype=dtype, device=w.device)
-    lib.call("stc_pack_conv_weight", w, out, Cout, Cin, R, S, inner, int(transpose_flip), dtype_code(dtype), stream_ptr())
+    if im2col_pad:
+        mode, inner, shape_out = 2, im2col_pad, (1, Cout, im2col_pad)
+    else:
+        mode = int(transpose_flip)
+        inner, outer = (Cout, Cin) if transpose_flip else (Cin, Cout)
+        shape_out = (R * S, outer, inner)
+    if _STEP_CACHE is not None:
+        hit = _STEP_CACHE.pack(w, dtype, mode, inner, shape_out)
+        if hit is not None:
+            return hit
+    out = torch.empty(shape_out, dtype=dtype, device=w.device)
+    lib.call("stc_pack_conv_weight", w, out, Cout, Cin, R, S, inner, mode, dtype_code(dtype), stream_ptr())
     return out
+
+
+def _wgrad_ws(n, device):
+    if _STEP_CACHE is not None:
+        return _STEP_CACHE.workspace(n, device)
+    return torch.zeros(n, dtype=torch.float32, device=device)
 
 
 def conv_fprop(x, wp, bias, residual, Cout: int, R: int, S: int, act: int = 0) -> torch.Tensor:
@@ -173,7 +274,7 @@ def conv_fprop(x, wp, bias, residual, Cout: int, R: int, S: int, act: int = 0) -
 def conv_wgrad(x, dy, R: int, S: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     N, H, W, Cin = x.shape
     Cout = dy.shape[-1]
-    ws = torch.zeros(R * S * Cin * Cout, dtype=torch.float32, device=x.device)
+    ws = _wgrad_ws(R * S * Cin * Cout, x.device)
     _dense("conv_wgrad", 2.0 * N * H * W * Cin * Cout * R * S,
            lambda: lib.call("stc_conv_wgrad", x, dy, ws, N, H, W, Cin, Cout, R, S, dtype_code(x.dtype), config.engine, stream_ptr()))
     if out is None:
@@ -213,12 +314,18 @@ class _Fanout(Function):
 
     @staticmethod
     def backward(ctx, *grads):
-        acc = None
-        for g in grads:
-            if g is None:
-                continue
-            g = _chk(g)
-            acc = g if acc is None else add(acc, g)
+        gs = [_chk(g) for g in grads if g is not None]
+        if not gs:
+            return None, None
+        acc = gs[0]
+        i = 1
+        while i < len(gs):  # up to three more addends per pass
+            grp = gs[i:i + 3]
+            out = torch.empty_like(acc)
+            lib.call("stc_add_n", acc, grp[0], grp[1] if len(grp) > 1 else None, grp[2] if len(grp) > 2 else None, out,
+                     acc.numel(), dtype_code(acc.dtype), stream_ptr())
+            acc = out
+            i += 3
         return acc, None
 
 
@@ -304,8 +411,7 @@ class _ConvBnAct(Function):
         ctx.im2col = _use_im2col(x, weight)
         if ctx.im2col:
             x = _im2col(x, R, S)          # (N,H,W,64): saved instead of the 3-channel image for the wgrad GEMM
-            wp = torch.empty((1, Cout, 64), dtype=x.dtype, device=x.device)
-            lib.call("stc_pack_conv_weight", weight, wp, Cout, Cin, R, S, 64, 2, dtype_code(x.dtype), stream_ptr())
+            wp = pack_weight(weight, x.dtype, im2col_pad=64)
             y = conv_fprop(x, wp, bias, None, Cout, 1, 1)
         else:
             wp = pack_weight(weight, x.dtype)
@@ -337,7 +443,7 @@ class _ConvBnAct(Function):
         if ctx.im2col:
             if ctx.needs_input_grad[0]:
                 raise RuntimeError("im2col conv path does not provide an input gradient (it is only used for the image conv)")
-            ws = torch.zeros(64 * Cout, dtype=torch.float32, device=dy.device)
+            ws = _wgrad_ws(64 * Cout, dy.device)
             _dense("conv_wgrad", 2.0 * P * 64 * Cout,
                    lambda: lib.call("stc_conv_wgrad", x, dy, ws, N, H, W, 64, Cout, 1, 1, dtype_code(x.dtype), config.engine, stream_ptr()))
             dw = _grad_buf(pw, weight.shape, dy.device)
@@ -472,6 +578,37 @@ def upcat(skip, low, align_corners=True):
 # ---------------------------------------------------------------------------------------------
 # CoordAtt: pooled descriptors and the additive attention map
 # ---------------------------------------------------------------------------------------------
+class _CoordAttPool(Function):
+    """x -> (y, x_alias): y = row/col means (N,H+W,C); x_alias is x itself, to be consumed by coordatt_apply.  Having both
+    consumers of x behind ONE node lets backward form dx = d(x_alias) + dy_h/W + dy_w/H in a single pass."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _chk(x)
+        N, H, W, C = x.shape
+        y = torch.empty((N, H + W, C), dtype=x.dtype, device=x.device)
+        lib.call("stc_rowcol_mean", x, y, N, H, W, C, dtype_code(x.dtype), stream_ptr())
+        ctx.shape = (N, H, W, C)
+        return y, x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dy, dxa):
+        N, H, W, C = ctx.shape
+        if dy is None:
+            return dxa
+        dy = _chk(dy)
+        if dxa is None:
+            dxa = torch.zeros((N, H, W, C), dtype=dy.dtype, device=dy.device)
+        dxa = _chk(dxa)
+        dx = torch.empty_like(dxa)
+        lib.call("stc_coordatt_dx", dxa, dy, dx, N, H, W, C, dtype_code(dy.dtype), stream_ptr())
+        return dx
+
+
+def coordatt_pool(x):
+    return _CoordAttPool.apply(x)
+
+
 class _RowColMean(Function):
     """(N,H,W,C) -> (N,H+W,C): rows 0..H-1 = mean over W, rows H.. = mean over H.  Its backward is folded
     into _CoordAttApply (which owns the only other use of x), so this node returns no grad for x."""

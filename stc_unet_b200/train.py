@@ -149,12 +149,17 @@ class Trainer:
         self.arena = ops.GradArena(self.flat.params)
         self.reducer = GradReducer(self.arena, bucket_mb)
         self.optim = FusedAdam(self.flat, self.arena, lr=lr, betas=betas)
+        self.cache = ops.StepCache()
 
     def step(self, img: torch.Tensor, gt_semantic_seg: torch.Tensor):
         """One training iteration; returns the (device) log-var tensors, no host sync."""
         ops.set_grad_arena(self.arena)
+        ops.set_step_cache(self.cache)
         try:
             self.optim.zero_grad()
+            self.arena.flat.zero_()          # one memset: kernels that accumulate (+=) into their gradient need zeros
+            self.arena.prezeroed = True
+            self.cache.begin_step()          # one batched weight-pack launch + one workspace memset (from step 2 on)
             self.reducer.reset()
             out = self.model.train_step(dict(img=img, img_metas=None, gt_semantic_seg=gt_semantic_seg))
             out["loss"].backward()
@@ -162,4 +167,6 @@ class Trainer:
             self.optim.step()
         finally:
             ops.set_grad_arena(None)
+            ops.set_step_cache(None)
+            self.arena.prezeroed = False
         return out["log_vars"]
