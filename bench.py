@@ -266,18 +266,34 @@ def main():
         summ = prof.summary()
         ops.set_profiler(None)
         step_ms_prof = t0.elapsed_time(t1) / psteps
-        tc = [(k, v) for k, v in summ.items() if k[1] == S._lib.ENGINE_TCGEN05]
-        tc_flops = sum(v["flops"] for _, v in tc)
-        tc_ms = sum(v["ms"] for _, v in tc)
-        tc_launches = sum(v["launches"] for _, v in tc)
-        if tc_ms > 0:
-            achieved = tc_flops / (tc_ms * 1e-3) / 1e12
-            roofline = dict(bound="tensor", kernel="stc::umma_kernel (tcgen05 implicit GEMM: conv fprop/dgrad/wgrad, linear, attention GEMMs)",
-                            achieved=achieved, peak=peaks["tflops_sustained"], unit="TFLOP/s", frac=achieved / peaks["tflops_sustained"],
-                            peak_source=f"{peaks['source']} (sustained cuBLAS bf16; kernel timed inside a long step)", traffic=None,
-                            launches_per_step=tc_launches // psteps, avg_launch_ms=tc_ms / max(tc_launches, 1),
-                            algorithmic_tflop_per_step=tc_flops / psteps / 1e12, share_of_step=tc_ms / psteps / step_ms_prof)
-        breakdown = {f"{k[0]}:{'tcgen05' if k[1] == S._lib.ENGINE_TCGEN05 else 'simt'}":
+        KNAME = {1: "simt", 2: "stc::umma_kernel", 3: "stc::umma_convh_kernel", 4: "stc::umma_wgradh_kernel"}
+        per_kernel = {}
+        for (kind, eng), v in summ.items():
+            d = per_kernel.setdefault(eng, dict(launches=0, flops=0.0, ms=0.0))
+            for f in d:
+                d[f] += v[f]
+        tensor = {e: v for e, v in per_kernel.items() if e >= 2}
+        tc_ms = sum(v["ms"] for v in tensor.values())
+        if tensor:
+            dom = max(tensor, key=lambda e: tensor[e]["ms"])     # the dominant kernel of the step
+            dv = tensor[dom]
+            achieved = dv["flops"] / (dv["ms"] * 1e-3) / 1e12
+            all_achieved = sum(v["flops"] for v in tensor.values()) / (tc_ms * 1e-3) / 1e12
+            # dram bytes per launch from the committed `ncu --set full` capture of this kernel (profiles/), if one exists
+            traffic = None
+            tp = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+            if os.path.exists(tp):
+                traffic = json.load(open(tp)).get(KNAME[dom])
+            roofline = dict(bound="tensor", kernel=KNAME[dom], achieved=achieved, peak=peaks["tflops_sustained"], unit="TFLOP/s",
+                            frac=achieved / peaks["tflops_sustained"],
+                            peak_source=f"{peaks['source']} (sustained cuBLAS bf16; kernel timed inside a long step)", traffic=traffic,
+                            launches_per_step=dv["launches"] // psteps, avg_launch_ms=dv["ms"] / max(dv["launches"], 1),
+                            algorithmic_tflop_per_step=dv["flops"] / psteps / 1e12, share_of_step=dv["ms"] / psteps / step_ms_prof,
+                            all_tcgen05_kernels=dict(achieved=all_achieved, frac=all_achieved / peaks["tflops_sustained"],
+                                                     share_of_step=tc_ms / psteps / step_ms_prof,
+                                                     per_kernel={KNAME[e]: dict(launches=v["launches"] // psteps, ms=v["ms"] / psteps,
+                                                                                tflops=v["flops"] / (v["ms"] * 1e-3) / 1e12) for e, v in tensor.items()}))
+        breakdown = {f"{k[0]}:{KNAME.get(k[1], k[1])}":
                      dict(launches=v["launches"] // psteps, ms=v["ms"] / psteps, tflops=(v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 else 0.0)
                      for k, v in summ.items()}
 

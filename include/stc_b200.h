@@ -101,8 +101,11 @@ typedef struct {
     float alpha, beta;
 } stc_gemm_desc;
 int stc_gemm(const void* A, const void* B, void* C, const stc_gemm_desc* d, int dtype, int engine, void* stream);
-/* STC_ENGINE_SIMT or STC_ENGINE_TCGEN05: the engine the last stc_conv_fprop / stc_conv_wgrad / stc_gemm call on this
- * thread actually ran (bench.py attributes FLOPs and launch counts with it). */
+/* Which kernel the last stc_conv_fprop / stc_conv_wgrad / stc_gemm call on this thread actually launched (bench.py attributes
+ * FLOPs and launch counts with it): STC_ENGINE_SIMT, STC_ENGINE_TCGEN05 (stc::umma_kernel), STC_KERNEL_CONVH
+ * (stc::umma_convh_kernel) or STC_KERNEL_WGRADH (stc::umma_wgradh_kernel). */
+#define STC_KERNEL_CONVH 3
+#define STC_KERNEL_WGRADH 4
 int stc_dense_last_engine(void);
 
 /* row softmax over the last dim: P = softmax(scale * S) ; rows x L (MHA, L = H*W tokens). */

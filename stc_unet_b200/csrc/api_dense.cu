@@ -32,7 +32,7 @@ extern "C" int stc_conv_fprop(const void* x, const void* wp, const float* bias, 
     cudaStream_t st = (cudaStream_t)stream;
     bool elig = conv_umma_eligible(Cin, Cout, dtype);
     if (engine != STC_ENGINE_SIMT && elig && conv_convh_eligible(W, Cin, Cout, R, S, dtype)) {
-        g_last_engine = STC_ENGINE_TCGEN05;  // halo-reuse variant of the tcgen05 engine
+        g_last_engine = STC_KERNEL_CONVH;  // halo-reuse variant of the tcgen05 engine
         return conv_fprop_convh(x, wp, bias, residual, y, N, H, W, Cin, Cout, R, S, act, st);
     }
     if (engine == STC_ENGINE_TCGEN05) {
@@ -54,7 +54,7 @@ extern "C" int stc_conv_wgrad(const void* x, const void* dy, float* dw_ws, int N
     cudaStream_t st = (cudaStream_t)stream;
     bool elig = dtype == STC_BF16 && Cin % 64 == 0 && Cout % 64 == 0;
     if (engine != STC_ENGINE_SIMT && elig && conv_wgradh_eligible(W, Cin, Cout, R, S, dtype)) {
-        g_last_engine = STC_ENGINE_TCGEN05;  // halo-reuse variant
+        g_last_engine = STC_KERNEL_WGRADH;  // halo-reuse variant
         return conv_wgrad_wgradh(x, dy, dw_ws, N, H, W, Cin, Cout, R, S, st);
     }
     if (engine == STC_ENGINE_TCGEN05) {
