@@ -153,6 +153,11 @@ int stc_upcat_fwd(const void* skip, const void* low, void* out, int N, int H, in
 int stc_upcat_bwd(const void* dout, void* dskip, void* dlow, int N, int H, int W, int Cs, int h, int w, int Cu,
                   int align_corners, int dtype, void* stream);
 
+/* torch.cat([a, b], dim=1) on NHWC rows (UpConvBlock.forward, mmseg/models/utils/up_conv_block.py:99; FCNHead concat_input,
+ * fcn_head.py:81) and its adjoint (a or b may be NULL to drop that half). */
+int stc_concat_channels(const void* a, const void* b, void* out, long long P, int Ca, int Cb, int dtype, void* stream);
+int stc_split_channels(const void* cat, void* a, void* b, long long P, int Ca, int Cb, int dtype, void* stream);
+
 /* ---------------------------------------------------------------- CoordAtt (K10; unet_head.py:131-146,57) */
 /* y[n, 0:H, c] = mean_w x ; y[n, H:H+W, c] = mean_h x  ; y is (N, H+W, C) */
 int stc_rowcol_mean(const void* x, void* y, int N, int H, int W, int C, int dtype, void* stream);

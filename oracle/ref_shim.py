@@ -86,6 +86,36 @@ def _identity_decorator_factory(*_a, **_k):
     return deco
 
 
+class _RefConvModule(nn.Module):
+    """Restatement of mmcv.cnn.ConvModule (mmcv-full 1.7.0, not in this image; semantics from its documented behaviour:
+    order conv -> norm -> act, bias='auto' => no conv bias when a norm layer follows, children named conv / bn / activate,
+    ReLU inplace).  Call sites: unet.py:66-75,199-208; up_conv_block.py:84-93; fcn_head.py:45-65.  Not pinned by any numeric
+    test of the reference."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias="auto",
+                 conv_cfg=None, norm_cfg=None, act_cfg=dict(type="ReLU"), inplace=True, **_):
+        super().__init__()
+        self.with_norm = norm_cfg is not None
+        self.with_activation = act_cfg is not None
+        if bias == "auto":
+            bias = not self.with_norm
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride=stride, padding=padding, dilation=dilation,
+                              groups=groups, bias=bias)
+        if self.with_norm:
+            self.bn = nn.SyncBatchNorm(out_channels) if norm_cfg.get("type") == "SyncBN" else nn.BatchNorm2d(out_channels)
+        if self.with_activation:
+            assert act_cfg.get("type") == "ReLU"
+            self.activate = nn.ReLU(inplace=inplace)
+
+    def forward(self, x):
+        x = self.conv(x)
+        if self.with_norm:
+            x = self.bn(x)
+        if self.with_activation:
+            x = self.activate(x)
+        return x
+
+
 def _mod(name):
     m = types.ModuleType(name)
     m.__path__ = []  # behave like a package
@@ -125,7 +155,18 @@ def load_reference():
     mmcv.is_list_of = lambda seq, t: isinstance(seq, list) and all(isinstance(s, t) for s in seq)
     cnn = _mod("mmcv.cnn")
     cnn.MODELS = R
-    cnn.ConvModule = None  # family B only; not needed for the files loaded here
+    cnn.ConvModule = _RefConvModule
+    cnn.UPSAMPLE_LAYERS = _Registry("upsample")
+    cnn.build_activation_layer = lambda cfg: nn.ReLU(inplace=cfg.get("inplace", False))
+    cnn.build_norm_layer = lambda cfg, n, postfix="": ("bn" + str(postfix), nn.BatchNorm2d(n))
+
+    def _build_upsample_layer(cfg, *args, **kwargs):
+        cfg = dict(cfg)
+        typ = cfg.pop("type")
+        if typ == "deconv":
+            return nn.ConvTranspose2d(*args, **kwargs, **cfg)
+        return cnn.UPSAMPLE_LAYERS.module_dict[typ](*args, **kwargs, **cfg)
+    cnn.build_upsample_layer = _build_upsample_layer
     bricks = _mod("mmcv.cnn.bricks")
     reg = _mod("mmcv.cnn.bricks.registry")
     reg.NORM_LAYERS = _Registry("norm")
@@ -182,6 +223,11 @@ def load_reference():
     dh = _load("mmseg.models.decode_heads.decode_head", "mmseg/models/decode_heads/decode_head.py")
     uh = _load("mmseg.models.decode_heads.unet_head", "mmseg/models/decode_heads/unet_head.py")
     ub = _load("mmseg.models.backbones.unet_backbone", "mmseg/models/backbones/unet_backbone.py")
+    mutils = _mod("mmseg.models.utils")
+    ucb = _load("mmseg.models.utils.up_conv_block", "mmseg/models/utils/up_conv_block.py")
+    mutils.UpConvBlock = ucb.UpConvBlock
+    unet_b = _load("mmseg.models.backbones.unet", "mmseg/models/backbones/unet.py")
+    fcn = _load("mmseg.models.decode_heads.fcn_head", "mmseg/models/decode_heads/fcn_head.py")
     _mod("mmseg.core.evaluation")
     met = _load("mmseg.core.evaluation.metrics", "mmseg/core/evaluation/metrics.py")
 
@@ -191,7 +237,8 @@ def load_reference():
         DiceLoss=dl.DiceLoss, accuracy=acc.accuracy, resize=w.resize,
         intersect_and_union=met.intersect_and_union, backbone_mod=ub, head_mod=uh,
         KernelSelectAttention=ub.KernelSelectAttention, TransformerBlock=ub.TransformerBlock,
-        CoordAtt=uh.CoordAtt, metrics_mod=met)
+        CoordAtt=uh.CoordAtt, metrics_mod=met, UNet=unet_b.UNet, FCNHead=fcn.FCNHead, BasicConvBlock=unet_b.BasicConvBlock,
+        InterpConv=unet_b.InterpConv, UpConvBlock=ucb.UpConvBlock)
     _LOADED["ns"] = ns
     return ns
 
@@ -238,3 +285,19 @@ def build_reference_model(stc: bool, num_classes: int, dropout_ratio: float = 0.
     bb.init_weights()
     hd.init_weights()
     return revert_sync_batchnorm(bb), revert_sync_batchnorm(hd)
+
+
+def build_reference_model_b(num_classes: int, dropout_ratio: float = 0.0, seed: int = 0, base_channels: int = 64, num_stages: int = 5):
+    """(UNet, FCNHead) as configs/_base_/models/fcn_unet_s5-d16.py:3-34 builds them (BN instead of SyncBN, torch default init:
+    mmcv's Kaiming init_cfg is not restated — parity tests share the state_dict instead)."""
+    ns = load_reference()
+    torch.manual_seed(seed)
+    norm_cfg = dict(type="BN", requires_grad=True)
+    bb = ns.UNet(in_channels=3, base_channels=base_channels, num_stages=num_stages, strides=(1,) * num_stages,
+                 enc_num_convs=(2,) * num_stages, dec_num_convs=(2,) * (num_stages - 1), downsamples=(True,) * (num_stages - 1),
+                 enc_dilations=(1,) * num_stages, dec_dilations=(1,) * (num_stages - 1), with_cp=False, conv_cfg=None,
+                 norm_cfg=norm_cfg, act_cfg=dict(type="ReLU"), upsample_cfg=dict(type="InterpConv"), norm_eval=False)
+    hd = ns.FCNHead(in_channels=base_channels, in_index=num_stages - 1, channels=base_channels, num_convs=1, concat_input=False,
+                    dropout_ratio=dropout_ratio, num_classes=num_classes, norm_cfg=norm_cfg, align_corners=False,
+                    loss_decode=dict(type="CrossEntropyLoss", use_sigmoid=False, loss_weight=1.0))
+    return bb, hd

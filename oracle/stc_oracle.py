@@ -301,3 +301,57 @@ def metrics_from_confusion(cm: np.ndarray, beta: float = 1.0) -> Dict[str, np.nd
                "Dice": 2 * tp / (row + col), "Precision": prec, "Recall": rec,
                "Fscore": (1 + beta ** 2) * prec * rec / (beta ** 2 * prec + rec)}
     return out
+
+
+# --------------------------------------------------------------------------
+# family B: mmseg UNet (backbones/unet.py) + FCNHead (decode_heads/fcn_head.py)
+# --------------------------------------------------------------------------
+def conv_module(sd: SD, p: str, x, train, ns, k: int):
+    """mmcv ConvModule: conv (no bias when a norm follows) -> BN -> ReLU (unet.py:66-75)."""
+    x = F.conv2d(x, sd[p + ".conv.weight"], sd.get(p + ".conv.bias"), padding=k // 2)
+    if p + ".bn.weight" in sd:
+        x = batch_norm(sd, p + ".bn", x, train, ns)
+    return torch.relu(x)
+
+
+def basic_conv_block(sd: SD, p: str, x, train, ns):
+    i = 0
+    while f"{p}.convs.{i}.conv.weight" in sd:
+        x = conv_module(sd, f"{p}.convs.{i}", x, train, ns, 3)
+        i += 1
+    return x
+
+
+def unet_b_forward(sd: SD, x, train: bool = True, new_stats: Optional[dict] = None) -> List[torch.Tensor]:
+    """UNet.forward (unet.py:404-415) for strides all 1 / MaxPool downsampling / InterpConv upsampling:
+    encoder stage i = [MaxPool2d(2)] + BasicConvBlock; decoder i = UpConvBlock(skip=enc_i, x): InterpConv (bilinear x2,
+    align_corners=False, then 1x1 ConvModule) -> cat[skip, x] -> BasicConvBlock (up_conv_block.py:95-102)."""
+    enc = []
+    i = 0
+    while any(k.startswith(f"encoder.{i}.") for k in sd):
+        if i > 0:
+            x = F.max_pool2d(x, 2)
+        blk = f"encoder.{i}.{1 if i > 0 else 0}"
+        x = basic_conv_block(sd, blk, x, train, new_stats)
+        enc.append(x)
+        i += 1
+    outs = [x]
+    for j in reversed(range(len(enc) - 1)):
+        up = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
+        up = conv_module(sd, f"decoder.{j}.upsample.interp_upsample.1", up, train, new_stats, 1)
+        x = basic_conv_block(sd, f"decoder.{j}.conv_block", torch.cat([enc[j], up], dim=1), train, new_stats)
+        outs.append(x)
+    return outs
+
+
+def fcn_head_forward(sd: SD, feats: List[torch.Tensor], in_index: int, train: bool = True, new_stats: Optional[dict] = None):
+    """FCNHead.forward (fcn_head.py:67-88) with num_convs ConvModules, optional concat_input, then cls_seg (no dropout)."""
+    x = feats[in_index]
+    f = x
+    i = 0
+    while f"convs.{i}.conv.weight" in sd:
+        f = conv_module(sd, f"convs.{i}", f, train, new_stats, sd[f"convs.{i}.conv.weight"].shape[-1])
+        i += 1
+    if "conv_cat.conv.weight" in sd:
+        f = conv_module(sd, "conv_cat", torch.cat([x, f], dim=1), train, new_stats, sd["conv_cat.conv.weight"].shape[-1])
+    return F.conv2d(f, sd["conv_seg.weight"], sd["conv_seg.bias"])

@@ -487,3 +487,43 @@ extern "C" int stc_pack_conv_weights_batched(const int64_t* table, const int64_t
                                                                                             n, (T*)dst, total)));
     return check_launch("pack_conv_weights_batched");
 }
+
+// ------------------------------------------------------------------------------------
+// channel concat / split on NHWC rows: out[p] = [a[p] (Ca) | b[p] (Cb)]   (UpConvBlock.forward's torch.cat, up_conv_block.py:99)
+// ------------------------------------------------------------------------------------
+template <typename T, bool SPLIT>
+__global__ void concat_channels_kernel(T* __restrict__ a, T* __restrict__ b, T* __restrict__ cat, int Ca, int Cb, long long total) {
+    const int la = Ca >> 3, lt = (Ca + Cb) >> 3;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        int lv = (int)(i % lt);
+        long long p = i / lt;
+        T* side = lv < la ? a + p * Ca + lv * 8 : b + p * Cb + (lv - la) * 8;
+        Vec8<T> v;
+        if (SPLIT) {
+            if ((lv < la && a) || (lv >= la && b)) { v.load(cat + i * 8); v.store(side); }
+        } else {
+            v.load(side);
+            v.store(cat + i * 8);
+        }
+    }
+}
+
+extern "C" int stc_concat_channels(const void* a, const void* b, void* out, long long P, int Ca, int Cb, int dtype, void* stream) {
+    STC_REQUIRE(Ca % 8 == 0 && Cb % 8 == 0, "concat_channels: channel counts must be multiples of 8");
+    long long total = P * ((Ca + Cb) / 8);
+    if (total <= 0) return STC_OK;
+    int blocks = (int)min((long long)num_sms() * 8, (long long)ceil_div(total, 256));
+    STC_DISPATCH_DTYPE(dtype, (concat_channels_kernel<T, false><<<blocks, 256, 0, (cudaStream_t)stream>>>((T*)a, (T*)b, (T*)out, Ca, Cb, total)));
+    return check_launch("concat_channels");
+}
+
+extern "C" int stc_split_channels(const void* cat, void* a, void* b, long long P, int Ca, int Cb, int dtype, void* stream) {
+    STC_REQUIRE(Ca % 8 == 0 && Cb % 8 == 0, "split_channels: channel counts must be multiples of 8");
+    long long total = P * ((Ca + Cb) / 8);
+    if (total <= 0) return STC_OK;
+    int blocks = (int)min((long long)num_sms() * 8, (long long)ceil_div(total, 256));
+    STC_DISPATCH_DTYPE(dtype, (concat_channels_kernel<T, true><<<blocks, 256, 0, (cudaStream_t)stream>>>((T*)a, (T*)b, (T*)cat, Ca, Cb, total)));
+    return check_launch("split_channels");
+}

@@ -1018,3 +1018,54 @@ class _Scale(Function):
 
 def scale(x, alpha):
     return x if float(alpha) == 1.0 else _Scale.apply(x, alpha)
+
+
+# ---------------------------------------------------------------------------------------------
+# family B helpers: stand-alone bilinear x2 (InterpConv) and channel concat (UpConvBlock)
+# ---------------------------------------------------------------------------------------------
+class _Upsample2x(Function):
+    @staticmethod
+    def forward(ctx, low, align_corners: bool):
+        low = _chk(low)
+        N, h, w, C = low.shape
+        out = torch.empty((N, 2 * h, 2 * w, C), dtype=low.dtype, device=low.device)
+        lib.call("stc_upcat_fwd", None, low, out, N, 2 * h, 2 * w, 0, h, w, C, int(align_corners), dtype_code(low.dtype), stream_ptr())
+        ctx.meta = (N, h, w, C, int(align_corners))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        N, h, w, C, ac = ctx.meta
+        dout = _chk(dout)
+        dlow = torch.empty((N, h, w, C), dtype=dout.dtype, device=dout.device)
+        lib.call("stc_upcat_bwd", dout, None, dlow, N, 2 * h, 2 * w, 0, h, w, C, ac, dtype_code(dout.dtype), stream_ptr())
+        return dlow, None
+
+
+def upsample2x(x, align_corners=False):
+    return _Upsample2x.apply(x, align_corners)
+
+
+class _ConcatChannels(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = _chk(a), _chk(b)
+        Ca, Cb = a.shape[-1], b.shape[-1]
+        out = torch.empty((*a.shape[:-1], Ca + Cb), dtype=a.dtype, device=a.device)
+        lib.call("stc_concat_channels", a, b, out, a.numel() // Ca, Ca, Cb, dtype_code(a.dtype), stream_ptr())
+        ctx.meta = (Ca, Cb)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        Ca, Cb = ctx.meta
+        g = _chk(g)
+        P = g.numel() // (Ca + Cb)
+        ga = torch.empty((*g.shape[:-1], Ca), dtype=g.dtype, device=g.device) if ctx.needs_input_grad[0] else None
+        gb = torch.empty((*g.shape[:-1], Cb), dtype=g.dtype, device=g.device) if ctx.needs_input_grad[1] else None
+        lib.call("stc_split_channels", g, ga, gb, P, Ca, Cb, dtype_code(g.dtype), stream_ptr())
+        return ga, gb
+
+
+def concat_channels(a, b):
+    return _ConcatChannels.apply(a, b)

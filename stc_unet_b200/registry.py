@@ -14,7 +14,18 @@ import os
 
 import torch.nn as nn
 
-HAVE_MMSEG = importlib.util.find_spec("mmcv") is not None and importlib.util.find_spec("mmseg") is not None
+def _have(name: str) -> bool:
+    import sys
+    mod = sys.modules.get(name)
+    if mod is not None:   # already imported: real package unless it is the oracle's import stub
+        return not getattr(sys.modules.get("mmcv"), "_stc_stub", False) and getattr(mod, "__spec__", None) is not None
+    try:
+        return importlib.util.find_spec(name) is not None
+    except (ValueError, ImportError):
+        return False
+
+
+HAVE_MMSEG = _have("mmcv") and _have("mmseg")
 
 
 class _LocalRegistry:

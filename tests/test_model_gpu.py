@@ -272,3 +272,39 @@ def test_trainer_step_matches_plain_backward(dtype):
         # two runs of the SAME path differ by a few percent in the deep gradients, so only the bulk is compared
         assert statistics.median(errs) <= 0.1
     assert abs(float(lv["loss"]) - float(losses["loss_bce"] + losses["loss_dice"])) < 1e-3
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_family_b_unet_fcn_parity(dtype):
+    """mmseg UNet + FCNHead (family B): InterpConv (bilinear align_corners=False + 1x1 ConvModule), channel concat, bias-free
+    ConvModules, CE-only loss — against the fp64 oracle."""
+    from oracle import stc_oracle as O
+    from tests.test_oracle import build_ours_b
+    bb, hd = build_ours_b(3, base=64, stages=4, dtype=dtype)
+    bb.init_weights(); hd.init_weights()
+    bb, hd = bb.cuda(), hd.cuda()
+    img, gt = inputs(2, 3, 64, 64)
+    conv = lambda v: v.detach().double() if v.is_floating_point() else v.detach().clone()
+    bsd = {k: conv(v).requires_grad_(v.is_floating_point() and "running" not in k) for k, v in bb.state_dict().items()}
+    hsd = {k: conv(v).requires_grad_(v.is_floating_point() and "running" not in k) for k, v in hd.state_dict().items()}
+    ref_logits = O.fcn_head_forward(hsd, O.unet_b_forward(bsd, img.double(), True, None), 3, True, None)
+    ref = O.losses(ref_logits, gt)
+    ref["loss_bce"].backward()
+    feats = bb(img)
+    assert [tuple(f.shape) for f in feats] == [(2, 512, 8, 8), (2, 256, 16, 16), (2, 128, 32, 32), (2, 64, 64, 64)]
+    losses = hd.forward_train(feats, None, gt, None)
+    assert set(losses) == {"loss_ce", "acc_seg"}
+    losses["loss_ce"].backward()
+    tol = 1e-4 if dtype == "fp32" else 3e-2
+    assert abs(float(losses["loss_ce"]) - float(ref["loss_bce"])) <= tol
+    errs = []
+    for mod, sd in ((bb, bsd), (hd, hsd)):
+        for name, p in mod.named_parameters():
+            assert p.grad is not None, name
+            errs.append(rel_l2(p.grad, sd[name].grad))
+    assert statistics.median(errs) <= (2e-2 if dtype == "fp32" else 0.6)   # random-init decision flips, see module docstring
+    with torch.no_grad():
+        b2, h2 = build_ours_b(3, base=64, stages=4, dtype=dtype)
+        b2.init_weights(); h2.init_weights()
+        out = h2.cuda()(b2.cuda()(img))
+    assert rel_l2(out, ref_logits) <= (1e-4 if dtype == "fp32" else 6e-2)

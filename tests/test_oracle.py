@@ -168,3 +168,54 @@ def test_slide_windows_match_reference_grid():
                 want.append((max(y2 - hc, 0), max(x2 - wc, 0), y2, x2))
         assert O.slide_windows(H, W, crop, stride) == want == S.slide_windows(H, W, crop, stride)
     assert len(O.slide_windows(512, 512, (256, 256), (170, 170))) == 9
+
+
+def build_ours_b(num_classes, base=16, stages=4, dtype="bf16", seed=0):
+    import stc_unet_b200 as S
+    torch.manual_seed(seed)
+    norm = dict(type="BN", requires_grad=True)
+    bb = S.build_backbone(dict(type="UNet", in_channels=3, base_channels=base, num_stages=stages, strides=(1,) * stages,
+                               enc_num_convs=(2,) * stages, dec_num_convs=(2,) * (stages - 1), downsamples=(True,) * (stages - 1),
+                               enc_dilations=(1,) * stages, dec_dilations=(1,) * (stages - 1), with_cp=False, conv_cfg=None, norm_cfg=norm,
+                               act_cfg=dict(type="ReLU"), upsample_cfg=dict(type="InterpConv"), norm_eval=False, compute_dtype=dtype))
+    hd = S.build_head(dict(type="FCNHead", in_channels=base, in_index=stages - 1, channels=base, num_convs=1, concat_input=False,
+                           dropout_ratio=0.0, num_classes=num_classes, norm_cfg=norm, align_corners=False,
+                           loss_decode=dict(type="CrossEntropyLoss", use_sigmoid=False, loss_weight=1.0)))
+    return bb, hd
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="/root/reference not present (GPU box)")
+def test_family_b_oracle_and_state_dict_match_reference():
+    """mmseg UNet-S5-D16 + FCNHead (configs/_base_/models/fcn_unet_s5-d16.py): our containers have the reference's state_dict,
+    the oracle restatement reproduces the reference modules (ConvModule itself is a restatement: mmcv is not installed),
+    and the output shape table of tests/test_models/test_backbones/test_unet.py holds."""
+    rb, rh = ref_shim.build_reference_model_b(3, base_channels=16, num_stages=4)
+    bb, hd = build_ours_b(3)
+    for ours, ref in ((bb, rb), (hd, rh)):
+        so, sr = ours.state_dict(), ref.state_dict()
+        assert {k: tuple(v.shape) for k, v in so.items()} == {k: tuple(v.shape) for k, v in sr.items()}
+        ours.load_state_dict(sr, strict=True)
+    x = torch.rand(2, 3, 32, 32)
+    y = torch.randint(0, 3, (2, 1, 32, 32))
+    feats = rb(x)
+    assert [tuple(f.shape) for f in feats] == [(2, 128, 4, 4), (2, 64, 8, 8), (2, 32, 16, 16), (2, 16, 32, 32)]
+    l = rh.forward_train(feats, None, y, None)
+    l["loss_ce"].backward()
+    bsd, hsd = as_leaf(rb.state_dict()), as_leaf(rh.state_dict())
+    logits = O.fcn_head_forward(hsd, O.unet_b_forward(bsd, x, True, {}), 3, True, {})
+    out = O.losses(logits, y)
+    out["loss_bce"].backward()
+    assert abs(float(out["loss_bce"]) - float(l["loss_ce"])) < 1e-5
+    for mod, sd in ((rb, bsd), (rh, hsd)):
+        for name, p in mod.named_parameters():
+            if p.grad.norm() > 1e-6:
+                assert rel_l2(sd[name].grad, p.grad) < 2e-2, name
+    # full-size S5-D16 shape table (test_unet.py: strides all 1 on 128x128 -> 1024@8 ... 64@128)
+    b5, _ = ref_shim.build_reference_model_b(2, base_channels=4, num_stages=5)
+    with torch.no_grad():
+        assert [tuple(f.shape) for f in b5(torch.rand(1, 3, 64, 64))] == [(1, 64, 4, 4), (1, 32, 8, 8), (1, 16, 16, 16), (1, 8, 32, 32), (1, 4, 64, 64)]
+    with pytest.raises(AssertionError):
+        b5(torch.rand(1, 3, 65, 65))
+    import stc_unet_b200 as S
+    with pytest.raises(AssertionError):   # same argument validation as unet.py:324-355
+        S.build_backbone(dict(type="UNet", num_stages=5, strides=(1, 1, 1, 1)))
