@@ -307,4 +307,9 @@ def test_family_b_unet_fcn_parity(dtype):
         b2, h2 = build_ours_b(3, base=64, stages=4, dtype=dtype)
         b2.init_weights(); h2.init_weights()
         out = h2.cuda()(b2.cuda()(img))
-    assert rel_l2(out, ref_logits) <= (1e-4 if dtype == "fp32" else 6e-2)
+    if dtype == "fp32":
+        assert rel_l2(out, ref_logits) <= 1e-4
+    else:   # the reference's bf16 path (autocast) as the yardstick
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            ac = O.fcn_head_forward(h2.state_dict(), O.unet_b_forward(b2.state_dict(), img, True, None), 3, True, None).float()
+        assert rel_l2(out, ref_logits) <= max(2e-2, 1.25 * rel_l2(ac, ref_logits))
