@@ -75,3 +75,37 @@ def test_grad_arena_layout_and_bucket_plan():
     assert buckets[0][1] == arena.total and buckets[-1][0] == 0
     assert all(buckets[i][0] == buckets[i + 1][1] for i in range(len(buckets) - 1))
     assert sum(b[2] for b in buckets) == len(ps) and owner[4] == 0 and owner[0] == len(buckets) - 1
+
+
+def test_metrics_from_confusion_follow_reference_definitions():
+    """tests/test_metrics.py:29-85 (legacy_mean_iou / legacy_mean_dice / legacy_mean_fscore from the bincount matrix), incl.
+    nan_to_num; and NOT the fork's inflated values (metrics.py:454-457)."""
+    import numpy as np
+    from oracle import stc_oracle as O
+    from stc_unet_b200.metrics import metrics_from_confusion
+    rng = np.random.RandomState(0)
+    C = 19
+    pred = rng.randint(0, C, size=(10, 30, 30)); label = rng.randint(0, C, size=(10, 30, 30)); label[:, 2, 5:10] = 255
+    label[label == 7] = 3        # an absent class -> NaNs
+    pred[pred == 7] = 3
+    cm = O.confusion_matrix(pred, label, C, 255)
+    tot = cm.astype(np.float32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        all_acc = np.diag(tot).sum() / tot.sum()
+        acc = np.diag(tot) / tot.sum(axis=1)
+        iou = np.diag(tot) / (tot.sum(axis=1) + tot.sum(axis=0) - np.diag(tot))
+        dice = 2 * np.diag(tot) / (tot.sum(axis=1) + tot.sum(axis=0))
+        prec = np.diag(tot) / tot.sum(axis=0)
+        fscore = 2 * prec * acc / (prec + acc)
+    m = metrics_from_confusion(cm, ["mIoU", "mDice", "mFscore"])
+    assert np.allclose(m["aAcc"], all_acc) and np.allclose(m["Acc"], acc, equal_nan=True) and np.allclose(m["IoU"], iou, equal_nan=True)
+    assert np.allclose(m["Dice"], dice, equal_nan=True) and np.allclose(m["Fscore"], fscore, equal_nan=True)
+    assert np.allclose(m["Precision"], prec, equal_nan=True) and np.allclose(m["Recall"], acc, equal_nan=True)
+    assert np.isnan(m["IoU"][7])
+    m2 = metrics_from_confusion(cm, "mIoU", nan_to_num=-1)
+    assert m2["IoU"][7] == -1 and m2["Acc"][7] == -1
+    with pytest.raises(KeyError):
+        metrics_from_confusion(cm, ["unsupported"])
+    # uniformly random 3-class predictions score ~1/3 accuracy (the fork's tampered code reports 0.80 here)
+    p3, l3 = rng.randint(0, 3, 10000), rng.randint(0, 3, 10000)
+    assert abs(metrics_from_confusion(O.confusion_matrix(p3, l3, 3))["aAcc"] - 1 / 3) < 0.03

@@ -313,3 +313,37 @@ def test_family_b_unet_fcn_parity(dtype):
         with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
             ac = O.fcn_head_forward(h2.state_dict(), O.unet_b_forward(b2.state_dict(), img, True, None), 3, True, None).float()
         assert rel_l2(out, ref_logits) <= max(2e-2, 1.25 * rel_l2(ac, ref_logits))
+
+
+def test_slide_inference_config4_512_and_confusion_meter():
+    """BASELINE.json configs[3]: test_cfg mode='slide', crop 256 / stride 170 on 512x512 slices (9 windows per slice, all
+    windows of the batch in one forward), argmax, and the integer confusion matrix — vs the fp64 oracle, bit-exact histogram."""
+    import numpy as np
+    import stc_unet_b200 as S
+    from oracle import stc_oracle as O
+    from stc_unet_b200.metrics import ConfusionMeter
+    bb, hd = build(True, 3, "fp32")
+    seg = S.EncoderDecoder(bb, hd, test_cfg=dict(mode="slide", crop_size=(256, 256), stride=(170, 170))).cuda().eval()
+    g = torch.Generator().manual_seed(21)
+    img = torch.rand(2, 3, 512, 512, generator=g).cuda()
+    label = torch.randint(0, 3, (2, 512, 512), generator=g).to(torch.uint8)
+    label[:, :7] = 255
+    assert len(S.slide_windows(512, 512, (256, 256), (170, 170))) == 9
+    bsd = {k: v.double() if v.is_floating_point() else v for k, v in bb.state_dict().items()}
+    hsd = {k: v.double() if v.is_floating_point() else v for k, v in hd.state_dict().items()}
+    enc = lambda t: O.head_forward(hsd, O.backbone_forward(bsd, t, False, None), False, None)
+    with torch.no_grad():
+        ref_pred = O.simple_test(O.slide_inference(enc, img.double(), 3, (256, 256), (170, 170)))
+    pred = seg.inference_device(img)
+    assert float((pred == ref_pred).float().mean()) >= 0.999
+    meter = ConfusionMeter(3, 255)
+    meter.update(pred[0], label[0].cuda())
+    meter.update(pred[1], label[1].cuda())
+    want = O.confusion_matrix(pred.cpu().numpy(), label.numpy(), 3, 255)
+    assert np.array_equal(meter.cm.cpu().numpy(), want)
+    per_image = [O.intersect_and_union(pred[i].cpu().numpy(), label[i].numpy(), 3, 255) for i in range(2)]
+    for j, a in enumerate(meter.pre_eval_tuple()):
+        assert np.array_equal(a.numpy(), per_image[0][j] + per_image[1][j])
+    res = meter.compute(["mIoU", "mDice"])
+    ref_m = O.metrics_from_confusion(want)
+    assert abs(res["mIoU"] - float(np.nanmean(ref_m["IoU"]))) < 1e-12 and abs(res["aAcc"] - float(ref_m["aAcc"])) < 1e-12
