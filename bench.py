@@ -233,7 +233,7 @@ def main():
     gpu_launches = sum(LAUNCHES.get(n, 1) for n in names)
     ms_per_step = ms_total / args.steps
     value = world * args.batch / (ms_per_step / 1e3)
-    loss_val = float(last["lv"]["loss"])
+    loss_val = float(last["lv"]["loss"].detach())
 
     # ---- end to end: pinned host buffers -> H2D -> step -> D2H of the loss, every step
     e2e = None
@@ -327,5 +327,32 @@ def main():
         dist.destroy_process_group()
 
 
+def _main_with_clean_stdout():
+    """stdout must carry exactly ONE JSON line: everything else that libraries print there (e.g. NCCL's version banner)
+    is diverted to stderr by pointing fd 1 at fd 2 while the benchmark runs."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    lines = []
+    real_print = print
+
+    def capture(*a, **k):
+        if k.get("file") in (None, sys.stdout):
+            lines.append(" ".join(str(x) for x in a))
+        else:
+            real_print(*a, **k)
+    import builtins
+    builtins.print = capture
+    try:
+        main()
+    finally:
+        builtins.print = real_print
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    for ln in lines:
+        real_print(ln, flush=True)
+
+
 if __name__ == "__main__":
-    main()
+    _main_with_clean_stdout()
