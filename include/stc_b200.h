@@ -158,6 +158,14 @@ int stc_upcat_bwd(const void* dout, void* dskip, void* dlow, int N, int H, int W
 int stc_concat_channels(const void* a, const void* b, void* out, long long P, int Ca, int Cb, int dtype, void* stream);
 int stc_split_channels(const void* cat, void* a, void* b, long long P, int Ca, int Cb, int dtype, void* stream);
 
+/* UNet++ DecoderBlock input (segmentation_models_pytorch 0.2.0, used by decode_heads/unetpp_head.py:16): out = cat([in0', in1, .., in4])
+ * along channels, in0' = nearest x2 upsample of in0 when up0 != 0 (in0 is then (N,H/2,W/2,c0)).  Unused inputs: NULL / 0 channels.
+ * The adjoint writes d_k for every non-NULL pointer (2x2 block sums for the upsampled input). */
+int stc_catn_fwd(const void* in0, const void* in1, const void* in2, const void* in3, const void* in4, int c0, int c1, int c2, int c3,
+                 int c4, void* out, int N, int H, int W, int up0, int dtype, void* stream);
+int stc_catn_bwd(const void* dout, void* d0, void* d1, void* d2, void* d3, void* d4, int c0, int c1, int c2, int c3, int c4, int N, int H,
+                 int W, int up0, int dtype, void* stream);
+
 /* ---------------------------------------------------------------- CoordAtt (K10; unet_head.py:131-146,57) */
 /* y[n, 0:H, c] = mean_w x ; y[n, H:H+W, c] = mean_h x  ; y is (N, H+W, C) */
 int stc_rowcol_mean(const void* x, void* y, int N, int H, int W, int C, int dtype, void* stream);

@@ -355,3 +355,48 @@ def fcn_head_forward(sd: SD, feats: List[torch.Tensor], in_index: int, train: bo
     if "conv_cat.conv.weight" in sd:
         f = conv_module(sd, "conv_cat", torch.cat([x, f], dim=1), train, new_stats, sd["conv_cat.conv.weight"].shape[-1])
     return F.conv2d(f, sd["conv_seg.weight"], sd["conv_seg.bias"])
+
+
+# --------------------------------------------------------------------------
+# config 5: UnetPlusPlus head = smp.UnetPlusPlus(encoder_name="vgg16", classes=64) + cls_seg (unetpp_head.py:11-22)
+# PARITY UNPINNED: segmentation_models_pytorch 0.2.0 is not vendored under /root/reference and not installed; this restates its
+# published design (torchvision VGG16 features split at the max-pools; UNet++ nested decoder with nearest x2 up-sampling, dense
+# skip concatenation [x, dense.., feature], two conv3x3(no bias)-BN-ReLU per block, decoder channels (256,128,64,32,16);
+# 3x3 segmentation head).  No reference test covers it; the only anchors are the call site and the channel bookkeeping.
+# --------------------------------------------------------------------------
+_VGG16_CFG = (64, 64, "M", 128, 128, "M", 256, 256, 256, "M", 512, 512, 512, "M", 512, 512, 512, "M")
+
+
+def unetpp_forward(sd: SD, img, train: bool = True, new_stats: Optional[dict] = None):
+    x, feats, idx = img, [], 0
+    for v in _VGG16_CFG:
+        if v == "M":
+            feats.append(x)
+            x = F.max_pool2d(x, 2)
+            idx += 1
+        else:
+            x = torch.relu(F.conv2d(x, sd[f"model.encoder.features.{idx}.weight"], sd[f"model.encoder.features.{idx}.bias"], padding=1))
+            idx += 2
+    feats.append(x)
+    f = feats[1:][::-1]
+
+    def block(name, x, skips):
+        x = F.interpolate(x, scale_factor=2, mode="nearest")
+        if skips:
+            x = torch.cat([x] + skips, dim=1)
+        for c in ("conv1", "conv2"):
+            p = f"model.decoder.blocks.{name}.{c}"
+            x = torch.relu(batch_norm(sd, p + ".1", F.conv2d(x, sd[p + ".0.weight"], None, padding=1), train, new_stats))
+        return x
+    depth, dense = 4, {}
+    for l in range(depth):
+        for d in range(depth - l):
+            if l == 0:
+                dense[f"x_{d}_{d}"] = block(f"x_{d}_{d}", f[d], [f[d + 1]])
+            else:
+                li = d + l
+                cat = [dense[f"x_{i}_{li}"] for i in range(d + 1, li + 1)] + [f[li + 1]]
+                dense[f"x_{d}_{li}"] = block(f"x_{d}_{li}", dense[f"x_{d}_{li - 1}"], cat)
+    y = block(f"x_0_{depth}", dense[f"x_0_{depth - 1}"], [])
+    y = F.conv2d(y, sd["model.segmentation_head.0.weight"], sd["model.segmentation_head.0.bias"], padding=1)
+    return F.conv2d(y, sd["conv_seg.weight"], sd["conv_seg.bias"])

@@ -8,6 +8,7 @@ from . import _lib, ops, registry  # noqa: F401
 from .modules import (BaseDecodeHead, CoordAtt, CrossEntropyLoss, DiceLoss, DoubleConv, Down, InConv,  # noqa: F401
                       KernelSelectAttention, TransformerBlock, TransformerLayer, UnetBackbone, UnetHead, Up)
 from .modules_b import BasicConvBlock, ConvModule, FCNHead, InterpConv, UNet, UpConvBlock  # noqa: F401
+from .modules_pp import EncoderDecoderFull, UnetPlusPlus  # noqa: F401
 from .registry import BACKBONES, HEADS, LOSSES, MODELS, SEGMENTORS, build_backbone, build_head, build_loss, build_segmentor  # noqa: F401
 from .segmentor import EncoderDecoder, slide_windows  # noqa: F401
 

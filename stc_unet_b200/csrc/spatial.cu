@@ -724,3 +724,115 @@ extern "C" int stc_linear_f32_bwd(const float* x, const float* W, const float* d
     linear_f32_bwd_kernel<<<ceil_div(total, 128), 128, 0, (cudaStream_t)stream>>>(x, W, dy, dx, dW, db, rows, in, out);
     return check_launch("linear_f32_bwd");
 }
+
+// ---------------------------------------------------------------- n-ary channel concat with optional nearest x2 on input 0
+// UNet++ DecoderBlock (segmentation_models_pytorch 0.2.0, decoder blocks x_i_j): x = interpolate(x, 2, 'nearest');
+// x = cat([x, skip]) where skip is itself a cat of dense features.  out[n,h,w,:] = [in0 | in1 | ... ] with in0 read at
+// (h/2, w/2) when up0 != 0.  The adjoint sums the 2x2 block for in0.
+namespace stc {
+struct CatN {
+    const void* in[5];
+    void* din[5];
+    int ch[5];
+    int n;
+};
+
+template <typename T>
+__global__ void catn_fwd_kernel(CatN a, T* __restrict__ out, int H, int W, int Ct, int up0, long long total) {
+    const int lanes = Ct >> 3;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        int lv = (int)(i % lanes);
+        long long p = i / lanes;
+        int c = lv * 8, k = 0;
+        while (k < a.n - 1 && c >= a.ch[k]) { c -= a.ch[k]; ++k; }
+        long long src = p;
+        if (k == 0 && up0) {
+            int w_ = (int)(p % W), h_ = (int)((p / W) % H);
+            long long n_ = p / ((long long)W * H);
+            src = (n_ * (H >> 1) + (h_ >> 1)) * (long long)(W >> 1) + (w_ >> 1);
+        }
+        Vec8<T> v;
+        v.load(reinterpret_cast<const T*>(a.in[k]) + src * a.ch[k] + c);
+        v.store(out + i * 8);
+    }
+}
+
+// one thread per (input-k pixel, 8 channels): gathers from dout
+template <typename T>
+__global__ void catn_bwd_kernel(CatN a, const T* __restrict__ dout, int H, int W, int Ct, int up0, int k, int coff, long long total) {
+    const int lanes = a.ch[k] >> 3;
+    T* dst = reinterpret_cast<T*>(a.din[k]);
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        int lv = (int)(i % lanes);
+        long long p = i / lanes;
+        Vec8<T> v;
+        if (k == 0 && up0) {
+            const int w2 = W >> 1, h2 = H >> 1;
+            int w_ = (int)(p % w2), h_ = (int)((p / w2) % h2);
+            long long n_ = p / ((long long)w2 * h2);
+            float acc[8] = {};
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                    Vec8<T> g;
+                    g.load(dout + ((n_ * H + 2 * h_ + dy) * (long long)W + 2 * w_ + dx) * Ct + coff + lv * 8);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[e] += g.v[e];
+                }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v.v[e] = acc[e];
+        } else {
+            v.load(dout + p * Ct + coff + lv * 8);
+        }
+        v.store(dst + i * 8);
+    }
+}
+}  // namespace stc
+
+extern "C" int stc_catn_fwd(const void* in0, const void* in1, const void* in2, const void* in3, const void* in4, int c0, int c1, int c2,
+                            int c3, int c4, void* out, int N, int H, int W, int up0, int dtype, void* stream) {
+    stc::CatN a;
+    const void* ins[5] = {in0, in1, in2, in3, in4};
+    int chs[5] = {c0, c1, c2, c3, c4};
+    a.n = 0;
+    int Ct = 0;
+    for (int k = 0; k < 5; ++k) {
+        if (!ins[k] || chs[k] <= 0) break;
+        STC_REQUIRE(chs[k] % 8 == 0, "catn_fwd: channel counts must be multiples of 8");
+        a.in[a.n] = ins[k]; a.din[a.n] = nullptr; a.ch[a.n] = chs[k]; Ct += chs[k]; ++a.n;
+    }
+    STC_REQUIRE(a.n >= 1 && (!up0 || (H % 2 == 0 && W % 2 == 0)), "catn_fwd: bad arguments");
+    long long total = (long long)N * H * W * (Ct / 8);
+    if (total <= 0) return STC_OK;
+    STC_DISPATCH_DTYPE(dtype, (catn_fwd_kernel<T><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(a, (T*)out, H, W, Ct, up0, total)));
+    return check_launch("catn_fwd");
+}
+
+extern "C" int stc_catn_bwd(const void* dout, void* d0, void* d1, void* d2, void* d3, void* d4, int c0, int c1, int c2, int c3, int c4,
+                            int N, int H, int W, int up0, int dtype, void* stream) {
+    stc::CatN a;
+    void* ds[5] = {d0, d1, d2, d3, d4};
+    int chs[5] = {c0, c1, c2, c3, c4};
+    a.n = 0;
+    int Ct = 0;
+    for (int k = 0; k < 5; ++k) {
+        if (chs[k] <= 0) break;
+        a.in[a.n] = nullptr; a.din[a.n] = ds[k]; a.ch[a.n] = chs[k]; Ct += chs[k]; ++a.n;
+    }
+    int coff = 0;
+    for (int k = 0; k < a.n; ++k) {
+        if (a.din[k]) {
+            long long pix = (k == 0 && up0) ? (long long)N * (H / 2) * (W / 2) : (long long)N * H * W;
+            long long total = pix * (a.ch[k] / 8);
+            STC_DISPATCH_DTYPE(dtype, (catn_bwd_kernel<T><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(a, (const T*)dout, H, W, Ct, up0, k,
+                                                                                                            coff, total)));
+        }
+        coff += a.ch[k];
+    }
+    return check_launch("catn_bwd");
+}

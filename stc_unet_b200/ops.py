@@ -476,8 +476,13 @@ class _Conv(Function):
         if residual is not None:
             residual = _chk(residual)
         Cout, Cin, R, S = weight.shape
-        wp = pack_weight(weight, x.dtype)
-        y = conv_fprop(x, wp, bias, residual, Cout, R, S, act)
+        ctx.im2col = _use_im2col(x, weight)
+        if ctx.im2col:   # small-Cin conv (VGG16's first conv in UNet++): K=64 1x1 conv on the tensor cores
+            x = _im2col(x, R, S)
+            y = conv_fprop(x, pack_weight(weight, x.dtype, im2col_pad=64), bias, residual, Cout, 1, 1, act)
+        else:
+            wp = pack_weight(weight, x.dtype)
+            y = conv_fprop(x, wp, bias, residual, Cout, R, S, act)
         ctx.save_for_backward(x, weight, y if act != 0 else None)
         ctx.meta = (act, R, S, pobjs, bias is not None, residual is not None)
         return y
@@ -496,6 +501,16 @@ class _Conv(Function):
         Cout = weight.shape[0]
         P = dz.numel() // Cout
         dbias = colsum(P, Cout, dz, _grad_buf(pbias, (Cout,), dz.device)) if has_bias else None
+        if ctx.im2col:
+            if ctx.needs_input_grad[0]:
+                raise RuntimeError("im2col conv path does not provide an input gradient (image convs only)")
+            N_, H_, W_, _ = x.shape
+            ws = _wgrad_ws(64 * Cout, dz.device)
+            _dense("conv_wgrad", 2.0 * P * 64 * Cout,
+                   lambda: lib.call("stc_conv_wgrad", x, dz, ws, N_, H_, W_, 64, Cout, 1, 1, dtype_code(x.dtype), config.engine, stream_ptr()))
+            dw = _grad_buf(pw, weight.shape, dz.device)
+            lib.call("stc_unpack_im2col_wgrad", ws, dw, Cout, weight.shape[1], R, S, stream_ptr())
+            return None, dw, dbias, (dz if (has_res and ctx.needs_input_grad[3]) else None), None, None
         dw = conv_wgrad(x, dz, R, S, _grad_buf(pw, weight.shape, dz.device)) if ctx.needs_input_grad[1] else None
         dx = None
         if ctx.needs_input_grad[0]:
@@ -1069,3 +1084,33 @@ class _ConcatChannels(Function):
 
 def concat_channels(a, b):
     return _ConcatChannels.apply(a, b)
+
+
+class _CatN(Function):
+    """cat([x0', x1, ..]) along channels; x0' = nearest x2 upsample of x0 when up0 (UNet++ DecoderBlock)."""
+
+    @staticmethod
+    def forward(ctx, up0: bool, *xs):
+        xs = [_chk(x) for x in xs]
+        assert 1 <= len(xs) <= 5
+        N, h, w, _ = xs[0].shape
+        H, W = (2 * h, 2 * w) if up0 else (h, w)
+        chs = [x.shape[-1] for x in xs]
+        out = torch.empty((N, H, W, sum(chs)), dtype=xs[0].dtype, device=xs[0].device)
+        pad = [None] * (5 - len(xs))
+        lib.call("stc_catn_fwd", *xs, *pad, *chs, *([0] * (5 - len(xs))), out, N, H, W, int(up0), dtype_code(out.dtype), stream_ptr())
+        ctx.meta = (N, H, W, chs, int(up0), [tuple(x.shape) for x in xs])
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        N, H, W, chs, up0, shapes = ctx.meta
+        g = _chk(g)
+        ds = [torch.empty(shp, dtype=g.dtype, device=g.device) if ctx.needs_input_grad[i + 1] else None for i, shp in enumerate(shapes)]
+        pad = [None] * (5 - len(ds))
+        lib.call("stc_catn_bwd", g, *ds, *pad, *chs, *([0] * (5 - len(chs))), N, H, W, up0, dtype_code(g.dtype), stream_ptr())
+        return (None, *ds)
+
+
+def cat_channels_n(xs, up0=False):
+    return _CatN.apply(up0, *xs)

@@ -348,3 +348,41 @@ def test_slide_inference_config4_512_and_confusion_meter():
     res = meter.compute(["mIoU", "mDice"])
     ref_m = O.metrics_from_confusion(want)
     assert abs(res["mIoU"] - float(np.nanmean(ref_m["IoU"]))) < 1e-12 and abs(res["aAcc"] - float(ref_m["aAcc"])) < 1e-12
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_unetpp_config5_parity(dtype):
+    """my_config/UNet++.py: EncoderDecoderFull + UnetPlusPlus (VGG16 encoder + nested dense-skip decoder).  The oracle is a
+    restatement of smp 0.2.0's published design (parity UNPINNED: smp is neither vendored nor installed)."""
+    import stc_unet_b200 as S
+    from oracle import stc_oracle as O
+    torch.manual_seed(0)
+    seg = S.build_segmentor(dict(type="EncoderDecoderFull", decode_head=dict(
+        type="UnetPlusPlus", num_classes=2, norm_cfg=dict(type="BN", requires_grad=True), loss_decode=LOSS_CFG, dropout_ratio=0.0,
+        compute_dtype=dtype))).cuda().train()
+    hd = seg.decode_head
+    keys = list(hd.state_dict())
+    assert "model.encoder.features.0.weight" in keys and "model.decoder.blocks.x_0_4.conv2.1.running_var" in keys
+    assert "model.segmentation_head.0.bias" in keys and hd.model.decoder.blocks["x_0_2"].conv1[0].weight.shape == (64, 128 + 768, 3, 3)
+    img, gt = inputs(2, 2, 64, 64)
+    conv = lambda v: v.detach().double() if v.is_floating_point() else v.detach().clone()
+    sd = {k: conv(v).requires_grad_(v.is_floating_point() and "running" not in k) for k, v in hd.state_dict().items()}
+    ref_logits = O.unetpp_forward(sd, img.double(), True, None)
+    ref = O.losses(ref_logits, gt)
+    (ref["loss_bce"] + ref["loss_dice"]).backward()
+    out = seg.train_step(dict(img=img, img_metas=None, gt_semantic_seg=gt))
+    out["loss"].backward()
+    tol = 1e-4 if dtype == "fp32" else 3e-2
+    assert abs(float(out["loss"]) - float(ref["loss_bce"] + ref["loss_dice"])) <= tol
+    errs = []
+    for name, p in hd.named_parameters():
+        assert p.grad is not None, name
+        if name.endswith("conv1.0.weight") or name.endswith("conv2.0.weight") or "encoder" in name or "segmentation_head" in name:
+            errs.append(rel_l2(p.grad, sd[name].grad))
+    assert statistics.median(errs) <= (2e-2 if dtype == "fp32" else 0.6)
+    seg.eval()
+    with torch.no_grad():
+        logits = seg.encode_decode(img)
+        ref_eval = O.unetpp_forward({k: conv(v) for k, v in hd.state_dict().items()}, img.double(), False, None)
+    assert logits.shape == (2, 2, 64, 64)
+    assert rel_l2(logits, ref_eval) <= (1e-4 if dtype == "fp32" else 8e-2)

@@ -375,3 +375,27 @@ def test_gemm_layouts_simt(S):
     for a, b in ((qo, qr), (ko, kr), (vo, vr)):
         assert rel_l2(a.grad, b.grad) < 1e-4
     ops.config.engine = S._lib.ENGINE_AUTO
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("chs,up0", [((16, 8), True), ((32, 16, 8, 24, 40), True), ((8, 8, 16), False), ((16,), True)])
+def test_catn(S, dt, chs, up0):
+    """UNet++ DecoderBlock input: cat([nearest_x2(x0), skips...]) and its backward (nearest backward = 2x2 sum)."""
+    from stc_unet_b200 import ops
+    torch.manual_seed(0)
+    N, h, w = 2, 5, 7
+    H, W = (2 * h, 2 * w) if up0 else (h, w)
+    xs = [torch.randn(N, c, (h if i == 0 else H), (w if i == 0 else W), device=dev()) for i, c in enumerate(chs)]
+    if dt == torch.bfloat16:
+        xs = [bf16_round(x) for x in xs]
+    rs = [x.clone().requires_grad_(True) for x in xs]
+    first = F.interpolate(rs[0], scale_factor=2, mode="nearest") if up0 else rs[0]
+    ref = torch.cat([first] + rs[1:], dim=1)
+    os_ = [nhwc(x).to(dt).requires_grad_(True) for x in xs]
+    out = ops.cat_channels_n(os_, up0=up0)
+    assert torch.equal(nchw(out.float()), ref.detach())
+    go = torch.randn_like(ref)
+    ref.backward(go)
+    out.backward(nhwc(go).to(dt))
+    for o, r in zip(os_, rs):
+        assert rel_l2(nchw(o.grad.float()), r.grad) < tol(dt)

@@ -219,3 +219,21 @@ def test_family_b_oracle_and_state_dict_match_reference():
     import stc_unet_b200 as S
     with pytest.raises(AssertionError):   # same argument validation as unet.py:324-355
         S.build_backbone(dict(type="UNet", num_stages=5, strides=(1, 1, 1, 1)))
+
+
+def test_unetpp_structure_and_oracle_shapes():
+    """Config 5 host structure (no GPU): smp key layout and channel bookkeeping, oracle restatement runs on the same state_dict."""
+    import stc_unet_b200 as S
+    hd = S.build_head(dict(type="UnetPlusPlus", num_classes=2, norm_cfg=dict(type="BN"), dropout_ratio=0.0,
+                           loss_decode=[dict(type="CrossEntropyLoss", loss_name="loss_bce"), dict(type="DiceLoss", loss_name="loss_dice")]))
+    sd = hd.state_dict()
+    blocks = hd.model.decoder.blocks
+    assert sorted(blocks) == sorted([f"x_{d}_{l}" for l in range(4) for d in range(l + 1)] + ["x_0_4"])
+    want = {"x_0_0": (256, 1024), "x_1_1": (512, 1024), "x_0_1": (128, 1280), "x_2_2": (256, 768), "x_0_2": (64, 896),
+            "x_3_3": (128, 384), "x_0_3": (32, 576), "x_0_4": (16, 32)}
+    for k, (co, ci) in want.items():
+        assert blocks[k].conv1[0].weight.shape == (co, ci, 3, 3), k
+    assert sd["model.encoder.features.28.weight"].shape == (512, 512, 3, 3) and sd["model.segmentation_head.0.weight"].shape == (64, 16, 3, 3)
+    img = torch.rand(1, 3, 32, 32)
+    with torch.no_grad():
+        assert O.unetpp_forward(sd, img, False).shape == (1, 2, 32, 32)
