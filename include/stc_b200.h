@@ -166,6 +166,11 @@ int stc_catn_fwd(const void* in0, const void* in1, const void* in2, const void* 
 int stc_catn_bwd(const void* dout, void* d0, void* d1, void* d2, void* d3, void* d4, int c0, int c1, int c2, int c3, int c4, int N, int H,
                  int W, int up0, int dtype, void* stream);
 
+/* DeconvModule (mmseg/models/backbones/unet.py:89-147: ConvTranspose2d(k=4, s=2, p=1) -> BN -> ReLU): the transposed conv runs as a 3x3
+ * conv to 4*C sub-pixel channels (host builds that weight) followed by this pixel shuffle,
+ *   hi[n, 2h+py, 2w+px, c] = lo[n, h, w, (py*2+px)*C + c];  inverse != 0 moves hi -> lo (the adjoint).  lo is (N,H,W,4C), hi (N,2H,2W,C). */
+int stc_depth_to_space2(const void* src, void* dst, int N, int H, int W, int C, int inverse, int dtype, void* stream);
+
 /* ---------------------------------------------------------------- CoordAtt (K10; unet_head.py:131-146,57) */
 /* y[n, 0:H, c] = mean_w x ; y[n, H:H+W, c] = mean_h x  ; y is (N, H+W, C) */
 int stc_rowcol_mean(const void* x, void* y, int N, int H, int W, int C, int dtype, void* stream);

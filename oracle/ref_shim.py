@@ -287,7 +287,8 @@ def build_reference_model(stc: bool, num_classes: int, dropout_ratio: float = 0.
     return revert_sync_batchnorm(bb), revert_sync_batchnorm(hd)
 
 
-def build_reference_model_b(num_classes: int, dropout_ratio: float = 0.0, seed: int = 0, base_channels: int = 64, num_stages: int = 5):
+def build_reference_model_b(num_classes: int, dropout_ratio: float = 0.0, seed: int = 0, base_channels: int = 64, num_stages: int = 5,
+                            upsample: str = "InterpConv"):
     """(UNet, FCNHead) as configs/_base_/models/fcn_unet_s5-d16.py:3-34 builds them (BN instead of SyncBN, torch default init:
     mmcv's Kaiming init_cfg is not restated — parity tests share the state_dict instead)."""
     ns = load_reference()
@@ -296,7 +297,7 @@ def build_reference_model_b(num_classes: int, dropout_ratio: float = 0.0, seed: 
     bb = ns.UNet(in_channels=3, base_channels=base_channels, num_stages=num_stages, strides=(1,) * num_stages,
                  enc_num_convs=(2,) * num_stages, dec_num_convs=(2,) * (num_stages - 1), downsamples=(True,) * (num_stages - 1),
                  enc_dilations=(1,) * num_stages, dec_dilations=(1,) * (num_stages - 1), with_cp=False, conv_cfg=None,
-                 norm_cfg=norm_cfg, act_cfg=dict(type="ReLU"), upsample_cfg=dict(type="InterpConv"), norm_eval=False)
+                 norm_cfg=norm_cfg, act_cfg=dict(type="ReLU"), upsample_cfg=dict(type=upsample), norm_eval=False)
     hd = ns.FCNHead(in_channels=base_channels, in_index=num_stages - 1, channels=base_channels, num_convs=1, concat_input=False,
                     dropout_ratio=dropout_ratio, num_classes=num_classes, norm_cfg=norm_cfg, align_corners=False,
                     loss_decode=dict(type="CrossEntropyLoss", use_sigmoid=False, loss_weight=1.0))

@@ -323,7 +323,7 @@ def basic_conv_block(sd: SD, p: str, x, train, ns):
 
 
 def unet_b_forward(sd: SD, x, train: bool = True, new_stats: Optional[dict] = None) -> List[torch.Tensor]:
-    """UNet.forward (unet.py:404-415) for strides all 1 / MaxPool downsampling / InterpConv upsampling:
+    """UNet.forward (unet.py:404-415) for strides all 1 / MaxPool downsampling / InterpConv or DeconvModule upsampling:
     encoder stage i = [MaxPool2d(2)] + BasicConvBlock; decoder i = UpConvBlock(skip=enc_i, x): InterpConv (bilinear x2,
     align_corners=False, then 1x1 ConvModule) -> cat[skip, x] -> BasicConvBlock (up_conv_block.py:95-102)."""
     enc = []
@@ -337,8 +337,13 @@ def unet_b_forward(sd: SD, x, train: bool = True, new_stats: Optional[dict] = No
         i += 1
     outs = [x]
     for j in reversed(range(len(enc) - 1)):
-        up = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
-        up = conv_module(sd, f"decoder.{j}.upsample.interp_upsample.1", up, train, new_stats, 1)
+        dk = f"decoder.{j}.upsample.deconv_upsamping"
+        if dk + ".0.weight" in sd:   # DeconvModule (unet.py:89-147): ConvTranspose2d(4, 2, 1) -> BN -> ReLU
+            up = F.conv_transpose2d(x, sd[dk + ".0.weight"], sd[dk + ".0.bias"], stride=2, padding=1)
+            up = torch.relu(batch_norm(sd, dk + ".1", up, train, new_stats))
+        else:
+            up = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
+            up = conv_module(sd, f"decoder.{j}.upsample.interp_upsample.1", up, train, new_stats, 1)
         x = basic_conv_block(sd, f"decoder.{j}.conv_block", torch.cat([enc[j], up], dim=1), train, new_stats)
         outs.append(x)
     return outs

@@ -836,3 +836,34 @@ extern "C" int stc_catn_bwd(const void* dout, void* d0, void* d1, void* d2, void
     }
     return check_launch("catn_bwd");
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// depth-to-space (pixel shuffle by 2) on NHWC: hi[n, 2h+py, 2w+px, c] <-> lo[n, h, w, (py*2+px)*C + c]
+// (second half of the ConvTranspose2d(k=4,s=2,p=1) = [3x3 conv to 4C sub-pixel channels] decomposition; its adjoint is the inverse move)
+// ------------------------------------------------------------------------------------------------------------
+namespace stc {
+template <typename T>
+__global__ void d2s_kernel(const T* __restrict__ src, T* __restrict__ dst, int H, int W, int C, int inverse, long long total) {
+    const int lanes = C >> 3;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {      // i indexes the hi-res tensor (N,2H,2W,C) in 8-channel lanes: coalesced on that side
+        int lv = (int)(i % lanes);
+        long long p = i / lanes;
+        int x = (int)(p % (2 * W)), y = (int)((p / (2 * W)) % (2 * H));
+        long long n = p / (4LL * W * H);
+        long long lo = (((n * H + (y >> 1)) * W + (x >> 1)) * 4 + ((y & 1) * 2 + (x & 1))) * C + lv * 8;
+        Vec8<T> v;
+        if (inverse) { v.load(src + i * 8); v.store(dst + lo); }
+        else         { v.load(src + lo);    v.store(dst + i * 8); }
+    }
+}
+}  // namespace stc
+
+extern "C" int stc_depth_to_space2(const void* src, void* dst, int N, int H, int W, int C, int inverse, int dtype, void* stream) {
+    STC_REQUIRE(src && dst && C % 8 == 0 && N >= 0 && H >= 0 && W >= 0, "depth_to_space2: channels must be a multiple of 8");
+    long long total = (long long)N * H * W * 4 * (C / 8);
+    if (total <= 0) return STC_OK;
+    STC_DISPATCH_DTYPE(dtype, (d2s_kernel<T><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>((const T*)src, (T*)dst, H, W, C, inverse, total)));
+    return check_launch("depth_to_space2");
+}

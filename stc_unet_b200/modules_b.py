@@ -104,10 +104,31 @@ class InterpConv(nn.Module):
 
 
 class DeconvModule(nn.Module):
-    def __init__(self, *a, **k):
+    """unet.py:89-147: ConvTranspose2d(kernel_size, stride=scale_factor, padding=(k-s)/2) -> norm -> act; state_dict keys
+    `deconv_upsamping.{0,1}.*` as in the reference.  Built for the default geometry (kernel 4, scale 2)."""
+
+    def __init__(self, in_channels, out_channels, with_cp=False, norm_cfg=dict(type="BN"), act_cfg=dict(type="ReLU"), *, kernel_size=4,
+                 scale_factor=2):
         super().__init__()
-        raise NotImplementedError("DeconvModule (ConvTranspose2d 4/2/1 upsampler, unet.py:89-147) is not built yet; "
-                                  "UNet-S5-D16's default upsample_cfg is InterpConv")
+        assert (kernel_size - scale_factor >= 0) and (kernel_size - scale_factor) % 2 == 0, (
+            f"kernel_size should be greater than or equal to scale_factor and (kernel_size - scale_factor) should be even numbers, "
+            f"while the kernel size is {kernel_size} and scale_factor is {scale_factor}.")
+        if (kernel_size, scale_factor) != (4, 2):
+            raise NotImplementedError("DeconvModule: only kernel_size=4, scale_factor=2 (the reference default) has a CUDA path")
+        self.with_cp = with_cp
+        deconv = nn.ConvTranspose2d(in_channels, out_channels, kernel_size=kernel_size, stride=scale_factor,
+                                    padding=(kernel_size - scale_factor) // 2)
+        assert norm_cfg is not None and norm_cfg.get("type") in ("BN", "SyncBN"), "DeconvModule: BN / SyncBN only"
+        norm = (nn.SyncBatchNorm if norm_cfg["type"] == "SyncBN" else nn.BatchNorm2d)(out_channels)
+        for p in norm.parameters():
+            p.requires_grad = norm_cfg.get("requires_grad", True)
+        assert act_cfg is None or act_cfg.get("type") == "ReLU", "DeconvModule: ReLU only"
+        self.act = ACT_NONE if act_cfg is None else ACT_RELU
+        self.deconv_upsamping = nn.Sequential(deconv, norm, nn.ReLU(inplace=True) if act_cfg is not None else nn.Identity())
+
+    def forward(self, x):
+        deconv, norm = self.deconv_upsamping[0], self.deconv_upsamping[1]
+        return ops.bn_act(ops.deconv4x2(x, deconv.weight, deconv.bias, bias_feeds_train_bn=norm.training), norm, self.act, norm.training)
 
 
 _UPSAMPLE = {"InterpConv": InterpConv, "DeconvModule": DeconvModule}

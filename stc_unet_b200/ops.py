@@ -237,7 +237,7 @@ def set_step_cache(c: Optional[StepCache]):
     _STEP_CACHE = c
 
 
-def pack_weight(w: torch.Tensor, dtype: torch.dtype, transpose_flip: bool = False, im2col_pad: int = 0) -> torch.Tensor:
+def pack_weight(w: torch.Tensor, dtype: torch.dtype, transpose_flip: bool = False, im2col_pad: int = 0, cache: bool = True) -> torch.Tensor:
     """Conv2d.weight (Cout,Cin,R,S) fp32 -> packed `dtype` operand: [R*S][Cout][Cin] (fprop), [R*S][Cin][Cout] with flipped
     taps (dgrad, transpose_flip) or [1][Cout][im2col_pad] with k = tap*Cin + ci (im2col)."""
     Cout, Cin, R, S = w.shape
@@ -247,7 +247,7 @@ def pack_weight(w: torch.Tensor, dtype: torch.dtype, transpose_flip: bool = Fals
         mode = int(transpose_flip)
         inner, outer = (Cout, Cin) if transpose_flip else (Cin, Cout)
         shape_out = (R * S, outer, inner)
-    if _STEP_CACHE is not None:
+    if _STEP_CACHE is not None and cache:   # cache=False: weights derived inside the step (DeconvModule) are not stable storage
         hit = _STEP_CACHE.pack(w, dtype, mode, inner, shape_out)
         if hit is not None:
             return hit
@@ -481,7 +481,7 @@ class _Conv(Function):
             x = _im2col(x, R, S)
             y = conv_fprop(x, pack_weight(weight, x.dtype, im2col_pad=64), bias, residual, Cout, 1, 1, act)
         else:
-            wp = pack_weight(weight, x.dtype)
+            wp = pack_weight(weight, x.dtype, cache=len(pobjs) < 3 or not pobjs[2])
             y = conv_fprop(x, wp, bias, residual, Cout, R, S, act)
         ctx.save_for_backward(x, weight, y if act != 0 else None)
         ctx.meta = (act, R, S, pobjs, bias is not None, residual is not None)
@@ -491,7 +491,7 @@ class _Conv(Function):
     def backward(ctx, dy):
         x, weight, y = ctx.saved_tensors
         act, R, S, pobjs, has_bias, has_res = ctx.meta
-        pw, pbias = pobjs
+        pw, pbias = pobjs[0], pobjs[1]
         dy = _chk(dy)
         if act != 0:
             dz = torch.empty_like(dy)
@@ -514,7 +514,7 @@ class _Conv(Function):
         dw = conv_wgrad(x, dz, R, S, _grad_buf(pw, weight.shape, dz.device)) if ctx.needs_input_grad[1] else None
         dx = None
         if ctx.needs_input_grad[0]:
-            wpt = pack_weight(weight, dz.dtype, transpose_flip=True)
+            wpt = pack_weight(weight, dz.dtype, transpose_flip=True, cache=len(pobjs) < 3 or not pobjs[2])
             dx = conv_fprop(dz, wpt, None, None, weight.shape[1], R, S)
         dres = dz if (has_res and ctx.needs_input_grad[3]) else None
         return dx, dw, dbias, dres, None, None
@@ -1114,3 +1114,97 @@ class _CatN(Function):
 
 def cat_channels_n(xs, up0=False):
     return _CatN.apply(up0, *xs)
+
+
+# ---------------------------------------------------------------------------------------------
+# DeconvModule (unet.py:89-147): ConvTranspose2d(4, 2, 1) = 3x3 conv to 4*Cout sub-pixel channels + pixel shuffle, then BN + act
+# ---------------------------------------------------------------------------------------------
+class _DepthToSpace2(Function):
+    @staticmethod
+    def forward(ctx, z):
+        z = _chk(z)
+        N, H, W, C4 = z.shape
+        out = torch.empty((N, 2 * H, 2 * W, C4 // 4), dtype=z.dtype, device=z.device)
+        lib.call("stc_depth_to_space2", z, out, N, H, W, C4 // 4, 0, dtype_code(z.dtype), stream_ptr())
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = _chk(dout)
+        N, H2, W2, C = dout.shape
+        dz = torch.empty((N, H2 // 2, W2 // 2, 4 * C), dtype=dout.dtype, device=dout.device)
+        lib.call("stc_depth_to_space2", dout, dz, N, H2 // 2, W2 // 2, C, 1, dtype_code(dout.dtype), stream_ptr())
+        return dz
+
+
+def depth_to_space2(z):
+    return _DepthToSpace2.apply(z)
+
+
+class _BnAct(Function):
+    """Stand-alone BatchNorm + activation on an NHWC tensor (the norm after DeconvModule's pixel shuffle)."""
+
+    @staticmethod
+    def forward(ctx, y, gamma, beta, bn: BNState, act: int, pobjs):
+        y = _chk(y)
+        C = y.shape[-1]
+        P = y.numel() // C
+        mean, invstd, count = _bn_forward_stats(y, P, C, bn)
+        a = torch.empty_like(y)
+        lib.call("stc_bn_apply", y, mean, invstd, gamma, beta, a, P, C, act, dtype_code(y.dtype), stream_ptr())
+        ctx.save_for_backward(y, gamma, beta, mean, invstd)
+        ctx.meta = (act, bn, count, pobjs)
+        return a
+
+    @staticmethod
+    def backward(ctx, da):
+        y, gamma, beta, mean, invstd = ctx.saved_tensors
+        act, bn, count, (pg, pb) = ctx.meta
+        C = y.shape[-1]
+        dy, dgamma, dbeta = _bn_backward(y, _chk(da), mean, invstd, gamma, beta, y.numel() // C, C, act, bn, count, pg, pb)
+        return dy, dgamma, dbeta, None, None, None
+
+
+def bn_act(y, bn: torch.nn.modules.batchnorm._BatchNorm, act: int, training: bool):
+    sync = isinstance(bn, torch.nn.SyncBatchNorm)
+    state = BNState(bn.running_mean, bn.running_var, bn.num_batches_tracked, 0.1 if bn.momentum is None else bn.momentum, bn.eps,
+                    training or not bn.track_running_stats, sync=sync, group=getattr(bn, "process_group", None) if sync else None)
+    return _BnAct.apply(y, bn.weight, bn.bias, state, act, (bn.weight, bn.bias))
+
+
+_DECONV_TAPS = ((3, 1, 4), (4, 2, 0))   # [output parity][3x3 tap] -> 4x4 kernel index (4 = no contribution)
+
+
+def deconv4x2_weight_as_conv3(weight: torch.Tensor) -> torch.Tensor:
+    """ConvTranspose2d(k=4,s=2,p=1).weight (Cin,Cout,4,4) -> the equivalent 3x3 correlation weight (4*Cout, Cin, 3, 3) whose output
+    channel (py*2+px)*Cout + co is output pixel (2m+py, 2l+px): oy = 2*iy - 1 + ky, so parity 0 reads rows m-1 (ky=3), m (ky=1) and
+    parity 1 reads rows m (ky=2), m+1 (ky=0).  Plain differentiable index ops on the (small) weight: autograd maps the gradient back."""
+    Cin, Cout = weight.shape[:2]
+    idx = torch.tensor(_DECONV_TAPS, device=weight.device)                   # (2, 3)
+    wp = torch.cat([weight, weight.new_zeros(Cin, Cout, 1, 4)], dim=2)       # ky = 4 -> zero row
+    wp = torch.cat([wp, wp.new_zeros(Cin, Cout, 5, 1)], dim=3)               # kx = 4 -> zero column
+    w = wp[:, :, idx][:, :, :, :, idx]                                       # (Cin, Cout, py, r, px, s)
+    return w.permute(2, 4, 1, 0, 3, 5).reshape(4 * Cout, Cin, 3, 3).contiguous()
+
+
+class _BiasIntoTrainBN(Function):
+    """Identity on a conv bias that feeds a train-mode BN: its gradient is exactly zero (the batch mean removes it), so return
+    zeros instead of the rounding noise a column sum of dy would give (same rule as _ConvBnAct)."""
+
+    @staticmethod
+    def forward(ctx, bias):
+        ctx.pobj = bias
+        return bias.view_as(bias)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _grad_buf(ctx.pobj, tuple(g.shape), g.device, zero=True)
+
+
+def deconv4x2(x, weight, bias=None, bias_feeds_train_bn: bool = False):
+    """ConvTranspose2d(Cin, Cout, kernel_size=4, stride=2, padding=1) on NHWC x: (N,H,W,Cin) -> (N,2H,2W,Cout)."""
+    w3 = deconv4x2_weight_as_conv3(weight)
+    if bias is not None and bias_feeds_train_bn:
+        bias = _BiasIntoTrainBN.apply(bias)
+    b4 = bias.repeat(4) if bias is not None else None
+    return depth_to_space2(_Conv.apply(x, w3, b4, None, 0, (None, None, True)))

@@ -275,13 +275,14 @@ def test_trainer_step_matches_plain_backward(dtype):
     assert abs(float(lv["loss"]) - float(losses["loss_bce"] + losses["loss_dice"])) < 1e-3
 
 
+@pytest.mark.parametrize("upsample", ["InterpConv", "DeconvModule"])
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
-def test_family_b_unet_fcn_parity(dtype):
-    """mmseg UNet + FCNHead (family B): InterpConv (bilinear align_corners=False + 1x1 ConvModule), channel concat, bias-free
-    ConvModules, CE-only loss — against the fp64 oracle."""
+def test_family_b_unet_fcn_parity(dtype, upsample):
+    """mmseg UNet + FCNHead (family B): InterpConv (bilinear align_corners=False + 1x1 ConvModule) or DeconvModule
+    (ConvTranspose2d 4/2/1 + BN + ReLU) up-samplers, channel concat, bias-free ConvModules, CE-only loss — against the fp64 oracle."""
     from oracle import stc_oracle as O
     from tests.test_oracle import build_ours_b
-    bb, hd = build_ours_b(3, base=64, stages=4, dtype=dtype)
+    bb, hd = build_ours_b(3, base=64, stages=4, dtype=dtype, upsample=upsample)
     bb.init_weights(); hd.init_weights()
     bb, hd = bb.cuda(), hd.cuda()
     img, gt = inputs(2, 3, 64, 64)
@@ -305,7 +306,7 @@ def test_family_b_unet_fcn_parity(dtype):
             errs.append(rel_l2(p.grad, sd[name].grad))
     assert statistics.median(errs) <= (2e-2 if dtype == "fp32" else 0.6)   # random-init decision flips, see module docstring
     with torch.no_grad():
-        b2, h2 = build_ours_b(3, base=64, stages=4, dtype=dtype)
+        b2, h2 = build_ours_b(3, base=64, stages=4, dtype=dtype, upsample=upsample)
         b2.init_weights(); h2.init_weights()
         out = h2.cuda()(b2.cuda()(img))
     if dtype == "fp32":

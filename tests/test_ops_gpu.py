@@ -1,5 +1,6 @@
 """Kernel-level parity (GPU): every C-ABI op against a plain PyTorch fp32 reference of the same op.
 Tolerances: fp32 path 1e-5 (1e-4 is the north-star bound for whole-model fp32); bf16 path 2e-2."""
+import copy
 import math
 
 import pytest
@@ -399,3 +400,40 @@ def test_catn(S, dt, chs, up0):
     out.backward(nhwc(go).to(dt))
     for o, r in zip(os_, rs):
         assert rel_l2(nchw(o.grad.float()), r.grad) < tol(dt)
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("engine", ["simt", "auto"])
+def test_deconv4x2_bn_relu(S, dt, engine):
+    """DeconvModule (unet.py:89-147) = ConvTranspose2d(4,2,1) + BN(train) + ReLU vs torch fp64."""
+    from stc_unet_b200 import ops
+    from stc_unet_b200.modules_b import DeconvModule
+    ops.config.engine = S._lib.ENGINE_SIMT if engine == "simt" else S._lib.ENGINE_AUTO
+    try:
+        torch.manual_seed(0)
+        m = DeconvModule(64, 32).cuda().train()
+        with torch.no_grad():
+            m.deconv_upsamping[1].weight.uniform_(0.5, 1.5); m.deconv_upsamping[1].bias.uniform_(-0.2, 0.2)
+        x = torch.randn(2, 64, 9, 16, device=dev())
+        if dt == torch.bfloat16:
+            x = bf16_round(x)
+        ref = copy.deepcopy(m.deconv_upsamping).double()
+        xr = x.double().requires_grad_(True)
+        yr = ref(xr)
+        xo = nhwc(x).to(dt).requires_grad_(True)
+        yo = m(xo)
+        assert yo.shape == (2, 18, 32, 32)
+        assert rel_l2(nchw(yo.float()), yr) < (1e-5 if dt == torch.float32 else 2e-2)
+        go = torch.randn_like(yr)
+        yr.backward(go)
+        yo.backward(nhwc(go.float()).to(dt))
+        t = 1e-4 if dt == torch.float32 else 4e-2
+        assert rel_l2(nchw(xo.grad.float()), xr.grad) < t
+        assert rel_l2(m.deconv_upsamping[0].weight.grad, ref[0].weight.grad) < t
+        assert rel_l2(m.deconv_upsamping[1].weight.grad, ref[1].weight.grad) < t
+        # dbeta = sum of masked upstream values: a cancelling sum that moves with every bf16 ReLU decision flip
+        assert rel_l2(m.deconv_upsamping[1].bias.grad, ref[1].bias.grad) < (t if dt == torch.float32 else 0.15)
+        assert m.deconv_upsamping[0].bias.grad.abs().max() == 0   # bias feeds a train-mode BN: exactly zero
+        assert rel_l2(m.deconv_upsamping[1].running_var, ref[1].running_var) < (1e-5 if dt == torch.float32 else 1e-2)
+    finally:
+        ops.config.engine = S._lib.ENGINE_AUTO

@@ -170,14 +170,14 @@ def test_slide_windows_match_reference_grid():
     assert len(O.slide_windows(512, 512, (256, 256), (170, 170))) == 9
 
 
-def build_ours_b(num_classes, base=16, stages=4, dtype="bf16", seed=0):
+def build_ours_b(num_classes, base=16, stages=4, dtype="bf16", seed=0, upsample="InterpConv"):
     import stc_unet_b200 as S
     torch.manual_seed(seed)
     norm = dict(type="BN", requires_grad=True)
     bb = S.build_backbone(dict(type="UNet", in_channels=3, base_channels=base, num_stages=stages, strides=(1,) * stages,
                                enc_num_convs=(2,) * stages, dec_num_convs=(2,) * (stages - 1), downsamples=(True,) * (stages - 1),
                                enc_dilations=(1,) * stages, dec_dilations=(1,) * (stages - 1), with_cp=False, conv_cfg=None, norm_cfg=norm,
-                               act_cfg=dict(type="ReLU"), upsample_cfg=dict(type="InterpConv"), norm_eval=False, compute_dtype=dtype))
+                               act_cfg=dict(type="ReLU"), upsample_cfg=dict(type=upsample), norm_eval=False, compute_dtype=dtype))
     hd = S.build_head(dict(type="FCNHead", in_channels=base, in_index=stages - 1, channels=base, num_convs=1, concat_input=False,
                            dropout_ratio=0.0, num_classes=num_classes, norm_cfg=norm, align_corners=False,
                            loss_decode=dict(type="CrossEntropyLoss", use_sigmoid=False, loss_weight=1.0)))
@@ -237,3 +237,33 @@ def test_unetpp_structure_and_oracle_shapes():
     img = torch.rand(1, 3, 32, 32)
     with torch.no_grad():
         assert O.unetpp_forward(sd, img, False).shape == (1, 2, 32, 32)
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="/root/reference not present (GPU box)")
+def test_family_b_deconv_upsampler_matches_reference():
+    """upsample_cfg=dict(type='DeconvModule') (unet.py:89-147): same state_dict keys as the reference module, the oracle restatement
+    reproduces the reference forward/backward, and the 3x3-sub-pixel weight mapping used by the CUDA path equals conv_transpose2d."""
+    rb, _ = ref_shim.build_reference_model_b(3, base_channels=16, num_stages=3, upsample="DeconvModule")
+    bb, _ = build_ours_b(3, stages=3, upsample="DeconvModule")
+    so, sr = bb.state_dict(), rb.state_dict()
+    assert {k: tuple(v.shape) for k, v in so.items()} == {k: tuple(v.shape) for k, v in sr.items()}
+    assert "decoder.0.upsample.deconv_upsamping.0.bias" in so and so["decoder.1.upsample.deconv_upsamping.0.weight"].shape == (64, 32, 4, 4)
+    x = torch.rand(2, 3, 16, 16)
+    feats = rb(x)
+    feats[-1].square().mean().backward()
+    bsd = as_leaf(rb.state_dict())
+    mine = O.unet_b_forward(bsd, x, True, {})
+    mine[-1].square().mean().backward()
+    for a, b in zip(mine, feats):
+        assert rel_l2(a, b) < 1e-5
+    for name, p in rb.named_parameters():
+        if p.grad.norm() > 1e-6:
+            assert rel_l2(bsd[name].grad, p.grad) < 2e-2, name
+    from stc_unet_b200.ops import deconv4x2_weight_as_conv3
+    xx, w, b = torch.randn(2, 5, 6, 7, dtype=torch.float64), torch.randn(5, 3, 4, 4, dtype=torch.float64), torch.randn(3, dtype=torch.float64)
+    z = F.conv2d(xx, deconv4x2_weight_as_conv3(w), b.repeat(4), padding=1)
+    y = z.view(2, 2, 2, 3, 6, 7).permute(0, 3, 4, 1, 5, 2).reshape(2, 3, 12, 14)
+    assert (y - F.conv_transpose2d(xx, w, b, stride=2, padding=1)).abs().max() < 1e-12
+    import stc_unet_b200 as S
+    with pytest.raises(AssertionError):
+        S.modules_b.DeconvModule(8, 8, kernel_size=3)
