@@ -58,7 +58,9 @@ int stc_nchw_to_nhwc(const float* src, void* dst, int N, int C, int H, int W, in
 int stc_pack_conv_weight(const float* w, void* dst, int Cout, int Cin, int R, int S, int inner_pad,
                          int transpose_flip, int dtype, void* stream);
 /* Every weight pack of a step in one launch.  table: n rows of 8 int64 {src device pointer (fp32 OIHW), dst element offset,
- * Cout, Cin, R, S, inner_pad, mode (0 fprop, 1 dgrad, 2 im2col)}; prefix: n+1 cumulative packed element counts. */
+ * Cout, Cin, R, S, inner_pad, mode (0 fprop, 1 dgrad, 2 im2col)}; prefix: n+1 cumulative WORK-ITEM counts, an item being one (co,ci) pair
+ * (Cout*Cin per row) for modes 0/1 - which must have inner_pad == Cin resp. Cout - and one output element (Cout*inner_pad) for mode 2;
+ * total = prefix[n]. */
 int stc_pack_conv_weights_batched(const int64_t* table, const int64_t* prefix, int n, void* dst, long long total, int dtype,
                                   void* stream);
 /* wgrad workspace [R*S][Cin][Cout] fp32 -> Conv2d.weight.grad (Cout,Cin,R,S) fp32
@@ -152,6 +154,20 @@ int stc_upcat_fwd(const void* skip, const void* low, void* out, int N, int H, in
                   int align_corners, int dtype, void* stream);
 int stc_upcat_bwd(const void* dout, void* dskip, void* dlow, int N, int H, int W, int Cs, int h, int w, int Cu,
                   int align_corners, int dtype, void* stream);
+
+/* Up.forward fused (decode_heads/unet_head.py:50-60 with CoordAtt, :131-146): the concatenated tensor cat = [skip, pad(up(low))] is
+ * never written.  stc_upcat_pool: y (N,H+W,Cs+Cu) = row means (rows 0..H-1) and column means (rows H..) of cat.
+ * stc_upcat_apply_fwd: out = cat + a_h*a_w with a (N,H+W,Cs+Cu); a == NULL gives out = cat.
+ * stc_upcat_apply_bwd: g = dout + dy_h/W + dy_w/H (dyhw (N,H+W,Cs+Cu) = gradient of the pooled descriptor, may be NULL);
+ * dskip = g[..., :Cs], dlow = adjoint of the bilinear x2 applied to g[..., Cs:]; either output may be NULL.
+ * stc_upcat_fused_ok returns 1 when these row-structured kernels support the shape ((Cs+Cu)/8 <= 256 lanes). */
+int stc_upcat_fused_ok(int N, int H, int W, int Cs, int h, int w, int Cu);
+int stc_upcat_pool(const void* skip, const void* low, void* y, int N, int H, int W, int Cs, int h, int w, int Cu, int align_corners, int dtype,
+                   void* stream);
+int stc_upcat_apply_fwd(const void* skip, const void* low, const void* a, void* out, int N, int H, int W, int Cs, int h, int w, int Cu,
+                        int align_corners, int dtype, void* stream);
+int stc_upcat_apply_bwd(const void* dout, const void* dyhw, void* dskip, void* dlow, int N, int H, int W, int Cs, int h, int w, int Cu,
+                        int align_corners, int dtype, void* stream);
 
 /* torch.cat([a, b], dim=1) on NHWC rows (UpConvBlock.forward, mmseg/models/utils/up_conv_block.py:99; FCNHead concat_input,
  * fcn_head.py:81) and its adjoint (a or b may be NULL to drop that half). */

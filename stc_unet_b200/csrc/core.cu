@@ -364,10 +364,53 @@ __global__ void im2col_kernel(const T* __restrict__ x, T* __restrict__ out, int 
     }
 }
 
+// one block per image row: the R input rows it needs are staged in shared memory (zero halo included), a per-k offset table replaces
+// the div/mod chain, and the (W x Kpad) output row is written with fully coalesced 16-byte stores
+template <typename T>
+__global__ void __launch_bounds__(256) im2col_rows_kernel(const T* __restrict__ x, T* __restrict__ out, int H, int W, int Cin, int R, int S,
+                                                          int Kpad) {
+    extern __shared__ __align__(16) unsigned char im2col_smem[];
+    int* koff = reinterpret_cast<int*>(im2col_smem);
+    T* tile = reinterpret_cast<T*>(koff + Kpad);
+    const int rowlen = (W + S - 1) * Cin, K = R * S * Cin, pr = R / 2, ps = S / 2;
+    const long long nh = blockIdx.x, n = nh / H;
+    const int h_ = (int)(nh % H);
+    for (int k = threadIdx.x; k < Kpad; k += 256) {
+        int tp = k / Cin, ci = k - tp * Cin;
+        koff[k] = k < K ? (tp / S) * rowlen + (tp % S) * Cin + ci : -1;
+    }
+    for (int idx = threadIdx.x; idx < R * rowlen; idx += 256) {
+        const int r = idx / rowlen, c = idx - r * rowlen;
+        const int hh = h_ + r - pr, cc = c - ps * Cin;
+        float v = 0.f;
+        if (hh >= 0 && hh < H && cc >= 0 && cc < W * Cin) v = ldf(x + ((n * H + hh) * (long long)W) * Cin + cc);
+        stf(tile + idx, v);
+    }
+    __syncthreads();
+    const int kv = Kpad >> 3;
+    T* orow = out + nh * (long long)W * Kpad;
+    for (int item = threadIdx.x; item < W * kv; item += 256) {
+        const int w_ = item / kv, v8 = item - w_ * kv;
+        Vec8<T> o;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int off = koff[v8 * 8 + e];
+            o.v[e] = off >= 0 ? ldf(tile + off + w_ * Cin) : 0.f;
+        }
+        o.store(orow + (long long)item * 8);
+    }
+}
+
 extern "C" int stc_im2col(const void* x, void* out, int N, int H, int W, int Cin, int R, int S, int Kpad, int dtype, void* stream) {
     STC_REQUIRE(Kpad % 8 == 0 && Kpad >= R * S * Cin, "im2col: Kpad=%d must be a multiple of 8 and >= R*S*Cin=%d", Kpad, R * S * Cin);
     long long total = (long long)N * H * W * (Kpad / 8);
     if (total <= 0) return STC_OK;
+    const size_t smem = sizeof(int) * Kpad + (size_t)R * (W + S - 1) * Cin * (dtype == STC_BF16 ? 2 : 4);
+    if (smem <= 48 * 1024) {
+        STC_DISPATCH_DTYPE(dtype, (im2col_rows_kernel<T><<<(unsigned)((long long)N * H), 256, smem, (cudaStream_t)stream>>>((const T*)x, (T*)out, H, W,
+                                                                                                                       Cin, R, S, Kpad)));
+        return check_launch("im2col");
+    }
     int blocks = (int)min((long long)num_sms() * 16, (long long)ceil_div(total, 256));
     STC_DISPATCH_DTYPE(dtype, (im2col_kernel<T><<<blocks, 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)out, H, W, Cin, R, S, Kpad, total)));
     return check_launch("im2col");
@@ -439,6 +482,10 @@ extern "C" int stc_add_n(const void* a, const void* b, const void* c, const void
 // all weight packs of a training step in ONE launch.  table: n rows of 8 int64
 // {src ptr, dst element offset, Cout, Cin, R, S, inner_pad, mode}; prefix: n+1 cumulative element counts.
 // ------------------------------------------------------------------------------------
+// Work item = one (co, ci) pair: the thread reads that pair's R*S contiguous source floats once and writes one element per tap.
+// mode 0 (fprop, [tap][Cout][Cin]): ci fastest -> coalesced reads and writes; mode 1 (dgrad, [tap'][Cin][Cout], flipped taps): co fastest ->
+// coalesced writes, each thread's R*S-float source run is consumed through L1.  mode 2 (im2col, [Cout][Kpad]): item = one output element.
+// prefix[] counts ITEMS (Cout*Cin for modes 0/1, Cout*Kpad for mode 2).
 template <typename T>
 __global__ void pack_batched_kernel(const long long* __restrict__ table, const long long* __restrict__ prefix, int n,
                                     T* __restrict__ dst_base, long long total) {
@@ -454,28 +501,28 @@ __global__ void pack_batched_kernel(const long long* __restrict__ table, const l
         const float* w = reinterpret_cast<const float*>(e[0]);
         const int Cout = (int)e[2], Cin = (int)e[3], R = (int)e[4], S = (int)e[5], inner_pad = (int)e[6], tf = (int)e[7];
         const long long j = i - prefix[lo];
-        const int inner = (int)(j % inner_pad);
-        float v = 0.f;
+        T* dst = dst_base + e[1];
+        const int RS = R * S;
         if (tf == 2) {
-            const int RS = R * S;
+            const int inner = (int)(j % inner_pad);
             const long long co = j / inner_pad;
+            float v = 0.f;
             if (inner < RS * Cin) {
                 int tp = inner / Cin, ci = inner - tp * Cin;
                 v = w[((co * Cin + ci) * RS) + tp];
             }
+            stf(dst + j, v);
+        } else if (tf == 0) {
+            const int ci = (int)(j % Cin), co = (int)(j / Cin);
+            const float* src = w + (long long)j * RS;                  // (co*Cin + ci) * RS
+            const long long plane = (long long)Cout * Cin;
+            for (int tap = 0; tap < RS; ++tap) stf(dst + tap * plane + (long long)co * Cin + ci, src[tap]);
         } else {
-            long long t = j / inner_pad;
-            const int outer_n = tf ? Cin : Cout;
-            const int outer = (int)(t % outer_n);
-            const int tap = (int)(t / outer_n);
-            const int r = tap / S, sx = tap % S;
-            if (!tf) {
-                if (inner < Cin) v = w[(((long long)outer * Cin + inner) * R + r) * S + sx];
-            } else {
-                if (inner < Cout) v = w[(((long long)inner * Cin + outer) * R + (R - 1 - r)) * S + (S - 1 - sx)];
-            }
+            const int co = (int)(j % Cout), ci = (int)(j / Cout);
+            const float* src = w + ((long long)co * Cin + ci) * RS;
+            const long long plane = (long long)Cout * Cin;
+            for (int tap = 0; tap < RS; ++tap) stf(dst + (RS - 1 - tap) * plane + (long long)ci * Cout + co, src[tap]);
         }
-        stf(dst_base + e[1] + j, v);
     }
 }
 

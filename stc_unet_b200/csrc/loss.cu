@@ -73,31 +73,39 @@ __global__ void __launch_bounds__(256) cls_bwd_dx_kernel(const float* __restrict
     }
 }
 
-// dW[k][c] += sum_p dl[k][p] x[p][c] for 4 classes starting at k0; db likewise
+// dW[k][c] += sum_p dl[k][p] x[p][c] for 4 classes starting at k0; db likewise.  grid (G, N): one image per blockIdx.y, so the pixel
+// loop is a pointer walk and the Dropout2d mask (per image and channel) is applied once, after the sum.
 template <typename T>
 __global__ void __launch_bounds__(256) cls_bwd_dw_kernel(const float* __restrict__ dl, const T* __restrict__ x, const float* __restrict__ mask,
                                                          float* __restrict__ dW, float* __restrict__ db, long long HW, int Cin, int Ccls,
-                                                         long long P, int k0) {
+                                                         int k0) {
     __shared__ float smem[256 * 8 * 4];
     const int lanes = Cin >> 3, lv = threadIdx.x % lanes, r0 = threadIdx.x / lanes, rstep = 256 / lanes;
+    const long long n = blockIdx.y;
     float acc[4][8] = {};
     float bs[4] = {};
-    for (long long p = (long long)blockIdx.x * rstep + r0; p < P; p += (long long)gridDim.x * rstep) {
-        long long n = p / HW, hw = p - n * HW;
+    const T* xn = x + n * HW * Cin + lv * 8;
+    const float* dn = dl + (n * Ccls + k0) * HW;
+    const int nk = min(4, Ccls - k0);
+    for (long long hw = (long long)blockIdx.x * rstep + r0; hw < HW; hw += (long long)gridDim.x * rstep) {
         Vec8<T> v;
-        v.load(x + p * Cin + lv * 8);
-        if (mask) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v.v[e] *= mask[n * Cin + lv * 8 + e];
-        }
+        v.load(xn + hw * Cin);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            if (k0 + j < Ccls) {
-                float g = dl[(n * Ccls + k0 + j) * HW + hw];
-                if (lv == 0) bs[j] += g;
+            if (j < nk) {
+                const float g = dn[j * HW + hw];
+                bs[j] += g;
 #pragma unroll
                 for (int e = 0; e < 8; ++e) acc[j][e] = fmaf(g, v.v[e], acc[j][e]);
             }
+        }
+    }
+    if (mask) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float m = mask[n * Cin + lv * 8 + e];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j][e] *= m;
         }
     }
     block_reduce_lanes_emit<4>(acc, lanes, smem, Cin, [&](int q, int c, float s) {
@@ -354,9 +362,9 @@ extern "C" int stc_cls_bwd(const float* dlogits, const void* x, const float* W, 
         STC_DISPATCH_DTYPE(dtype, (cls_bwd_dx_kernel<T><<<ceil_div(P, 256), 256, smem, st>>>(dlogits, W, mask, (T*)dx, HW, Cin, Ccls, P)));
     }
     if (dW) {
-        int G = reduce_blocks(P, Cin / 8);
+        dim3 grid((unsigned)max(1, reduce_blocks(P, Cin / 8) / max(N, 1)), (unsigned)N);
         for (int k0 = 0; k0 < Ccls; k0 += 4)
-            STC_DISPATCH_DTYPE(dtype, (cls_bwd_dw_kernel<T><<<G, 256, 0, st>>>(dlogits, (const T*)x, mask, dW, db, HW, Cin, Ccls, P, k0)));
+            STC_DISPATCH_DTYPE(dtype, (cls_bwd_dw_kernel<T><<<grid, 256, 0, st>>>(dlogits, (const T*)x, mask, dW, db, HW, Cin, Ccls, k0)));
     }
     return check_launch("cls_bwd");
 }

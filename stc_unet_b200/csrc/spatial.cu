@@ -557,6 +557,12 @@ static inline int ew_blocks(long long work) {
 
 using namespace stc;
 
+extern "C" int stc_upcat_fused_ok(int N, int H, int W, int Cs, int h, int w, int Cu);
+extern "C" int stc_upcat_apply_fwd(const void* skip, const void* low, const void* a, void* out, int N, int H, int W, int Cs, int h, int w, int Cu,
+                                   int align_corners, int dtype, void* stream);
+extern "C" int stc_upcat_apply_bwd(const void* dout, const void* dyhw, void* dskip, void* dlow, int N, int H, int W, int Cs, int h, int w, int Cu,
+                                   int align_corners, int dtype, void* stream);
+
 #define REQ_VEC(C, name) STC_REQUIRE((C) % 8 == 0, name ": channel count %d must be a multiple of 8", (int)(C))
 
 extern "C" int stc_maxpool2_fwd(const void* x, void* y, int N, int H, int W, int C, int dtype, void* stream) {
@@ -583,6 +589,8 @@ extern "C" int stc_upcat_fwd(const void* skip, const void* low, void* out, int N
     REQ_VEC(Cs, "upcat_fwd");
     REQ_VEC(Cu, "upcat_fwd");
     STC_REQUIRE(H >= 2 * h && W >= 2 * w, "upcat_fwd: skip (%d,%d) smaller than upsampled (%d,%d)", H, W, 2 * h, 2 * w);
+    if (stc_upcat_fused_ok(N, H, W, Cs, h, w, Cu))   // row-structured kernels (upcat_fused.cu); the ones below are the wide-channel fallback
+        return stc_upcat_apply_fwd(skip, low, nullptr, out, N, H, W, Cs, h, w, Cu, align_corners, dtype, stream);
     long long total = (long long)N * H * W * ((Cs + Cu) / 8);
     STC_DISPATCH_DTYPE(dtype, (upcat_fwd_kernel<T><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>((const T*)skip, (const T*)low, (T*)out,
                                                                                                      H, W, Cs, h, w, Cu, align_corners, total)));
@@ -593,6 +601,8 @@ extern "C" int stc_upcat_bwd(const void* dout, void* dskip, void* dlow, int N, i
                              int align_corners, int dtype, void* stream) {
     REQ_VEC(Cs, "upcat_bwd");
     REQ_VEC(Cu, "upcat_bwd");
+    if (stc_upcat_fused_ok(N, H, W, Cs, h, w, Cu))
+        return stc_upcat_apply_bwd(dout, nullptr, dskip, dlow, N, H, W, Cs, h, w, Cu, align_corners, dtype, stream);
     cudaStream_t st = (cudaStream_t)stream;
     if (dskip && Cs > 0) {
         long long total = (long long)N * H * W * (Cs / 8);

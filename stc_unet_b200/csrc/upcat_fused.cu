@@ -1,0 +1,365 @@
+// Up.forward (decode_heads/unet_head.py:50-60) as three row-structured passes that never materialise the concatenated tensor:
+//
+//   cat = [skip, pad(bilinear_x2(low))]                       (virtual)
+//   y   = row / column means of cat                           stc_upcat_pool        (CoordAtt pool_h / pool_w, unet_head.py:134-136)
+//   out = cat + a_h * a_w                                     stc_upcat_apply_fwd   (`self.ca(x) + x`, unet_head.py:57); a == NULL: out = cat
+//   g   = dout + dy_h / W + dy_w / H  ->  dskip, dlow         stc_upcat_apply_bwd   (adjoint of cat and of the two means in one pass)
+//
+// Every block owns one image row (n, y): a thread keeps its 8-channel lane for the whole launch, the row-constant terms
+// (vertical interpolation weights, a_h / dy_h) live in registers and the x loop is load -> fma -> store with pointer bumps only.
+// HBM-bound; algorithmic bytes: fwd = |skip| + |low| + |out|, pool = |skip| + |low| per pass (two passes), bwd = |dout| + |dskip| + |dlow|.
+#include "common.cuh"
+
+namespace stc {
+
+struct Lerp {
+    int i0, i1;
+    float l0, l1;
+};
+// nn.Upsample(scale_factor=2, bilinear): source position of output index o; scale = (in-1)/(out-1) for align_corners=True
+__device__ __forceinline__ Lerp lerp_src(int o, int in, float scale, int align) {
+    Lerp r;
+    float src = align ? scale * (float)o : fmaxf(0.5f * ((float)o + 0.5f) - 0.5f, 0.f);
+    r.i0 = min((int)src, in - 1);
+    r.i1 = r.i0 + (r.i0 < in - 1 ? 1 : 0);
+    r.l1 = src - (float)r.i0;
+    r.l0 = 1.f - r.l1;
+    return r;
+}
+static inline float lerp_scale(int in, int out) { return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f; }
+
+struct UpCatGeom {
+    int H, W, Cs, h, w, Cu, align, py, px;
+    float sy, sx;
+};
+static UpCatGeom make_geom(int H, int W, int Cs, int h, int w, int Cu, int align) {
+    UpCatGeom g{H, W, Cs, h, w, Cu, align, (H - 2 * h) / 2, (W - 2 * w) / 2, lerp_scale(h, 2 * h), lerp_scale(w, 2 * w)};
+    return g;
+}
+
+// value of the virtual cat tensor at (n, y, x) for a LOW lane (channel offset cl inside low), given the row's vertical weights
+template <typename T>
+__device__ __forceinline__ void low_value(const T* __restrict__ lown, const UpCatGeom& g, bool row_valid, const Lerp& iy, int x, int cl,
+                                          float (&v)[8]) {
+    const int ox = x - g.px;
+    if (!row_valid || ox < 0 || ox >= 2 * g.w) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = 0.f;
+        return;
+    }
+    const Lerp ix = lerp_src(ox, g.w, g.sx, g.align);
+    Vec8<T> a00, a01, a10, a11;
+    const T* r0 = lown + (long long)iy.i0 * g.w * g.Cu + cl;
+    const T* r1 = lown + (long long)iy.i1 * g.w * g.Cu + cl;
+    a00.load(r0 + (long long)ix.i0 * g.Cu);
+    a01.load(r0 + (long long)ix.i1 * g.Cu);
+    a10.load(r1 + (long long)ix.i0 * g.Cu);
+    a11.load(r1 + (long long)ix.i1 * g.Cu);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = iy.l0 * (ix.l0 * a00.v[k] + ix.l1 * a01.v[k]) + iy.l1 * (ix.l0 * a10.v[k] + ix.l1 * a11.v[k]);
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+// grid (gx, H, N); block 256; lanes = (Cs+Cu)/8 <= 256
+template <typename T, bool HAS_A>
+__global__ void __launch_bounds__(256) upcat_apply_rows_kernel(const T* __restrict__ skip, const T* __restrict__ low, const T* __restrict__ a,
+                                                               T* __restrict__ out, UpCatGeom g) {
+    const int Ct = g.Cs + g.Cu, lanes = Ct >> 3, ls = g.Cs >> 3, rstep = 256 / lanes;
+    if ((int)threadIdx.x >= rstep * lanes) return;
+    const int lv = threadIdx.x % lanes, r0 = threadIdx.x / lanes;
+    const int y = blockIdx.y;
+    const long long n = blockIdx.z;
+    const bool is_low = lv >= ls;
+    const int oy = y - g.py;
+    const bool row_valid = oy >= 0 && oy < 2 * g.h;
+    Lerp iy = lerp_src(row_valid ? oy : 0, g.h, g.sy, g.align);
+    float ah[8];
+    if (HAS_A) {
+        Vec8<T> t;
+        t.load(a + (n * (g.H + g.W) + y) * (long long)Ct + lv * 8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) ah[k] = t.v[k];
+    }
+    const T* srow = skip + ((n * g.H + y) * (long long)g.W) * g.Cs + lv * 8;
+    const T* lown = low + n * (long long)g.h * g.w * g.Cu;
+    const T* aw = HAS_A ? a + (n * (g.H + g.W) + g.H) * (long long)Ct + lv * 8 : nullptr;
+    T* orow = out + ((n * g.H + y) * (long long)g.W) * Ct + lv * 8;
+    for (int x = blockIdx.x * rstep + r0; x < g.W; x += gridDim.x * rstep) {
+        Vec8<T> v;
+        if (!is_low) v.load(srow + (long long)x * g.Cs);
+        else low_value(lown, g, row_valid, iy, x, (lv - ls) * 8, v.v);
+        if (HAS_A) {
+            Vec8<T> w_;
+            w_.load(aw + (long long)x * Ct);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v.v[k] = fmaf(ah[k], w_.v[k], v.v[k]);
+        }
+        v.store(orow + (long long)x * Ct);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ row / column means of the virtual cat
+// thread per (n, y, lane) sums over x  [rows 0..H-1 of the descriptor], thread per (n, x, lane) sums over y  [rows H..H+W-1]
+template <typename T>
+__global__ void __launch_bounds__(128) upcat_pool_kernel(const T* __restrict__ skip, const T* __restrict__ low, T* __restrict__ yout, int N,
+                                                         UpCatGeom g) {
+    const int Ct = g.Cs + g.Cu, lanes = Ct >> 3, ls = g.Cs >> 3;
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long n_row = (long long)N * g.H * lanes, n_col = (long long)N * g.W * lanes;
+    if (i >= n_row + n_col) return;
+    float acc[8] = {};
+    Vec8<T> o;
+    if (i < n_row) {
+        const int lv = (int)(i % lanes);
+        const long long nh = i / lanes, n = nh / g.H;
+        const int y = (int)(nh % g.H);
+        if (lv < ls) {
+            const T* b = skip + nh * (long long)g.W * g.Cs + lv * 8;
+            for (int x = 0; x < g.W; ++x) {
+                Vec8<T> v;
+                v.load(b + (long long)x * g.Cs);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] += v.v[k];
+            }
+        } else {
+            const int oy = y - g.py;
+            const bool row_valid = oy >= 0 && oy < 2 * g.h;
+            const Lerp iy = lerp_src(row_valid ? oy : 0, g.h, g.sy, g.align);
+            const T* lown = low + n * (long long)g.h * g.w * g.Cu;
+            for (int x = 0; x < g.W; ++x) {
+                float v[8];
+                low_value(lown, g, row_valid, iy, x, (lv - ls) * 8, v);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] += v[k];
+            }
+        }
+        const float sc = 1.f / (float)g.W;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o.v[k] = acc[k] * sc;
+        o.store(yout + (n * (g.H + g.W) + y) * (long long)Ct + lv * 8);
+    } else {
+        const long long j = i - n_row;
+        const int lv = (int)(j % lanes);
+        const long long nw = j / lanes, n = nw / g.W;
+        const int x = (int)(nw % g.W);
+        if (lv < ls) {
+            const T* b = skip + (n * g.H * (long long)g.W + x) * g.Cs + lv * 8;
+            for (int y = 0; y < g.H; ++y) {
+                Vec8<T> v;
+                v.load(b + (long long)y * g.W * g.Cs);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] += v.v[k];
+            }
+        } else {
+            const T* lown = low + n * (long long)g.h * g.w * g.Cu;
+            for (int y = 0; y < g.H; ++y) {
+                const int oy = y - g.py;
+                const bool row_valid = oy >= 0 && oy < 2 * g.h;
+                const Lerp iy = lerp_src(row_valid ? oy : 0, g.h, g.sy, g.align);
+                float v[8];
+                low_value(lown, g, row_valid, iy, x, (lv - ls) * 8, v);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] += v[k];
+            }
+        }
+        const float sc = 1.f / (float)g.H;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o.v[k] = acc[k] * sc;
+        o.store(yout + (n * (g.H + g.W) + g.H + x) * (long long)Ct + lv * 8);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+// skip half: dskip[n,y,x,:] = dout[n,y,x,:Cs] + dyh[n,y,:Cs]/W + dyw[n,x,:Cs]/H.   grid (gx, H, N), lanes = Cs/8
+template <typename T, bool HAS_DY>
+__global__ void __launch_bounds__(256) upcat_bwd_skip_rows_kernel(const T* __restrict__ dout, const T* __restrict__ dyhw, T* __restrict__ dskip,
+                                                                  UpCatGeom g) {
+    const int Ct = g.Cs + g.Cu, lanes = g.Cs >> 3, rstep = 256 / lanes;
+    if ((int)threadIdx.x >= rstep * lanes) return;
+    const int lv = threadIdx.x % lanes, r0 = threadIdx.x / lanes;
+    const int y = blockIdx.y;
+    const long long n = blockIdx.z;
+    float dh[8];
+    const float iw = 1.f / (float)g.W, ih = 1.f / (float)g.H;
+    if (HAS_DY) {
+        Vec8<T> t;
+        t.load(dyhw + (n * (g.H + g.W) + y) * (long long)Ct + lv * 8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dh[k] = t.v[k] * iw;
+    }
+    const T* drow = dout + ((n * g.H + y) * (long long)g.W) * Ct + lv * 8;
+    const T* dw = HAS_DY ? dyhw + (n * (g.H + g.W) + g.H) * (long long)Ct + lv * 8 : nullptr;
+    T* srow = dskip + ((n * g.H + y) * (long long)g.W) * g.Cs + lv * 8;
+    for (int x = blockIdx.x * rstep + r0; x < g.W; x += gridDim.x * rstep) {
+        Vec8<T> v;
+        v.load(drow + (long long)x * Ct);
+        if (HAS_DY) {
+            Vec8<T> w_;
+            w_.load(dw + (long long)x * Ct);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v.v[k] += dh[k] + w_.v[k] * ih;
+        }
+        v.store(srow + (long long)x * g.Cs);
+    }
+}
+
+// weights with which low index j receives from the up-sampled indices around it: candidates lo .. lo+STC_NC-1 (statically indexed so
+// the table stays in registers; entries past the last real tap carry weight 0)
+#define STC_NC 7
+struct Taps {
+    int lo;
+    float wt[STC_NC];
+};
+__device__ __forceinline__ Taps adjoint_taps(int j, int in, float scale, int align) {
+    Taps t;
+    const int out = 2 * in;
+    int hi;
+    if (align) {
+        t.lo = scale > 0.f ? max(0, (int)floorf((float)(j - 1) / scale)) : 0;
+        hi = scale > 0.f ? min(out - 1, (int)ceilf((float)(j + 1) / scale)) : out - 1;
+    } else {
+        t.lo = max(0, 2 * j - 2);
+        hi = min(out - 1, 2 * j + 3);
+    }
+#pragma unroll
+    for (int c = 0; c < STC_NC; ++c) {
+        const int o = t.lo + c;
+        float wgt = 0.f;
+        if (o <= hi) {
+            const Lerp l = lerp_src(o, in, scale, align);
+            wgt = (l.i0 == j ? l.l0 : 0.f) + (l.i1 == j ? l.l1 : 0.f);
+        }
+        t.wt[c] = wgt;
+    }
+    return t;
+}
+
+// low half (gather form of the adjoint).  grid (gx, h, N), lanes = Cu/8; one block per low-res row jy
+template <typename T, bool HAS_DY>
+__global__ void __launch_bounds__(256) upcat_bwd_low_rows_kernel(const T* __restrict__ dout, const T* __restrict__ dyhw, T* __restrict__ dlow,
+                                                                 UpCatGeom g) {
+    const int Ct = g.Cs + g.Cu, lanes = g.Cu >> 3, rstep = 256 / lanes;
+    if ((int)threadIdx.x >= rstep * lanes) return;
+    const int lv = threadIdx.x % lanes, r0 = threadIdx.x / lanes;
+    const int jy = blockIdx.y;
+    const long long n = blockIdx.z;
+    const float iw = 1.f / (float)g.W, ih = 1.f / (float)g.H;
+    const Taps ty = adjoint_taps(jy, g.h, g.sy, g.align);
+    const int cofs = g.Cs + lv * 8;
+    // row-constant part: sum_t wy_t * dyh[n, oy_t + py] / W   (multiplied by the sum of wx below)
+    float dh[8] = {};
+    float wysum = 0.f;
+#pragma unroll
+    for (int t = 0; t < STC_NC; ++t) {
+        wysum += ty.wt[t];
+        if (HAS_DY && ty.wt[t] != 0.f) {
+            Vec8<T> v;
+            v.load(dyhw + (n * (g.H + g.W) + ty.lo + t + g.py) * (long long)Ct + cofs);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) dh[k] = fmaf(ty.wt[t] * iw, v.v[k], dh[k]);
+        }
+    }
+    const T* dn = dout + (n * g.H + ty.lo + g.py) * (long long)g.W * Ct + cofs;
+    const T* dwp = HAS_DY ? dyhw + (n * (g.H + g.W) + g.H) * (long long)Ct + cofs : nullptr;
+    T* lrow = dlow + ((n * g.h + jy) * (long long)g.w) * g.Cu + lv * 8;
+    for (int jx = blockIdx.x * rstep + r0; jx < g.w; jx += gridDim.x * rstep) {
+        const Taps tx = adjoint_taps(jx, g.w, g.sx, g.align);
+        float acc[8] = {};
+        float wxsum = 0.f;
+#pragma unroll
+        for (int s = 0; s < STC_NC; ++s) {
+            if (tx.wt[s] == 0.f) continue;
+            wxsum += tx.wt[s];
+            const long long xoff = (long long)(tx.lo + s + g.px) * Ct;
+#pragma unroll
+            for (int t = 0; t < STC_NC; ++t) {
+                if (ty.wt[t] == 0.f) continue;
+                Vec8<T> v;
+                v.load(dn + (long long)t * g.W * Ct + xoff);
+                const float ww = ty.wt[t] * tx.wt[s];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] = fmaf(ww, v.v[k], acc[k]);
+            }
+            if (HAS_DY) {
+                Vec8<T> v;
+                v.load(dwp + xoff);
+                const float ww = tx.wt[s] * wysum * ih;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] = fmaf(ww, v.v[k], acc[k]);
+            }
+        }
+        Vec8<T> o;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o.v[k] = HAS_DY ? fmaf(dh[k], wxsum, acc[k]) : acc[k];
+        o.store(lrow + (long long)jx * g.Cu);
+    }
+}
+
+static inline bool rows_ok(int C) { return C > 0 && C % 8 == 0 && C / 8 <= 256; }
+static inline dim3 rows_grid(int Wd, int Hd, int N, int lanes) {
+    int rstep = 256 / lanes;
+    int gx = (Wd + rstep * 4 - 1) / (rstep * 4);   // ~4 pixels per thread
+    return dim3((unsigned)(gx < 1 ? 1 : gx), (unsigned)Hd, (unsigned)N);
+}
+
+}  // namespace stc
+
+using namespace stc;
+
+extern "C" int stc_upcat_fused_ok(int N, int H, int W, int Cs, int h, int w, int Cu) {
+    return (Cs % 8 == 0 && Cu % 8 == 0 && Cu > 0 && rows_ok(Cs + Cu) && H >= 2 * h && W >= 2 * w && H <= 65535 && N <= 65535) ? 1 : 0;
+}
+
+extern "C" int stc_upcat_apply_fwd(const void* skip, const void* low, const void* a, void* out, int N, int H, int W, int Cs, int h, int w, int Cu,
+                                   int align_corners, int dtype, void* stream) {
+    STC_REQUIRE(stc_upcat_fused_ok(N, H, W, Cs, h, w, Cu), "upcat_apply_fwd: unsupported shape (N=%d H=%d W=%d Cs=%d h=%d w=%d Cu=%d)", N, H, W, Cs, h,
+                w, Cu);
+    STC_REQUIRE(low && out && (skip || Cs == 0), "upcat_apply_fwd: null pointer");
+    if ((long long)N * H * W == 0) return STC_OK;
+    UpCatGeom g = make_geom(H, W, Cs, h, w, Cu, align_corners);
+    dim3 grid = rows_grid(W, H, N, (Cs + Cu) / 8);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a) {
+        STC_DISPATCH_DTYPE(dtype, (upcat_apply_rows_kernel<T, true><<<grid, 256, 0, st>>>((const T*)skip, (const T*)low, (const T*)a, (T*)out, g)));
+    } else {
+        STC_DISPATCH_DTYPE(dtype, (upcat_apply_rows_kernel<T, false><<<grid, 256, 0, st>>>((const T*)skip, (const T*)low, nullptr, (T*)out, g)));
+    }
+    return check_launch("upcat_apply_fwd");
+}
+
+extern "C" int stc_upcat_pool(const void* skip, const void* low, void* y, int N, int H, int W, int Cs, int h, int w, int Cu, int align_corners,
+                              int dtype, void* stream) {
+    STC_REQUIRE(stc_upcat_fused_ok(N, H, W, Cs, h, w, Cu), "upcat_pool: unsupported shape");
+    STC_REQUIRE(low && y && (skip || Cs == 0), "upcat_pool: null pointer");
+    UpCatGeom g = make_geom(H, W, Cs, h, w, Cu, align_corners);
+    long long total = (long long)N * (H + W) * ((Cs + Cu) / 8);
+    if (total == 0) return STC_OK;
+    STC_DISPATCH_DTYPE(dtype, (upcat_pool_kernel<T><<<ceil_div(total, 128), 128, 0, (cudaStream_t)stream>>>((const T*)skip, (const T*)low, (T*)y, N, g)));
+    return check_launch("upcat_pool");
+}
+
+extern "C" int stc_upcat_apply_bwd(const void* dout, const void* dyhw, void* dskip, void* dlow, int N, int H, int W, int Cs, int h, int w, int Cu,
+                                   int align_corners, int dtype, void* stream) {
+    STC_REQUIRE(stc_upcat_fused_ok(N, H, W, Cs, h, w, Cu), "upcat_apply_bwd: unsupported shape");
+    STC_REQUIRE(dout, "upcat_apply_bwd: null pointer");
+    if ((long long)N * H * W == 0) return STC_OK;
+    UpCatGeom g = make_geom(H, W, Cs, h, w, Cu, align_corners);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dskip && Cs > 0) {
+        dim3 grid = rows_grid(W, H, N, Cs / 8);
+        if (dyhw) {
+            STC_DISPATCH_DTYPE(dtype, (upcat_bwd_skip_rows_kernel<T, true><<<grid, 256, 0, st>>>((const T*)dout, (const T*)dyhw, (T*)dskip, g)));
+        } else {
+            STC_DISPATCH_DTYPE(dtype, (upcat_bwd_skip_rows_kernel<T, false><<<grid, 256, 0, st>>>((const T*)dout, nullptr, (T*)dskip, g)));
+        }
+    }
+    if (dlow) {
+        dim3 grid = rows_grid(w, h, N, Cu / 8);
+        if (dyhw) {
+            STC_DISPATCH_DTYPE(dtype, (upcat_bwd_low_rows_kernel<T, true><<<grid, 256, 0, st>>>((const T*)dout, (const T*)dyhw, (T*)dlow, g)));
+        } else {
+            STC_DISPATCH_DTYPE(dtype, (upcat_bwd_low_rows_kernel<T, false><<<grid, 256, 0, st>>>((const T*)dout, nullptr, (T*)dlow, g)));
+        }
+    }
+    return check_launch("upcat_apply_bwd");
+}

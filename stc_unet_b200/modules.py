@@ -221,6 +221,11 @@ class CoordAtt(nn.Module):
     def forward_add(self, x):  # x NHWC
         N, H, W, C = x.shape
         y, xb = ops.coordatt_pool(x)                              # (N, H+W, C) descriptors + pass-through of x
+        return ops.coordatt_apply(xb, self.attention(y, N, H, W))
+
+    def attention(self, y, N, H, W):
+        """(N, H+W, C) pooled descriptors -> (N, H+W, C) attention factors [a_h ; a_w]  (unet_head.py:137-145)."""
+        C = y.shape[-1]
         # conv1 + bn1 + h_swish over the N*(H+W) descriptors, as a (N, H+W, 1, C) image
         y = ops.conv_bn_act(y.view(N, H + W, 1, C), self.conv1, self.bn1, ACT_HSWISH, self.training)
         mip = y.shape[-1]
@@ -229,7 +234,7 @@ class CoordAtt(nn.Module):
         ah = ops.conv2d(ops.slice_rows(ya, 0, H), self.conv_h.weight, self.conv_h.bias, act=ACT_SIGMOID)
         aw = ops.conv2d(ops.slice_rows(yb, H, W), self.conv_w.weight, self.conv_w.bias, act=ACT_SIGMOID)
         a = ops.cat_rows(ah, aw)                                  # (N, H+W, 1, C)
-        return ops.coordatt_apply(xb, a.view(N, H + W, C))
+        return a.view(N, H + W, C)
 
 
 class Up(nn.Module):
@@ -245,9 +250,10 @@ class Up(nn.Module):
         self.conv = DoubleConv(in_ch, out_ch)
 
     def forward(self, x1, x2):  # both NHWC; x2 = skip
-        x = ops.upcat(x2, x1, align_corners=True)
-        if self.se:
-            x = self.ca.forward_add(x)
+        if self.se:   # cat, CoordAtt pooling and `ca(x) + x` without ever writing the concatenated tensor
+            x = ops.upcat_coordatt(x2, x1, True, self.ca.attention)
+        else:
+            x = ops.upcat(x2, x1, align_corners=True)
         return self.conv(x)
 
 

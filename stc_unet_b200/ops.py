@@ -191,10 +191,11 @@ class StepCache:
             rows.append([ptr, off, Cout, Cin, R, S, inner_pad, mode])
             self.packs[key] = (off, n)
             off += (n + 7) // 8 * 8            # keep every packed tensor 16-byte aligned (TMA base alignment)
-            prefix.append(prefix[-1] + n)
+            assert mode == 2 or inner_pad == (Cout if mode == 1 else Cin)
+            prefix.append(prefix[-1] + (n if mode == 2 else Cout * Cin))   # work items: (co,ci) pairs, or elements for im2col
             self.dtype = dt
         self.total = prefix[-1]
-        # dst offsets are padded, the work index space (prefix) is dense
+        # dst offsets are padded, the work-item index space (prefix) is dense
         self.arena = torch.empty(max(off, 8), dtype=self.dtype, device=dev)
         self.table = torch.tensor(rows, dtype=torch.int64, device=dev)
         self.prefix = torch.tensor(prefix, dtype=torch.int64, device=dev)
@@ -588,6 +589,83 @@ class _UpCat(Function):
 
 def upcat(skip, low, align_corners=True):
     return _UpCat.apply(skip, low, align_corners)
+
+
+# ---------------------------------------------------------------------------------------------
+# Up.forward with CoordAtt, fused: cat = [skip, up(low)] is never materialised (csrc/upcat_fused.cu)
+# ---------------------------------------------------------------------------------------------
+class _UpCatShared:
+    """Hand-over between the two nodes below: _UpCatApply.backward leaves dout here, _UpCatPool.backward (which autograd can only
+    run afterwards: its dy depends on da) folds it with dy into ONE pass that writes dskip and dlow."""
+
+    def __init__(self):
+        self.dout = None
+
+
+class _UpCatPool(Function):
+    @staticmethod
+    def forward(ctx, skip, low, align_corners: bool, shared: _UpCatShared):
+        skip, low = _chk(skip), _chk(low)
+        N, H, W, Cs = skip.shape
+        _, h, w, Cu = low.shape
+        y = torch.empty((N, H + W, Cs + Cu), dtype=skip.dtype, device=skip.device)
+        lib.call("stc_upcat_pool", skip, low, y, N, H, W, Cs, h, w, Cu, int(align_corners), dtype_code(skip.dtype), stream_ptr())
+        ctx.meta = (N, H, W, Cs, h, w, Cu, int(align_corners), shared, skip.dtype, skip.device)
+        ctx.set_materialize_grads(False)
+        return y, skip.view_as(skip), low.view_as(low)
+
+    @staticmethod
+    def backward(ctx, dy, gs, gl):
+        N, H, W, Cs, h, w, Cu, ac, shared, dt, dev = ctx.meta
+        assert gs is None and gl is None, "the skip/low aliases of upcat_coordatt must only feed its apply node"
+        dout, shared.dout = shared.dout, None
+        if dout is None and dy is None:
+            return None, None, None, None
+        if dout is None:
+            dout = torch.zeros((N, H, W, Cs + Cu), dtype=dt, device=dev)
+        dskip = torch.empty((N, H, W, Cs), dtype=dt, device=dev) if ctx.needs_input_grad[0] else None
+        dlow = torch.empty((N, h, w, Cu), dtype=dt, device=dev) if ctx.needs_input_grad[1] else None
+        lib.call("stc_upcat_apply_bwd", dout, None if dy is None else _chk(dy), dskip, dlow, N, H, W, Cs, h, w, Cu, ac, dtype_code(dt),
+                 stream_ptr())
+        return dskip, dlow, None, None
+
+
+class _UpCatApply(Function):
+    @staticmethod
+    def forward(ctx, skip, low, a, align_corners: bool, shared: _UpCatShared):
+        N, H, W, Cs = skip.shape
+        _, h, w, Cu = low.shape
+        a = _chk(a)
+        out = torch.empty((N, H, W, Cs + Cu), dtype=skip.dtype, device=skip.device)
+        lib.call("stc_upcat_apply_fwd", skip, low, a, out, N, H, W, Cs, h, w, Cu, int(align_corners), dtype_code(skip.dtype), stream_ptr())
+        ctx.save_for_backward(a)
+        ctx.meta = (N, H, W, Cs + Cu, shared)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (a,) = ctx.saved_tensors
+        N, H, W, C, shared = ctx.meta
+        dout = _chk(dout)
+        shared.dout = dout
+        da = None
+        if ctx.needs_input_grad[2]:
+            da = torch.empty_like(a)
+            lib.call("stc_coordatt_apply_bwd", dout, a, da, N, H, W, C, dtype_code(dout.dtype), stream_ptr())
+        return None, None, da, None, None
+
+
+def upcat_coordatt(skip, low, align_corners, attention):
+    """out = cat + a_h*a_w with cat = [skip, pad(bilinear_x2(low))] and a = attention(row/col means of cat)  (Up.forward with se=True).
+    Falls back to upcat + coordatt_pool/apply for channel counts the fused kernels do not take."""
+    N, H, W, Cs = skip.shape
+    _, h, w, Cu = low.shape
+    if not lib.raw("stc_upcat_fused_ok")(N, H, W, Cs, h, w, Cu):
+        y, xb = coordatt_pool(upcat(skip, low, align_corners))
+        return coordatt_apply(xb, attention(y, N, H, W))
+    shared = _UpCatShared()
+    y, s_alias, l_alias = _UpCatPool.apply(skip, low, align_corners, shared)
+    return _UpCatApply.apply(s_alias, l_alias, attention(y, N, H, W), align_corners, shared)
 
 
 # ---------------------------------------------------------------------------------------------

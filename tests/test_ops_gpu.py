@@ -437,3 +437,56 @@ def test_deconv4x2_bn_relu(S, dt, engine):
         assert rel_l2(m.deconv_upsamping[1].running_var, ref[1].running_var) < (1e-5 if dt == torch.float32 else 1e-2)
     finally:
         ops.config.engine = S._lib.ENGINE_AUTO
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("shape", [(2, 16, 16, 6, 7, 12, 14), (1, 8, 24, 5, 4, 11, 9), (2, 64, 64, 8, 8, 16, 16)])
+def test_upcat_coordatt_fused(S, dt, shape):
+    """Up.forward with CoordAtt without the concatenated tensor: out = cat + a_h*a_w, a = f(row/col means of cat), and the single-pass
+    adjoint (dout + dy_h/W + dy_w/H -> dskip, dlow) vs the plain torch composition in fp64 (incl. the padded odd-size case)."""
+    from stc_unet_b200 import ops
+    N, Cs, Cu, h, w, H, W = shape
+    torch.manual_seed(1)
+    skip, low = torch.randn(N, Cs, H, W, device=dev()), torch.randn(N, Cu, h, w, device=dev())
+    mix = torch.randn(Cs + Cu, device=dev()) * 0.5
+    if dt == torch.bfloat16:
+        skip, low = bf16_round(skip), bf16_round(low)
+    sr, lr = skip.double().requires_grad_(True), low.double().requires_grad_(True)
+    up = F.interpolate(lr, scale_factor=2, mode="bilinear", align_corners=True)
+    dy_, dx_ = H - up.shape[2], W - up.shape[3]
+    cat = torch.cat([sr, F.pad(up, (dx_ // 2, dx_ - dx_ // 2, dy_ // 2, dy_ - dy_ // 2))], dim=1)
+    att = lambda t: torch.sigmoid(t * mix.to(t.dtype).view(1, -1, 1, 1))
+    ref = cat + att(cat.mean(3, keepdim=True)) * att(cat.mean(2, keepdim=True))
+    so, lo = nhwc(skip).to(dt).requires_grad_(True), nhwc(low).to(dt).requires_grad_(True)
+    out = ops.upcat_coordatt(so, lo, True, lambda y, n_, h_, w_: torch.sigmoid(y.float() * mix).to(y.dtype))
+    assert rel_l2(nchw(out.float()), ref) < (1e-6 if dt == torch.float32 else 1e-2)
+    go = torch.randn_like(ref)
+    ref.backward(go)
+    out.backward(nhwc(go.float()).to(dt))
+    assert rel_l2(nchw(so.grad.float()), sr.grad) < tol(dt)
+    assert rel_l2(nchw(lo.grad.float()), lr.grad) < tol(dt)
+
+
+def test_step_cache_batched_pack_matches_single_packs(S):
+    """StepCache replay: ONE stc_pack_conv_weights_batched launch must reproduce every individual stc_pack_conv_weight result
+    (fprop, flipped/transposed dgrad and im2col orientations), also after the weights changed."""
+    from stc_unet_b200 import ops
+    torch.manual_seed(0)
+    ws = [torch.randn(s, device=dev()) for s in [(64, 32, 3, 3), (128, 64, 5, 5), (32, 3, 3, 3), (64, 64, 1, 1), (16, 40, 7, 7)]]
+    reqs = [(ws[0], False, 0), (ws[0], True, 0), (ws[1], False, 0), (ws[1], True, 0), (ws[2], False, 64), (ws[3], False, 0), (ws[3], True, 0),
+            (ws[4], True, 0), (ws[4], False, 0)]
+    cache = ops.StepCache()
+    ops.set_step_cache(cache)
+    try:
+        cache.begin_step()                                  # record
+        for w, tf, pad in reqs:
+            ops.pack_weight(w, torch.bfloat16, transpose_flip=tf, im2col_pad=pad)
+        for w in ws:
+            w.mul_(1.5).add_(0.25)                          # "optimizer step"
+        cache.begin_step()                                  # finalize + first replay (one batched launch)
+        got = [ops.pack_weight(w, torch.bfloat16, transpose_flip=tf, im2col_pad=pad).clone() for w, tf, pad in reqs]
+    finally:
+        ops.set_step_cache(None)
+    for (w, tf, pad), g in zip(reqs, got):
+        ref = ops.pack_weight(w, torch.bfloat16, transpose_flip=tf, im2col_pad=pad)
+        assert g.shape == ref.shape and torch.equal(g, ref), (tuple(w.shape), tf, pad)
