@@ -160,10 +160,13 @@ int stc_upcat_bwd(const void* dout, void* dskip, void* dlow, int N, int H, int W
  * stc_upcat_apply_fwd: out = cat + a_h*a_w with a (N,H+W,Cs+Cu); a == NULL gives out = cat.
  * stc_upcat_apply_bwd: g = dout + dy_h/W + dy_w/H (dyhw (N,H+W,Cs+Cu) = gradient of the pooled descriptor, may be NULL);
  * dskip = g[..., :Cs], dlow = adjoint of the bilinear x2 applied to g[..., Cs:]; either output may be NULL.
+ * stc_upcat_pool needs a caller-provided workspace of stc_upcat_pool_ws_bytes (fp32 partial reductions of low: the means of the up-sampled
+ * half are linear in low, so low is reduced with the adjoint interpolation weights and the result interpolated).
  * stc_upcat_fused_ok returns 1 when these row-structured kernels support the shape ((Cs+Cu)/8 <= 256 lanes). */
 int stc_upcat_fused_ok(int N, int H, int W, int Cs, int h, int w, int Cu);
-int stc_upcat_pool(const void* skip, const void* low, void* y, int N, int H, int W, int Cs, int h, int w, int Cu, int align_corners, int dtype,
-                   void* stream);
+long long stc_upcat_pool_ws_bytes(int N, int h, int w, int Cu);
+int stc_upcat_pool(const void* skip, const void* low, void* y, int N, int H, int W, int Cs, int h, int w, int Cu, int align_corners, void* ws,
+                   long long ws_bytes, int dtype, void* stream);
 int stc_upcat_apply_fwd(const void* skip, const void* low, const void* a, void* out, int N, int H, int W, int Cs, int h, int w, int Cu,
                         int align_corners, int dtype, void* stream);
 int stc_upcat_apply_bwd(const void* dout, const void* dyhw, void* dskip, void* dlow, int N, int H, int W, int Cs, int h, int w, int Cu,

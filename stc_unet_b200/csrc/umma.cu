@@ -11,6 +11,7 @@
 // warps 2..5 = epilogue (TMEM -> registers -> global).  smem ring of `stages` A/B slots (128B-swizzled),
 // two TMEM accumulator stages of 256 columns so the epilogue of tile i overlaps the main loop of tile i+1.
 #include <cuda.h>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "umma.cuh"
@@ -22,6 +23,7 @@ enum { MODE_CONV = 0, MODE_GEMM = 1, MODE_WGRAD = 2 };
 struct alignas(64) UmmaParams {
     CUtensorMap tmA;
     CUtensorMap tmB;
+    CUtensorMap tmC;   // output map for the staged (shared memory + TMA store) epilogue, see store_tma
     int mode;
     int num_tiles, num_n_tiles, num_m_tiles;
     int num_k_iters;  // conv/gemm: k iterations per tile; wgrad: total pixel tiles
@@ -45,7 +47,13 @@ struct alignas(64) UmmaParams {
     int act, out_dtype, Cout;
     long long ldc, sC1, sC2;
     float alpha;
+    // store_tma: each epilogue warp stages 32 rows x 64 bf16 columns in a 128B-swizzled 4 KB buffer (two per warp) and one lane
+    // issues a TMA store of that box -> full 128-byte lines instead of 32 scattered 16-byte row segments per instruction
+    int store_tma;
 };
+
+constexpr uint32_t kStageBufBytes = 32 * 128;   // 32 rows x 64 bf16
+constexpr uint32_t kStagingBytes = 4 * 2 * kStageBufBytes;
 
 struct TileInfo {
     int nt, mt;
@@ -102,7 +110,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_cons
     // 1024B alignment for the 128B swizzle atoms
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    const uint32_t staging_bytes = p.store_tma ? kStagingBytes : 0u;   // right after the ring, 1024-byte aligned like it
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes + staging_bytes);
     // bars: [0,stages) full, [stages,2*stages) empty, then tmem_full[2], tmem_empty[2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
 
@@ -117,6 +126,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_cons
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&p.tmA);
         ptx::prefetch_tensormap(&p.tmB);
+        if (p.store_tma) ptx::prefetch_tensormap(&p.tmC);
         for (int s = 0; s < p.stages; ++s) {
             ptx::mbar_init(full_bar(s), 1);
             ptx::mbar_init(empty_bar(s), 1);
@@ -233,7 +243,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_cons
         // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
         const int q = warp & 3;  // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;
-        int acc = 0;
+        int acc = 0, stage_buf = 0;
         uint32_t acc_phase[2] = {0, 0};
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             TileInfo t = decode_tile(p, tile);
@@ -257,6 +267,80 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_cons
             ptx::mbar_wait(tfull_bar(acc), acc_phase[acc]);
             ptx::tc_fence_after();
             const uint32_t t_addr = tmem_base + acc * kAccCols + ((uint32_t)(q * 32) << 16);
+            if (p.store_tma) {
+                // ---- staged epilogue: TMEM -> registers -> swizzled smem -> TMA store (bf16 out, CONV / GEMM modes) ----
+                int c1, c2, c3;   // box origin below the channel coordinate
+                if (p.mode == MODE_CONV) {
+                    const int r0 = q * 32;
+                    c1 = t.w0 + (r0 & (p.BW - 1));
+                    c2 = t.h0 + (r0 >> p.bw_shift);
+                    c3 = t.n_img;
+                } else {
+                    c1 = t.mt * 128 + q * 32;
+                    c2 = t.b2;
+                    c3 = t.b1;
+                }
+                const uint32_t stg0 = smem_base + p.stages * stage_bytes + (uint32_t)q * 2u * kStageBufBytes;
+                for (int c = 0; c < p.BN; c += 64) {
+                    const uint32_t stg = stg0 + (uint32_t)stage_buf * kStageBufBytes;
+                    if (lane == 0) ptx::bulk_wait_read<1>();   // the store issued from this buffer two chunks ago has read it
+                    __syncwarp();
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        uint32_t v[32];
+                        ptx::tmem_ld_32x32(t_addr + c + half * 32, v);
+                        ptx::tmem_ld_wait();
+                        float f[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+                        if (p.bias) {
+                            const float* b = p.bias + t.nt * p.BN + c + half * 32;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] += __ldg(b + j);
+                        }
+                        if (p.residual && valid) {
+                            const uint4* r = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.residual) + off + c + half * 32);
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                uint4 rv = __ldg(r + g);
+                                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    float2 x = __bfloat1622float2(h[e]);
+                                    f[g * 8 + 2 * e] += x.x;
+                                    f[g * 8 + 2 * e + 1] += x.y;
+                                }
+                            }
+                        }
+                        if (p.act != STC_ACT_NONE) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] = epi_act(f[j], p.act);
+                        }
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            uint4 ov;
+                            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(f[g * 8 + 2 * e], f[g * 8 + 2 * e + 1]);
+                            // 128B swizzle: 16-byte chunk index XOR (row mod 8); the buffer is 1024-byte aligned
+                            ptx::st_shared_v4(stg + (uint32_t)lane * 128u + (uint32_t)(((half * 4 + g) ^ (lane & 7)) << 4), ov);
+                        }
+                    }
+                    ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        ptx::tma_store_4d(&p.tmC, stg, t.nt * p.BN + c, c1, c2, c3);
+                        ptx::bulk_commit();
+                    }
+                    stage_buf ^= 1;
+                }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+                acc_phase[acc] ^= 1;
+                acc ^= 1;
+                continue;
+            }
             for (int c = 0; c < p.BN; c += 32) {
                 uint32_t v[32];
                 ptx::tmem_ld_32x32(t_addr + c, v);
@@ -322,6 +406,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_cons
             acc_phase[acc] ^= 1;
             acc ^= 1;
         }
+        if (p.store_tma && lane == 0) ptx::bulk_wait<0>();   // all output boxes written before the CTA retires
     }
 
     ptx::tc_fence_before();
@@ -379,6 +464,11 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t
     return STC_OK;
 }
 
+static bool getenv_off(const char* name) {
+    const char* v = getenv(name);
+    return v && v[0] == '0';
+}
+
 static int pick_bn(int n) {
     const int cands[] = {256, 192, 128, 96, 64, 32};
     for (int c : cands)
@@ -392,7 +482,7 @@ int encode_map_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* 
 int umma_pick_bn(int n) { return pick_bn(n); }
 
 static int launch(UmmaParams& p, cudaStream_t st) {
-    size_t smem = (size_t)p.stages * (p.a_stage_bytes + p.b_stage_bytes) + (2 * p.stages + 4) * 8 + 16 + 1024;
+    size_t smem = (size_t)p.stages * (p.a_stage_bytes + p.b_stage_bytes) + (p.store_tma ? kStagingBytes : 0) + (2 * p.stages + 4) * 8 + 16 + 1024;
     static bool attr_set[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -426,8 +516,8 @@ static void conv_geometry(UmmaParams& p, int H, int W, int R, int S, int Cin) {
     p.cin_chunks = Cin / 64;
 }
 
-static int pick_stages(uint32_t stage_bytes) {
-    int s = (int)((200 * 1024) / stage_bytes);
+static int pick_stages(uint32_t stage_bytes, bool staged_epilogue = false) {
+    int s = (int)(((staged_epilogue ? 192 : 200) * 1024) / stage_bytes);
     if (s > 8) s = 8;
     return s;
 }
@@ -468,7 +558,16 @@ int conv_fprop_umma(const void* x, const void* wp, const float* bias, const void
     p.a_lbo = 0; p.a_sbo = 1024; p.a_kstep_bytes = 32;
     p.b_lbo = 0; p.b_sbo = 1024; p.b_kstep_bytes = 32;
     p.idesc = make_idesc_bf16(128, p.BN, 0, 0);
-    p.stages = pick_stages(p.a_stage_bytes + p.b_stage_bytes);
+    p.store_tma = (p.BN % 64 == 0 && !getenv_off("STC_TMA_STORE")) ? 1 : 0;
+    if (p.store_tma) {   // per epilogue warp: 32 tile rows = a (bw32 x 32/bw32) pixel patch, 64 channels
+        const uint32_t bw32 = (uint32_t)(p.BW < 32 ? p.BW : 32);
+        uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+        uint64_t str[4] = {2, (uint64_t)Cout * 2, (uint64_t)W * Cout * 2, (uint64_t)H * W * Cout * 2};
+        uint32_t box[4] = {64, bw32, 32 / bw32, 1};
+        int rc = encode_map(&p.tmC, y, 4, dims, str, box);
+        if (rc) return rc;
+    }
+    p.stages = pick_stages(p.a_stage_bytes + p.b_stage_bytes, p.store_tma);
     p.out = y; p.bias = bias; p.residual = residual; p.act = act; p.out_dtype = STC_BF16; p.Cout = Cout;
     p.alpha = 1.f;
     return launch(p, st);
@@ -588,7 +687,15 @@ int gemm_umma(const void* A, const void* B, void* C, const stc_gemm_desc* d, int
     }
     p.b_stage_bytes = (uint32_t)p.BN * 128;
     p.idesc = make_idesc_bf16(128, p.BN, p.a_mn_major, p.b_mn_major);
-    p.stages = pick_stages(p.a_stage_bytes + p.b_stage_bytes);
+    p.store_tma = (out_dtype == STC_BF16 && p.BN % 64 == 0 && ((uintptr_t)C & 15) == 0 && !getenv_off("STC_TMA_STORE")) ? 1 : 0;
+    if (p.store_tma) {
+        uint64_t dims[4] = {(uint64_t)d->N, (uint64_t)d->M, b2, b1};
+        uint64_t str[4] = {2, (uint64_t)d->sCm * 2, (uint64_t)(d->sC2 ? d->sC2 : 8) * 2, (uint64_t)(d->sC1 ? d->sC1 : 8) * 2};
+        uint32_t box[4] = {64, 32, 1, 1};
+        int rc = encode_map(&p.tmC, C, 4, dims, str, box);
+        if (rc) return rc;
+    }
+    p.stages = pick_stages(p.a_stage_bytes + p.b_stage_bytes, p.store_tma);
     p.out = C; p.out_dtype = out_dtype; p.Cout = d->N;
     p.ldc = d->sCm; p.sC1 = d->sC1; p.sC2 = d->sC2; p.alpha = d->alpha;
     return launch(p, st);

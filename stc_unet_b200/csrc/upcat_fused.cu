@@ -59,35 +59,65 @@ __device__ __forceinline__ void low_value(const T* __restrict__ lown, const UpCa
     for (int k = 0; k < 8; ++k) v[k] = iy.l0 * (ix.l0 * a00.v[k] + ix.l1 * a01.v[k]) + iy.l1 * (ix.l0 * a10.v[k] + ix.l1 * a11.v[k]);
 }
 
+// weights with which low index j receives from the up-sampled indices around it: candidates lo .. lo+STC_NC-1 (statically indexed so
+// the table stays in registers; entries past the last real tap carry weight 0)
+#define STC_NC 7
+struct Taps {
+    int lo;
+    float wt[STC_NC];
+};
+__device__ __forceinline__ Taps adjoint_taps(int j, int in, float scale, int align) {
+    Taps t;
+    const int out = 2 * in;
+    int hi;
+    if (align) {
+        t.lo = scale > 0.f ? max(0, (int)floorf((float)(j - 1) / scale)) : 0;
+        hi = scale > 0.f ? min(out - 1, (int)ceilf((float)(j + 1) / scale)) : out - 1;
+    } else {
+        t.lo = max(0, 2 * j - 2);
+        hi = min(out - 1, 2 * j + 3);
+    }
+#pragma unroll
+    for (int c = 0; c < STC_NC; ++c) {
+        const int o = t.lo + c;
+        float wgt = 0.f;
+        if (o <= hi) {
+            const Lerp l = lerp_src(o, in, scale, align);
+            wgt = (l.i0 == j ? l.l0 : 0.f) + (l.i1 == j ? l.l1 : 0.f);
+        }
+        t.wt[c] = wgt;
+    }
+    return t;
+}
+
 // ------------------------------------------------------------------------------------------------ forward
-// grid (gx, H, N); block 256; lanes = (Cs+Cu)/8 <= 256
-template <typename T, bool HAS_A>
-__global__ void __launch_bounds__(256) upcat_apply_rows_kernel(const T* __restrict__ skip, const T* __restrict__ low, const T* __restrict__ a,
-                                                               T* __restrict__ out, UpCatGeom g) {
-    const int Ct = g.Cs + g.Cu, lanes = Ct >> 3, ls = g.Cs >> 3, rstep = 256 / lanes;
+// Two launches, one per half of the channel range, so every warp runs ONE code path (copy or interpolate).
+// grid (gx, H, N); block 256; lanes = (channels of this half)/8 <= 256; the half starts at channel `c0` of the output row.
+template <typename T, bool HAS_A, bool IS_LOW>
+__global__ void __launch_bounds__(256) upcat_apply_rows_kernel(const T* __restrict__ src, const T* __restrict__ a, T* __restrict__ out,
+                                                               UpCatGeom g) {
+    const int Ct = g.Cs + g.Cu, Ch = IS_LOW ? g.Cu : g.Cs, c0 = IS_LOW ? g.Cs : 0, lanes = Ch >> 3, rstep = 256 / lanes;
     if ((int)threadIdx.x >= rstep * lanes) return;
     const int lv = threadIdx.x % lanes, r0 = threadIdx.x / lanes;
     const int y = blockIdx.y;
     const long long n = blockIdx.z;
-    const bool is_low = lv >= ls;
     const int oy = y - g.py;
     const bool row_valid = oy >= 0 && oy < 2 * g.h;
-    Lerp iy = lerp_src(row_valid ? oy : 0, g.h, g.sy, g.align);
+    const Lerp iy = lerp_src(row_valid ? oy : 0, g.h, g.sy, g.align);
     float ah[8];
     if (HAS_A) {
         Vec8<T> t;
-        t.load(a + (n * (g.H + g.W) + y) * (long long)Ct + lv * 8);
+        t.load(a + (n * (g.H + g.W) + y) * (long long)Ct + c0 + lv * 8);
 #pragma unroll
         for (int k = 0; k < 8; ++k) ah[k] = t.v[k];
     }
-    const T* srow = skip + ((n * g.H + y) * (long long)g.W) * g.Cs + lv * 8;
-    const T* lown = low + n * (long long)g.h * g.w * g.Cu;
-    const T* aw = HAS_A ? a + (n * (g.H + g.W) + g.H) * (long long)Ct + lv * 8 : nullptr;
-    T* orow = out + ((n * g.H + y) * (long long)g.W) * Ct + lv * 8;
+    const T* srow = IS_LOW ? src + n * (long long)g.h * g.w * g.Cu : src + ((n * g.H + y) * (long long)g.W) * g.Cs + lv * 8;
+    const T* aw = HAS_A ? a + (n * (g.H + g.W) + g.H) * (long long)Ct + c0 + lv * 8 : nullptr;
+    T* orow = out + ((n * g.H + y) * (long long)g.W) * Ct + c0 + lv * 8;
     for (int x = blockIdx.x * rstep + r0; x < g.W; x += gridDim.x * rstep) {
         Vec8<T> v;
-        if (!is_low) v.load(srow + (long long)x * g.Cs);
-        else low_value(lown, g, row_valid, iy, x, (lv - ls) * 8, v.v);
+        if (!IS_LOW) v.load(srow + (long long)x * g.Cs);
+        else low_value(srow, g, row_valid, iy, x, lv * 8, v.v);
         if (HAS_A) {
             Vec8<T> w_;
             w_.load(aw + (long long)x * Ct);
@@ -99,74 +129,101 @@ __global__ void __launch_bounds__(256) upcat_apply_rows_kernel(const T* __restri
 }
 
 // ------------------------------------------------------------------------------------------------ row / column means of the virtual cat
-// thread per (n, y, lane) sums over x  [rows 0..H-1 of the descriptor], thread per (n, x, lane) sums over y  [rows H..H+W-1]
+// skip half: plain sums.  thread per (n, y, lane) sums over x  [descriptor rows 0..H-1], thread per (n, x, lane) sums over y  [rows H..]
 template <typename T>
-__global__ void __launch_bounds__(128) upcat_pool_kernel(const T* __restrict__ skip, const T* __restrict__ low, T* __restrict__ yout, int N,
-                                                         UpCatGeom g) {
-    const int Ct = g.Cs + g.Cu, lanes = Ct >> 3, ls = g.Cs >> 3;
+__global__ void __launch_bounds__(128) pool_skip_kernel(const T* __restrict__ skip, T* __restrict__ yout, int N, UpCatGeom g) {
+    const int Ct = g.Cs + g.Cu, lanes = g.Cs >> 3;
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long n_row = (long long)N * g.H * lanes, n_col = (long long)N * g.W * lanes;
     if (i >= n_row + n_col) return;
-    float acc[8] = {};
-    Vec8<T> o;
-    if (i < n_row) {
-        const int lv = (int)(i % lanes);
-        const long long nh = i / lanes, n = nh / g.H;
-        const int y = (int)(nh % g.H);
-        if (lv < ls) {
-            const T* b = skip + nh * (long long)g.W * g.Cs + lv * 8;
-            for (int x = 0; x < g.W; ++x) {
-                Vec8<T> v;
-                v.load(b + (long long)x * g.Cs);
+    float acc0[8] = {}, acc1[8] = {};
+    const bool rowpart = i < n_row;
+    const long long j = rowpart ? i : i - n_row;
+    const int lv = (int)(j % lanes);
+    const long long q = j / lanes;                    // n*H + y   or   n*W + x
+    const int cnt = rowpart ? g.W : g.H;
+    const long long n = q / (rowpart ? g.H : g.W);
+    const int r = (int)(q % (rowpart ? g.H : g.W));
+    const T* b = rowpart ? skip + q * (long long)g.W * g.Cs + lv * 8 : skip + (n * g.H * (long long)g.W + r) * g.Cs + lv * 8;
+    const long long step = rowpart ? g.Cs : (long long)g.W * g.Cs;
+    int t = 0;
+    for (; t + 1 < cnt; t += 2) {                      // two independent accumulators: two loads in flight per thread
+        Vec8<T> v0, v1;
+        v0.load(b + t * step);
+        v1.load(b + (t + 1) * step);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) acc[k] += v.v[k];
-            }
-        } else {
-            const int oy = y - g.py;
-            const bool row_valid = oy >= 0 && oy < 2 * g.h;
-            const Lerp iy = lerp_src(row_valid ? oy : 0, g.h, g.sy, g.align);
-            const T* lown = low + n * (long long)g.h * g.w * g.Cu;
-            for (int x = 0; x < g.W; ++x) {
-                float v[8];
-                low_value(lown, g, row_valid, iy, x, (lv - ls) * 8, v);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) acc[k] += v[k];
-            }
-        }
-        const float sc = 1.f / (float)g.W;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) o.v[k] = acc[k] * sc;
-        o.store(yout + (n * (g.H + g.W) + y) * (long long)Ct + lv * 8);
-    } else {
-        const long long j = i - n_row;
-        const int lv = (int)(j % lanes);
-        const long long nw = j / lanes, n = nw / g.W;
-        const int x = (int)(nw % g.W);
-        if (lv < ls) {
-            const T* b = skip + (n * g.H * (long long)g.W + x) * g.Cs + lv * 8;
-            for (int y = 0; y < g.H; ++y) {
-                Vec8<T> v;
-                v.load(b + (long long)y * g.W * g.Cs);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) acc[k] += v.v[k];
-            }
-        } else {
-            const T* lown = low + n * (long long)g.h * g.w * g.Cu;
-            for (int y = 0; y < g.H; ++y) {
-                const int oy = y - g.py;
-                const bool row_valid = oy >= 0 && oy < 2 * g.h;
-                const Lerp iy = lerp_src(row_valid ? oy : 0, g.h, g.sy, g.align);
-                float v[8];
-                low_value(lown, g, row_valid, iy, x, (lv - ls) * 8, v);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) acc[k] += v[k];
-            }
-        }
-        const float sc = 1.f / (float)g.H;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) o.v[k] = acc[k] * sc;
-        o.store(yout + (n * (g.H + g.W) + g.H + x) * (long long)Ct + lv * 8);
+        for (int k = 0; k < 8; ++k) { acc0[k] += v0.v[k]; acc1[k] += v1.v[k]; }
     }
+    if (t < cnt) {
+        Vec8<T> v0;
+        v0.load(b + t * step);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc0[k] += v0.v[k];
+    }
+    Vec8<T> o;
+    const float sc = 1.f / (float)cnt;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o.v[k] = (acc0[k] + acc1[k]) * sc;
+    o.store(yout + (n * (g.H + g.W) + (rowpart ? r : g.H + r)) * (long long)Ct + lv * 8);
+}
+
+// low half, step 1: the means of the UP-SAMPLED tensor are linear in low, so reduce low itself with the adjoint interpolation weights:
+//   R[n,i,c] = sum_j wx[j] low[n,i,j,c]   (wx[j] = total weight with which column j feeds the 2w up-sampled columns)
+//   S[n,j,c] = sum_i wy[i] low[n,i,j,c]
+// tmp is fp32 (N, h + w, Cu).  thread per (n, i, lane) / (n, j, lane) as above.
+template <typename T>
+__global__ void __launch_bounds__(128) pool_low_reduce_kernel(const T* __restrict__ low, float* __restrict__ tmp, int N, UpCatGeom g) {
+    const int lanes = g.Cu >> 3;
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long n_row = (long long)N * g.h * lanes, n_col = (long long)N * g.w * lanes;
+    if (i >= n_row + n_col) return;
+    float acc[8] = {};
+    const bool rowpart = i < n_row;
+    const long long j = rowpart ? i : i - n_row;
+    const int lv = (int)(j % lanes);
+    const long long q = j / lanes;
+    const int cnt = rowpart ? g.w : g.h, dim = rowpart ? g.h : g.w;
+    const long long n = q / dim;
+    const int r = (int)(q % dim);
+    const T* b = rowpart ? low + q * (long long)g.w * g.Cu + lv * 8 : low + (n * g.h * (long long)g.w + r) * g.Cu + lv * 8;
+    const long long step = rowpart ? g.Cu : (long long)g.w * g.Cu;
+    const float scale = rowpart ? g.sx : g.sy;
+    for (int t = 0; t < cnt; ++t) {
+        const Taps tp = adjoint_taps(t, cnt, scale, g.align);
+        float wsum = 0.f;
+#pragma unroll
+        for (int c = 0; c < STC_NC; ++c) wsum += tp.wt[c];
+        Vec8<T> v;
+        v.load(b + t * step);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(wsum, v.v[k], acc[k]);
+    }
+    float* o = tmp + (n * (g.h + g.w) + (rowpart ? r : g.h + r)) * (long long)g.Cu + lv * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = acc[k];
+}
+
+// low half, step 2: y[n, y, Cs + c] = interp_y(R)[y] / W  and  y[n, H + x, Cs + c] = interp_x(S)[x] / H  (zero outside the padded window)
+template <typename T>
+__global__ void pool_low_finish_kernel(const float* __restrict__ tmp, T* __restrict__ yout, int N, UpCatGeom g) {
+    const int Ct = g.Cs + g.Cu;
+    const long long total = (long long)N * (g.H + g.W) * g.Cu;
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % g.Cu);
+    const long long q = i / g.Cu;
+    const long long n = q / (g.H + g.W);
+    const int r = (int)(q % (g.H + g.W));
+    const bool rowpart = r < g.H;
+    const int o = rowpart ? r - g.py : r - g.H - g.px;
+    const int in = rowpart ? g.h : g.w;
+    float v = 0.f;
+    if (o >= 0 && o < 2 * in) {
+        const Lerp l = lerp_src(o, in, rowpart ? g.sy : g.sx, g.align);
+        const float* t = tmp + (n * (g.h + g.w) + (rowpart ? 0 : g.h)) * (long long)g.Cu + c;
+        v = (l.l0 * t[(long long)l.i0 * g.Cu] + l.l1 * t[(long long)l.i1 * g.Cu]) / (float)(rowpart ? g.W : g.H);
+    }
+    stf(yout + q * Ct + g.Cs + c, v);
 }
 
 // ------------------------------------------------------------------------------------------------ backward
@@ -201,37 +258,6 @@ __global__ void __launch_bounds__(256) upcat_bwd_skip_rows_kernel(const T* __res
         }
         v.store(srow + (long long)x * g.Cs);
     }
-}
-
-// weights with which low index j receives from the up-sampled indices around it: candidates lo .. lo+STC_NC-1 (statically indexed so
-// the table stays in registers; entries past the last real tap carry weight 0)
-#define STC_NC 7
-struct Taps {
-    int lo;
-    float wt[STC_NC];
-};
-__device__ __forceinline__ Taps adjoint_taps(int j, int in, float scale, int align) {
-    Taps t;
-    const int out = 2 * in;
-    int hi;
-    if (align) {
-        t.lo = scale > 0.f ? max(0, (int)floorf((float)(j - 1) / scale)) : 0;
-        hi = scale > 0.f ? min(out - 1, (int)ceilf((float)(j + 1) / scale)) : out - 1;
-    } else {
-        t.lo = max(0, 2 * j - 2);
-        hi = min(out - 1, 2 * j + 3);
-    }
-#pragma unroll
-    for (int c = 0; c < STC_NC; ++c) {
-        const int o = t.lo + c;
-        float wgt = 0.f;
-        if (o <= hi) {
-            const Lerp l = lerp_src(o, in, scale, align);
-            wgt = (l.i0 == j ? l.l0 : 0.f) + (l.i1 == j ? l.l1 : 0.f);
-        }
-        t.wt[c] = wgt;
-    }
-    return t;
 }
 
 // low half (gather form of the adjoint).  grid (gx, h, N), lanes = Cu/8; one block per low-res row jy
@@ -317,24 +343,41 @@ extern "C" int stc_upcat_apply_fwd(const void* skip, const void* low, const void
     STC_REQUIRE(low && out && (skip || Cs == 0), "upcat_apply_fwd: null pointer");
     if ((long long)N * H * W == 0) return STC_OK;
     UpCatGeom g = make_geom(H, W, Cs, h, w, Cu, align_corners);
-    dim3 grid = rows_grid(W, H, N, (Cs + Cu) / 8);
     cudaStream_t st = (cudaStream_t)stream;
+    if (Cs > 0) {
+        dim3 grid = rows_grid(W, H, N, Cs / 8);
+        if (a) {
+            STC_DISPATCH_DTYPE(dtype, (upcat_apply_rows_kernel<T, true, false><<<grid, 256, 0, st>>>((const T*)skip, (const T*)a, (T*)out, g)));
+        } else {
+            STC_DISPATCH_DTYPE(dtype, (upcat_apply_rows_kernel<T, false, false><<<grid, 256, 0, st>>>((const T*)skip, nullptr, (T*)out, g)));
+        }
+    }
+    dim3 grid = rows_grid(W, H, N, Cu / 8);
     if (a) {
-        STC_DISPATCH_DTYPE(dtype, (upcat_apply_rows_kernel<T, true><<<grid, 256, 0, st>>>((const T*)skip, (const T*)low, (const T*)a, (T*)out, g)));
+        STC_DISPATCH_DTYPE(dtype, (upcat_apply_rows_kernel<T, true, true><<<grid, 256, 0, st>>>((const T*)low, (const T*)a, (T*)out, g)));
     } else {
-        STC_DISPATCH_DTYPE(dtype, (upcat_apply_rows_kernel<T, false><<<grid, 256, 0, st>>>((const T*)skip, (const T*)low, nullptr, (T*)out, g)));
+        STC_DISPATCH_DTYPE(dtype, (upcat_apply_rows_kernel<T, false, true><<<grid, 256, 0, st>>>((const T*)low, nullptr, (T*)out, g)));
     }
     return check_launch("upcat_apply_fwd");
 }
 
+extern "C" long long stc_upcat_pool_ws_bytes(int N, int h, int w, int Cu) { return (long long)N * (h + w) * Cu * (long long)sizeof(float); }
+
 extern "C" int stc_upcat_pool(const void* skip, const void* low, void* y, int N, int H, int W, int Cs, int h, int w, int Cu, int align_corners,
-                              int dtype, void* stream) {
+                              void* ws, long long ws_bytes, int dtype, void* stream) {
     STC_REQUIRE(stc_upcat_fused_ok(N, H, W, Cs, h, w, Cu), "upcat_pool: unsupported shape");
     STC_REQUIRE(low && y && (skip || Cs == 0), "upcat_pool: null pointer");
+    STC_REQUIRE(ws && ws_bytes >= stc_upcat_pool_ws_bytes(N, h, w, Cu), "upcat_pool: workspace too small");
     UpCatGeom g = make_geom(H, W, Cs, h, w, Cu, align_corners);
-    long long total = (long long)N * (H + W) * ((Cs + Cu) / 8);
-    if (total == 0) return STC_OK;
-    STC_DISPATCH_DTYPE(dtype, (upcat_pool_kernel<T><<<ceil_div(total, 128), 128, 0, (cudaStream_t)stream>>>((const T*)skip, (const T*)low, (T*)y, N, g)));
+    if ((long long)N * (H + W) == 0) return STC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (Cs > 0) {
+        long long total = (long long)N * (H + W) * (Cs / 8);
+        STC_DISPATCH_DTYPE(dtype, (pool_skip_kernel<T><<<ceil_div(total, 128), 128, 0, st>>>((const T*)skip, (T*)y, N, g)));
+    }
+    long long t1 = (long long)N * (h + w) * (Cu / 8), t2 = (long long)N * (H + W) * Cu;
+    STC_DISPATCH_DTYPE(dtype, (pool_low_reduce_kernel<T><<<ceil_div(t1, 128), 128, 0, st>>>((const T*)low, (float*)ws, N, g)));
+    STC_DISPATCH_DTYPE(dtype, (pool_low_finish_kernel<T><<<ceil_div(t2, 256), 256, 0, st>>>((const float*)ws, (T*)y, N, g)));
     return check_launch("upcat_pool");
 }
 

@@ -102,9 +102,11 @@ def _grad_buf(param, shape, device, zero=False) -> torch.Tensor:
 # with the call's algorithmic FLOPs, plus a count of every kernel-launching C-ABI call
 # ---------------------------------------------------------------------------------------------
 class LaunchProfiler:
-    def __init__(self, time_dense: bool = False):
+    def __init__(self, time_dense: bool = False, time_all: bool = False):
         self.time_dense = time_dense
+        self.time_all = time_all  # CUDA events around EVERY C-ABI call (tools/step_profile.py)
         self.records = []       # (kind, engine, flops, start_event, end_event)
+        self.all_records = []   # (entry point, bytes of the tensor arguments, start_event, end_event)
         self.calls = 0
 
     def dense(self, kind, flops, fn):
@@ -138,7 +140,13 @@ def set_profiler(p: Optional[LaunchProfiler]):
     if p is not None:
         def counting_call(self_, name, *args, _o=_orig):
             p.calls += 1
-            return _o(self_, name, *args)
+            if not p.time_all:
+                return _o(self_, name, *args)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            _o(self_, name, *args)
+            e.record()
+            p.all_records.append((name, sum(a.numel() * a.element_size() for a in args if isinstance(a, torch.Tensor)), s, e))
         lib.call = counting_call.__get__(lib, type(lib))
     elif "call" in lib.__dict__:
         del lib.__dict__["call"]
@@ -609,7 +617,8 @@ class _UpCatPool(Function):
         N, H, W, Cs = skip.shape
         _, h, w, Cu = low.shape
         y = torch.empty((N, H + W, Cs + Cu), dtype=skip.dtype, device=skip.device)
-        lib.call("stc_upcat_pool", skip, low, y, N, H, W, Cs, h, w, Cu, int(align_corners), dtype_code(skip.dtype), stream_ptr())
+        ws = _workspace(skip.device, lib.raw("stc_upcat_pool_ws_bytes")(N, h, w, Cu))
+        lib.call("stc_upcat_pool", skip, low, y, N, H, W, Cs, h, w, Cu, int(align_corners), ws, ws.numel(), dtype_code(skip.dtype), stream_ptr())
         ctx.meta = (N, H, W, Cs, h, w, Cu, int(align_corners), shared, skip.dtype, skip.device)
         ctx.set_materialize_grads(False)
         return y, skip.view_as(skip), low.view_as(low)

@@ -1,4 +1,4 @@
-"""Runs one conv shape a few times (for ncu).  usage: one_conv.py Cin Cout HW k [N] [mode: fprop|wgrad]"""
+"""Runs one conv shape a few times (for ncu).  usage: one_conv.py Cin Cout HW k [N] [mode: fprop|wgrad|both]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -14,9 +14,9 @@ w = torch.randn(co, ci, k, k, device=dev) / (ci * k * k) ** 0.5
 wp = ops.pack_weight(w, BF)
 ws = torch.zeros(k * k * ci * co, device=dev)
 for _ in range(4):
-    if mode == "fprop":
+    if mode in ("fprop", "both"):
         y = ops.conv_fprop(x, wp, None, None, co, k, k)
-    else:
+    if mode in ("wgrad", "both"):
         S._lib.lib.call("stc_conv_wgrad", x, dy, ws, N, hw, hw, ci, co, k, k, 1, 0, S._lib.stream_ptr())
 torch.cuda.synchronize()
 print("ok")
