@@ -143,48 +143,73 @@ __global__ void bn_apply_generic_kernel(const T* __restrict__ y, const float* __
 }
 
 // ---------------------------------------------------------------- backward
-template <typename T>
+// g = dout * act'(z) with the activation resolved at compile time for ReLU (every DoubleConv / KSA branch): a select, no multiply
+template <int ACT>
+__device__ __forceinline__ float act_mask(float d, float z, int act) {
+    if (ACT == STC_ACT_RELU) return z > 0.f ? d : 0.f;
+    return d * act_grad(z, act);
+}
+
+// ACT = STC_ACT_RELU: specialised; ACT = -1: run-time `act`.  Per element: z = fma(v, sc, sh), xh = fma(v, is, -mu*is), g, two sums.
+template <typename T, int ACT>
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* __restrict__ y, const T* __restrict__ dout,
                                                             const float* __restrict__ mean, const float* __restrict__ invstd,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             float* __restrict__ partial, long long P, int C, int act) {
     __shared__ float smem[256 * 16];
     const int lanes = C >> 3, lv = threadIdx.x % lanes, r0 = threadIdx.x / lanes, rstep = 256 / lanes;
-    float mu[8], is[8], ga[8], be[8];
+    constexpr bool kExact = sizeof(T) == 4;   // fp32 storage: subtract the mean first (see bn_bwd_apply_rows_kernel)
+    float is[8], nm[8], sc[8], sh[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        mu[k] = mean[lv * 8 + k];
+        const float mu = mean[lv * 8 + k];
         is[k] = invstd[lv * 8 + k];
-        ga[k] = gamma[lv * 8 + k];
-        be[k] = beta[lv * 8 + k];
+        nm[k] = kExact ? mu : -mu * is[k];
+        sc[k] = gamma[lv * 8 + k] * is[k];
+        sh[k] = kExact ? beta[lv * 8 + k] : beta[lv * 8 + k] - mu * sc[k];
     }
+    auto zx = [&](float v, int k, float& z, float& xh) {
+        if (kExact) {
+            const float vc = v - nm[k];
+            z = fmaf(vc, sc[k], sh[k]);
+            xh = vc * is[k];
+        } else {
+            z = fmaf(v, sc[k], sh[k]);
+            xh = fmaf(v, is[k], nm[k]);
+        }
+    };
     float acc[2][8] = {};
     // two rows per iteration: four independent 16/32-byte loads in flight per thread
     const long long step = (long long)gridDim.x * rstep;
     long long p = (long long)blockIdx.x * rstep + r0;
-    for (; p + step < P; p += 2 * step) {
+    const T* yp = y + p * C + lv * 8;
+    const T* dp = dout + p * C + lv * 8;
+    const long long bump = step * C;
+    for (; p + step < P; p += 2 * step, yp += 2 * bump, dp += 2 * bump) {
         Vec8<T> v0, d0, v1, d1;
-        v0.load(y + p * C + lv * 8);
-        d0.load(dout + p * C + lv * 8);
-        v1.load(y + (p + step) * C + lv * 8);
-        d1.load(dout + (p + step) * C + lv * 8);
+        v0.load(yp);
+        d0.load(dp);
+        v1.load(yp + bump);
+        d1.load(dp + bump);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            float xh0 = (v0.v[k] - mu[k]) * is[k], xh1 = (v1.v[k] - mu[k]) * is[k];
-            float g0 = d0.v[k] * act_grad(fmaf(xh0, ga[k], be[k]), act);
-            float g1 = d1.v[k] * act_grad(fmaf(xh1, ga[k], be[k]), act);
+            float z0, x0, z1, x1;
+            zx(v0.v[k], k, z0, x0);
+            zx(v1.v[k], k, z1, x1);
+            const float g0 = act_mask<ACT>(d0.v[k], z0, act), g1 = act_mask<ACT>(d1.v[k], z1, act);
             acc[0][k] += g0 + g1;
-            acc[1][k] = fmaf(g0, xh0, fmaf(g1, xh1, acc[1][k]));
+            acc[1][k] = fmaf(g0, x0, fmaf(g1, x1, acc[1][k]));
         }
     }
-    for (; p < P; p += step) {
+    for (; p < P; p += step, yp += bump, dp += bump) {
         Vec8<T> v, d;
-        v.load(y + p * C + lv * 8);
-        d.load(dout + p * C + lv * 8);
+        v.load(yp);
+        d.load(dp);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            float xh = (v.v[k] - mu[k]) * is[k];
-            float g = d.v[k] * act_grad(fmaf(xh, ga[k], be[k]), act);
+            float z, xh;
+            zx(v.v[k], k, z, xh);
+            const float g = act_mask<ACT>(d.v[k], z, act);
             acc[0][k] += g;
             acc[1][k] = fmaf(g, xh, acc[1][k]);
         }
@@ -284,36 +309,76 @@ __global__ void __launch_bounds__(256) bn_apply_rows_kernel(const T* __restrict_
     }
 }
 
-template <typename T>
+// dy = sc * (g - c1 - xh * c2) = sc * g + A * v + B  with A = -sc*c2*is, B = sc*(c2*is*mu - c1): z, select, two FMAs per element
+template <typename T, int ACT>
 __global__ void __launch_bounds__(256) bn_bwd_apply_rows_kernel(const T* __restrict__ y, const T* __restrict__ dout,
                                                                 const float* __restrict__ mean, const float* __restrict__ invstd,
                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                 const double* __restrict__ sums, float inv_count, T* __restrict__ dy,
                                                                 long long P, int C, int act, int eval) {
     const int lanes = C >> 3, lv = threadIdx.x % lanes, r0 = threadIdx.x / lanes, rstep = 256 / lanes;
-    float sc[8], sh[8], mu[8], is[8], c1[8], c2[8];
+    // fp32 storage keeps the subtract-first form (v - mu) * is: the folded A*v + B loses |mu|/std digits, which only bf16 storage hides
+    constexpr bool kExact = sizeof(T) == 4;
+    float sc[8], sh[8], A[8], B[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        int c = lv * 8 + k;
-        mu[k] = mean[c];
-        is[k] = invstd[c];
-        sc[k] = gamma[c] * is[k];
-        sh[k] = beta[c] - mu[k] * sc[k];
-        c1[k] = eval ? 0.f : (float)sums[c] * inv_count;
-        c2[k] = eval ? 0.f : (float)sums[C + c] * inv_count;
+        const int c = lv * 8 + k;
+        const float mu = mean[c], is = invstd[c];
+        sc[k] = gamma[c] * is;
+        sh[k] = beta[c] - mu * sc[k];
+        const float c1 = eval ? 0.f : (float)sums[c] * inv_count;
+        const float c2 = eval ? 0.f : (float)sums[C + c] * inv_count;
+        if (kExact) {          // out = sc*g + (v - mu) * A + B
+            A[k] = -sc[k] * c2 * is;
+            B[k] = -sc[k] * c1;
+            sh[k] = mu;        // reused as the mean; z is recomputed from (v - mu) below
+        } else {
+            A[k] = -sc[k] * c2 * is;
+            B[k] = sc[k] * (c2 * is * mu - c1);
+        }
     }
+    const float* be = beta + lv * 8;
+    float bek[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) bek[k] = kExact ? be[k] : 0.f;
+    auto elem = [&](float v, float d, int k) -> float {
+        if (kExact) {
+            const float vc = v - sh[k];
+            const float g = act_mask<ACT>(d, fmaf(vc, sc[k], bek[k]), act);
+            return fmaf(sc[k], g, fmaf(A[k], vc, B[k]));
+        }
+        const float g = act_mask<ACT>(d, fmaf(v, sc[k], sh[k]), act);
+        return fmaf(sc[k], g, fmaf(A[k], v, B[k]));
+    };
     const long long step = (long long)gridDim.x * rstep;
-    for (long long p = (long long)blockIdx.x * rstep + r0; p < P; p += step) {
-        Vec8<T> v, d;
-        v.load(y + p * C + lv * 8);
-        d.load(dout + p * C + lv * 8);
+    long long p = (long long)blockIdx.x * rstep + r0;
+    const long long bump = step * C;
+    const T* yp = y + p * C + lv * 8;
+    const T* dp = dout + p * C + lv * 8;
+    T* op = dy + p * C + lv * 8;
+    for (; p + step < P; p += 2 * step, yp += 2 * bump, dp += 2 * bump, op += 2 * bump) {
+        Vec8<T> v0, d0, v1, d1;
+        v0.load(yp);
+        d0.load(dp);
+        v1.load(yp + bump);
+        d1.load(dp + bump);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            float g = d.v[k] * act_grad(fmaf(v.v[k], sc[k], sh[k]), act);
-            float xh = (v.v[k] - mu[k]) * is[k];
-            v.v[k] = sc[k] * (g - c1[k] - xh * c2[k]);
+            v0.v[k] = elem(v0.v[k], d0.v[k], k);
+            v1.v[k] = elem(v1.v[k], d1.v[k], k);
         }
-        v.store(dy + p * C + lv * 8);
+        v0.store(op);
+        v1.store(op + bump);
+    }
+    for (; p < P; p += step, yp += bump, dp += bump, op += bump) {
+        Vec8<T> v, d;
+        v.load(yp);
+        d.load(dp);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            v.v[k] = elem(v.v[k], d.v[k], k);
+        }
+        v.store(op);
     }
 }
 
@@ -392,8 +457,13 @@ extern "C" int stc_bn_bwd_reduce(const void* y, const void* dout, const float* m
     if (vec_ok(C) && ((((uintptr_t)y) | ((uintptr_t)dout)) & 15) == 0) {
         int lanes = C / 8, G = reduce_blocks(P, lanes);
         STC_REQUIRE(ws && ws_bytes >= (long long)G * 2 * C * (long long)sizeof(float), "bn_bwd_reduce: workspace too small");
-        STC_DISPATCH_DTYPE(dtype, (bn_bwd_reduce_kernel<T><<<G, 256, 0, st>>>((const T*)y, (const T*)dout, mean, invstd, gamma, beta,
-                                                                             (float*)ws, P, C, act)));
+        if (act == STC_ACT_RELU) {
+            STC_DISPATCH_DTYPE(dtype, (bn_bwd_reduce_kernel<T, STC_ACT_RELU><<<G, 256, 0, st>>>((const T*)y, (const T*)dout, mean, invstd, gamma,
+                                                                                               beta, (float*)ws, P, C, act)));
+        } else {
+            STC_DISPATCH_DTYPE(dtype, (bn_bwd_reduce_kernel<T, -1><<<G, 256, 0, st>>>((const T*)y, (const T*)dout, mean, invstd, gamma, beta,
+                                                                                     (float*)ws, P, C, act)));
+        }
         reduce_partials_kernel<<<ceil_div((long long)2 * C * 32, 128), 128, 0, st>>>((const float*)ws, sums, G, 2 * C);
     } else {
         STC_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
@@ -412,8 +482,13 @@ extern "C" int stc_bn_bwd_apply(const void* y, const void* dout, const float* me
     if (total <= 0) return STC_OK;
     int vec = (C % 8 == 0 && ((((uintptr_t)y) | ((uintptr_t)dout) | ((uintptr_t)dy)) & 15) == 0) ? 1 : 0;
     if (vec && vec_ok(C)) {
-        STC_DISPATCH_DTYPE(dtype, (bn_bwd_apply_rows_kernel<T><<<rows_blocks(P, C / 8), 256, 0, st>>>(
-                                      (const T*)y, (const T*)dout, mean, invstd, gamma, beta, sums, (float)(1.0 / count), (T*)dy, P, C, act, eval)));
+        if (act == STC_ACT_RELU) {
+            STC_DISPATCH_DTYPE(dtype, (bn_bwd_apply_rows_kernel<T, STC_ACT_RELU><<<rows_blocks(P, C / 8), 256, 0, st>>>(
+                                          (const T*)y, (const T*)dout, mean, invstd, gamma, beta, sums, (float)(1.0 / count), (T*)dy, P, C, act, eval)));
+        } else {
+            STC_DISPATCH_DTYPE(dtype, (bn_bwd_apply_rows_kernel<T, -1><<<rows_blocks(P, C / 8), 256, 0, st>>>(
+                                          (const T*)y, (const T*)dout, mean, invstd, gamma, beta, sums, (float)(1.0 / count), (T*)dy, P, C, act, eval)));
+        }
         return check_launch("bn_bwd_apply");
     }
     long long work = vec ? total / 8 : total;

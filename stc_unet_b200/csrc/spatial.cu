@@ -177,13 +177,59 @@ __global__ void upcat_bwd_low_kernel(const T* __restrict__ dout, T* __restrict__
 }
 
 // ---------------------------------------------------------------- CoordAtt pieces
+// acc += sum_t x[t*xs] (* w[t*ws]); four independent 16-byte loads in flight per thread (the loop is latency-bound otherwise)
+template <typename T, bool WEIGHTED>
+__device__ __forceinline__ void rowcol_accumulate(const T* __restrict__ x, long long xs, const T* __restrict__ w, long long ws, int cnt,
+                                                  float (&acc)[8]) {
+    float a1[8] = {}, a2[8] = {}, a3[8] = {};
+    int t = 0;
+    for (; t + 3 < cnt; t += 4) {
+        Vec8<T> v0, v1, v2, v3;
+        v0.load(x + t * xs); v1.load(x + (t + 1) * xs); v2.load(x + (t + 2) * xs); v3.load(x + (t + 3) * xs);
+        if (WEIGHTED) {
+            Vec8<T> w0, w1, w2, w3;
+            w0.load(w + t * ws); w1.load(w + (t + 1) * ws); w2.load(w + (t + 2) * ws); w3.load(w + (t + 3) * ws);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                acc[k] = fmaf(v0.v[k], w0.v[k], acc[k]); a1[k] = fmaf(v1.v[k], w1.v[k], a1[k]);
+                a2[k] = fmaf(v2.v[k], w2.v[k], a2[k]); a3[k] = fmaf(v3.v[k], w3.v[k], a3[k]);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { acc[k] += v0.v[k]; a1[k] += v1.v[k]; a2[k] += v2.v[k]; a3[k] += v3.v[k]; }
+        }
+    }
+    for (; t < cnt; ++t) {
+        Vec8<T> v0;
+        v0.load(x + t * xs);
+        if (WEIGHTED) {
+            Vec8<T> w0;
+            w0.load(w + t * ws);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] = fmaf(v0.v[k], w0.v[k], acc[k]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] += v0.v[k];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] += a1[k] + a2[k] + a3[k];
+}
+
+
 // row part: thread per (n,h,lane) loops over w;  col part: thread per (n,w,lane) loops over h
 template <typename T, bool WEIGHTED>
 __global__ void rowcol_reduce_kernel(const T* __restrict__ x, const T* __restrict__ a, T* __restrict__ y, int N, int H, int W, int C) {
     const int lanes = C >> 3;
-    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    long long n_row = (long long)N * H * lanes, n_col = (long long)N * W * lanes;
-    if (i >= n_row + n_col) return;
+    // image-major work order: the column pass of image n runs right after its row pass and finds the image still in L2
+    long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long per_img = (long long)(H + W) * lanes;
+    if (i0 >= per_img * N) return;
+    const long long n_ = i0 / per_img;
+    const long long rem = i0 - n_ * per_img;
+    const long long n_row = (long long)N * H * lanes;
+    // map back onto the original (row items first, then column items) numbering used below
+    const long long i = rem < (long long)H * lanes ? n_ * H * lanes + rem : n_row + n_ * W * lanes + (rem - (long long)H * lanes);
     float acc[8] = {};
     if (i < n_row) {
         int lv = (int)(i % lanes);
@@ -191,19 +237,8 @@ __global__ void rowcol_reduce_kernel(const T* __restrict__ x, const T* __restric
         long long n = nh / H;
         int hh = (int)(nh % H);
         const T* b = x + nh * (long long)W * C + lv * 8;
-        for (int ww = 0; ww < W; ++ww) {
-            Vec8<T> v;
-            v.load(b + (long long)ww * C);
-            if (WEIGHTED) {
-                Vec8<T> wv;
-                wv.load(a + (n * (H + W) + H + ww) * (long long)C + lv * 8);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) acc[k] = fmaf(v.v[k], wv.v[k], acc[k]);
-            } else {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) acc[k] += v.v[k];
-            }
-        }
+        const T* ab = WEIGHTED ? a + (n * (H + W) + H) * (long long)C + lv * 8 : nullptr;
+        rowcol_accumulate<T, WEIGHTED>(b, C, ab, C, W, acc);
         Vec8<T> o;
         float sc = WEIGHTED ? 1.f : 1.f / (float)W;
 #pragma unroll
@@ -216,19 +251,8 @@ __global__ void rowcol_reduce_kernel(const T* __restrict__ x, const T* __restric
         long long n = nw / W;
         int ww = (int)(nw % W);
         const T* b = x + (n * H * (long long)W + ww) * C + lv * 8;
-        for (int hh = 0; hh < H; ++hh) {
-            Vec8<T> v;
-            v.load(b + (long long)hh * W * C);
-            if (WEIGHTED) {
-                Vec8<T> wv;
-                wv.load(a + (n * (H + W) + hh) * (long long)C + lv * 8);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) acc[k] = fmaf(v.v[k], wv.v[k], acc[k]);
-            } else {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) acc[k] += v.v[k];
-            }
-        }
+        const T* ab = WEIGHTED ? a + (n * (H + W)) * (long long)C + lv * 8 : nullptr;
+        rowcol_accumulate<T, WEIGHTED>(b, (long long)W * C, ab, C, H, acc);
         Vec8<T> o;
         float sc = WEIGHTED ? 1.f : 1.f / (float)H;
 #pragma unroll

@@ -352,7 +352,10 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_cons
                 if (p.mode == MODE_WGRAD) {
                     float* o = reinterpret_cast<float*>(p.out) + off + c;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) atomicAdd(o + j, f[j]);
+                    for (int j = 0; j < 32; j += 4)   // 16-byte vector reductions: 4x fewer L2 atomic instructions
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j), "f"(f[j]), "f"(f[j + 1]), "f"(f[j + 2]),
+                                     "f"(f[j + 3])
+                                     : "memory");
                     continue;
                 }
                 if (p.bias) {
@@ -600,7 +603,9 @@ int conv_wgrad_umma(const void* x, const void* dy, float* ws, int N, int H, int 
     p.num_n_tiles = Cout / p.BN;
     p.num_k_iters = N * p.tiles_h * p.tiles_w;  // pixel tiles of 128
     int base_tiles = p.num_m_tiles * p.num_n_tiles;
-    int splits = (num_sms() * 2 + base_tiles - 1) / base_tiles;
+    // split-K so that one wave of CTAs covers the tiles: every extra split costs a full 128 x BN fp32 reduction into the workspace
+    int splits = num_sms() / base_tiles;
+    if (const char* e = getenv("STC_WGRAD_WAVES")) splits = (num_sms() * atoi(e) + base_tiles - 1) / base_tiles;
     if (splits > p.num_k_iters) splits = p.num_k_iters;
     if (splits < 1) splits = 1;
     p.k_per_split = (p.num_k_iters + splits - 1) / splits;

@@ -23,6 +23,8 @@ namespace stc {
 struct alignas(64) ConvHParams {
     CUtensorMap tmA;  // NHWC activations {C, W, H, N}, box {64, 128+S-1, 1, 1}
     CUtensorMap tmB;  // packed weights {Cin, Cout, taps}, box {64, BN, 1}
+    CUtensorMap tmC;  // output {Cout, W, H, N}, box {64, 32, 1, 1}: staged epilogue (see umma.cu), used when `staged`
+    int staged;
     int H, W, R, S, cin_chunks, T, BN, num_n_tiles;
     int strips_h, strips_w, num_strips;
     int a_slots, b_stages;
@@ -36,6 +38,8 @@ struct alignas(64) ConvHParams {
 };
 
 constexpr int kConvHThreads = 224;
+constexpr uint32_t kConvHStageBuf = 32 * 128;                   // 32 pixels x 64 bf16 channels, 128B-swizzled
+constexpr uint32_t kConvHStagingBytes = 4 * 2 * kConvHStageBuf;  // two buffers per epilogue warp
 
 __device__ __forceinline__ float convh_act(float v, int act) {
     if (act == STC_ACT_RELU) return fmaxf(v, 0.f);
@@ -65,7 +69,8 @@ __global__ void __launch_bounds__(kConvHThreads, 1) umma_convh_kernel(const __gr
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t a_bytes = (uint32_t)p.a_slots * p.a_slot_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a_bytes + (size_t)p.b_stages * p.b_stage_bytes);
+    const uint32_t ring_bytes = (uint32_t)(a_bytes + (size_t)p.b_stages * p.b_stage_bytes);   // a multiple of 1024
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ring_bytes + (p.staged ? kConvHStagingBytes : 0u));
     // bars: a_full[a_slots], a_empty[a_slots], b_full[b_stages], b_empty[b_stages], tmem_full[2], tmem_empty[2]
     const int nb = 2 * p.a_slots + 2 * p.b_stages + 4;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + nb);
@@ -228,8 +233,9 @@ __global__ void __launch_bounds__(kConvHThreads, 1) umma_convh_kernel(const __gr
         // ===================== epilogue =====================
         const int q = warp & 3;
         const int row = q * 32 + lane;
-        int acc = 0;
+        int acc = 0, stage_buf = 0;
         uint32_t acc_phase[2] = {0, 0};
+        const uint32_t stg0 = smem_base + ring_bytes + (uint32_t)q * 2u * kConvHStageBuf;
         for (int st = blockIdx.x; st < p.num_strips; st += gridDim.x) {
             Strip s = decode_strip(p, st);
             const int w = s.w0 + row;
@@ -241,6 +247,62 @@ __global__ void __launch_bounds__(kConvHThreads, 1) umma_convh_kernel(const __gr
                 const bool valid = w < p.W;
                 const long long off = (((long long)s.n_img * p.H + h) * p.W + w) * p.Cout + (long long)s.nt * p.BN;
                 const uint32_t t_addr = tmem_base + acc * 256 + t * p.BN + ((uint32_t)(q * 32) << 16);
+                if (p.staged) {
+                    // TMEM -> registers -> swizzled smem box -> TMA store (full 128-byte lines; out-of-range pixels clipped by TMA)
+                    for (int c = 0; c < p.BN; c += 64) {
+                        const uint32_t stg = stg0 + (uint32_t)stage_buf * kConvHStageBuf;
+                        if (lane == 0) ptx::bulk_wait_read<1>();
+                        __syncwarp();
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+                            uint32_t v[32];
+                            ptx::tmem_ld_32x32(t_addr + c + half * 32, v);
+                            ptx::tmem_ld_wait();
+                            float f[32];
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                            if (p.bias) {
+                                const float* b = p.bias + s.nt * p.BN + c + half * 32;
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) f[j] += __ldg(b + j);
+                            }
+                            if (p.residual && valid) {
+                                const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.residual) + off + c + half * 32);
+#pragma unroll
+                                for (int g = 0; g < 4; ++g) {
+                                    uint4 rv = __ldg(rp + g);
+                                    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        float2 x = __bfloat1622float2(h2[e]);
+                                        f[g * 8 + 2 * e] += x.x;
+                                        f[g * 8 + 2 * e + 1] += x.y;
+                                    }
+                                }
+                            }
+                            if (p.act != STC_ACT_NONE) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) f[j] = convh_act(f[j], p.act);
+                            }
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                uint4 ov;
+                                __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(f[g * 8 + 2 * e], f[g * 8 + 2 * e + 1]);
+                                ptx::st_shared_v4(stg + (uint32_t)lane * 128u + (uint32_t)(((half * 4 + g) ^ (lane & 7)) << 4), ov);
+                            }
+                        }
+                        ptx::fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) {
+                            ptx::tma_store_4d(&p.tmC, stg, s.nt * p.BN + c, s.w0 + q * 32, h, s.n_img);
+                            ptx::bulk_commit();
+                        }
+                        stage_buf ^= 1;
+                    }
+                    continue;
+                }
                 for (int c = 0; c < p.BN; c += 32) {
                     uint32_t v[32];
                     ptx::tmem_ld_32x32(t_addr + c, v);
@@ -289,6 +351,7 @@ __global__ void __launch_bounds__(kConvHThreads, 1) umma_convh_kernel(const __gr
             acc_phase[acc] ^= 1;
             acc ^= 1;
         }
+        if (p.staged && lane == 0) ptx::bulk_wait<0>();
     }
 
     ptx::tc_fence_before();
@@ -303,9 +366,19 @@ __global__ void __launch_bounds__(kConvHThreads, 1) umma_convh_kernel(const __gr
 int encode_map_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
 int umma_pick_bn(int n);
 
-static int convh_plan(int Cout, int R, int& BN, int& T, int& a_slots, int& b_stages) {
+// The staged (TMA store) epilogue costs 32 KB of shared memory; it pays where the tile's K is short (3x3: the write-back is a large
+// share of the tile time) and is skipped where it would shrink the halo ring of the long-K 5x5 / 7x7 layers.  STC_CONVH_STAGED=<max R>.
+static int convh_staged_max_r() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("STC_CONVH_STAGED"); v = e ? atoi(e) : 3; }
+    return v;
+}
+
+static int convh_plan(int Cout, int R, int& BN, int& T, int& a_slots, int& b_stages, int& staged) {
     BN = umma_pick_bn(Cout);
     if (BN == 0 || BN > 256) return 0;
+    staged = (BN % 64 == 0 && BN <= 128 && R <= convh_staged_max_r()) ? 1 : 0;   // BN = 256 needs the smem for its weight ring
+    const size_t staging = staged ? kConvHStagingBytes : 0;
     const int tmax = 256 / BN;  // two accumulator stages of 256 TMEM columns
     const int cands[] = {4, 2, 1};
     for (int t : cands) {
@@ -313,7 +386,7 @@ static int convh_plan(int Cout, int R, int& BN, int& T, int& a_slots, int& b_sta
         for (int extra = 3; extra >= 1; --extra) {
             for (int bs = 4; bs >= 2; --bs) {
                 int slots = t + R - 1 + extra;
-                size_t smem = (size_t)slots * 17408 + (size_t)bs * BN * 128 + (2 * slots + 2 * bs + 4) * 8 + 16 + 1024;
+                size_t smem = (size_t)slots * 17408 + (size_t)bs * BN * 128 + staging + (2 * slots + 2 * bs + 4) * 8 + 16 + 1024;
                 if (smem <= 225 * 1024) {
                     T = t; a_slots = slots; b_stages = bs;
                     return 1;
@@ -328,15 +401,15 @@ bool conv_convh_eligible(int W, int Cin, int Cout, int R, int S, int dtype) {
     static int disabled = -1;
     if (disabled < 0) { const char* e = getenv("STC_CONVH"); disabled = (e && e[0] == '0') ? 1 : 0; }
     if (disabled) return false;
-    int BN, T, a, b;
-    return dtype == STC_BF16 && W >= 128 && Cin % 64 == 0 && R == S && (R == 3 || R == 5 || R == 7) && convh_plan(Cout, R, BN, T, a, b);
+    int BN, T, a, b, sg;
+    return dtype == STC_BF16 && W >= 128 && Cin % 64 == 0 && R == S && (R == 3 || R == 5 || R == 7) && convh_plan(Cout, R, BN, T, a, b, sg);
 }
 
 int conv_fprop_convh(const void* x, const void* wp, const float* bias, const void* residual, void* y, int N, int H, int W, int Cin,
                      int Cout, int R, int S, int act, cudaStream_t st) {
     ConvHParams p;
     memset(&p, 0, sizeof(p));
-    STC_REQUIRE(convh_plan(Cout, R, p.BN, p.T, p.a_slots, p.b_stages), "conv_fprop_convh: no plan for Cout=%d R=%d", Cout, R);
+    STC_REQUIRE(convh_plan(Cout, R, p.BN, p.T, p.a_slots, p.b_stages, p.staged), "conv_fprop_convh: no plan for Cout=%d R=%d", Cout, R);
     STC_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)wp & 15) == 0 && ((uintptr_t)y & 15) == 0, "conv_fprop_convh: unaligned pointer");
     const int bwh = 128 + S - 1;
     {
@@ -351,6 +424,13 @@ int conv_fprop_convh(const void* x, const void* wp, const float* bias, const voi
         uint64_t str[3] = {2, (uint64_t)Cin * 2, (uint64_t)Cout * Cin * 2};
         uint32_t box[3] = {64, (uint32_t)p.BN, 1};
         int rc = encode_map_bf16(&p.tmB, wp, 3, dims, str, box);
+        if (rc) return rc;
+    }
+    if (p.staged) {
+        uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+        uint64_t str[4] = {2, (uint64_t)Cout * 2, (uint64_t)W * Cout * 2, (uint64_t)H * W * Cout * 2};
+        uint32_t box[4] = {64, 32, 1, 1};
+        int rc = encode_map_bf16(&p.tmC, y, 4, dims, str, box);
         if (rc) return rc;
     }
     p.H = H; p.W = W; p.R = R; p.S = S; p.cin_chunks = Cin / 64;
@@ -368,7 +448,8 @@ int conv_fprop_convh(const void* x, const void* wp, const float* bias, const voi
         p.bo_mode = bo;
     }
     p.out = y; p.bias = bias; p.residual = residual; p.act = act; p.Cout = Cout;
-    size_t smem = (size_t)p.a_slots * p.a_slot_bytes + (size_t)p.b_stages * p.b_stage_bytes + (2 * p.a_slots + 2 * p.b_stages + 4) * 8 + 16 + 1024;
+    size_t smem = (size_t)p.a_slots * p.a_slot_bytes + (size_t)p.b_stages * p.b_stage_bytes + (p.staged ? kConvHStagingBytes : 0) +
+                  (2 * p.a_slots + 2 * p.b_stages + 4) * 8 + 16 + 1024;
     static bool attr_set[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);

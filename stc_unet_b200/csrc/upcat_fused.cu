@@ -133,18 +133,19 @@ __global__ void __launch_bounds__(256) upcat_apply_rows_kernel(const T* __restri
 template <typename T>
 __global__ void __launch_bounds__(128) pool_skip_kernel(const T* __restrict__ skip, T* __restrict__ yout, int N, UpCatGeom g) {
     const int Ct = g.Cs + g.Cu, lanes = g.Cs >> 3;
+    // image-major work order: the column pass of image n follows its row pass closely enough to find the image still in L2
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const long long n_row = (long long)N * g.H * lanes, n_col = (long long)N * g.W * lanes;
-    if (i >= n_row + n_col) return;
+    const long long per_img = (long long)(g.H + g.W) * lanes;
+    if (i >= per_img * N) return;
     float acc0[8] = {}, acc1[8] = {};
-    const bool rowpart = i < n_row;
-    const long long j = rowpart ? i : i - n_row;
+    const long long n = i / per_img;
+    const long long rem = i - n * per_img;
+    const bool rowpart = rem < (long long)g.H * lanes;
+    const long long j = rowpart ? rem : rem - (long long)g.H * lanes;
     const int lv = (int)(j % lanes);
-    const long long q = j / lanes;                    // n*H + y   or   n*W + x
+    const int r = (int)(j / lanes);                   // y (row pass) or x (column pass)
     const int cnt = rowpart ? g.W : g.H;
-    const long long n = q / (rowpart ? g.H : g.W);
-    const int r = (int)(q % (rowpart ? g.H : g.W));
-    const T* b = rowpart ? skip + q * (long long)g.W * g.Cs + lv * 8 : skip + (n * g.H * (long long)g.W + r) * g.Cs + lv * 8;
+    const T* b = rowpart ? skip + (n * g.H + r) * (long long)g.W * g.Cs + lv * 8 : skip + (n * g.H * (long long)g.W + r) * g.Cs + lv * 8;
     const long long step = rowpart ? g.Cs : (long long)g.W * g.Cs;
     int t = 0;
     for (; t + 1 < cnt; t += 2) {                      // two independent accumulators: two loads in flight per thread
@@ -173,11 +174,21 @@ __global__ void __launch_bounds__(128) pool_skip_kernel(const T* __restrict__ sk
 // tmp is fp32 (N, h + w, Cu).  thread per (n, i, lane) / (n, j, lane) as above.
 template <typename T>
 __global__ void __launch_bounds__(128) pool_low_reduce_kernel(const T* __restrict__ low, float* __restrict__ tmp, int N, UpCatGeom g) {
+    extern __shared__ float wtab[];   // [0, w): column weights wx[j];  [w, w + h): row weights wy[i]
+    for (int t = threadIdx.x; t < g.w + g.h; t += blockDim.x) {
+        const bool isx = t < g.w;
+        const Taps tp = adjoint_taps(isx ? t : t - g.w, isx ? g.w : g.h, isx ? g.sx : g.sy, g.align);
+        float wsum = 0.f;
+#pragma unroll
+        for (int c = 0; c < STC_NC; ++c) wsum += tp.wt[c];
+        wtab[t] = wsum;
+    }
+    __syncthreads();
     const int lanes = g.Cu >> 3;
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long n_row = (long long)N * g.h * lanes, n_col = (long long)N * g.w * lanes;
     if (i >= n_row + n_col) return;
-    float acc[8] = {};
+    float acc0[8] = {}, acc1[8] = {};
     const bool rowpart = i < n_row;
     const long long j = rowpart ? i : i - n_row;
     const int lv = (int)(j % lanes);
@@ -187,20 +198,26 @@ __global__ void __launch_bounds__(128) pool_low_reduce_kernel(const T* __restric
     const int r = (int)(q % dim);
     const T* b = rowpart ? low + q * (long long)g.w * g.Cu + lv * 8 : low + (n * g.h * (long long)g.w + r) * g.Cu + lv * 8;
     const long long step = rowpart ? g.Cu : (long long)g.w * g.Cu;
-    const float scale = rowpart ? g.sx : g.sy;
-    for (int t = 0; t < cnt; ++t) {
-        const Taps tp = adjoint_taps(t, cnt, scale, g.align);
-        float wsum = 0.f;
+    const float* wt = rowpart ? wtab : wtab + g.w;
+    int t = 0;
+    for (; t + 1 < cnt; t += 2) {
+        Vec8<T> v0, v1;
+        v0.load(b + t * step);
+        v1.load(b + (t + 1) * step);
+        const float w0 = wt[t], w1 = wt[t + 1];
 #pragma unroll
-        for (int c = 0; c < STC_NC; ++c) wsum += tp.wt[c];
-        Vec8<T> v;
-        v.load(b + t * step);
+        for (int k = 0; k < 8; ++k) { acc0[k] = fmaf(w0, v0.v[k], acc0[k]); acc1[k] = fmaf(w1, v1.v[k], acc1[k]); }
+    }
+    if (t < cnt) {
+        Vec8<T> v0;
+        v0.load(b + t * step);
+        const float w0 = wt[t];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = fmaf(wsum, v.v[k], acc[k]);
+        for (int k = 0; k < 8; ++k) acc0[k] = fmaf(w0, v0.v[k], acc0[k]);
     }
     float* o = tmp + (n * (g.h + g.w) + (rowpart ? r : g.h + r)) * (long long)g.Cu + lv * 8;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = acc[k];
+    for (int k = 0; k < 8; ++k) o[k] = acc0[k] + acc1[k];
 }
 
 // low half, step 2: y[n, y, Cs + c] = interp_y(R)[y] / W  and  y[n, H + x, Cs + c] = interp_x(S)[x] / H  (zero outside the padded window)
@@ -260,11 +277,20 @@ __global__ void __launch_bounds__(256) upcat_bwd_skip_rows_kernel(const T* __res
     }
 }
 
-// low half (gather form of the adjoint).  grid (gx, h, N), lanes = Cu/8; one block per low-res row jy
+// low half (gather form of the adjoint).  grid (gx, h, N), lanes = Cu/8; one block per low-res row jy.  The per-column tap tables
+// (first up-sampled column + STC_NC weights) are built once per block in shared memory.
 template <typename T, bool HAS_DY>
 __global__ void __launch_bounds__(256) upcat_bwd_low_rows_kernel(const T* __restrict__ dout, const T* __restrict__ dyhw, T* __restrict__ dlow,
                                                                  UpCatGeom g) {
+    extern __shared__ float xtab[];   // per jx: [lo (as int bits), wt[0..STC_NC)]
     const int Ct = g.Cs + g.Cu, lanes = g.Cu >> 3, rstep = 256 / lanes;
+    for (int jx = threadIdx.x; jx < g.w; jx += 256) {
+        const Taps tx = adjoint_taps(jx, g.w, g.sx, g.align);
+        xtab[jx * (STC_NC + 1)] = __int_as_float(tx.lo);
+#pragma unroll
+        for (int c = 0; c < STC_NC; ++c) xtab[jx * (STC_NC + 1) + 1 + c] = tx.wt[c];
+    }
+    __syncthreads();
     if ((int)threadIdx.x >= rstep * lanes) return;
     const int lv = threadIdx.x % lanes, r0 = threadIdx.x / lanes;
     const int jy = blockIdx.y;
@@ -288,28 +314,31 @@ __global__ void __launch_bounds__(256) upcat_bwd_low_rows_kernel(const T* __rest
     const T* dn = dout + (n * g.H + ty.lo + g.py) * (long long)g.W * Ct + cofs;
     const T* dwp = HAS_DY ? dyhw + (n * (g.H + g.W) + g.H) * (long long)Ct + cofs : nullptr;
     T* lrow = dlow + ((n * g.h + jy) * (long long)g.w) * g.Cu + lv * 8;
+    const long long rowpitch = (long long)g.W * Ct;
     for (int jx = blockIdx.x * rstep + r0; jx < g.w; jx += gridDim.x * rstep) {
-        const Taps tx = adjoint_taps(jx, g.w, g.sx, g.align);
+        const float* tx = xtab + jx * (STC_NC + 1);
+        const int xlo = __float_as_int(tx[0]) + g.px;
         float acc[8] = {};
         float wxsum = 0.f;
 #pragma unroll
         for (int s = 0; s < STC_NC; ++s) {
-            if (tx.wt[s] == 0.f) continue;
-            wxsum += tx.wt[s];
-            const long long xoff = (long long)(tx.lo + s + g.px) * Ct;
+            const float wx = tx[1 + s];
+            if (wx == 0.f) continue;
+            wxsum += wx;
+            const T* col = dn + (long long)(xlo + s) * Ct;
 #pragma unroll
             for (int t = 0; t < STC_NC; ++t) {
                 if (ty.wt[t] == 0.f) continue;
                 Vec8<T> v;
-                v.load(dn + (long long)t * g.W * Ct + xoff);
-                const float ww = ty.wt[t] * tx.wt[s];
+                v.load(col + t * rowpitch);
+                const float ww = ty.wt[t] * wx;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) acc[k] = fmaf(ww, v.v[k], acc[k]);
             }
             if (HAS_DY) {
                 Vec8<T> v;
-                v.load(dwp + xoff);
-                const float ww = tx.wt[s] * wysum * ih;
+                v.load(dwp + (long long)(xlo + s) * Ct);
+                const float ww = wx * wysum * ih;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) acc[k] = fmaf(ww, v.v[k], acc[k]);
             }
@@ -333,7 +362,8 @@ static inline dim3 rows_grid(int Wd, int Hd, int N, int lanes) {
 using namespace stc;
 
 extern "C" int stc_upcat_fused_ok(int N, int H, int W, int Cs, int h, int w, int Cu) {
-    return (Cs % 8 == 0 && Cu % 8 == 0 && Cu > 0 && rows_ok(Cs + Cu) && H >= 2 * h && W >= 2 * w && H <= 65535 && N <= 65535) ? 1 : 0;
+    return (Cs % 8 == 0 && Cu % 8 == 0 && Cu > 0 && rows_ok(Cs + Cu) && H >= 2 * h && W >= 2 * w && H <= 65535 && N <= 65535 && w <= 1536 &&
+            h + w <= 8192) ? 1 : 0;
 }
 
 extern "C" int stc_upcat_apply_fwd(const void* skip, const void* low, const void* a, void* out, int N, int H, int W, int Cs, int h, int w, int Cu,
@@ -376,7 +406,7 @@ extern "C" int stc_upcat_pool(const void* skip, const void* low, void* y, int N,
         STC_DISPATCH_DTYPE(dtype, (pool_skip_kernel<T><<<ceil_div(total, 128), 128, 0, st>>>((const T*)skip, (T*)y, N, g)));
     }
     long long t1 = (long long)N * (h + w) * (Cu / 8), t2 = (long long)N * (H + W) * Cu;
-    STC_DISPATCH_DTYPE(dtype, (pool_low_reduce_kernel<T><<<ceil_div(t1, 128), 128, 0, st>>>((const T*)low, (float*)ws, N, g)));
+    STC_DISPATCH_DTYPE(dtype, (pool_low_reduce_kernel<T><<<ceil_div(t1, 128), 128, sizeof(float) * (size_t)(h + w), st>>>((const T*)low, (float*)ws, N, g)));
     STC_DISPATCH_DTYPE(dtype, (pool_low_finish_kernel<T><<<ceil_div(t2, 256), 256, 0, st>>>((const float*)ws, (T*)y, N, g)));
     return check_launch("upcat_pool");
 }
@@ -398,10 +428,12 @@ extern "C" int stc_upcat_apply_bwd(const void* dout, const void* dyhw, void* dsk
     }
     if (dlow) {
         dim3 grid = rows_grid(w, h, N, Cu / 8);
+        const size_t sm = sizeof(float) * (size_t)w * (STC_NC + 1);
+        STC_REQUIRE(sm <= 48 * 1024, "upcat_apply_bwd: w=%d too wide for the tap table", w);
         if (dyhw) {
-            STC_DISPATCH_DTYPE(dtype, (upcat_bwd_low_rows_kernel<T, true><<<grid, 256, 0, st>>>((const T*)dout, (const T*)dyhw, (T*)dlow, g)));
+            STC_DISPATCH_DTYPE(dtype, (upcat_bwd_low_rows_kernel<T, true><<<grid, 256, sm, st>>>((const T*)dout, (const T*)dyhw, (T*)dlow, g)));
         } else {
-            STC_DISPATCH_DTYPE(dtype, (upcat_bwd_low_rows_kernel<T, false><<<grid, 256, 0, st>>>((const T*)dout, nullptr, (T*)dlow, g)));
+            STC_DISPATCH_DTYPE(dtype, (upcat_bwd_low_rows_kernel<T, false><<<grid, 256, sm, st>>>((const T*)dout, nullptr, (T*)dlow, g)));
         }
     }
     return check_launch("upcat_apply_bwd");

@@ -25,6 +25,12 @@ for (N, hw, ci, co, k) in [(16, 64, 512, 512, 1), (16, 32, 512, 512, 1), (16, 64
     timeit(lambda: ops.conv_fprop(x, wp, None, None, co, k, k), fl, f"conv {ci}->{co} k{k} @{hw} N{N}")
     if k == 1:
         timeit(lambda: ops.conv_fprop(x, wp, None, res, co, k, k), fl, f"conv {ci}->{co} k{k} @{hw} N{N} +residual")
+for (N, hw, ci, co, k) in [(16, 64, 512, 512, 1), (16, 32, 512, 512, 1), (16, 64, 512, 512, 3), (16, 64, 256, 512, 3), (16, 32, 512, 512, 3), (16, 64, 1024, 256, 3)]:
+    x = torch.randn(N, hw, hw, ci, device=dev).to(BF)
+    dy = torch.randn(N, hw, hw, co, device=dev).to(BF)
+    ws = torch.zeros(k * k * ci * co, device=dev)
+    timeit(lambda: S._lib.lib.call("stc_conv_wgrad", x, dy, ws, N, hw, hw, ci, co, k, k, 1, 0, S._lib.stream_ptr()), 2.0 * N * hw * hw * ci * co * k * k,
+           f"wgrad {ci}->{co} k{k} @{hw} N{N}")
 # attention GEMMs: heads*N = 32 batches, L = 4096, hd = 256
 L, hd, B = 4096, 256, 32
 q = torch.randn(B, L, hd, device=dev).to(BF); kk = torch.randn(B, L, hd, device=dev).to(BF); v = torch.randn(B, L, hd, device=dev).to(BF)
