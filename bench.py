@@ -248,7 +248,22 @@ def main():
         for i in range(2):
             e2e_step(i)
         ms_e2e = timed(e2e_step, args.steps) / args.steps
-        e2e = dict(value=world * args.batch / (ms_e2e / 1e3), unit="img/s", h2d_bytes_per_step=bi, d2h_bytes_per_step=4, ms_per_step=ms_e2e)
+        e2e = dict(value=world * args.batch / (ms_e2e / 1e3), unit="img/s", h2d_bytes_per_step=bi, d2h_bytes_per_step=4, ms_per_step=ms_e2e,
+                   input="reference interface: fp32 NCHW images + int64 labels from pinned host memory")
+        # the same step fed the way a GPU-side input pipeline would: decoded uint8 HWC pixels + uint8 labels,
+        # normalised / widened on the device; same pixel values as above up to 8-bit quantisation
+        u_img = [(t.permute(0, 2, 3, 1) * 255).round().to(torch.uint8).contiguous().pin_memory() for t in h_img]
+        u_gt = [t.to(torch.uint8).pin_memory() for t in h_gt]
+        seg.backbone.img_norm_cfg = dict(mean=[0.0], std=[255.0], to_rgb=False)
+
+        def e2e_u8_step(i):
+            lv = trainer.step(u_img[i % pool].to(dev, non_blocking=True), u_gt[i % pool].to(dev, non_blocking=True))
+            last["host_loss"] = float(lv["loss"])
+        for i in range(2):
+            e2e_u8_step(i)
+        ms_u8 = timed(e2e_u8_step, args.steps) / args.steps
+        e2e["uint8_pipeline"] = dict(value=world * args.batch / (ms_u8 / 1e3), unit="img/s", ms_per_step=ms_u8,
+                                     h2d_bytes_per_step=u_img[0].numel() + u_gt[0].numel())
 
     # ---- roofline of the dominant kernel (umma_kernel = tcgen05 implicit GEMM): CUDA events per launch, 2 extra steps
     roofline, breakdown = None, None

@@ -53,6 +53,12 @@ int stc_num_sms(void);
 /* image (N,C,H,W) fp32 NCHW -> NHWC `dtype` with channels zero-padded to Cpad (input of
  * UnetBackbone.forward, unet_backbone.py:36). */
 int stc_nchw_to_nhwc(const float* src, void* dst, int N, int C, int H, int W, int Cpad, int dtype, void* stream);
+/* Input pipeline on the device (replaces Normalize + DefaultFormatBundle, mmseg/datasets/pipelines/formatting.py:179-217):
+ * src = decoded 8-bit HWC pixels (P = N*H*W pixels, C <= 4 channels), dst = NHWC `dtype` with Cpad channels,
+ * dst[p][c] = (src[p][swap_rb ? C-1-c : c] - mean[c]) * inv_std[c].  stc_widen_u8_i64: 8-bit label maps -> int64. */
+int stc_image_u8_to_nhwc(const uint8_t* src, void* dst, const float* mean, const float* inv_std, long long P, int C, int Cpad, int swap_rb,
+                         int dtype, void* stream);
+int stc_widen_u8_i64(const uint8_t* src, int64_t* dst, long long n, void* stream);
 /* Conv2d.weight (Cout,Cin,R,S) fp32 -> packed [R*S][Cout][CinPad] `dtype` (K-major per tap).
  * transpose_flip != 0 packs the dgrad operand: [(R-1-r)*S+(S-1-s)][Cin][CoutPad] = W[co][ci][r][s]. */
 int stc_pack_conv_weight(const float* w, void* dst, int Cout, int Cin, int R, int S, int inner_pad,

@@ -77,6 +77,44 @@ extern "C" int stc_nchw_to_nhwc(const float* src, void* dst, int N, int C, int H
     return check_launch("nchw_to_nhwc");
 }
 
+// Device side of the input pipeline: decoded 8-bit HWC pixels -> normalised NHWC activations.  Replaces the host-side
+// Normalize + ImageToTensor/DefaultFormatBundle (mmseg/datasets/pipelines/transforms.py Normalize, formatting.py:179-217): the loader ships
+// 3 B/pixel instead of 12.  dst[p][c] = (src[p][swap ? C-1-c : c] - mean[c]) * inv_std[c] for c < C, 0 for the padding channels.
+template <typename T>
+__global__ void image_u8_kernel(const uint8_t* __restrict__ src, T* __restrict__ dst, const float* __restrict__ mean,
+                                const float* __restrict__ inv_std, long long P, int C, int Cpad, int swap_rb) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < P; p += stride) {
+        for (int c = 0; c < Cpad; ++c) {
+            float v = 0.f;
+            if (c < C) v = ((float)src[p * C + (swap_rb ? C - 1 - c : c)] - mean[c]) * inv_std[c];
+            stf(dst + p * Cpad + c, v);
+        }
+    }
+}
+
+extern "C" int stc_image_u8_to_nhwc(const uint8_t* src, void* dst, const float* mean, const float* inv_std, long long P, int C, int Cpad,
+                                    int swap_rb, int dtype, void* stream) {
+    STC_REQUIRE(src && dst && mean && inv_std && C >= 1 && C <= 4 && Cpad >= C, "image_u8_to_nhwc: bad arguments (C=%d, Cpad=%d)", C, Cpad);
+    if (P <= 0) return STC_OK;
+    int blocks = (int)min((long long)num_sms() * 16, (long long)ceil_div(P, 256));
+    STC_DISPATCH_DTYPE(dtype, (image_u8_kernel<T><<<blocks, 256, 0, (cudaStream_t)stream>>>(src, (T*)dst, mean, inv_std, P, C, Cpad, swap_rb)));
+    return check_launch("image_u8_to_nhwc");
+}
+
+// 8-bit label maps (as stored in the annotation PNGs) -> the int64 maps the loss / histogram kernels index with
+__global__ void widen_u8_i64_kernel(const uint8_t* __restrict__ src, int64_t* __restrict__ dst, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
+}
+
+extern "C" int stc_widen_u8_i64(const uint8_t* src, int64_t* dst, long long n, void* stream) {
+    if (n <= 0) return STC_OK;
+    int blocks = (int)min((long long)num_sms() * 16, (long long)ceil_div(n, 256));
+    widen_u8_i64_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, n);
+    return check_launch("widen_u8_i64");
+}
+
 template <typename T>
 __global__ void pack_w_kernel(const float* __restrict__ w, T* __restrict__ dst, int Cout, int Cin, int R, int S,
                               int inner_pad, int tf, long long total) {

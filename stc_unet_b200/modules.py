@@ -168,7 +168,7 @@ class UnetBackbone(BaseModule):
         self.compute_dtype = _DTYPES[compute_dtype] if isinstance(compute_dtype, str) else compute_dtype
 
     def forward(self, x) -> List[torch.Tensor]:
-        h = ops.image_to_nhwc(x, self.compute_dtype)  # raises on non-CUDA input: there is no CPU path
+        h = ops.image_to_nhwc(x, self.compute_dtype, getattr(self, "img_norm_cfg", None))  # raises on non-CUDA input: no CPU path
         x1 = self.inc(h)
         ctx, tr = bool(self.context_layer), self.transformer_block
         x1a, x1b = ops.fanout(x1, 2) if ctx else (x1, x1)
@@ -332,7 +332,7 @@ class BaseDecodeHead(BaseModule):
             raise NotImplementedError("seg_logit/seg_label size mismatch: UnetHead always predicts at label resolution")
         seg_label = seg_label.squeeze(1)
         losses_decode = self.loss_decode if isinstance(self.loss_decode, nn.ModuleList) else [self.loss_decode]
-        ce, dice, acc = ops.seg_loss(seg_logit.float(), seg_label.long(), self.ignore_index, 1.0)
+        ce, dice, acc = ops.seg_loss(seg_logit.float(), ops.labels_to_int64(seg_label), self.ignore_index, 1.0)
         fused = {"ce": ce, "dice": dice}
         for ld in losses_decode:
             if hasattr(ld, "from_fused"):
@@ -395,7 +395,7 @@ class CrossEntropyLoss(nn.Module):
     def forward(self, cls_score, label, weight=None, avg_factor=None, reduction_override=None, ignore_index=-100, **kwargs):
         if weight is not None or avg_factor is not None or reduction_override not in (None, "mean"):
             raise NotImplementedError("CrossEntropyLoss (stc_unet_b200): weight/avg_factor/reduction_override unsupported")
-        ce, _, _ = ops.seg_loss(cls_score.float(), label.long(), ignore_index, 1.0)
+        ce, _, _ = ops.seg_loss(cls_score.float(), ops.labels_to_int64(label), ignore_index, 1.0)
         return ops.scale(ce, self.loss_weight)
 
     @property
@@ -424,7 +424,7 @@ class DiceLoss(nn.Module):
     def forward(self, pred, target, avg_factor=None, reduction_override=None, **kwargs):
         if avg_factor is not None or reduction_override not in (None, "mean"):
             raise NotImplementedError("DiceLoss (stc_unet_b200): avg_factor/reduction_override unsupported")
-        _, dice, _ = ops.seg_loss(pred.float(), target.long(), self.ignore_index, float(self.smooth))
+        _, dice, _ = ops.seg_loss(pred.float(), ops.labels_to_int64(target), self.ignore_index, float(self.smooth))
         return ops.scale(dice, self.loss_weight)
 
     @property

@@ -221,7 +221,7 @@ class UNet(BaseModule):
 
     def forward(self, x):
         self._check_input_divisible(x)
-        h = ops.image_to_nhwc(x, self.compute_dtype)
+        h = ops.image_to_nhwc(x, self.compute_dtype, getattr(self, "img_norm_cfg", None))
         enc_outs = []
         last = len(self.encoder) - 1
         for i, enc in enumerate(self.encoder):

@@ -156,7 +156,7 @@ class UnetPlusPlus(BaseDecodeHead):
         self.compute_dtype = _DTYPES[compute_dtype] if isinstance(compute_dtype, str) else compute_dtype
 
     def forward(self, x):  # x: the IMAGE (N,3,H,W) — EncoderDecoderFull has no backbone
-        h = ops.image_to_nhwc(x, self.compute_dtype)
+        h = ops.image_to_nhwc(x, self.compute_dtype, getattr(self, "img_norm_cfg", None))
         return self.cls_seg(self.model(h))
 
 

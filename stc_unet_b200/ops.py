@@ -982,17 +982,56 @@ class _SegLoss(Function):
 
 
 def seg_loss(logits, label, ignore_index=255, smooth=1.0):
-    return _SegLoss.apply(logits, label, ignore_index, smooth)
+    return _SegLoss.apply(logits, labels_to_int64(label), ignore_index, smooth)
 
 
 # ---------------------------------------------------------------------------------------------
 # layout conversion and inference / metric helpers (no autograd)
 # ---------------------------------------------------------------------------------------------
-def image_to_nhwc(img: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+_NORM_CACHE = {}
+
+
+def _norm_vectors(device, C, mean, std):
+    key = (device.type, device.index, C, tuple(mean), tuple(std))
+    hit = _NORM_CACHE.get(key)
+    if hit is None:
+        m = torch.tensor([float(mean[i % len(mean)]) for i in range(C)], dtype=torch.float32, device=device)
+        r = torch.tensor([1.0 / float(std[i % len(std)]) for i in range(C)], dtype=torch.float32, device=device)
+        hit = _NORM_CACHE[key] = (m, r)
+    return hit
+
+
+def image_to_nhwc(img: torch.Tensor, dtype: torch.dtype, norm_cfg: Optional[dict] = None) -> torch.Tensor:
+    """Module input -> NHWC activations.  float (N,C,H,W): the reference's interface (already normalised by its CPU pipeline).
+    uint8 (N,H,W,C): decoded pixels straight from the loader; `norm_cfg = dict(mean, std, to_rgb)` (the config's img_norm_cfg,
+    my_config/STC-UNet.py:35) is applied on the device."""
+    if img.dtype == torch.uint8:
+        img = _chk(img)
+        if img.dim() != 4 or img.shape[-1] > 4:
+            raise ValueError(f"uint8 images must be (N, H, W, C<=4) as decoded, got {tuple(img.shape)}")
+        N, H, W, C = img.shape
+        cfg = norm_cfg or {}
+        mean, inv_std = _norm_vectors(img.device, C, cfg.get("mean", [0.0]), cfg.get("std", [1.0]))
+        out = torch.empty((N, H, W, C), dtype=dtype, device=img.device)
+        lib.call("stc_image_u8_to_nhwc", img, out, mean, inv_std, N * H * W, C, C, int(bool(cfg.get("to_rgb", False))), dtype_code(dtype),
+                 stream_ptr())
+        return out
     img = _chk(img.float())
     N, C, H, W = img.shape
     out = torch.empty((N, H, W, C), dtype=dtype, device=img.device)
     lib.call("stc_nchw_to_nhwc", img, out, N, C, H, W, C, dtype_code(dtype), stream_ptr())
+    return out
+
+
+def labels_to_int64(label: torch.Tensor) -> torch.Tensor:
+    """8-bit label maps (annotation PNGs) are widened on the device; int64 passes through."""
+    if label.dtype == torch.int64:
+        return label
+    if label.dtype != torch.uint8:
+        raise TypeError(f"labels must be int64 or uint8, got {label.dtype}")
+    label = _chk(label)
+    out = torch.empty(label.shape, dtype=torch.int64, device=label.device)
+    lib.call("stc_widen_u8_i64", label, out, label.numel(), stream_ptr())
     return out
 
 

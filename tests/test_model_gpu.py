@@ -387,3 +387,28 @@ def test_unetpp_config5_parity(dtype):
         ref_eval = O.unetpp_forward({k: conv(v) for k, v in hd.state_dict().items()}, img.double(), False, None)
     assert logits.shape == (2, 2, 64, 64)
     assert rel_l2(logits, ref_eval) <= (1e-4 if dtype == "fp32" else 8e-2)
+
+
+def test_uint8_input_pipeline_matches_float_path():
+    """decoded uint8 HWC pixels + uint8 labels, normalised on the device, give exactly the losses and gradients of the
+    reference interface (float NCHW image normalised on the host, int64 labels)."""
+    import stc_unet_b200 as S
+    bb, hd = build(True, 3, "bf16")
+    seg = S.EncoderDecoder(bb, hd).cuda().train()
+    cfg = dict(mean=[123.675, 116.28, 103.53], std=[58.395, 57.12, 57.375], to_rgb=True)
+    seg.backbone.img_norm_cfg = cfg
+    g = torch.Generator().manual_seed(5)
+    raw = torch.randint(0, 256, (2, 64, 64, 3), generator=g, dtype=torch.uint8)          # BGR HWC as cv2 decodes it
+    lab = torch.randint(0, 3, (2, 1, 64, 64), generator=g, dtype=torch.uint8)
+    lab[:, :, :2] = 255
+    mean, std = torch.tensor(cfg["mean"]), torch.tensor(cfg["std"])
+    ref_img = ((raw.flip(-1).float() - mean) / std).permute(0, 3, 1, 2).contiguous()     # mmcv.imnormalize + ImageToTensor
+    outs = []
+    for img, gt in ((ref_img.cuda(), lab.long().cuda()), (raw.cuda(), lab.cuda())):
+        seg.zero_grad(set_to_none=True)
+        torch.manual_seed(11)                                                            # same Dropout2d mask
+        out = seg.train_step(dict(img=img, img_metas=None, gt_semantic_seg=gt))
+        out["loss"].backward()
+        outs.append((float(out["loss"]), seg.backbone.inc.conv.conv[0].weight.grad.clone(), seg.decode_head.conv_seg.weight.grad.clone()))
+    assert abs(outs[0][0] - outs[1][0]) <= 2e-3 * abs(outs[0][0])
+    assert rel_l2(outs[1][2], outs[0][2]) < 2e-2 and rel_l2(outs[1][1], outs[0][1]) < 0.2   # bf16 input rounding differs by <= 1 ulp

@@ -490,3 +490,20 @@ def test_step_cache_batched_pack_matches_single_packs(S):
     for (w, tf, pad), g in zip(reqs, got):
         ref = ops.pack_weight(w, torch.bfloat16, transpose_flip=tf, im2col_pad=pad)
         assert g.shape == ref.shape and torch.equal(g, ref), (tuple(w.shape), tf, pad)
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_image_u8_and_label_widen(S, dt):
+    from stc_unet_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    raw = torch.randint(0, 256, (2, 9, 7, 3), generator=g, dtype=torch.uint8).cuda()
+    cfg = dict(mean=[10.0, 20.0, 30.0], std=[2.0, 4.0, 8.0], to_rgb=True)
+    out = ops.image_to_nhwc(raw, dt, cfg)
+    ref = (raw.flip(-1).float() - torch.tensor(cfg["mean"], device="cuda")) / torch.tensor(cfg["std"], device="cuda")
+    assert out.shape == (2, 9, 7, 3) and rel_l2(out.float(), ref) < (1e-6 if dt == torch.float32 else 4e-3)
+    assert torch.equal(ops.image_to_nhwc(raw, torch.float32), raw.float())               # default: mean 0, std 1, no channel swap
+    lab = torch.randint(0, 256, (3, 5, 11), generator=g, dtype=torch.uint8).cuda()
+    wide = ops.labels_to_int64(lab)
+    assert wide.dtype == torch.int64 and torch.equal(wide, lab.long())
+    with pytest.raises(TypeError):
+        ops.labels_to_int64(lab.int())
