@@ -161,6 +161,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="single GPU: launch the step eagerly instead of replaying the captured CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -211,26 +212,38 @@ def main():
 
     last = {}
 
+    # launches per step, counted on one eager step (a replayed graph launches the same kernels without passing through Python)
+    _names = []
+    _orig = S._lib.lib.call
+
+    def _tally(name, *a):
+        _names.append(name)
+        return _orig(name, *a)
+    for i in range(3):
+        trainer.step(d_img[i % pool], d_gt[i % pool])
+    S._lib.lib.call = _tally
+    trainer.step(d_img[0], d_gt[0])
+    if "call" in S._lib.lib.__dict__:
+        del S._lib.lib.__dict__["call"]
+    launches_per_step = sum(LAUNCHES.get(n, 1) for n in _names)
+    use_graph = world == 1 and not args.no_graph
+    if use_graph:   # the whole step (fwd + loss + bwd + Adam, ~1000 launches) captured once and replayed; same kernels, no launch gaps
+        trainer.capture(d_img[0], d_gt[0])
+
     def dev_step(i):
-        last["lv"] = trainer.step(d_img[i % pool], d_gt[i % pool])
+        if use_graph:
+            last["lv"] = trainer.step_graph(d_img[i % pool], d_gt[i % pool])
+        else:
+            last["lv"] = trainer.step(d_img[i % pool], d_gt[i % pool])
 
     for i in range(args.warmup):
         dev_step(i)
-    names = []
-    _orig_call = S._lib.lib.call
-
-    def tally(name, *a):
-        names.append(name)
-        return _orig_call(name, *a)
-    S._lib.lib.call = tally
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ms_total = timed(dev_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
-    if "call" in S._lib.lib.__dict__:
-        del S._lib.lib.__dict__["call"]
-    gpu_launches = sum(LAUNCHES.get(n, 1) for n in names)
+    gpu_launches = launches_per_step * args.steps
     ms_per_step = ms_total / args.steps
     value = world * args.batch / (ms_per_step / 1e3)
     loss_val = float(last["lv"]["loss"].detach())
@@ -240,11 +253,49 @@ def main():
     if not args.no_e2e:
         bi = h_img[0].numel() * 4 + h_gt[0].numel() * 8
 
-        def e2e_step(i):
-            img = h_img[i % pool].to(dev, non_blocking=True)
-            gt = h_gt[i % pool].to(dev, non_blocking=True)
-            lv = trainer.step(img, gt)
-            last["host_loss"] = float(lv["loss"])   # D2H read of the step's result
+        class Prefetcher:
+            """What a training loader does: the H2D copy of step i+1's batch runs on a copy stream while step i computes.  Every
+            step's inputs still travel host -> device inside the timed region; only the waiting is overlapped."""
+
+            def __init__(self, imgs, gts):
+                self.imgs, self.gts = imgs, gts
+                self.stream = torch.cuda.Stream()
+                self.slots = [(torch.empty_like(imgs[0], device=dev), torch.empty_like(gts[0], device=dev)) for _ in range(2)]
+                self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+                self.consumed = [None, None]
+                self.next = None
+
+            def issue(self, i):
+                k = i % 2
+                if self.consumed[k] is not None:
+                    self.stream.wait_event(self.consumed[k])      # the step that last read this slot has taken its copy
+                with torch.cuda.stream(self.stream):
+                    self.slots[k][0].copy_(self.imgs[i % pool], non_blocking=True)
+                    self.slots[k][1].copy_(self.gts[i % pool], non_blocking=True)
+                    self.ready[k].record(self.stream)
+                self.next = i
+
+            def take(self, i):
+                if self.next != i:
+                    self.issue(i)
+                k = i % 2
+                torch.cuda.current_stream().wait_event(self.ready[k])
+                return self.slots[k]
+
+            def release(self, i):
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream())
+                self.consumed[i % 2] = ev
+
+        def make_e2e_step(pf):
+            def step(i):
+                img, gt = pf.take(i)
+                lv = trainer.step_graph(img, gt) if use_graph else trainer.step(img, gt)
+                pf.release(i)
+                pf.issue(i + 1)                                   # enqueue the next batch's H2D before blocking on this step's result
+                last["host_loss"] = float(lv["loss"])            # D2H read of the step's result
+            return step
+        e2e_step = make_e2e_step(Prefetcher(h_img, h_gt))
         for i in range(2):
             e2e_step(i)
         ms_e2e = timed(e2e_step, args.steps) / args.steps
@@ -256,9 +307,10 @@ def main():
         u_gt = [t.to(torch.uint8).pin_memory() for t in h_gt]
         seg.backbone.img_norm_cfg = dict(mean=[0.0], std=[255.0], to_rgb=False)
 
-        def e2e_u8_step(i):
-            lv = trainer.step(u_img[i % pool].to(dev, non_blocking=True), u_gt[i % pool].to(dev, non_blocking=True))
-            last["host_loss"] = float(lv["loss"])
+        if use_graph:
+            trainer.capture(u_img[0].to(dev), u_gt[0].to(dev))
+
+        e2e_u8_step = make_e2e_step(Prefetcher(u_img, u_gt))
         for i in range(2):
             e2e_u8_step(i)
         ms_u8 = timed(e2e_u8_step, args.steps) / args.steps
@@ -276,7 +328,7 @@ def main():
         t0.record()
         psteps = 2
         for i in range(psteps):
-            dev_step(i)
+            trainer.step(d_img[i % pool], d_gt[i % pool])   # eager: the per-launch events need the Python-level calls
         t1.record()
         summ = prof.summary()
         ops.set_profiler(None)
@@ -331,7 +383,7 @@ def main():
         fl = FWD_GMAC_PER_IMG[args.model] * 2 * 3 * 1e9   # fwd+bwd algorithmic FLOP per image
         line = dict(metric=METRIC, value=value, unit="img/s", n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_per_step,
                     higher_is_better=True, scaling="weak", vs_baseline=None, dtype=args.dtype, data="synthetic",
-                    config=dict(workload=workload_name(args), parallelism=f"dp{world}", sync_bn=world > 1,
+                    config=dict(workload=workload_name(args), parallelism=f"dp{world}", sync_bn=world > 1, cuda_graph=bool(use_graph),
                                 cache="per-step working set (tens of GB of activations) >> 126 MB L2; 2 distinct input batches alternate",
                                 optimizer="fused Adam lr=1e-5", dropout_ratio=0.1),
                     model_tflops_per_s=value * fl / 1e12, model_frac_of_peak=value * fl / 1e12 / world / peaks["tflops_sustained"],

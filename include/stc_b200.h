@@ -278,6 +278,10 @@ int stc_confusion_hist(const int64_t* pred, const void* label, int label_is_u8, 
 /* torch.optim.Adam semantics on a flat fp32 buffer; step is 1-based. */
 int stc_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                   float eps, float weight_decay, int step, void* stream);
+/* Same update with the learning rate and the step counter in DEVICE memory (dyn = {lr, beta1^t, beta2^t} fp32, step int32): a captured
+ * CUDA graph of the whole training step can be replayed while bias corrections and LR schedules keep advancing. */
+int stc_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, float* dyn, int* step, float beta1, float beta2, float eps,
+                      float weight_decay, void* stream);
 
 #ifdef __cplusplus
 }

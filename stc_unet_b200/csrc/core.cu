@@ -2,6 +2,7 @@
 #include <stdarg.h>
 
 #include "common.cuh"
+#include "reduce.cuh"
 
 namespace stc {
 
@@ -302,10 +303,41 @@ __global__ void colsum_kernel(const T* __restrict__ x, float* __restrict__ out, 
     }
 }
 
+// vector path: a thread keeps one 8-channel lane and walks rows with two 16-byte loads in flight; one atomicAdd per (block, channel)
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_rows_kernel(const T* __restrict__ x, float* __restrict__ out, long long P, int C) {
+    __shared__ float smem[256 * 8];
+    const int lanes = C >> 3, lv = threadIdx.x % lanes, r0 = threadIdx.x / lanes, rstep = 256 / lanes;
+    float acc[1][8] = {};
+    float acc1[8] = {};
+    const long long step = (long long)gridDim.x * rstep;
+    long long p = (long long)blockIdx.x * rstep + r0;
+    for (; p + step < P; p += 2 * step) {
+        Vec8<T> v0, v1;
+        v0.load(x + p * C + lv * 8);
+        v1.load(x + (p + step) * C + lv * 8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { acc[0][k] += v0.v[k]; acc1[k] += v1.v[k]; }
+    }
+    if (p < P) {
+        Vec8<T> v0;
+        v0.load(x + p * C + lv * 8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[0][k] += v0.v[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[0][k] += acc1[k];
+    block_reduce_lanes_emit<1>(acc, lanes, smem, C, [&](int, int c, float s) { atomicAdd(out + c, s); });
+}
+
 extern "C" int stc_colsum(const void* x, float* out, long long P, int C, int accumulate, int dtype, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (!accumulate) STC_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * C, st));
     if (P <= 0) return STC_OK;
+    if (vec_ok(C) && (((uintptr_t)x) & 15) == 0 && P >= 1024) {
+        STC_DISPATCH_DTYPE(dtype, (colsum_rows_kernel<T><<<reduce_blocks(P, C / 8), 256, 0, st>>>((const T*)x, out, P, C)));
+        return check_launch("colsum");
+    }
     int gx = ceil_div(C, 32);
     int gy = (int)max(1LL, min((long long)ceil_div(P, 64), (long long)(num_sms() * 8 / gx + 1)));
     dim3 grid(gx, gy);
@@ -341,6 +373,46 @@ extern "C" int stc_adam_step(float* p, const float* g, float* m, float* v, long 
     int blocks = (int)min((long long)num_sms() * 16, (long long)ceil_div(n, 256));
     adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2s);
     return check_launch("adam");
+}
+
+// Graph-capturable variant: the step counter and the learning rate live in device memory, so a captured training step can be
+// replayed while the bias corrections and an LR schedule keep advancing.  dyn = {lr, beta1^t, beta2^t} (fp32), updated by the
+// tick kernel that precedes the update.
+__global__ void adam_tick_kernel(float* __restrict__ dyn, int* __restrict__ step, float b1, float b2) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const int t = *step + 1;
+        *step = t;
+        dyn[1] = powf(b1, (float)t);
+        dyn[2] = powf(b2, (float)t);
+    }
+}
+
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                long long n, const float* __restrict__ dyn, float b1, float b2, float eps, float wd) {
+    const float lr = dyn[0], bc1 = 1.f - dyn[1], bc2_sqrt = sqrtf(1.f - dyn[2]);
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        float gi = g[i], pi = p[i];
+        if (wd != 0.f) gi += wd * pi;
+        float mi = b1 * m[i] + (1.f - b1) * gi;
+        float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] = pi - (lr / bc1) * (mi / denom);
+    }
+}
+
+extern "C" int stc_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, float* dyn, int* step, float beta1, float beta2,
+                                 float eps, float weight_decay, void* stream) {
+    if (n <= 0) return STC_OK;
+    STC_REQUIRE(dyn && step, "adam_step_dev: null state pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    adam_tick_kernel<<<1, 32, 0, st>>>(dyn, step, beta1, beta2);
+    int blocks = (int)min((long long)num_sms() * 16, (long long)ceil_div(n, 256));
+    adam_dev_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, n, dyn, beta1, beta2, eps, weight_decay);
+    return check_launch("adam_dev");
 }
 
 // ------------------------------------------------------------------------------------

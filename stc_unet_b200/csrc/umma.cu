@@ -312,7 +312,10 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_cons
                                 }
                             }
                         }
-                        if (p.act != STC_ACT_NONE) {
+                        if (p.act == STC_ACT_RELU) {   // uniform branch per chunk: a per-element switch compiles to a jump table
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                        } else if (p.act != STC_ACT_NONE) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) f[j] = epi_act(f[j], p.act);
                         }
@@ -383,7 +386,10 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_cons
                         for (int j = 0; j < 32; ++j) f[j] += __ldg(r + j);
                     }
                 }
-                if (p.act != STC_ACT_NONE) {
+                if (p.act == STC_ACT_RELU) {   // uniform branch per chunk: a per-element switch compiles to a jump table
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                } else if (p.act != STC_ACT_NONE) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = epi_act(f[j], p.act);
                 }

@@ -280,7 +280,10 @@ __global__ void __launch_bounds__(kConvHThreads, 1) umma_convh_kernel(const __gr
                                     }
                                 }
                             }
-                            if (p.act != STC_ACT_NONE) {
+                            if (p.act == STC_ACT_RELU) {   // uniform branch per chunk: a per-element switch compiles to a jump table
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                            } else if (p.act != STC_ACT_NONE) {
 #pragma unroll
                                 for (int j = 0; j < 32; ++j) f[j] = convh_act(f[j], p.act);
                             }
@@ -330,7 +333,10 @@ __global__ void __launch_bounds__(kConvHThreads, 1) umma_convh_kernel(const __gr
                             }
                         }
                     }
-                    if (p.act != STC_ACT_NONE) {
+                    if (p.act == STC_ACT_RELU) {   // uniform branch per chunk: a per-element switch compiles to a jump table
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                    } else if (p.act != STC_ACT_NONE) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) f[j] = convh_act(f[j], p.act);
                     }

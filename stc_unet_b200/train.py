@@ -120,6 +120,11 @@ class FusedAdam:
         self.m = torch.zeros_like(flat_params.flat)
         self.v = torch.zeros_like(flat_params.flat)
         self.t = 0
+        # device-resident copies of (lr, beta^t) and the step counter for the graph-capturable update
+        self.dyn = torch.zeros(3, dtype=torch.float32, device=flat_params.flat.device)
+        self.step_count_dev = torch.zeros(1, dtype=torch.int32, device=flat_params.flat.device)
+        self._lr_on_dev = None
+        self._t_on_dev = None
 
     def zero_grad(self, set_to_none: bool = True):
         for p in self.fp.params:
@@ -130,6 +135,22 @@ class FusedAdam:
         self.t += 1
         lib.call("stc_adam_step", self.fp.flat, self.arena.flat, self.m, self.v, self.fp.total, float(g["lr"]),
                  float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]), self.t, stream_ptr())
+
+    def sync_device_state(self):
+        """Host -> device: step counter and learning rate (call outside a captured region, e.g. before each graph replay)."""
+        lr = float(self.param_groups[0]["lr"])
+        if self._lr_on_dev != lr:
+            self.dyn[0:1].fill_(lr)
+            self._lr_on_dev = lr
+        if self._t_on_dev != self.t:        # eager steps ran in between: re-seed the device counter
+            self.step_count_dev.fill_(self.t)
+            self._t_on_dev = self.t
+
+    def step_dev(self):
+        """The same update with lr / step read from device memory (capturable); sync_device_state() must have run."""
+        g = self.param_groups[0]
+        lib.call("stc_adam_step_dev", self.fp.flat, self.arena.flat, self.m, self.v, self.fp.total, self.dyn, self.step_count_dev,
+                 float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]), stream_ptr())
 
     def state_dict(self):
         return dict(step=self.t, exp_avg=self.m, exp_avg_sq=self.v, param_groups=[{k: v for k, v in self.param_groups[0].items() if k != "params"}])
@@ -150,8 +171,10 @@ class Trainer:
         self.reducer = GradReducer(self.arena, bucket_mb)
         self.optim = FusedAdam(self.flat, self.arena, lr=lr, betas=betas)
         self.cache = ops.StepCache()
+        self.steps_done = 0
+        self._graph = None
 
-    def step(self, img: torch.Tensor, gt_semantic_seg: torch.Tensor):
+    def step(self, img: torch.Tensor, gt_semantic_seg: torch.Tensor, _device_adam: bool = False):
         """One training iteration; returns the (device) log-var tensors, no host sync."""
         ops.set_grad_arena(self.arena)
         ops.set_step_cache(self.cache)
@@ -164,9 +187,51 @@ class Trainer:
             out = self.model.train_step(dict(img=img, img_metas=None, gt_semantic_seg=gt_semantic_seg))
             out["loss"].backward()
             self.reducer.finish()
-            self.optim.step()
+            if _device_adam:
+                self.optim.step_dev()
+            else:
+                self.optim.step()
         finally:
             ops.set_grad_arena(None)
             ops.set_step_cache(None)
             self.arena.prezeroed = False
+        self.steps_done += 1
         return out["log_vars"]
+
+    # ---- whole-step CUDA graph: ~1000 launches replayed as one graph (no tracing compiler involved: the kernels are ours) ----
+    def capture(self, img: torch.Tensor, gt_semantic_seg: torch.Tensor):
+        """Captures fwd + loss + bwd + Adam for inputs of this shape/dtype.  Runs the eager warm-up steps the StepCache needs
+        first (they are real training steps).  Afterwards step_graph() replays it on new data."""
+        if _dist_on():
+            raise RuntimeError("Trainer.capture: the captured step is single-GPU only (NCCL buckets stay on the eager path)")
+        while self.steps_done < 3:                      # StepCache: record, finalize, replay
+            self.step(img, gt_semantic_seg)
+        self._static_img = img.clone()
+        self._static_gt = gt_semantic_seg.clone()
+        opt = self.optim
+        opt.sync_device_state()                         # continue the eager step count on the device
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                   # one eager pass on the device-state Adam so every lazy init is done
+            self.step(self._static_img, self._static_gt, _device_adam=True)
+        opt.t += 1
+        opt._t_on_dev = opt.t
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._static_out = self.step(self._static_img, self._static_gt, _device_adam=True)
+        return self
+
+    def step_graph(self, img: torch.Tensor, gt_semantic_seg: torch.Tensor):
+        """Replays the captured step on new data (host or device tensors; copied into the static input buffers)."""
+        if self._graph is None:
+            raise RuntimeError("Trainer.step_graph: call capture() first")
+        self._static_img.copy_(img, non_blocking=True)
+        self._static_gt.copy_(gt_semantic_seg, non_blocking=True)
+        self.optim.sync_device_state()
+        self._graph.replay()
+        self.optim.t += 1
+        self.optim._t_on_dev = self.optim.t
+        self.steps_done += 1
+        return self._static_out

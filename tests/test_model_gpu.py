@@ -412,3 +412,34 @@ def test_uint8_input_pipeline_matches_float_path():
         outs.append((float(out["loss"]), seg.backbone.inc.conv.conv[0].weight.grad.clone(), seg.decode_head.conv_seg.weight.grad.clone()))
     assert abs(outs[0][0] - outs[1][0]) <= 2e-3 * abs(outs[0][0])
     assert rel_l2(outs[1][2], outs[0][2]) < 2e-2 and rel_l2(outs[1][1], outs[0][1]) < 0.2   # bf16 input rounding differs by <= 1 ulp
+
+
+def test_trainer_cuda_graph_matches_eager():
+    """Trainer.capture / step_graph: the captured whole-step graph (fwd + loss + bwd + device-state Adam) trains like the eager
+    step on the same data sequence (dropout off; wgrad reductions use atomics, so agreement is close, not bitwise)."""
+    import stc_unet_b200 as S
+    from stc_unet_b200.train import Trainer
+    g = torch.Generator().manual_seed(3)
+    imgs = [torch.rand(2, 3, 64, 64, generator=g).cuda() for _ in range(4)]
+    gts = [torch.randint(0, 3, (2, 1, 64, 64), generator=g).cuda() for _ in range(4)]
+    losses = {}
+    for mode in ("eager", "graph"):
+        bb, hd = build(True, 3, "fp32", posbn=True)
+        seg = S.EncoderDecoder(bb, hd).cuda().train()
+        tr = Trainer(seg, lr=1e-3)
+        seq = []
+        for s in range(3):                                   # StepCache warm-up: real steps in both modes
+            seq.append(float(tr.step(imgs[s % 4], gts[s % 4])["loss"]))
+        if mode == "graph":
+            tr.capture(imgs[3], gts[3])                      # note: capture() itself performs one more real step on these inputs
+        else:
+            tr.step(imgs[3], gts[3])
+        for s in range(4, 10):
+            lv = tr.step_graph(imgs[s % 4], gts[s % 4]) if mode == "graph" else tr.step(imgs[s % 4], gts[s % 4])
+            seq.append(float(lv["loss"]))
+        losses[mode] = seq
+        if mode == "graph":
+            assert tr.optim.t == 10 and int(tr.optim.step_count_dev) == 10
+    for a, b in zip(losses["eager"], losses["graph"]):
+        assert abs(a - b) <= 2e-3 * max(1.0, abs(a)), (losses["eager"], losses["graph"])
+    assert losses["graph"][-1] < losses["graph"][0]          # it does train

@@ -1,0 +1,22 @@
+"""One launch of each dominant tcgen05 kernel at its heaviest in-step shape (for `ncu --set full`): halo fprop L1 64->64 k7 and k3,
+halo wgrad L1 64->64 k7, Linear 512x512 @65536 rows (fprop + wgrad), QK^T."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import stc_unet_b200 as S
+from stc_unet_b200 import ops
+BF = torch.bfloat16; dev = torch.device("cuda:0")
+def conv(ci, co, hw, k, N=16, wgrad=False):
+    x = torch.randn(N, hw, hw, ci, device=dev).to(BF); dy = torch.randn(N, hw, hw, co, device=dev).to(BF)
+    w = torch.randn(co, ci, k, k, device=dev) / (ci * k * k) ** 0.5
+    wp = ops.pack_weight(w, BF); ws = torch.zeros(k * k * ci * co, device=dev)
+    for _ in range(2):
+        if wgrad: S._lib.lib.call("stc_conv_wgrad", x, dy, ws, N, hw, hw, ci, co, k, k, 1, 0, S._lib.stream_ptr())
+        else: ops.conv_fprop(x, wp, None, None, co, k, k)
+    torch.cuda.synchronize()
+conv(64, 64, 512, 7); conv(64, 64, 512, 3); conv(64, 64, 512, 7, wgrad=True); conv(512, 512, 64, 1); conv(512, 512, 64, 1, wgrad=True)
+L, hd, B = 4096, 256, 32
+q = torch.randn(B, L, hd, device=dev).to(BF); kk = torch.randn(B, L, hd, device=dev).to(BF); sc = torch.empty(B, L, L, device=dev, dtype=BF)
+for _ in range(2):
+    ops.gemm(q, kk, sc, L, L, hd, B, 1, (L * hd, 0, hd, 1), (L * hd, 0, 1, hd), (L * L, 0, L))
+torch.cuda.synchronize(); print("ok")
