@@ -226,7 +226,7 @@ def main():
     if "call" in S._lib.lib.__dict__:
         del S._lib.lib.__dict__["call"]
     launches_per_step = sum(LAUNCHES.get(n, 1) for n in _names)
-    use_graph = world == 1 and not args.no_graph
+    use_graph = world == 1 and not args.no_graph   # multi-GPU capture (NCCL inside the graph) hung when tried: eager there
     if use_graph:   # the whole step (fwd + loss + bwd + Adam, ~1000 launches) captured once and replayed; same kernels, no launch gaps
         trainer.capture(d_img[0], d_gt[0])
 

@@ -15,6 +15,7 @@ containers are nn.SyncBatchNorm and torch.distributed is initialised.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -203,7 +204,9 @@ class Trainer:
         """Captures fwd + loss + bwd + Adam for inputs of this shape/dtype.  Runs the eager warm-up steps the StepCache needs
         first (they are real training steps).  Afterwards step_graph() replays it on new data."""
         if _dist_on():
-            raise RuntimeError("Trainer.capture: the captured step is single-GPU only (NCCL buckets stay on the eager path)")
+            # tried at N=2 (NCCL bucket all-reduces + SyncBN exchanges inside the capture): the capture hangs, so the multi-GPU
+            # step stays on the eager path
+            raise RuntimeError("Trainer.capture: the captured step is single-GPU only")
         while self.steps_done < 3:                      # StepCache: record, finalize, replay
             self.step(img, gt_semantic_seg)
         self._static_img = img.clone()
