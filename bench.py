@@ -347,17 +347,19 @@ def main():
             achieved = dv["flops"] / (dv["ms"] * 1e-3) / 1e12
             all_achieved = sum(v["flops"] for v in tensor.values()) / (tc_ms * 1e-3) / 1e12
             # dram bytes per launch from the committed `ncu --set full` capture of this kernel (profiles/), if one exists
-            traffic = None
+            traffic, traffic_detail = None, None
             tp = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
             if os.path.exists(tp):
-                traffic = json.load(open(tp)).get(KNAME[dom])
+                traffic_detail = json.load(open(tp)).get(KNAME[dom])
+                if traffic_detail:   # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel (the launch is named)
+                    traffic = traffic_detail["dram_bytes_read"] + traffic_detail["dram_bytes_write"]
             roofline = dict(bound="tensor", kernel=KNAME[dom], achieved=achieved, peak=peaks["tflops_sustained"], unit="TFLOP/s",
                             frac=achieved / peaks["tflops_sustained"],
                             peak_source=f"{peaks['source']} (sustained cuBLAS bf16; kernel timed inside a long step)", traffic=traffic,
-                            launches_per_step=dv["launches"] // psteps, avg_launch_ms=dv["ms"] / max(dv["launches"], 1),
-                            algorithmic_tflop_per_step=dv["flops"] / psteps / 1e12, share_of_step=dv["ms"] / psteps / step_ms_prof,
+                            traffic_detail=traffic_detail, launches_per_step=dv["launches"] // psteps, avg_launch_ms=dv["ms"] / max(dv["launches"], 1),
+                            algorithmic_tflop_per_step=dv["flops"] / psteps / 1e12, share_of_step=dv["ms"] / psteps / ms_per_step,
                             all_tcgen05_kernels=dict(achieved=all_achieved, frac=all_achieved / peaks["tflops_sustained"],
-                                                     share_of_step=tc_ms / psteps / step_ms_prof,
+                                                     share_of_step=tc_ms / psteps / ms_per_step,
                                                      per_kernel={KNAME[e]: dict(launches=v["launches"] // psteps, ms=v["ms"] / psteps,
                                                                                 tflops=v["flops"] / (v["ms"] * 1e-3) / 1e12) for e, v in tensor.items()}))
         breakdown = {f"{k[0]}:{KNAME.get(k[1], k[1])}":

@@ -121,6 +121,10 @@ int stc_softmax_rows_fwd(const void* S, void* P, long long rows, int L, float sc
 /* dS = scale * P * (dP - sum_j dP_j P_j) */
 int stc_softmax_rows_bwd(const void* P, const void* dP, void* dS, long long rows, int L, float scale, int dtype,
                          void* stream);
+/* out[n][l][:] = x[n][l][:] - mean_l x[n][l][:]  (x: N x L x E tokens; mean_ws: N*E floats of scratch).  Used by the fp32 parity
+ * path of nn.MultiheadAttention (unet_backbone.py:195-209): softmax(QK^T) and dS are invariant under a common shift of the keys /
+ * values, and the centred products lose no digits to the common component. */
+int stc_center_tokens(const void* x, void* out, float* mean_ws, int N, int L, int E, int dtype, void* stream);
 
 /* ---------------------------------------------------------------- BatchNorm (K5/K6, C1/C2)
  * nn.SyncBatchNorm / BatchNorm2d train+eval (unet_backbone.py:64,121,124; unet_head.py:68,71,125). */

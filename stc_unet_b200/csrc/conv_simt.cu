@@ -14,13 +14,22 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     return v;
 }
 
+// Two-level accumulation: each 16-deep K tile is summed in fp32 FMAs from zero and the tile sums are added in fp64, so the
+// rounding error does not grow with K (a 1024-channel or 8192-pixel contraction keeps ~1e-7 relative accuracy).  This engine
+// is the exact-parity path; operands whose products share a large common component (BN-cancelled sums such as CoordAtt's
+// conv1 weight gradient) amplify accumulation error ~100x, which is what the reference's cuDNN/cuBLAS tiling also limits.
 #define STC_SIMT_COMPUTE()                                            \
-    _Pragma("unroll") for (int kk = 0; kk < TK; ++kk) {               \
-        float a[4], b[4];                                             \
-        _Pragma("unroll") for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i]; \
-        _Pragma("unroll") for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j]; \
+    {                                                                 \
+        float part[4][4] = {};                                        \
+        _Pragma("unroll") for (int kk = 0; kk < TK; ++kk) {           \
+            float a[4], b[4];                                         \
+            _Pragma("unroll") for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i]; \
+            _Pragma("unroll") for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j]; \
+            _Pragma("unroll") for (int i = 0; i < 4; ++i)             \
+                _Pragma("unroll") for (int j = 0; j < 4; ++j) part[i][j] = fmaf(a[i], b[j], part[i][j]); \
+        }                                                             \
         _Pragma("unroll") for (int i = 0; i < 4; ++i)                 \
-            _Pragma("unroll") for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]); \
+            _Pragma("unroll") for (int j = 0; j < 4; ++j) acc[i][j] += (double)part[i][j]; \
     }
 
 // ---------------------------------------------------------------- conv fprop / dgrad
@@ -51,7 +60,7 @@ __global__ void __launch_bounds__(256) conv_fprop_simt_kernel(const T* __restric
         rh[j] = (int)((mm / W) % H);
         rn[j] = (int)(mm / ((long long)W * H));
     }
-    float acc[4][4] = {};
+    double acc[4][4] = {};
     for (int k0 = 0; k0 < K; k0 += TK) {
         int k = k0 + lk;
         bool kok = k < K;
@@ -81,7 +90,7 @@ __global__ void __launch_bounds__(256) conv_fprop_simt_kernel(const T* __restric
         for (int j = 0; j < 4; ++j) {
             int n = n0 + tx * 4 + j;
             if (n >= Cout) continue;
-            float v = acc[i][j];
+            float v = (float)acc[i][j];
             if (bias) v += bias[n];
             if (residual) v += ldf(residual + m * Cout + n);
             stf(y + m * Cout + n, apply_act(v, act));
@@ -111,7 +120,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_simt_kernel(const T* __restric
     const int r = tap / S - pr, s = tap % S - ps;
     const int n = n0 + lm;
     const bool nok = n < Cout;
-    float acc[4][4] = {};
+    double acc[4][4] = {};
     for (long long k0 = p_begin; k0 < p_end; k0 += TK) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -139,7 +148,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_simt_kernel(const T* __restric
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             int nn = n0 + tx * 4 + j;
-            if (nn < Cout) atomicAdd(ws + (long long)mm * Cout + nn, acc[i][j]);
+            if (nn < Cout) atomicAdd(ws + (long long)mm * Cout + nn, (float)acc[i][j]);
         }
     }
 }
@@ -157,7 +166,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const T* __restrict__ A,
     C += b1 * d.sC1 + b2 * d.sC2;
     const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
     const bool a_kfast = d.sAk == 1, b_kfast = d.sBk == 1;
-    float acc[4][4] = {};
+    double acc[4][4] = {};
     for (int k0 = 0; k0 < d.K; k0 += TK) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -183,7 +192,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const T* __restrict__ A,
             int n = n0 + tx * 4 + j;
             if (n >= d.N) continue;
             T* c = C + (long long)m * d.sCm + n;
-            float v = d.alpha * acc[i][j];
+            float v = d.alpha * (float)acc[i][j];
             if (d.beta != 0.f) v += d.beta * ldf(c);
             stf(c, v);
         }

@@ -182,6 +182,9 @@ template <typename T, bool WEIGHTED>
 __device__ __forceinline__ void rowcol_accumulate(const T* __restrict__ x, long long xs, const T* __restrict__ w, long long ws, int cnt,
                                                   float (&acc)[8]) {
     float a1[8] = {}, a2[8] = {}, a3[8] = {};
+    // unweighted (pooling) sums are taken relative to the first element and un-shifted at the end: see pool_skip_kernel
+    Vec8<T> sh;
+    if (!WEIGHTED) sh.load(x);
     int t = 0;
     for (; t + 3 < cnt; t += 4) {
         Vec8<T> v0, v1, v2, v3;
@@ -196,7 +199,9 @@ __device__ __forceinline__ void rowcol_accumulate(const T* __restrict__ x, long 
             }
         } else {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { acc[k] += v0.v[k]; a1[k] += v1.v[k]; a2[k] += v2.v[k]; a3[k] += v3.v[k]; }
+            for (int k = 0; k < 8; ++k) {
+                acc[k] += v0.v[k] - sh.v[k]; a1[k] += v1.v[k] - sh.v[k]; a2[k] += v2.v[k] - sh.v[k]; a3[k] += v3.v[k] - sh.v[k];
+            }
         }
     }
     for (; t < cnt; ++t) {
@@ -209,11 +214,15 @@ __device__ __forceinline__ void rowcol_accumulate(const T* __restrict__ x, long 
             for (int k = 0; k < 8; ++k) acc[k] = fmaf(v0.v[k], w0.v[k], acc[k]);
         } else {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) acc[k] += v0.v[k];
+            for (int k = 0; k < 8; ++k) acc[k] += v0.v[k] - sh.v[k];
         }
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] += a1[k] + a2[k] + a3[k];
+    if (!WEIGHTED) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(sh.v[k], (float)cnt, acc[k]);
+    }
 }
 
 
@@ -581,6 +590,40 @@ static inline int ew_blocks(long long work) {
 
 using namespace stc;
 
+// ---------------------------------------------------------------- token centring (fp32 parity path of the attention blocks)
+// softmax_j(q_i . k_j) is unchanged when one vector is subtracted from every k_j, and dS (rows sum to 0) is unchanged when one
+// vector is subtracted from every v_j in dP = dO V^T / every k_j in dQ = dS K.  Removing the token mean takes the large common
+// component out of those products, so the fp32 rounding of S and dP no longer dominates dS (random init: tokens nearly equal).
+// mean[n][e] = mean_l x[n][l][e]: block = 8 row lanes x 32 channels, one block per (32-channel group, image), no atomics.
+template <typename T>
+__global__ void __launch_bounds__(256) token_mean_kernel(const T* __restrict__ x, float* __restrict__ mean, int L, int E) {
+    __shared__ float red[8][33];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5, e = blockIdx.x * 32 + cx;
+    const long long base = (long long)blockIdx.y * L * E;
+    float acc = 0.f;
+    if (e < E)
+        for (int l = ry; l < L; l += 8) acc += ldf(x + base + (long long)l * E + e);
+    red[ry][cx] = acc;
+    __syncthreads();
+    if (ry == 0 && e < E) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += red[k][cx];
+        mean[(long long)blockIdx.y * E + e] = s / (float)L;
+    }
+}
+template <typename T>
+__global__ void token_center_kernel(const T* __restrict__ x, const float* __restrict__ mean, T* __restrict__ out, long long LE, int E,
+                                    long long total) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        const long long n = i / LE;
+        const int e = (int)(i % E);
+        stf(out + i, ldf(x + i) - mean[n * E + e]);
+    }
+}
+
 extern "C" int stc_upcat_fused_ok(int N, int H, int W, int Cs, int h, int w, int Cu);
 extern "C" int stc_upcat_apply_fwd(const void* skip, const void* low, const void* a, void* out, int N, int H, int W, int Cs, int h, int w, int Cu,
                                    int align_corners, int dtype, void* stream);
@@ -714,6 +757,16 @@ extern "C" int stc_softmax3_fwd(const float* a, float* w, long long NC, void* st
 extern "C" int stc_softmax3_bwd(const float* w, const float* dw, float* da, long long NC, void* stream) {
     softmax3_bwd_kernel<<<ceil_div(NC, 256), 256, 0, (cudaStream_t)stream>>>(w, dw, da, NC);
     return check_launch("softmax3_bwd");
+}
+
+extern "C" int stc_center_tokens(const void* x, void* out, float* mean_ws, int N, int L, int E, int dtype, void* stream) {
+    if (N <= 0 || L <= 0 || E <= 0) return STC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long total = (long long)N * L * E;
+    dim3 grid(ceil_div(E, 32), N);
+    STC_DISPATCH_DTYPE(dtype, (token_mean_kernel<T><<<grid, 256, 0, st>>>((const T*)x, mean_ws, L, E)));
+    STC_DISPATCH_DTYPE(dtype, (token_center_kernel<T><<<ew_blocks(total), 256, 0, st>>>((const T*)x, mean_ws, (T*)out, (long long)L * E, E, total)));
+    return check_launch("center_tokens");
 }
 
 extern "C" int stc_softmax_rows_fwd(const void* S, void* P, long long rows, int L, float scale, int dtype, void* stream) {

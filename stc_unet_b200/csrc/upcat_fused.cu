@@ -147,24 +147,28 @@ __global__ void __launch_bounds__(128) pool_skip_kernel(const T* __restrict__ sk
     const int cnt = rowpart ? g.W : g.H;
     const T* b = rowpart ? skip + (n * g.H + r) * (long long)g.W * g.Cs + lv * 8 : skip + (n * g.H * (long long)g.W + r) * g.Cs + lv * 8;
     const long long step = rowpart ? g.Cs : (long long)g.W * g.Cs;
+    // shifted sums: mean = s + mean(v - s) with s = the first element.  Activations behind a BN sit on a common offset that the
+    // CoordAtt BN removes again; summing the offset-free part keeps the descriptor's FLUCTUATION accurate (as in bn_reduce)
+    Vec8<T> sh;
+    sh.load(b);
     int t = 0;
     for (; t + 1 < cnt; t += 2) {                      // two independent accumulators: two loads in flight per thread
         Vec8<T> v0, v1;
         v0.load(b + t * step);
         v1.load(b + (t + 1) * step);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { acc0[k] += v0.v[k]; acc1[k] += v1.v[k]; }
+        for (int k = 0; k < 8; ++k) { acc0[k] += v0.v[k] - sh.v[k]; acc1[k] += v1.v[k] - sh.v[k]; }
     }
     if (t < cnt) {
         Vec8<T> v0;
         v0.load(b + t * step);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc0[k] += v0.v[k];
+        for (int k = 0; k < 8; ++k) acc0[k] += v0.v[k] - sh.v[k];
     }
     Vec8<T> o;
     const float sc = 1.f / (float)cnt;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o.v[k] = (acc0[k] + acc1[k]) * sc;
+    for (int k = 0; k < 8; ++k) o.v[k] = fmaf(acc0[k] + acc1[k], sc, sh.v[k]);
     o.store(yout + (n * (g.H + g.W) + (rowpart ? r : g.H + r)) * (long long)Ct + lv * 8);
 }
 
@@ -199,25 +203,31 @@ __global__ void __launch_bounds__(128) pool_low_reduce_kernel(const T* __restric
     const T* b = rowpart ? low + q * (long long)g.w * g.Cu + lv * 8 : low + (n * g.h * (long long)g.w + r) * g.Cu + lv * 8;
     const long long step = rowpart ? g.Cu : (long long)g.w * g.Cu;
     const float* wt = rowpart ? wtab : wtab + g.w;
+    // shifted, as in pool_skip_kernel: sum_t w_t v_t = s * sum_t w_t + sum_t w_t (v_t - s)
+    Vec8<T> sh;
+    sh.load(b);
+    float wsum = 0.f;
     int t = 0;
     for (; t + 1 < cnt; t += 2) {
         Vec8<T> v0, v1;
         v0.load(b + t * step);
         v1.load(b + (t + 1) * step);
         const float w0 = wt[t], w1 = wt[t + 1];
+        wsum += w0 + w1;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { acc0[k] = fmaf(w0, v0.v[k], acc0[k]); acc1[k] = fmaf(w1, v1.v[k], acc1[k]); }
+        for (int k = 0; k < 8; ++k) { acc0[k] = fmaf(w0, v0.v[k] - sh.v[k], acc0[k]); acc1[k] = fmaf(w1, v1.v[k] - sh.v[k], acc1[k]); }
     }
     if (t < cnt) {
         Vec8<T> v0;
         v0.load(b + t * step);
         const float w0 = wt[t];
+        wsum += w0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc0[k] = fmaf(w0, v0.v[k], acc0[k]);
+        for (int k = 0; k < 8; ++k) acc0[k] = fmaf(w0, v0.v[k] - sh.v[k], acc0[k]);
     }
     float* o = tmp + (n * (g.h + g.w) + (rowpart ? r : g.h + r)) * (long long)g.Cu + lv * 8;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = acc0[k] + acc1[k];
+    for (int k = 0; k < 8; ++k) o[k] = fmaf(sh.v[k], wsum, acc0[k] + acc1[k]);
 }
 
 // low half, step 2: y[n, y, Cs + c] = interp_y(R)[y] / W  and  y[n, H + x, Cs + c] = interp_x(S)[x] / H  (zero outside the padded window)

@@ -458,7 +458,13 @@ class _ConvBnAct(Function):
             dw = _grad_buf(pw, weight.shape, dy.device)
             lib.call("stc_unpack_im2col_wgrad", ws, dw, Cout, weight.shape[1], R, S, stream_ptr())
             return None, dw, dbias, dgamma, dbeta, None, None, None
-        dw = conv_wgrad(x, dy, R, S, _grad_buf(pw, weight.shape, dy.device))
+        xw = x
+        if R == 1 and S == 1 and bn.training and x.dtype == torch.float32 and _sync_world(bn) == 1:
+            # exact-parity path: the rows of dy sum to zero (train-mode BN), so dW = dy^T x = dy^T (x - 1 c^T) for ANY c; with
+            # c = the column mean the contraction no longer multiplies the rounding residue of sum(dy) (and every dy rounding
+            # error) by the common offset of x — CoordAtt's conv1 sees descriptors ~100x larger than their fluctuation
+            xw = _center_tokens(x.view(1, N * H * W, x.shape[-1])).view_as(x)
+        dw = conv_wgrad(xw, dy, R, S, _grad_buf(pw, weight.shape, dy.device))
         dx = None
         if ctx.needs_input_grad[0]:
             wpt = pack_weight(weight, dy.dtype, transpose_flip=True)
@@ -831,6 +837,15 @@ def ksa_fuse(x, f0, f1, f2, fc, fcs):
 # ---------------------------------------------------------------------------------------------
 # Multi-head attention core: softmax(Q K^T / sqrt(hd)) V on (N, L, E) token tensors
 # ---------------------------------------------------------------------------------------------
+def _center_tokens(x: torch.Tensor) -> torch.Tensor:
+    """x (N, L, E) -> x - mean over the L tokens (stc_center_tokens)."""
+    N, L, E = x.shape
+    out = torch.empty_like(x)
+    ws = torch.empty(N * E, dtype=torch.float32, device=x.device)
+    lib.call("stc_center_tokens", x, out, ws, N, L, E, dtype_code(x.dtype), stream_ptr())
+    return out
+
+
 class _Attention(Function):
     @staticmethod
     def forward(ctx, q, k, v, heads: int):
@@ -840,6 +855,8 @@ class _Attention(Function):
         dev = q.device
         P = torch.empty((N, heads, L, L), dtype=q.dtype, device=dev)
         tok = (L * E, hd)  # batch strides of a (N, L, E) tensor split into heads
+        if q.dtype == torch.float32:   # exact-parity path: centred keys (same softmax, no common component in the fp32 scores)
+            k = _center_tokens(k)
         gemm(q, k, P, L, L, hd, N, heads, (*tok, E, 1), (*tok, 1, E), (heads * L * L, L * L, L))
         scale = 1.0 / math.sqrt(hd)
         lib.call("stc_softmax_rows_fwd", P, P, N * heads * L, L, scale, dtype_code(q.dtype), stream_ptr())
@@ -862,7 +879,8 @@ class _Attention(Function):
         dv = torch.empty_like(v)
         gemm(P, do, dv, L, hd, L, N, heads, (*pb, 1, L), (*tok, E, 1), (L * E, hd, E))            # dV = P^T dO
         dP = torch.empty_like(P)
-        gemm(do, v, dP, L, L, hd, N, heads, (*tok, E, 1), (*tok, 1, E), (*pb, L))                  # dP = dO V^T
+        vc = _center_tokens(v) if v.dtype == torch.float32 else v   # dS is invariant under a common shift of the values
+        gemm(do, vc, dP, L, L, hd, N, heads, (*tok, E, 1), (*tok, 1, E), (*pb, L))                  # dP = dO V^T
         lib.call("stc_softmax_rows_bwd", P, dP, dP, N * heads * L, L, scale, dtype_code(q.dtype), stream_ptr())
         dq = torch.empty_like(q)
         gemm(dP, k, dq, L, hd, L, N, heads, (*pb, L, 1), (*tok, E, 1), (L * E, hd, E))             # dQ = dS K

@@ -128,10 +128,11 @@ def test_fp32_parity(stc, C, posbn):
     e_ours, e_torch = grad_errors(got, ref64), grad_errors(ref32, ref64)
     check_bn_cancelled(got, ref64, 1e-3)
     if posbn:
+        # north-star bound, strictly, for EVERY gradient (measured: worst 2e-5).  The attention q/k projections (near-uniform
+        # softmax at random init) and CoordAtt's conv1 (descriptors ~100x their fluctuation) are ill-conditioned in fp32 — torch's
+        # own fp32 path is at 1-3e-4 there — and meet the bound because the fp32 path contracts CENTRED operands (ops._center_tokens)
         for k, e in e_ours.items():
-            # attention q/k projections sit behind a near-uniform softmax at random init: ill-conditioned even flip-free
-            qk = k[1].endswith((".q.weight", ".k.weight"))
-            assert e <= (max(3e-4, 5.0 * e_torch[k]) if qk else max(1e-4, 3.0 * e_torch[k])), (k, e, e_torch[k])
+            assert e <= 1e-4, (k, e, e_torch[k])
     else:
         assert statistics.median(e_ours.values()) <= max(1e-4, 1.5 * statistics.median(e_torch.values()))
         assert max(e_ours.values()) <= max(1e-4, 3.0 * max(e_torch.values()))

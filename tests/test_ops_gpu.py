@@ -258,6 +258,45 @@ def test_transformer_block(S, dt):
     ops.config.engine = S._lib.ENGINE_AUTO
 
 
+@pytest.mark.parametrize("dt", DT)
+def test_center_tokens(S, dt):
+    """stc_center_tokens: x - mean over the tokens of each image (the shift the fp32 attention path applies to K and V)."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for N, L, E in ((2, 24, 512), (3, 50, 40), (1, 1, 8)):
+        x = (torch.randn(N, L, E, device=dev(), generator=g) + 3.0).to(dt)
+        out = torch.empty_like(x)
+        ws = torch.empty(N * E, dtype=torch.float32, device=dev())
+        S._lib.lib.call("stc_center_tokens", x, out, ws, N, L, E, S._lib.dtype_code(dt), S._lib.stream_ptr())
+        ref = x.double() - x.double().mean(1, keepdim=True)
+        assert rel_l2(ws.view(N, E), x.double().mean(1)) < 1e-6
+        assert float((out.double() - ref).abs().max()) <= (1e-6 if dt == torch.float32 else 2e-2)
+
+
+def test_attention_fp32_nearly_uniform_tokens(S):
+    """Random-init STC-UNet feeds the MHA tokens that differ by ~1 % of their common component: softmax is nearly uniform and
+    dS = P (dP - sum P dP) cancels.  The centred fp32 path must keep dQ/dK at fp32 accuracy (this is what made the q/k weight
+    gradients of the whole-model parity test the least accurate entries before K/V were centred)."""
+    from stc_unet_b200 import ops
+    ops.config.engine = S._lib.ENGINE_SIMT
+    g = torch.Generator(device="cuda").manual_seed(5)
+    N, L, E, heads = 2, 96, 64, 2
+    common = torch.randn(N, 1, E, device=dev(), generator=g) * 4.0
+    mk = lambda: (common + 0.05 * torch.randn(N, L, E, device=dev(), generator=g)).requires_grad_(True)
+    q, k, v = mk(), mk(), mk()
+    o = ops.attention(q, k, v, heads)
+    go = torch.randn(N, L, E, device=dev(), generator=g)
+    o.backward(go)
+    qd, kd, vd = (t.detach().double().requires_grad_(True) for t in (q, k, v))
+    split = lambda t: t.view(N, L, heads, E // heads).transpose(1, 2)
+    P = torch.softmax(split(qd) @ split(kd).transpose(-1, -2) / math.sqrt(E // heads), -1)
+    ref = (P @ split(vd)).transpose(1, 2).reshape(N, L, E)
+    ref.backward(go.double())
+    assert rel_l2(o, ref) < 1e-6
+    for got, want, name in ((q.grad, qd.grad, "dq"), (k.grad, kd.grad, "dk"), (v.grad, vd.grad, "dv")):
+        assert rel_l2(got, want) < 2e-5, name
+    ops.config.engine = S._lib.ENGINE_AUTO
+
+
 @pytest.mark.parametrize("C", [2, 3, 5, 19])
 def test_cls_and_loss(S, C):
     from oracle import stc_oracle as O
