@@ -109,6 +109,11 @@ typedef struct {
     float alpha, beta;
 } stc_gemm_desc;
 int stc_gemm(const void* A, const void* B, void* C, const stc_gemm_desc* d, int dtype, int engine, void* stream);
+/* Same contraction with bf16 operands and an fp32 result (tcgen05 engine only; errors if the descriptor is not eligible).
+ * Used for the E x E products of a FOLDED pair of Linear layers: TransformerLayer applies q/k/v then MHA's in-projection, and
+ * fc1 then fc2, with nothing in between (unet_backbone.py:199-208), so y = x (W2 W1)^T is ONE token GEMM; the parameter
+ * gradients follow from G = dy^T x as dW2 = G W1^T and dW1 = W2^T G. */
+int stc_gemm_f32out(const void* A, const void* B, float* C, const stc_gemm_desc* d, void* stream);
 /* Which kernel the last stc_conv_fprop / stc_conv_wgrad / stc_gemm call on this thread actually launched (bench.py attributes
  * FLOPs and launch counts with it): STC_ENGINE_SIMT, STC_ENGINE_TCGEN05 (stc::umma_kernel), STC_KERNEL_CONVH
  * (stc::umma_convh_kernel) or STC_KERNEL_WGRADH (stc::umma_wgradh_kernel). */

@@ -86,3 +86,12 @@ extern "C" int stc_gemm(const void* A, const void* B, void* C, const stc_gemm_de
     g_last_engine = STC_ENGINE_SIMT;
     return gemm_simt(A, B, C, d, dtype, st);
 }
+
+/* bf16 operands, fp32 result: tcgen05 engine only (small weight-gradient products of a folded Linear pair). */
+extern "C" int stc_gemm_f32out(const void* A, const void* B, float* C, const stc_gemm_desc* d, void* stream) {
+    STC_REQUIRE(d && d->M > 0 && d->N > 0 && d->K > 0 && d->batch1 > 0 && d->batch2 > 0, "gemm_f32out: bad descriptor");
+    STC_REQUIRE(gemm_umma_eligible(d, STC_BF16), "gemm_f32out: descriptor not eligible for the tcgen05 engine");
+    STC_REQUIRE(((uintptr_t)C & 15) == 0 && d->sCm % 4 == 0, "gemm_f32out: C must be 16-byte aligned with a row stride multiple of 4");
+    g_last_engine = STC_ENGINE_TCGEN05;
+    return gemm_umma(A, B, C, d, STC_F32, (cudaStream_t)stream);
+}

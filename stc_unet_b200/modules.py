@@ -23,7 +23,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from ._lib import ACT_HSWISH, ACT_NONE, ACT_RELU, ACT_SIGMOID
+from ._lib import ACT_HSWISH, ACT_NONE, ACT_RELU, ACT_SIGMOID, ENGINE_SIMT
 from .registry import BACKBONES, HEADS, LOSSES, BaseModule, build_loss
 
 _DTYPES = {"bf16": torch.bfloat16, "bfloat16": torch.bfloat16, "fp32": torch.float32, "float32": torch.float32}
@@ -108,6 +108,15 @@ class TransformerLayer(nn.Module):
         self.num_heads = num_heads
 
     def forward(self, t):  # t (N, L, E)
+        if t.dtype == torch.bfloat16 and ops.config.fold_linear_pairs and ops.config.engine != ENGINE_SIMT:
+            # same function, fewer GEMMs: (q|k|v then in_proj) and (fc1 then fc2) have nothing in between, so each pair is
+            # applied as ONE folded E x E weight (ops._FusedLinearPairs); the fp32 parity path below keeps the reference's order
+            t0, t3 = ops.fanout(t, 2)
+            qkv = ops.fused_linear_pairs(t0, (self.q.weight, self.k.weight, self.v.weight), self.ma.in_proj_weight, self.ma.in_proj_bias)
+            o = ops.attention_packed(qkv, self.num_heads)
+            t = ops.linear_tokens(o, self.ma.out_proj.weight, self.ma.out_proj.bias, residual=t3)
+            ta, tb = ops.fanout(t, 2)
+            return ops.fused_linear_pairs(ta, (self.fc1.weight,), self.fc2.weight, None, residual=tb)
         t0, t1, t2, t3 = ops.fanout(t, 4)
         q = ops.linear_tokens(t0, self.q.weight)
         k = ops.linear_tokens(t1, self.k.weight)

@@ -22,6 +22,7 @@ from ._lib import GemmDesc, dtype_code, lib, stream_ptr
 # ---------------------------------------------------------------------------------------------
 class _Config:
     engine = _lib.ENGINE_AUTO       # dense engine selection passed to stc_conv_* / stc_gemm
+    fold_linear_pairs = True        # bf16 + tcgen05: q/k/v + in_proj and fc1 + fc2 of TransformerLayer run as folded GEMMs
 
 
 config = _Config()
@@ -926,6 +927,133 @@ class _InProj(Function):
             wpt = pack_weight(W[i * E:(i + 1) * E].view(E, E, 1, 1), g.dtype, transpose_flip=True)
             dins.append(conv_fprop(g.view(1, 1, rows, E), wpt, None, None, E, 1, 1).view(N, L, E))
         return dins[0], dins[1], dins[2], dW, db, None
+
+
+def _gemm_f32out(A, B, C, M, N, K, sA, sB, sCm):
+    """bf16 A(m,k), B(k,n) by element strides -> fp32 C (row stride sCm), tcgen05 engine (stc_gemm_f32out)."""
+    d = GemmDesc(M, N, K, 1, 1, 0, 0, sA[0], sA[1], 0, 0, sB[0], sB[1], 0, 0, sCm, 1.0, 0.0)
+    _dense("gemm", 2.0 * M * N * K, lambda: lib.call("stc_gemm_f32out", A, B, C, d, stream_ptr()))
+
+
+class _FusedLinearPairs(Function):
+    """J chained Linear pairs with nothing in between, folded into ONE token GEMM:
+
+        y[:, j*Eo:(j+1)*Eo] = (x W1_j^T) W2_j^T + b2_j  =  x (W2_j W1_j)^T + b2_j        (+ residual when J == 1)
+
+    TransformerLayer (unet_backbone.py:199-208) applies q/k/v (bias-free Linear) and then nn.MultiheadAttention's
+    in-projection, and fc1 then fc2, without any nonlinearity: q/k/v + in_proj are J = 3 pairs sharing x (one GEMM with
+    3E output columns, one dgrad GEMM that also sums the three input gradients, one wgrad GEMM), fc2(fc1(x)) + x is J = 1.
+    The folded weights W2_j W1_j (E x E, bf16 from the bf16 operands the unfolded path would use) cost four E^3 products per
+    pair and step; the parameter gradients follow from G_j = dy_j^T x:  dW2_j = G_j W1_j^T,  dW1_j = W2_j^T G_j.
+    W2 is passed whole ((J*Eo, Em), e.g. in_proj_weight) so its gradient is produced whole."""
+
+    @staticmethod
+    def forward(ctx, x, residual, W2, b2, pobjs, *W1s):
+        x = _chk(x)
+        J = len(W1s)
+        Em, Ei = W1s[0].shape
+        Eo = W2.shape[0] // J
+        rows = x.numel() // Ei
+        dev, dt = x.device, x.dtype
+        w2b = pack_weight(W2.view(J * Eo, Em, 1, 1), dt).view(J * Eo, Em)          # bf16 copies (batched by the StepCache)
+        w1b = [pack_weight(w.view(Em, Ei, 1, 1), dt).view(Em, Ei) for w in W1s]
+        weff = torch.empty((J * Eo, Ei), dtype=dt, device=dev)                       # fprop operand  [Cout][Cin]
+        wefft = torch.empty((Ei, J * Eo), dtype=dt, device=dev)                      # dgrad operand  [Cin][Cout]
+        for j in range(J):
+            # Weff_j[o][i] = sum_m W2_j[o][m] W1_j[m][i]
+            gemm(w2b[j * Eo:], w1b[j], weff[j * Eo:], Eo, Ei, Em, 1, 1, (0, 0, Em, 1), (0, 0, Ei, 1), (0, 0, Ei))
+            # WeffT[i][j*Eo + o] = the same, written transposed (A = W1_j^T, B = W2_j^T)
+            gemm(w1b[j], w2b[j * Eo:], wefft[:, j * Eo:], Ei, Eo, Em, 1, 1, (0, 0, 1, Ei), (0, 0, 1, Em), (0, 0, J * Eo))
+        if residual is not None:
+            residual = _chk(residual).view(1, 1, rows, J * Eo)
+        y = conv_fprop(x.view(1, 1, rows, Ei), weff.view(1, J * Eo, Ei), b2, residual, J * Eo, 1, 1)
+        ctx.save_for_backward(x, W2, wefft, w2b, *w1b)
+        ctx.meta = (J, Eo, Em, Ei, rows, pobjs, b2 is not None, residual is not None)
+        return y.view(*x.shape[:-1], J * Eo)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W2, wefft, w2b, *w1b = ctx.saved_tensors
+        J, Eo, Em, Ei, rows, pobjs, has_bias, has_res = ctx.meta
+        pW2, pb2, pW1s = pobjs
+        dy = _chk(dy)
+        dev = dy.device
+        db2 = colsum(rows, J * Eo, dy, _grad_buf(pb2, (J * Eo,), dev)) if has_bias else None
+        # G^T (Ei x J*Eo, fp32) = x^T dy: the ordinary 1x1 wgrad of the folded layer
+        gt = _wgrad_ws(Ei * J * Eo, dev)
+        _dense("conv_wgrad", 2.0 * rows * Ei * J * Eo,
+               lambda: lib.call("stc_conv_wgrad", x, dy, gt, 1, 1, rows, Ei, J * Eo, 1, 1, dtype_code(x.dtype), config.engine, stream_ptr()))
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = conv_fprop(dy.view(1, 1, rows, J * Eo), wefft.view(1, Ei, J * Eo), None, None, Ei, 1, 1).view(x.shape)
+        gtb = pack_weight(gt.view(Ei, J * Eo, 1, 1), x.dtype, cache=False).view(Ei, J * Eo)     # bf16 copy of G^T
+        dW2 = _grad_buf(pW2, (J * Eo, Em), dev)
+        dW1s = []
+        for j in range(J):
+            # dW2_j[o][m] = sum_i G_j[o][i] W1_j[m][i]     (A = G_j read transposed from G^T, B = W1_j^T)
+            _gemm_f32out(gtb[:, j * Eo:], w1b[j], dW2[j * Eo:], Eo, Em, Ei, (1, J * Eo), (1, Ei), Em)
+            # dW1_j[m][i] = sum_o W2_j[o][m] G_j[o][i]     (A = W2_j^T, B = G_j)
+            dW1 = _grad_buf(pW1s[j], (Em, Ei), dev)
+            _gemm_f32out(w2b[j * Eo:], gtb[:, j * Eo:], dW1, Em, Ei, Eo, (1, Em), (1, J * Eo), Ei)
+            dW1s.append(dW1)
+        dres = dy if (has_res and ctx.needs_input_grad[1]) else None
+        return (dx, dres, dW2, db2, None, *dW1s)
+
+
+def fused_linear_pairs(x, W1s, W2, b2=None, residual=None):
+    """x (..., Ei) -> (..., J*Eo): see _FusedLinearPairs.  W1s: J Linear weights (Em, Ei); W2: (J*Eo, Em); b2: (J*Eo) or None."""
+    return _FusedLinearPairs.apply(x, residual, W2, b2, (W2, b2, tuple(W1s)), *W1s)
+
+
+class _AttentionPacked(Function):
+    """_Attention on a packed (N, L, 3E) projection [q | k | v] (the output of the folded q/k/v + in_proj GEMM): the batched
+    GEMMs read the three column blocks in place by stride and write dq/dk/dv into one packed gradient."""
+
+    @staticmethod
+    def forward(ctx, qkv, heads: int):
+        qkv = _chk(qkv)
+        N, L, E3 = qkv.shape
+        E = E3 // 3
+        hd = E // heads
+        dev = qkv.device
+        q, k, v = qkv[..., :E], qkv[..., E:2 * E], qkv[..., 2 * E:]
+        P = torch.empty((N, heads, L, L), dtype=qkv.dtype, device=dev)
+        pk = (L * E3, hd)   # batch strides of a packed (N, L, 3E) tensor split into heads
+        gemm(q, k, P, L, L, hd, N, heads, (*pk, E3, 1), (*pk, 1, E3), (heads * L * L, L * L, L))
+        scale = 1.0 / math.sqrt(hd)
+        lib.call("stc_softmax_rows_fwd", P, P, N * heads * L, L, scale, dtype_code(qkv.dtype), stream_ptr())
+        o = torch.empty((N, L, E), dtype=qkv.dtype, device=dev)
+        gemm(P, v, o, L, hd, L, N, heads, (heads * L * L, L * L, L, 1), (*pk, E3, 1), (L * E, hd, E))
+        ctx.save_for_backward(qkv, P)
+        ctx.heads = heads
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        qkv, P = ctx.saved_tensors
+        heads = ctx.heads
+        do = _chk(do)
+        N, L, E3 = qkv.shape
+        E = E3 // 3
+        hd = E // heads
+        q, k, v = qkv[..., :E], qkv[..., E:2 * E], qkv[..., 2 * E:]
+        tok = (L * E, hd)
+        pk = (L * E3, hd)
+        pb = (heads * L * L, L * L)
+        scale = 1.0 / math.sqrt(hd)
+        dqkv = torch.empty_like(qkv)
+        dq, dk, dv = dqkv[..., :E], dqkv[..., E:2 * E], dqkv[..., 2 * E:]
+        gemm(P, do, dv, L, hd, L, N, heads, (*pb, 1, L), (*tok, E, 1), (*pk, E3))                   # dV = P^T dO
+        dP = torch.empty_like(P)
+        gemm(do, v, dP, L, L, hd, N, heads, (*tok, E, 1), (*pk, 1, E3), (*pb, L))                   # dP = dO V^T
+        lib.call("stc_softmax_rows_bwd", P, dP, dP, N * heads * L, L, scale, dtype_code(qkv.dtype), stream_ptr())
+        gemm(dP, k, dq, L, hd, L, N, heads, (*pb, L, 1), (*pk, E3, 1), (*pk, E3))                   # dQ = dS K
+        gemm(dP, q, dk, L, hd, L, N, heads, (*pb, 1, L), (*pk, E3, 1), (*pk, E3))                   # dK = dS^T Q
+        return dqkv, None
+
+
+def attention_packed(qkv, heads: int):
+    return _AttentionPacked.apply(qkv, heads)
 
 
 def in_proj(q, k, v, mha: torch.nn.MultiheadAttention):

@@ -169,3 +169,80 @@ def test_wgrad_halo_tcgen05(tc, shape):
     assert rel_l2(dw, w.grad) < 2e-3
     dw2 = tc.conv_wgrad(nhwc(x.float()).to(BF), nhwc(dy.float()).to(BF), k, k)
     assert rel_l2(dw2, w.grad) < 2e-3
+
+
+def test_folded_linear_pairs_tcgen05(tc):
+    """ops.fused_linear_pairs (q/k/v + in_proj as J = 3 folded pairs; fc1 + fc2 + residual as J = 1) against the unfolded fp64
+    composition: output, input gradient and EVERY parameter gradient (W1_j, whole W2, b2)."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    E, rows = 512, 384
+    rnd = lambda *s: torch.randn(*s, device=dev(), generator=g)
+    x = bf16_round(rnd(2, rows // 2, E))
+    for J, with_res in ((3, False), (1, True)):
+        W1 = [rnd(E, E) / math.sqrt(E) for _ in range(J)]
+        W2 = rnd(J * E, E) / math.sqrt(E)
+        b2 = rnd(J * E) if J == 3 else None
+        res = bf16_round(rnd(2, rows // 2, E)) if with_res else None
+        xr = x.double().requires_grad_(True)
+        W1r = [w.double().requires_grad_(True) for w in W1]
+        W2r = W2.double().requires_grad_(True)
+        b2r = b2.double().requires_grad_(True) if b2 is not None else None
+        ref = torch.cat([(xr @ W1r[j].t()) @ W2r[j * E:(j + 1) * E].t() for j in range(J)], -1)
+        if b2r is not None:
+            ref = ref + b2r
+        if res is not None:
+            ref = ref + res.double()
+        xo = x.to(BF).requires_grad_(True)
+        W1o = [w.clone().requires_grad_(True) for w in W1]
+        W2o = W2.clone().requires_grad_(True)
+        b2o = b2.clone().requires_grad_(True) if b2 is not None else None
+        reso = res.to(BF).requires_grad_(True) if res is not None else None
+        out = tc.fused_linear_pairs(xo, W1o, W2o, b2o, reso)
+        assert out.shape == (2, rows // 2, J * E)
+        assert rel_l2(out.float(), ref) < 8e-3
+        go = bf16_round(rnd(2, rows // 2, J * E))
+        ref.backward(go.double())
+        out.backward(go.to(BF))
+        assert rel_l2(xo.grad.float(), xr.grad) < 8e-3
+        assert rel_l2(W2o.grad, W2r.grad) < 8e-3
+        for a, b_ in zip(W1o, W1r):
+            assert rel_l2(a.grad, b_.grad) < 8e-3
+        if b2 is not None:
+            assert rel_l2(b2o.grad, b2r.grad) < 3e-3
+        if res is not None:
+            assert rel_l2(reso.grad.float(), go) < 1e-6
+
+
+@pytest.mark.parametrize("hw", [(8, 16), (16, 16)])
+def test_transformer_block_folded_matches_unfolded(hw):
+    """TransformerBlock in bf16 on the tcgen05 engine: the folded-pair path (default) and the reference-order path against the
+    fp64 oracle — the folded path must be at least as close (it rounds one intermediate less)."""
+    import stc_unet_b200 as S
+    from oracle import stc_oracle as O
+    from stc_unet_b200 import ops
+    torch.manual_seed(0)
+    N, (H, W) = 2, hw
+    tb = S.TransformerBlock(512, 512, 2, 2).to(dev())
+    sd = {"t." + k: v.detach().double().requires_grad_(True) for k, v in tb.state_dict().items()}
+    x = bf16_round(torch.randn(N, 512, H, W, device=dev()) * 0.5)
+    xr = x.double().requires_grad_(True)
+    ref = O.transformer_block(sd, "t", xr, heads=2, layers=2) + xr
+    go = torch.randn_like(ref)
+    ref.backward(go)
+    errs = {}
+    for fold in (True, False):
+        ops.config.fold_linear_pairs = fold
+        try:
+            tb.zero_grad()
+            xo = nhwc(x).to(BF).requires_grad_(True)
+            out = tb.forward_residual(xo)
+            out.backward(nhwc(go).to(BF))
+        finally:
+            ops.config.fold_linear_pairs = True
+        e = dict(out=rel_l2(nchw(out.float()), ref), dx=rel_l2(nchw(xo.grad.float()), xr.grad))
+        for name, p in tb.named_parameters():
+            e[name] = rel_l2(p.grad, sd["t." + name].grad)
+        errs[fold] = e
+    assert errs[True]["out"] < 2e-2 and errs[True]["dx"] < 4e-2
+    for k in errs[True]:
+        assert errs[True][k] <= max(6e-2, 1.5 * errs[False][k]), (k, errs[True][k], errs[False][k])
