@@ -153,6 +153,18 @@ int stc_bn_bwd_reduce(const void* y, const void* dout, const float* mean, const 
 /* dgamma = sums[C:2C], dbeta = sums[0:C] (taken from the LOCAL sums, before any SyncBN all-reduce, as
  * torch's SyncBatchNorm backward does). */
 int stc_bn_param_grads(const double* sums, float* dgamma, float* dbeta, int C, void* stream);
+/* The same backward with an IMPLICIT upstream gradient  d' = up_scale[n][c] * dout + up_shift[n][c] * shift_scale  (n = image,
+ * rows_per_image rows each; ReLU, train mode, C/8 a power of two <= 256 - stc_bn_bwd_aff_ok).  KernelSelectAttention
+ * (unet_backbone.py:86-98) hands each branch  df_k = softmax-weight_k[n,c] * dout + dS[n,c]/HW ; these entry points consume
+ * dout directly so the three df tensors are never written. */
+int stc_bn_bwd_aff_ok(int C);
+int stc_bn_bwd_reduce_aff(const void* y, const void* dout, const float* up_scale, const float* up_shift, float shift_scale,
+                          long long rows_per_image, int N, const float* mean, const float* invstd, const float* gamma,
+                          const float* beta, double* sums, int C, void* ws, long long ws_bytes, int dtype, void* stream);
+int stc_bn_bwd_apply_aff(const void* y, const void* dout, const float* up_scale, const float* up_shift, float shift_scale,
+                         long long rows_per_image, int N, const float* mean, const float* invstd, const float* gamma,
+                         const float* beta, const double* sums, double count, void* dy, int C, int dtype, void* stream);
+
 /* dy = gamma*invstd*(g - sum_g/count - xhat*sum_gx/count) (train); eval != 0: dy = gamma*invstd*g. */
 int stc_bn_bwd_apply(const void* y, const void* dout, const float* mean, const float* invstd, const float* gamma,
                      const float* beta, const double* sums, double count, void* dy,

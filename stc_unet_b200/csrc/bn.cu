@@ -151,15 +151,19 @@ __device__ __forceinline__ float act_mask(float d, float z, int act) {
 }
 
 // ACT = STC_ACT_RELU: specialised; ACT = -1: run-time `act`.  Per element: z = fma(v, sc, sh), xh = fma(v, is, -mu*is), g, two sums.
-template <typename T, int ACT>
+// AFF: the upstream gradient is given implicitly as  d' = ua[n][c] * dout + ub[n][c] * ub_scale  per image n (blockIdx.y) of
+// P = rows-per-image rows — KernelSelectAttention's branch gradients df_k = w_k[n,c] * dout + dS[n,c]/HW are never materialised.
+template <typename T, int ACT, bool AFF>
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* __restrict__ y, const T* __restrict__ dout,
                                                             const float* __restrict__ mean, const float* __restrict__ invstd,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                            float* __restrict__ partial, long long P, int C, int act) {
+                                                            float* __restrict__ partial, long long P, int C, int act,
+                                                            const float* __restrict__ ua, const float* __restrict__ ub, float ub_scale) {
     __shared__ float smem[256 * 16];
     const int lanes = C >> 3, lv = threadIdx.x % lanes, r0 = threadIdx.x / lanes, rstep = 256 / lanes;
     constexpr bool kExact = sizeof(T) == 4;   // fp32 storage: subtract the mean first (see bn_bwd_apply_rows_kernel)
     float is[8], nm[8], sc[8], sh[8];
+    float ua_r[8], ub_r[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const float mu = mean[lv * 8 + k];
@@ -167,7 +171,14 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* __restrict_
         nm[k] = kExact ? mu : -mu * is[k];
         sc[k] = gamma[lv * 8 + k] * is[k];
         sh[k] = kExact ? beta[lv * 8 + k] : beta[lv * 8 + k] - mu * sc[k];
+        ua_r[k] = AFF ? ua[(long long)blockIdx.y * C + lv * 8 + k] : 1.f;
+        ub_r[k] = AFF ? ub[(long long)blockIdx.y * C + lv * 8 + k] * ub_scale : 0.f;
     }
+    if (AFF) {
+        y += (long long)blockIdx.y * P * C;
+        dout += (long long)blockIdx.y * P * C;
+    }
+    auto up = [&](float d, int k) -> float { return AFF ? fmaf(ua_r[k], d, ub_r[k]) : d; };
     auto zx = [&](float v, int k, float& z, float& xh) {
         if (kExact) {
             const float vc = v - nm[k];
@@ -196,7 +207,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* __restrict_
             float z0, x0, z1, x1;
             zx(v0.v[k], k, z0, x0);
             zx(v1.v[k], k, z1, x1);
-            const float g0 = act_mask<ACT>(d0.v[k], z0, act), g1 = act_mask<ACT>(d1.v[k], z1, act);
+            const float g0 = act_mask<ACT>(up(d0.v[k], k), z0, act), g1 = act_mask<ACT>(up(d1.v[k], k), z1, act);
             acc[0][k] += g0 + g1;
             acc[1][k] = fmaf(g0, x0, fmaf(g1, x1, acc[1][k]));
         }
@@ -209,12 +220,13 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* __restrict_
         for (int k = 0; k < 8; ++k) {
             float z, xh;
             zx(v.v[k], k, z, xh);
-            const float g = act_mask<ACT>(d.v[k], z, act);
+            const float g = act_mask<ACT>(up(d.v[k], k), z, act);
             acc[0][k] += g;
             acc[1][k] = fmaf(g, xh, acc[1][k]);
         }
     }
-    block_reduce_lanes<2>(acc, lanes, lv, smem, partial, C);
+    const size_t block_row = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+    block_reduce_lanes_emit<2>(acc, lanes, smem, C, [&](int q, int c, float sv) { partial[(block_row * 2 + q) * C + c] = sv; });
 }
 
 template <typename T>
@@ -310,13 +322,25 @@ __global__ void __launch_bounds__(256) bn_apply_rows_kernel(const T* __restrict_
 }
 
 // dy = sc * (g - c1 - xh * c2) = sc * g + A * v + B  with A = -sc*c2*is, B = sc*(c2*is*mu - c1): z, select, two FMAs per element
-template <typename T, int ACT>
+template <typename T, int ACT, bool AFF>
 __global__ void __launch_bounds__(256) bn_bwd_apply_rows_kernel(const T* __restrict__ y, const T* __restrict__ dout,
                                                                 const float* __restrict__ mean, const float* __restrict__ invstd,
                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                 const double* __restrict__ sums, float inv_count, T* __restrict__ dy,
-                                                                long long P, int C, int act, int eval) {
+                                                                long long P, int C, int act, int eval,
+                                                                const float* __restrict__ ua, const float* __restrict__ ub, float ub_scale) {
     const int lanes = C >> 3, lv = threadIdx.x % lanes, r0 = threadIdx.x / lanes, rstep = 256 / lanes;
+    float ua_r[8], ub_r[8];   // AFF: see bn_bwd_reduce_kernel (P = rows per image, blockIdx.y = image)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        ua_r[k] = AFF ? ua[(long long)blockIdx.y * C + lv * 8 + k] : 1.f;
+        ub_r[k] = AFF ? ub[(long long)blockIdx.y * C + lv * 8 + k] * ub_scale : 0.f;
+    }
+    if (AFF) {
+        y += (long long)blockIdx.y * P * C;
+        dout += (long long)blockIdx.y * P * C;
+        dy += (long long)blockIdx.y * P * C;
+    }
     // fp32 storage keeps the subtract-first form (v - mu) * is: the folded A*v + B loses |mu|/std digits, which only bf16 storage hides
     constexpr bool kExact = sizeof(T) == 4;
     float sc[8], sh[8], A[8], B[8];
@@ -342,6 +366,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_rows_kernel(const T* __restr
 #pragma unroll
     for (int k = 0; k < 8; ++k) bek[k] = kExact ? be[k] : 0.f;
     auto elem = [&](float v, float d, int k) -> float {
+        if (AFF) d = fmaf(ua_r[k], d, ub_r[k]);
         if (kExact) {
             const float vc = v - sh[k];
             const float g = act_mask<ACT>(d, fmaf(vc, sc[k], bek[k]), act);
@@ -458,11 +483,11 @@ extern "C" int stc_bn_bwd_reduce(const void* y, const void* dout, const float* m
         int lanes = C / 8, G = reduce_blocks(P, lanes);
         STC_REQUIRE(ws && ws_bytes >= (long long)G * 2 * C * (long long)sizeof(float), "bn_bwd_reduce: workspace too small");
         if (act == STC_ACT_RELU) {
-            STC_DISPATCH_DTYPE(dtype, (bn_bwd_reduce_kernel<T, STC_ACT_RELU><<<G, 256, 0, st>>>((const T*)y, (const T*)dout, mean, invstd, gamma,
-                                                                                               beta, (float*)ws, P, C, act)));
+            STC_DISPATCH_DTYPE(dtype, (bn_bwd_reduce_kernel<T, STC_ACT_RELU, false><<<G, 256, 0, st>>>((const T*)y, (const T*)dout, mean, invstd, gamma,
+                                                                                                      beta, (float*)ws, P, C, act, nullptr, nullptr, 0.f)));
         } else {
-            STC_DISPATCH_DTYPE(dtype, (bn_bwd_reduce_kernel<T, -1><<<G, 256, 0, st>>>((const T*)y, (const T*)dout, mean, invstd, gamma, beta,
-                                                                                     (float*)ws, P, C, act)));
+            STC_DISPATCH_DTYPE(dtype, (bn_bwd_reduce_kernel<T, -1, false><<<G, 256, 0, st>>>((const T*)y, (const T*)dout, mean, invstd, gamma, beta,
+                                                                                            (float*)ws, P, C, act, nullptr, nullptr, 0.f)));
         }
         reduce_partials_kernel<<<ceil_div((long long)2 * C * 32, 128), 128, 0, st>>>((const float*)ws, sums, G, 2 * C);
     } else {
@@ -483,11 +508,13 @@ extern "C" int stc_bn_bwd_apply(const void* y, const void* dout, const float* me
     int vec = (C % 8 == 0 && ((((uintptr_t)y) | ((uintptr_t)dout) | ((uintptr_t)dy)) & 15) == 0) ? 1 : 0;
     if (vec && vec_ok(C)) {
         if (act == STC_ACT_RELU) {
-            STC_DISPATCH_DTYPE(dtype, (bn_bwd_apply_rows_kernel<T, STC_ACT_RELU><<<rows_blocks(P, C / 8), 256, 0, st>>>(
-                                          (const T*)y, (const T*)dout, mean, invstd, gamma, beta, sums, (float)(1.0 / count), (T*)dy, P, C, act, eval)));
+            STC_DISPATCH_DTYPE(dtype, (bn_bwd_apply_rows_kernel<T, STC_ACT_RELU, false><<<rows_blocks(P, C / 8), 256, 0, st>>>(
+                                          (const T*)y, (const T*)dout, mean, invstd, gamma, beta, sums, (float)(1.0 / count), (T*)dy, P, C, act, eval,
+                                          nullptr, nullptr, 0.f)));
         } else {
-            STC_DISPATCH_DTYPE(dtype, (bn_bwd_apply_rows_kernel<T, -1><<<rows_blocks(P, C / 8), 256, 0, st>>>(
-                                          (const T*)y, (const T*)dout, mean, invstd, gamma, beta, sums, (float)(1.0 / count), (T*)dy, P, C, act, eval)));
+            STC_DISPATCH_DTYPE(dtype, (bn_bwd_apply_rows_kernel<T, -1, false><<<rows_blocks(P, C / 8), 256, 0, st>>>(
+                                          (const T*)y, (const T*)dout, mean, invstd, gamma, beta, sums, (float)(1.0 / count), (T*)dy, P, C, act, eval,
+                                          nullptr, nullptr, 0.f)));
         }
         return check_launch("bn_bwd_apply");
     }
@@ -502,4 +529,41 @@ extern "C" int stc_bn_bwd_apply(const void* y, const void* dout, const float* me
 extern "C" int stc_bn_param_grads(const double* sums, float* dgamma, float* dbeta, int C, void* stream) {
     bn_param_grads_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, dgamma, dbeta, C);
     return check_launch("bn_param_grads");
+}
+
+/* BN backward with an IMPLICIT upstream gradient d' = up_scale[n][c] * dout + up_shift[n][c] * shift_scale (per image n of
+ * rows_per_image rows): KernelSelectAttention's branch gradients without the three df tensors.  ReLU, train mode, C/8 a power of two. */
+extern "C" int stc_bn_bwd_aff_ok(int C) { return vec_ok(C) ? 1 : 0; }
+
+extern "C" int stc_bn_bwd_reduce_aff(const void* y, const void* dout, const float* up_scale, const float* up_shift, float shift_scale,
+                                     long long rows_per_image, int N, const float* mean, const float* invstd, const float* gamma,
+                                     const float* beta, double* sums, int C, void* ws, long long ws_bytes, int dtype, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    STC_REQUIRE(rows_per_image > 0 && N > 0 && vec_ok(C) && ((((uintptr_t)y) | ((uintptr_t)dout)) & 15) == 0, "bn_bwd_reduce_aff: shape/alignment not supported");
+    const int lanes = C / 8;
+    int gx = reduce_blocks(rows_per_image * N, lanes) / N;
+    if (gx < 1) gx = 1;
+    const int G = gx * N;
+    STC_REQUIRE(ws && ws_bytes >= (long long)G * 2 * C * (long long)sizeof(float), "bn_bwd_reduce_aff: workspace too small");
+    dim3 grid(gx, N);
+    STC_DISPATCH_DTYPE(dtype, (bn_bwd_reduce_kernel<T, STC_ACT_RELU, true><<<grid, 256, 0, st>>>((const T*)y, (const T*)dout, mean, invstd, gamma, beta,
+                                                                                                (float*)ws, rows_per_image, C, STC_ACT_RELU,
+                                                                                                up_scale, up_shift, shift_scale)));
+    reduce_partials_kernel<<<ceil_div((long long)2 * C * 32, 128), 128, 0, st>>>((const float*)ws, sums, G, 2 * C);
+    return check_launch("bn_bwd_reduce_aff");
+}
+
+extern "C" int stc_bn_bwd_apply_aff(const void* y, const void* dout, const float* up_scale, const float* up_shift, float shift_scale,
+                                    long long rows_per_image, int N, const float* mean, const float* invstd, const float* gamma,
+                                    const float* beta, const double* sums, double count, void* dy, int C, int dtype, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    STC_REQUIRE(rows_per_image > 0 && N > 0 && vec_ok(C) && ((((uintptr_t)y) | ((uintptr_t)dout) | ((uintptr_t)dy)) & 15) == 0,
+                "bn_bwd_apply_aff: shape/alignment not supported");
+    int gx = rows_blocks(rows_per_image * N, C / 8) / N;
+    if (gx < 1) gx = 1;
+    dim3 grid(gx, N);
+    STC_DISPATCH_DTYPE(dtype, (bn_bwd_apply_rows_kernel<T, STC_ACT_RELU, true><<<grid, 256, 0, st>>>(
+                                  (const T*)y, (const T*)dout, mean, invstd, gamma, beta, sums, (float)(1.0 / count), (T*)dy, rows_per_image, C,
+                                  STC_ACT_RELU, 0, up_scale, up_shift, shift_scale)));
+    return check_launch("bn_bwd_apply_aff");
 }

@@ -23,6 +23,7 @@ from ._lib import GemmDesc, dtype_code, lib, stream_ptr
 class _Config:
     engine = _lib.ENGINE_AUTO       # dense engine selection passed to stc_conv_* / stc_gemm
     fold_linear_pairs = True        # bf16 + tcgen05: q/k/v + in_proj and fc1 + fc2 of TransformerLayer run as folded GEMMs
+    ksa_lazy_df = True              # KSA branch gradients are consumed implicitly by the BN backward kernels (no df tensors)
 
 
 config = _Config()
@@ -379,22 +380,34 @@ def _bn_forward_stats(y, P, C, bn: BNState):
     return mean, invstd, count
 
 
-def _bn_backward(y, dout, mean, invstd, gamma, beta, P, C, act, bn, count, pg, pb):
+def _bn_backward(y, dout, mean, invstd, gamma, beta, P, C, act, bn, count, pg, pb, aff=None):
+    """aff = (up_scale (N,C), up_shift (N,C), shift_scale, rows_per_image): the upstream gradient is up_scale*dout + up_shift*shift_scale
+    per image (KSA branches, see ksa_fuse) and is never materialised."""
     training = bn.training
     dev = y.device
     sums = torch.empty(2 * C, dtype=torch.float64, device=dev)
     nb = lib.raw("stc_bn_ws_bytes")(P, C)
     ws = _workspace(dev, nb)
     code = dtype_code(y.dtype)
-    lib.call("stc_bn_bwd_reduce", y, dout, mean, invstd, gamma, beta, sums, P, C, act, ws, ws.numel(), code, stream_ptr())
+    if aff is not None:
+        ua, ub, ubs, rows_img = aff
+        n_img = P // rows_img
+        lib.call("stc_bn_bwd_reduce_aff", y, dout, ua, ub, float(ubs), rows_img, n_img, mean, invstd, gamma, beta, sums, C, ws, ws.numel(),
+                 code, stream_ptr())
+    else:
+        lib.call("stc_bn_bwd_reduce", y, dout, mean, invstd, gamma, beta, sums, P, C, act, ws, ws.numel(), code, stream_ptr())
     dgamma = _grad_buf(pg, (C,), dev)
     dbeta = _grad_buf(pb, (C,), dev)
     lib.call("stc_bn_param_grads", sums, dgamma, dbeta, C, stream_ptr())
     if training and _sync_world(bn) > 1:
         dist.all_reduce(sums, group=bn.group)  # C2
     dy = torch.empty_like(y)
-    lib.call("stc_bn_bwd_apply", y, dout, mean, invstd, gamma, beta, sums, float(count), dy, P, C, act,
-             0 if training else 1, code, stream_ptr())
+    if aff is not None:
+        lib.call("stc_bn_bwd_apply_aff", y, dout, ua, ub, float(ubs), rows_img, n_img, mean, invstd, gamma, beta, sums, float(count), dy, C,
+                 code, stream_ptr())
+    else:
+        lib.call("stc_bn_bwd_apply", y, dout, mean, invstd, gamma, beta, sums, float(count), dy, P, C, act,
+                 0 if training else 1, code, stream_ptr())
     return dy, dgamma, dbeta
 
 
@@ -441,7 +454,12 @@ class _ConvBnAct(Function):
         da = _chk(da)
         N, H, W, Cout = y.shape
         P = N * H * W
-        dy, dgamma, dbeta = _bn_backward(y, da, mean, invstd, gamma, beta, P, Cout, act, bn, count, pg, pb)
+        aff = None
+        slot = getattr(ctx, "ksa_slot", None)      # set by ksa_fuse: `da` is KSA's raw dout, this branch's gradient is affine in it
+        if slot is not None and slot[0].ready:
+            box, k = slot
+            aff = (box.scale[k], box.shift, box.shift_scale, box.rows)
+        dy, dgamma, dbeta = _bn_backward(y, da, mean, invstd, gamma, beta, P, Cout, act, bn, count, pg, pb, aff)
         dbias = None
         if has_bias:
             if bn.training:
@@ -774,9 +792,16 @@ def coordatt_apply(x, a):
 # ---------------------------------------------------------------------------------------------
 # KernelSelectAttention fuse: out = x + sum_k softmax_k(fcs_k(fc(GAP(f0+f1+f2)))) * f_k
 # ---------------------------------------------------------------------------------------------
+class _KSALazy:
+    """Hand-over between _KSAFuse.backward and the three branch _ConvBnAct.backward nodes: df_k = scale[k] * dout + shift * shift_scale."""
+    def __init__(self):
+        self.ready, self.scale, self.shift, self.shift_scale, self.rows = False, None, None, 0.0, 0
+
+
 class _KSAFuse(Function):
     @staticmethod
-    def forward(ctx, x, f0, f1, f2, fc_w, fc_b, w0, b0, w1, b1, w2, b2, pobjs):
+    def forward(ctx, x, f0, f1, f2, fc_w, fc_b, w0, b0, w1, b1, w2, b2, pobjs, lazy=None):
+        ctx.lazy = lazy
         x, f0, f1, f2 = _chk(x), _chk(f0), _chk(f1), _chk(f2)
         N, H, W, C = x.shape
         HW = H * W
@@ -825,14 +850,28 @@ class _KSAFuse(Function):
         gfcW = _grad_buf(pobjs[0], fc_w.shape, dev, zero=True)
         gfcb = _grad_buf(pobjs[1], (d,), dev, zero=True)
         lib.call("stc_linear_f32_bwd", S, fc_w, dZ, dS, gfcW, gfcb, N, C, d, stream_ptr())
+        if ctx.lazy is not None:
+            # the branch BN backward kernels read dout themselves (stc_bn_bwd_*_aff): no df tensors (4 x |x| of traffic less per level)
+            lz = ctx.lazy
+            lz.scale, lz.shift, lz.shift_scale, lz.rows, lz.ready = wts, dS, 1.0 / HW, HW, True
+            return (dout, dout, dout, dout, gfcW, gfcb, *grads, None, None)
         df0, df1, df2 = torch.empty_like(f0), torch.empty_like(f1), torch.empty_like(f2)
         lib.call("stc_ksa_df", dout, wts, dS, df0, df1, df2, N, HW, C, code, stream_ptr())
-        return (dout, df0, df1, df2, gfcW, gfcb, *grads, None)
+        return (dout, df0, df1, df2, gfcW, gfcb, *grads, None, None)
 
 
 def ksa_fuse(x, f0, f1, f2, fc, fcs):
     ps = (fc.weight, fc.bias, fcs[0].weight, fcs[0].bias, fcs[1].weight, fcs[1].bias, fcs[2].weight, fcs[2].bias)
-    return _KSAFuse.apply(x, f0, f1, f2, *ps, ps)
+    lazy = None
+    fns = [f.grad_fn for f in (f0, f1, f2)]
+    C = x.shape[-1]
+    if (config.ksa_lazy_df and all(fn is not None and type(fn).__name__ == "_ConvBnActBackward" and fn.meta[0] == _lib.ACT_RELU
+                                   and fn.meta[1].training for fn in fns)
+            and len({id(fn) for fn in fns}) == 3 and lib.raw("stc_bn_bwd_aff_ok")(C)):
+        lazy = _KSALazy()
+        for k, fn in enumerate(fns):
+            fn.ksa_slot = (lazy, k)
+    return _KSAFuse.apply(x, f0, f1, f2, *ps, ps, lazy)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -929,10 +968,22 @@ class _InProj(Function):
         return dins[0], dins[1], dins[2], dW, db, None
 
 
-def _gemm_f32out(A, B, C, M, N, K, sA, sB, sCm):
-    """bf16 A(m,k), B(k,n) by element strides -> fp32 C (row stride sCm), tcgen05 engine (stc_gemm_f32out)."""
-    d = GemmDesc(M, N, K, 1, 1, 0, 0, sA[0], sA[1], 0, 0, sB[0], sB[1], 0, 0, sCm, 1.0, 0.0)
-    _dense("gemm", 2.0 * M * N * K, lambda: lib.call("stc_gemm_f32out", A, B, C, d, stream_ptr()))
+def _gemm_f32out(A, B, C, M, N, K, batch, sA, sB, sC):
+    """`batch` products of bf16 A(m,k), B(k,n) -> fp32 C on the tcgen05 engine (stc_gemm_f32out); element strides
+    sA = (batch, m, k), sB = (batch, k, n), sC = (batch, m)."""
+    d = GemmDesc(M, N, K, batch, 1, sA[0], 0, sA[1], sA[2], sB[0], 0, sB[1], sB[2], sC[0], 0, sC[1], 1.0, 0.0)
+    _dense("gemm", 2.0 * M * N * K * batch, lambda: lib.call("stc_gemm_f32out", A, B, C, d, stream_ptr()))
+
+
+def _uniform_stride(ts) -> Optional[int]:
+    """Element stride between consecutive tensors when they are equally spaced in memory (16-byte granular), else None.
+    Inside a Trainer step the bf16 weight packs (StepCache arena) and the gradient buffers (GradArena) of q/k/v are."""
+    if len(ts) < 2:
+        return 0
+    d = ts[1].data_ptr() - ts[0].data_ptr()
+    if d <= 0 or d % 16 or any(b.data_ptr() - a.data_ptr() != d for a, b in zip(ts[1:], ts[2:])):
+        return None
+    return d // ts[0].element_size()
 
 
 class _FusedLinearPairs(Function):
@@ -959,11 +1010,15 @@ class _FusedLinearPairs(Function):
         w1b = [pack_weight(w.view(Em, Ei, 1, 1), dt).view(Em, Ei) for w in W1s]
         weff = torch.empty((J * Eo, Ei), dtype=dt, device=dev)                       # fprop operand  [Cout][Cin]
         wefft = torch.empty((Ei, J * Eo), dtype=dt, device=dev)                      # dgrad operand  [Cin][Cout]
-        for j in range(J):
-            # Weff_j[o][i] = sum_m W2_j[o][m] W1_j[m][i]
-            gemm(w2b[j * Eo:], w1b[j], weff[j * Eo:], Eo, Ei, Em, 1, 1, (0, 0, Em, 1), (0, 0, Ei, 1), (0, 0, Ei))
-            # WeffT[i][j*Eo + o] = the same, written transposed (A = W1_j^T, B = W2_j^T)
-            gemm(w1b[j], w2b[j * Eo:], wefft[:, j * Eo:], Ei, Eo, Em, 1, 1, (0, 0, 1, Ei), (0, 0, 1, Em), (0, 0, J * Eo))
+        s1 = _uniform_stride(w1b)
+        # Weff_j[o][i] = sum_m W2_j[o][m] W1_j[m][i];  WeffT[i][j*Eo + o] = the same, written transposed (A = W1_j^T, B = W2_j^T)
+        if J > 1 and s1 is not None:      # the J products as ONE batched launch each
+            gemm(w2b, w1b[0], weff, Eo, Ei, Em, J, 1, (Eo * Em, 0, Em, 1), (s1, 0, Ei, 1), (Eo * Ei, 0, Ei))
+            gemm(w1b[0], w2b, wefft, Ei, Eo, Em, J, 1, (s1, 0, 1, Ei), (Eo * Em, 0, 1, Em), (Eo, 0, J * Eo))
+        else:
+            for j in range(J):
+                gemm(w2b[j * Eo:], w1b[j], weff[j * Eo:], Eo, Ei, Em, 1, 1, (0, 0, Em, 1), (0, 0, Ei, 1), (0, 0, Ei))
+                gemm(w1b[j], w2b[j * Eo:], wefft[:, j * Eo:], Ei, Eo, Em, 1, 1, (0, 0, 1, Ei), (0, 0, 1, Em), (0, 0, J * Eo))
         if residual is not None:
             residual = _chk(residual).view(1, 1, rows, J * Eo)
         y = conv_fprop(x.view(1, 1, rows, Ei), weff.view(1, J * Eo, Ei), b2, residual, J * Eo, 1, 1)
@@ -988,14 +1043,17 @@ class _FusedLinearPairs(Function):
             dx = conv_fprop(dy.view(1, 1, rows, J * Eo), wefft.view(1, Ei, J * Eo), None, None, Ei, 1, 1).view(x.shape)
         gtb = pack_weight(gt.view(Ei, J * Eo, 1, 1), x.dtype, cache=False).view(Ei, J * Eo)     # bf16 copy of G^T
         dW2 = _grad_buf(pW2, (J * Eo, Em), dev)
-        dW1s = []
-        for j in range(J):
-            # dW2_j[o][m] = sum_i G_j[o][i] W1_j[m][i]     (A = G_j read transposed from G^T, B = W1_j^T)
-            _gemm_f32out(gtb[:, j * Eo:], w1b[j], dW2[j * Eo:], Eo, Em, Ei, (1, J * Eo), (1, Ei), Em)
-            # dW1_j[m][i] = sum_o W2_j[o][m] G_j[o][i]     (A = W2_j^T, B = G_j)
-            dW1 = _grad_buf(pW1s[j], (Em, Ei), dev)
-            _gemm_f32out(w2b[j * Eo:], gtb[:, j * Eo:], dW1, Em, Ei, Eo, (1, Em), (1, J * Eo), Ei)
-            dW1s.append(dW1)
+        dW1s = [_grad_buf(pW1s[j], (Em, Ei), dev) for j in range(J)]
+        s1, sg = _uniform_stride(w1b), _uniform_stride(dW1s)
+        # dW2_j[o][m] = sum_i G_j[o][i] W1_j[m][i]     (A = G_j read transposed from G^T, B = W1_j^T)
+        # dW1_j[m][i] = sum_o W2_j[o][m] G_j[o][i]     (A = W2_j^T, B = G_j)
+        if J > 1 and s1 is not None and sg is not None:
+            _gemm_f32out(gtb, w1b[0], dW2, Eo, Em, Ei, J, (Eo, 1, J * Eo), (s1, 1, Ei), (Eo * Em, Em))
+            _gemm_f32out(w2b, gtb, dW1s[0], Em, Ei, Eo, J, (Eo * Em, 1, Em), (Eo, 1, J * Eo), (sg, Ei))
+        else:
+            for j in range(J):
+                _gemm_f32out(gtb[:, j * Eo:], w1b[j], dW2[j * Eo:], Eo, Em, Ei, 1, (0, 1, J * Eo), (0, 1, Ei), (0, Em))
+                _gemm_f32out(w2b[j * Eo:], gtb[:, j * Eo:], dW1s[j], Em, Ei, Eo, 1, (0, 1, Em), (0, 1, J * Eo), (0, Ei))
         dres = dy if (has_res and ctx.needs_input_grad[1]) else None
         return (dx, dres, dW2, db2, None, *dW1s)
 

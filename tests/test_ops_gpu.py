@@ -201,10 +201,13 @@ def test_coordatt_block(S, dt):
 
 
 @pytest.mark.parametrize("dt", DT)
-def test_ksa_block(S, dt):
+@pytest.mark.parametrize("lazy", [True, False])
+def test_ksa_block(S, dt, lazy):
+    """lazy: the branch gradients df_k = w_k*dout + dS/HW are consumed implicitly by stc_bn_bwd_*_aff; else stc_ksa_df writes them."""
     from oracle import stc_oracle as O
     from stc_unet_b200 import ops
     ops.config.engine = S._lib.ENGINE_SIMT
+    ops.config.ksa_lazy_df = lazy
     torch.manual_seed(0)
     C, N, H, W = 16, 2, 9, 8
     ksa = S.KernelSelectAttention(channel=C).to(dev())
@@ -229,6 +232,7 @@ def test_ksa_block(S, dt):
         else:
             assert rel_l2(p.grad, g_ref) < (t if dt == torch.float32 else 5e-2), name
     ops.config.engine = S._lib.ENGINE_AUTO
+    ops.config.ksa_lazy_df = True
 
 
 @pytest.mark.parametrize("dt", DT)
