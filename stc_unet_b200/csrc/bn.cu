@@ -51,7 +51,19 @@ __global__ void bn_unshift_kernel(const float* __restrict__ partial, const T* __
     int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= C) return;
     double s1 = 0.0, s2 = 0.0;
-    for (int g = lane; g < G; g += 32) {
+    // the G partial rows are read with 8 independent loads in flight per lane (this tiny kernel is pure load latency otherwise)
+    int g = lane;
+    for (; g + 7 * 32 < G; g += 8 * 32) {
+        float a[8], b[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a[u] = partial[(size_t)(g + u * 32) * 2 * C + c];
+            b[u] = partial[(size_t)(g + u * 32) * 2 * C + C + c];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { s1 += (double)a[u]; s2 += (double)b[u]; }
+    }
+    for (; g < G; g += 32) {
         s1 += (double)partial[(size_t)g * 2 * C + c];
         s2 += (double)partial[(size_t)g * 2 * C + C + c];
     }
@@ -559,8 +571,18 @@ extern "C" int stc_bn_bwd_apply_aff(const void* y, const void* dout, const float
     cudaStream_t st = (cudaStream_t)stream;
     STC_REQUIRE(rows_per_image > 0 && N > 0 && vec_ok(C) && ((((uintptr_t)y) | ((uintptr_t)dout) | ((uintptr_t)dy)) & 15) == 0,
                 "bn_bwd_apply_aff: shape/alignment not supported");
-    int gx = rows_blocks(rows_per_image * N, C / 8) / N;
-    if (gx < 1) gx = 1;
+    // whole waves: the grid is (at most) two times the number of blocks the chip holds at once (this variant needs more registers
+    // than the plain one, so num_sms * 8 blocks would leave a two-thirds-empty third wave)
+    int occ = 0;
+    if (dtype == STC_BF16) {
+        STC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_bwd_apply_rows_kernel<bf16, STC_ACT_RELU, true>, 256, 0));
+    } else {
+        STC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_bwd_apply_rows_kernel<float, STC_ACT_RELU, true>, 256, 0));
+    }
+    const long long want = (rows_per_image + (256 / (C / 8)) * 4 - 1) / ((256 / (C / 8)) * 4);   // >= 4 rows per thread
+    long long gxl = (long long)occ * num_sms() * 2 / N;
+    if (gxl > want) gxl = want;
+    const int gx = gxl < 1 ? 1 : (int)gxl;
     dim3 grid(gx, N);
     STC_DISPATCH_DTYPE(dtype, (bn_bwd_apply_rows_kernel<T, STC_ACT_RELU, true><<<grid, 256, 0, st>>>(
                                   (const T*)y, (const T*)dout, mean, invstd, gamma, beta, sums, (float)(1.0 / count), (T*)dy, rows_per_image, C,

@@ -304,38 +304,56 @@ __global__ void colsum_kernel(const T* __restrict__ x, float* __restrict__ out, 
 }
 
 // vector path: a thread keeps one 8-channel lane and walks rows with two 16-byte loads in flight; one atomicAdd per (block, channel)
+// Cc = channels of this column chunk (Cc/8 a power of two), ld = row stride; blockIdx.y selects the chunk, so widths such as
+// 1536 = 3 x 512 (the folded q|k|v projection) keep the 16-byte row-structured path.  Four loads in flight per thread.
 template <typename T>
-__global__ void __launch_bounds__(256) colsum_rows_kernel(const T* __restrict__ x, float* __restrict__ out, long long P, int C) {
+__global__ void __launch_bounds__(256) colsum_rows_kernel(const T* __restrict__ x, float* __restrict__ out, long long P, int Cc, int ld) {
     __shared__ float smem[256 * 8];
-    const int lanes = C >> 3, lv = threadIdx.x % lanes, r0 = threadIdx.x / lanes, rstep = 256 / lanes;
+    const int lanes = Cc >> 3, lv = threadIdx.x % lanes, r0 = threadIdx.x / lanes, rstep = 256 / lanes;
+    x += (long long)blockIdx.y * Cc;
+    out += (long long)blockIdx.y * Cc;
     float acc[1][8] = {};
-    float acc1[8] = {};
+    float acc1[8] = {}, acc2[8] = {}, acc3[8] = {};
     const long long step = (long long)gridDim.x * rstep;
     long long p = (long long)blockIdx.x * rstep + r0;
-    for (; p + step < P; p += 2 * step) {
-        Vec8<T> v0, v1;
-        v0.load(x + p * C + lv * 8);
-        v1.load(x + (p + step) * C + lv * 8);
+    for (; p + 3 * step < P; p += 4 * step) {
+        Vec8<T> v0, v1, v2, v3;
+        v0.load(x + p * ld + lv * 8);
+        v1.load(x + (p + step) * ld + lv * 8);
+        v2.load(x + (p + 2 * step) * ld + lv * 8);
+        v3.load(x + (p + 3 * step) * ld + lv * 8);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { acc[0][k] += v0.v[k]; acc1[k] += v1.v[k]; }
+        for (int k = 0; k < 8; ++k) { acc[0][k] += v0.v[k]; acc1[k] += v1.v[k]; acc2[k] += v2.v[k]; acc3[k] += v3.v[k]; }
     }
-    if (p < P) {
+    for (; p < P; p += step) {
         Vec8<T> v0;
-        v0.load(x + p * C + lv * 8);
+        v0.load(x + p * ld + lv * 8);
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[0][k] += v0.v[k];
     }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[0][k] += acc1[k];
-    block_reduce_lanes_emit<1>(acc, lanes, smem, C, [&](int, int c, float s) { atomicAdd(out + c, s); });
+    for (int k = 0; k < 8; ++k) acc[0][k] += acc1[k] + acc2[k] + acc3[k];
+    block_reduce_lanes_emit<1>(acc, lanes, smem, Cc, [&](int, int c, float s) { atomicAdd(out + c, s); });
+}
+
+// largest chunk width (8 * 2^k channels, at most 2048) that divides C; 0 if C is not a multiple of 8
+static inline int colsum_chunk(int C) {
+    if (C % 8) return 0;
+    int c = 8;
+    while (c * 2 <= 2048 && C % (c * 2) == 0) c *= 2;
+    return c;
 }
 
 extern "C" int stc_colsum(const void* x, float* out, long long P, int C, int accumulate, int dtype, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (!accumulate) STC_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * C, st));
     if (P <= 0) return STC_OK;
-    if (vec_ok(C) && (((uintptr_t)x) & 15) == 0 && P >= 1024) {
-        STC_DISPATCH_DTYPE(dtype, (colsum_rows_kernel<T><<<reduce_blocks(P, C / 8), 256, 0, st>>>((const T*)x, out, P, C)));
+    const int Cc = colsum_chunk(C);
+    if (Cc >= 64 && (((uintptr_t)x) & 15) == 0 && P >= 1024) {
+        const int chunks = C / Cc;
+        int gx = reduce_blocks(P, Cc / 8) / chunks;
+        dim3 grid(gx < 1 ? 1 : gx, chunks);
+        STC_DISPATCH_DTYPE(dtype, (colsum_rows_kernel<T><<<grid, 256, 0, st>>>((const T*)x, out, P, Cc, C)));
         return check_launch("colsum");
     }
     int gx = ceil_div(C, 32);

@@ -45,31 +45,49 @@ __global__ void __launch_bounds__(256) cls_fwd_kernel(const T* __restrict__ x, c
     }
 }
 
+// thread = (pixel, 8-channel lane): a warp stores 32/lanes pixels x lanes*16 B as one contiguous run (a thread-per-pixel mapping
+// writes 16 B into 32 different lines per store instruction).  grid (G, N): one image per blockIdx.y, its Dropout2d mask folded
+// into the shared-memory copy of the weights.
 template <typename T>
 __global__ void __launch_bounds__(256) cls_bwd_dx_kernel(const float* __restrict__ dl, const float* __restrict__ Wt,
                                                          const float* __restrict__ mask, T* __restrict__ dx, long long HW, int Cin,
-                                                         int Ccls, long long P) {
+                                                         int Ccls) {
     extern __shared__ float sw[];  // [Ccls][Cin]
-    for (int i = threadIdx.x; i < Ccls * Cin; i += blockDim.x) sw[i] = Wt[i];
+    const long long n = blockIdx.y;
+    for (int i = threadIdx.x; i < Ccls * Cin; i += blockDim.x) sw[i] = Wt[i] * (mask ? mask[n * Cin + i % Cin] : 1.f);
     __syncthreads();
-    long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (p >= P) return;
-    long long n = p / HW, hw = p - n * HW;
-    float g[kMaxCls];
-    for (int k = 0; k < Ccls; ++k) g[k] = dl[(n * Ccls + k) * HW + hw];
-    for (int c = 0; c < Cin; c += 8) {
+    const int lanes = Cin >> 3, lv = threadIdx.x % lanes, r0 = threadIdx.x / lanes, rstep = 256 / lanes;
+    const float* dn = dl + n * Ccls * HW;
+    T* on = dx + n * HW * Cin + lv * 8;
+    const float* wl = sw + lv * 8;
+    const long long step = (long long)gridDim.x * rstep;
+    long long hw = (long long)blockIdx.x * rstep + r0;
+    for (; hw + step < HW; hw += 2 * step) {      // two pixels per iteration
+        Vec8<T> v0, v1;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v0.v[e] = v1.v[e] = 0.f;
+        for (int k = 0; k < Ccls; ++k) {
+            const float g0 = dn[k * HW + hw], g1 = dn[k * HW + hw + step];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float w = wl[k * Cin + e];
+                v0.v[e] = fmaf(g0, w, v0.v[e]);
+                v1.v[e] = fmaf(g1, w, v1.v[e]);
+            }
+        }
+        v0.store(on + hw * Cin);
+        v1.store(on + (hw + step) * Cin);
+    }
+    for (; hw < HW; hw += step) {
         Vec8<T> v;
 #pragma unroll
         for (int e = 0; e < 8; ++e) v.v[e] = 0.f;
         for (int k = 0; k < Ccls; ++k) {
+            const float g = dn[k * HW + hw];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v.v[e] = fmaf(g[k], sw[k * Cin + c + e], v.v[e]);
+            for (int e = 0; e < 8; ++e) v.v[e] = fmaf(g, wl[k * Cin + e], v.v[e]);
         }
-        if (mask) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v.v[e] *= mask[n * Cin + c + e];
-        }
-        v.store(dx + p * Cin + c);
+        v.store(on + hw * Cin);
     }
 }
 
@@ -87,7 +105,23 @@ __global__ void __launch_bounds__(256) cls_bwd_dw_kernel(const float* __restrict
     const T* xn = x + n * HW * Cin + lv * 8;
     const float* dn = dl + (n * Ccls + k0) * HW;
     const int nk = min(4, Ccls - k0);
-    for (long long hw = (long long)blockIdx.x * rstep + r0; hw < HW; hw += (long long)gridDim.x * rstep) {
+    const long long step = (long long)gridDim.x * rstep;
+    long long hw = (long long)blockIdx.x * rstep + r0;
+    for (; hw + step < HW; hw += 2 * step) {      // two rows per iteration: two 16-byte loads in flight per thread
+        Vec8<T> v0, v1;
+        v0.load(xn + hw * Cin);
+        v1.load(xn + (hw + step) * Cin);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j < nk) {
+                const float g0 = dn[j * HW + hw], g1 = dn[j * HW + hw + step];
+                bs[j] += g0 + g1;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[j][e] = fmaf(g0, v0.v[e], fmaf(g1, v1.v[e], acc[j][e]));
+            }
+        }
+    }
+    for (; hw < HW; hw += step) {
         Vec8<T> v;
         v.load(xn + hw * Cin);
 #pragma unroll
@@ -111,10 +145,17 @@ __global__ void __launch_bounds__(256) cls_bwd_dw_kernel(const float* __restrict
     block_reduce_lanes_emit<4>(acc, lanes, smem, Cin, [&](int q, int c, float s) {
         if (k0 + q < Ccls) atomicAdd(dW + (long long)(k0 + q) * Cin + c, s);
     });
-    if (db && lv == 0) {
+    if (db) {   // block-level sum first: one global atomic per (block, class) instead of one per pixel-row thread
+        __shared__ float sb[4];
+        __syncthreads();
+        if (threadIdx.x < 4) sb[threadIdx.x] = 0.f;
+        __syncthreads();
+        if (lv == 0) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (k0 + j < Ccls && bs[j] != 0.f) atomicAdd(db + k0 + j, bs[j]);
+            for (int j = 0; j < 4; ++j) atomicAdd(&sb[j], bs[j]);
+        }
+        __syncthreads();
+        if (threadIdx.x < 4 && k0 + (int)threadIdx.x < Ccls) atomicAdd(db + k0 + threadIdx.x, sb[threadIdx.x]);
     }
 }
 
@@ -359,10 +400,24 @@ extern "C" int stc_cls_bwd(const float* dlogits, const void* x, const float* W, 
     long long P = (long long)N * HW;
     if (dx) {
         size_t smem = sizeof(float) * (size_t)Ccls * Cin;
-        STC_DISPATCH_DTYPE(dtype, (cls_bwd_dx_kernel<T><<<ceil_div(P, 256), 256, smem, st>>>(dlogits, W, mask, (T*)dx, HW, Cin, Ccls, P)));
+        const int rstep = 256 / (Cin / 8);
+        long long gx = (HW + (long long)rstep * 8 - 1) / ((long long)rstep * 8);          // ~8 pixels per thread
+        const long long cap = max(1LL, (long long)num_sms() * 16 / max(N, 1));
+        dim3 grid((unsigned)max(1LL, min(gx, cap)), (unsigned)N);
+        STC_DISPATCH_DTYPE(dtype, (cls_bwd_dx_kernel<T><<<grid, 256, smem, st>>>(dlogits, W, mask, (T*)dx, HW, Cin, Ccls)));
     }
     if (dW) {
-        dim3 grid((unsigned)max(1, reduce_blocks(P, Cin / 8) / max(N, 1)), (unsigned)N);
+        // one full wave: as many blocks as the chip holds at once (register / shared-memory limited), split over the N images
+        int occ = 0;
+        if (dtype == STC_BF16) {
+            STC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cls_bwd_dw_kernel<bf16>, 256, 0));
+        } else {
+            STC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cls_bwd_dw_kernel<float>, 256, 0));
+        }
+        const long long want = (HW + (256 / (Cin / 8)) * 8 - 1) / ((256 / (Cin / 8)) * 8);
+        long long gxl = (long long)occ * num_sms() / max(N, 1);
+        if (gxl > want) gxl = want;
+        dim3 grid((unsigned)(gxl < 1 ? 1 : gxl), (unsigned)N);
         for (int k0 = 0; k0 < Ccls; k0 += 4)
             STC_DISPATCH_DTYPE(dtype, (cls_bwd_dw_kernel<T><<<grid, 256, 0, st>>>(dlogits, (const T*)x, mask, dW, db, HW, Cin, Ccls, k0)));
     }

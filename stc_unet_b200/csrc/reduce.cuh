@@ -44,7 +44,15 @@ static __global__ void reduce_partials_kernel(const float* __restrict__ partial,
     int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (j >= len) return;
     double s = 0.0;
-    for (int g = lane; g < G; g += 32) s += (double)partial[(size_t)g * len + j];
+    int g = lane;
+    for (; g + 7 * 32 < G; g += 8 * 32) {   // 8 independent loads in flight per lane
+        float a[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a[u] = partial[(size_t)(g + u * 32) * len + j];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += (double)a[u];
+    }
+    for (; g < G; g += 32) s += (double)partial[(size_t)g * len + j];
     s = warp_sum(s);
     if (lane == 0) out[j] = s;
 }
