@@ -11,5 +11,6 @@ from .modules_b import BasicConvBlock, ConvModule, FCNHead, InterpConv, UNet, Up
 from .modules_pp import EncoderDecoderFull, UnetPlusPlus  # noqa: F401
 from .registry import BACKBONES, HEADS, LOSSES, MODELS, SEGMENTORS, build_backbone, build_head, build_loss, build_segmentor  # noqa: F401
 from .segmentor import EncoderDecoder, slide_windows  # noqa: F401
+from .optim import OPTIMIZERS, AdamB200, PolyLrUpdater, build_optimizer, load_checkpoint, poly_lr, save_checkpoint  # noqa: F401
 
 __version__ = "0.1.0"

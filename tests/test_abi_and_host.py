@@ -109,3 +109,58 @@ def test_metrics_from_confusion_follow_reference_definitions():
     # uniformly random 3-class predictions score ~1/3 accuracy (the fork's tampered code reports 0.80 here)
     p3, l3 = rng.randint(0, 3, 10000), rng.randint(0, 3, 10000)
     assert abs(metrics_from_confusion(O.confusion_matrix(p3, l3, 3))["aAcc"] - 1 / 3) < 0.03
+
+
+def test_poly_lr_matches_the_reference_schedule():
+    """lr_config = dict(policy='poly', power=0.9, min_lr=1e-6, by_epoch=True), 50 epochs, Adam lr 1e-5 (my_config/STC-UNet.py:87-93):
+    mmcv's PolyLrUpdaterHook formula, applied through param_groups like the hook does."""
+    import stc_unet_b200 as S
+    p = torch.nn.Parameter(torch.zeros(3))
+    opt = S.build_optimizer(torch.nn.ParameterList([p]), dict(type="Adam", lr=1e-5, betas=(0.9, 0.999)))
+    assert isinstance(opt, torch.optim.Adam)
+    upd = S.PolyLrUpdater(opt, max_progress=50, power=0.9, min_lr=1e-6, by_epoch=True)
+    seen = []
+    for epoch in range(50):
+        upd.before_epoch(epoch)
+        upd.before_iter(123)          # ignored: by_epoch
+        seen.append(opt.param_groups[0]["lr"])
+    assert seen[0] == pytest.approx(1e-5)
+    assert seen[25] == pytest.approx((1e-5 - 1e-6) * 0.5 ** 0.9 + 1e-6)
+    assert seen[49] == pytest.approx((1e-5 - 1e-6) * (1 / 50) ** 0.9 + 1e-6)
+    assert all(a > b for a, b in zip(seen, seen[1:]))
+    assert S.poly_lr(0.01, 40000, 40000, 1.0, 1e-4) == pytest.approx(1e-4)
+    with pytest.raises(KeyError):
+        S.build_optimizer(torch.nn.ParameterList([p]), dict(type="NoSuchOptimizer", lr=1.0))
+
+
+def test_checkpoint_round_trip_uses_the_reference_layout(tmp_path):
+    """save_checkpoint / load_checkpoint: mmcv's {'meta', 'state_dict'} layout, the reference's keys (backbone.* / decode_head.*), fp32
+    tensors on the CPU, nothing derived (packed bf16 operands) serialised; loading copies in place; 'module.' prefixes are stripped."""
+    import stc_unet_b200 as S
+    torch.manual_seed(0)
+    cfg_b = dict(type="UnetBackbone", in_channels=3, channel_list=[64, 128, 256, 512], context_layer="kernelselect", transformer_block=True)
+    cfg_h = dict(type="UnetHead", se=True, num_classes=3, channels=64, threshold=0.2, norm_cfg=dict(type="BN", requires_grad=True))
+    seg = S.EncoderDecoder(cfg_b, cfg_h)
+    path = str(tmp_path / "epoch_1.pth")
+    S.save_checkpoint(seg, path, meta=dict(epoch=1, iter=10))
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    assert set(ck) == {"meta", "state_dict"} and ck["meta"]["epoch"] == 1
+    sd = ck["state_dict"]
+    assert len(sd) == 233 + 102 and all(k.startswith(("backbone.", "decode_head.")) for k in sd)
+    assert all(v.device.type == "cpu" and v.dtype in (torch.float32, torch.int64) for v in sd.values())
+    seg2 = S.EncoderDecoder(cfg_b, cfg_h)
+    ptrs = {k: v.data_ptr() for k, v in seg2.state_dict().items()}
+    wrapped = OrderedDictPrefix(sd, "module.")
+    torch.save(dict(state_dict=wrapped), path)
+    S.load_checkpoint(seg2, path, strict=True)
+    for k, v in seg2.state_dict().items():
+        assert v.data_ptr() == ptrs[k]            # in place
+        assert torch.equal(v, sd[k]), k
+    torch.save(dict(state_dict={"backbone.bogus": torch.zeros(1)}), path)
+    with pytest.raises(RuntimeError):
+        S.load_checkpoint(seg2, path, strict=True)
+
+
+def OrderedDictPrefix(sd, prefix):
+    from collections import OrderedDict
+    return OrderedDict((prefix + k, v) for k, v in sd.items())

@@ -550,3 +550,40 @@ def test_image_u8_and_label_widen(S, dt):
     assert wide.dtype == torch.int64 and torch.equal(wide, lab.long())
     with pytest.raises(TypeError):
         ops.labels_to_int64(lab.int())
+
+
+def test_adam_b200_optimizer_matches_torch_adam(S):
+    """AdamB200 (the OPTIMIZERS entry for `optimizer = dict(type='AdamB200', ...)`) against torch.optim.Adam: foreign gradients are
+    copied into the flat arena, a parameter without a gradient is skipped entirely (as torch does), the LR can be changed through
+    param_groups (what mmcv's LR hooks do), and gradients produced by our kernels land in the arena without a copy."""
+    from stc_unet_b200 import ops
+    torch.manual_seed(0)
+    try:
+        ps = [torch.nn.Parameter(torch.randn(*s, device=dev())) for s in ((64, 32, 3, 3), (64,), (7, 5), (130,))]
+        ref = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+        opt = S.build_optimizer(torch.nn.ParameterList(ps), dict(type="AdamB200", lr=1e-2, betas=(0.9, 0.999), weight_decay=0.01))
+        assert isinstance(opt, S.AdamB200) and isinstance(opt, torch.optim.Optimizer)
+        topt = torch.optim.Adam(ref, lr=1e-2, betas=(0.9, 0.999), weight_decay=0.01)
+        for step in range(4):
+            opt.zero_grad(); topt.zero_grad()
+            for i, (p, r) in enumerate(zip(ps, ref)):
+                if step == 1 and i == 2:
+                    continue                      # no gradient for this parameter in this step
+                g = torch.randn_like(p)
+                p.grad, r.grad = g.clone(), g.clone()
+            if step == 2:
+                opt.param_groups[0]["lr"] = topt.param_groups[0]["lr"] = 3e-3
+            opt.step(); topt.step()
+        for p, r in zip(ps, ref):
+            assert rel_l2(p.data, r.data) < 1e-6
+        # gradients written by our kernels: conv weight grad aliases the arena (no copy in step())
+        conv = torch.nn.Conv2d(16, 16, 3, padding=1).to(dev())
+        opt2 = S.AdamB200(conv.parameters(), lr=1e-3)
+        x = torch.randn(2, 8, 8, 16, device=dev(), requires_grad=True)
+        ops.conv2d(x, conv.weight, conv.bias).sum().backward()
+        assert conv.weight.grad.data_ptr() == opt2.arena.view(conv.weight).data_ptr()
+        w0 = conv.weight.detach().clone()
+        opt2.step()
+        assert not torch.equal(w0, conv.weight.detach())
+    finally:
+        ops.set_grad_arena(None)
