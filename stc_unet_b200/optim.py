@@ -42,6 +42,7 @@ class AdamB200(torch.optim.Optimizer):
         self.exp_avg = torch.zeros_like(self.flat.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat.flat)
         self.t = 0
+        self.steps = {}                           # per-parameter step counts (they differ only if a parameter ever lacked a gradient)
         ops.set_grad_arena(self.arena)            # from now on our backward kernels write parameter gradients straight into the arena
 
     def zero_grad(self, set_to_none: bool = True):
@@ -56,36 +57,43 @@ class AdamB200(torch.optim.Optimizer):
                 loss = closure()
         g = self.param_groups[0]
         self.t += 1
-        # contiguous runs of parameters that HAVE a gradient (torch's Adam skips the others entirely); a gradient that is not
-        # already the arena view (produced by a foreign op, or replaced by gradient clipping) is copied in
-        runs, start = [], None
+        # contiguous runs of parameters that HAVE a gradient and share a step count (torch's Adam skips a parameter without a
+        # gradient entirely, so its own step count - the bias correction - lags afterwards); normally ONE run = one launch.
+        # A gradient that is not already the arena view (produced by a foreign op, or replaced by gradient clipping) is copied in.
+        runs, start, cur_t = [], None, None
         for p in self.flat.params:
             off, n = self.arena.offsets[id(p)]
             if p.grad is None:
                 if start is not None:
-                    runs.append((start, off)); start = None
+                    runs.append((start, off, cur_t)); start = None
                 continue
             view = self.arena.view(p)
             if p.grad.data_ptr() != view.data_ptr():
                 view.copy_(p.grad)
+            t = self.steps.get(id(p), 0) + 1
+            self.steps[id(p)] = t
+            if start is not None and t != cur_t:
+                runs.append((start, off, cur_t)); start = None
             if start is None:
-                start = off
+                start, cur_t = off, t
         if start is not None:
-            runs.append((start, self.arena.total))
-        for a, b in runs:
+            runs.append((start, self.arena.total, cur_t))
+        for a, b, t in runs:
             lib.call("stc_adam_step", self.flat.flat[a:], self.arena.flat[a:], self.exp_avg[a:], self.exp_avg_sq[a:], b - a, float(g["lr"]),
-                     float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]), self.t, stream_ptr())
+                     float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]), t, stream_ptr())
         return loss
 
     def state_dict(self):
         sd = super().state_dict()
-        sd["state"] = dict(step=self.t, exp_avg=self.exp_avg, exp_avg_sq=self.exp_avg_sq)
+        sd["state"] = dict(step=self.t, exp_avg=self.exp_avg, exp_avg_sq=self.exp_avg_sq,
+                           param_steps=[self.steps.get(id(p), 0) for p in self.flat.params])
         return sd
 
     def load_state_dict(self, sd):
         st = sd["state"]
         self.t = int(st["step"])
         self.exp_avg.copy_(st["exp_avg"]); self.exp_avg_sq.copy_(st["exp_avg_sq"])
+        self.steps = {id(p): int(t) for p, t in zip(self.flat.params, st.get("param_steps", [self.t] * len(self.flat.params)))}
         for k, v in sd["param_groups"][0].items():
             if k != "params":
                 self.param_groups[0][k] = v
