@@ -89,6 +89,12 @@ int stc_unpack_im2col_wgrad(const float* ws, float* dw, int Cout, int Cin, int R
 int stc_conv_fprop(const void* x, const void* wp, const float* bias, const void* residual, void* y,
                    int N, int H, int W, int Cin, int Cout, int R, int S, int act, int dtype, int engine,
                    void* stream);
+/* Conv2d followed by a train-mode BatchNorm (every DoubleConv / KSA branch, unet_backbone.py:120-125,62-66): y = conv(x) + bias
+ * AND the batch statistics sums = [sum_p y | sum_p y^2] (fp64, 2*Cout) of the stored outputs in one pass - out of the halo
+ * kernel's epilogue when it takes the shape, else conv + stc_bn_reduce.  ws: stc_bn_ws_bytes(N*H*W, Cout) bytes of scratch. */
+int stc_conv_bnstats_fused_ok(int W, int Cin, int Cout, int R, int S, int dtype, int engine);
+int stc_conv_fprop_bnstats(const void* x, const void* wp, const float* bias, void* y, int N, int H, int W, int Cin, int Cout,
+                           int R, int S, int dtype, int engine, double* sums, void* ws, long long ws_bytes, void* stream);
 /* dW[(r,s)][ci][co] (fp32 workspace, must be zeroed by the caller when accumulate==0 is wanted)
  * += sum_pixels x[p+(r,s)][ci] * dy[p][co].  Then stc_unpack_conv_wgrad -> OIHW. */
 int stc_conv_wgrad(const void* x, const void* dy, float* dw_ws, int N, int H, int W, int Cin, int Cout,

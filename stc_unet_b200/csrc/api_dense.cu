@@ -1,5 +1,7 @@
 // C-ABI entry points of the dense contractions: engine selection between the tcgen05 kernel
 // (umma.cu) and the fp32-accumulate SIMT kernel (conv_simt.cu).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace stc {
@@ -15,7 +17,9 @@ bool gemm_umma_eligible(const stc_gemm_desc*, int dtype);
 bool conv_convh_eligible(int W, int Cin, int Cout, int R, int S, int dtype);
 bool conv_wgradh_eligible(int W, int Cin, int Cout, int R, int S, int dtype);
 int conv_wgrad_wgradh(const void*, const void*, float*, int, int, int, int, int, int, int, cudaStream_t);
-int conv_fprop_convh(const void*, const void*, const float*, const void*, void*, int, int, int, int, int, int, int, int, cudaStream_t);
+int conv_fprop_convh(const void*, const void*, const float*, const void*, void*, int, int, int, int, int, int, int, int, cudaStream_t, float* stats = nullptr,
+                     int* stats_rows = nullptr);
+bool conv_convh_stats_ok(int Cout, int R);
 int gemm_umma(const void*, const void*, void*, const stc_gemm_desc*, int, cudaStream_t);
 }  // namespace stc
 
@@ -94,4 +98,39 @@ extern "C" int stc_gemm_f32out(const void* A, const void* B, float* C, const stc
     STC_REQUIRE(((uintptr_t)C & 15) == 0 && d->sCm % 4 == 0, "gemm_f32out: C must be 16-byte aligned with a row stride multiple of 4");
     g_last_engine = STC_ENGINE_TCGEN05;
     return gemm_umma(A, B, C, d, STC_F32, (cudaStream_t)stream);
+}
+
+/* Conv2d + the BatchNorm batch statistics of its output in one pass: y = conv(x) + bias and sums = [sum_p y | sum_p y^2] (fp64, 2*Cout)
+ * over all N*H*W pixels of the STORED outputs.  When the halo-reuse tcgen05 kernel takes the shape (and Cout is one N tile) the sums
+ * come out of its epilogue; otherwise the conv is followed by stc_bn_reduce.  ws: stc_bn_ws_bytes(P, Cout) bytes of scratch. */
+extern "C" int stc_bn_reduce(const void* y, double* sums, long long P, int C, void* ws, long long ws_bytes, int dtype, void* stream);
+namespace stc { int reduce_partials_f64(const float* partial, double* out, int G, int len, cudaStream_t st); }
+static bool bnstats_fused(int W, int Cin, int Cout, int R, int S, int dtype, int engine) {
+    static int fused_off = -1;
+    if (fused_off < 0) { const char* e = getenv("STC_BNSTATS_FUSED"); fused_off = (e && e[0] == '0') ? 1 : 0; }
+    static int min_k = -1;   // the column sums double the epilogue work: they only hide behind the MMAs of a long-K tile (measured on the
+    if (min_k < 0) { const char* e = getenv("STC_BNSTATS_MIN_K"); min_k = e ? atoi(e) : 1152; }   // 64-channel 3x3 layers: break-even)
+    return !fused_off && engine != STC_ENGINE_SIMT && conv_umma_eligible(Cin, Cout, dtype) && conv_convh_eligible(W, Cin, Cout, R, S, dtype) &&
+           conv_convh_stats_ok(Cout, R) && R * S * Cin >= min_k;
+}
+/* 1 if stc_conv_fprop_bnstats takes the statistics out of the conv epilogue for this shape (else it runs conv + stc_bn_reduce) */
+extern "C" int stc_conv_bnstats_fused_ok(int W, int Cin, int Cout, int R, int S, int dtype, int engine) {
+    return bnstats_fused(W, Cin, Cout, R, S, dtype, engine) ? 1 : 0;
+}
+
+extern "C" int stc_conv_fprop_bnstats(const void* x, const void* wp, const float* bias, void* y, int N, int H, int W, int Cin, int Cout, int R,
+                                      int S, int dtype, int engine, double* sums, void* ws, long long ws_bytes, void* stream) {
+    STC_REQUIRE(N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && (R & 1) && (S & 1) && sums && ws, "conv_fprop_bnstats: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long P = (long long)N * H * W;
+    if (bnstats_fused(W, Cin, Cout, R, S, dtype, engine) && ws_bytes >= (long long)num_sms() * 4 * 2 * Cout * (long long)sizeof(float)) {
+        g_last_engine = STC_KERNEL_CONVH;
+        int rows = 0;
+        int rc = conv_fprop_convh(x, wp, bias, nullptr, y, N, H, W, Cin, Cout, R, S, STC_ACT_NONE, st, (float*)ws, &rows);
+        if (rc) return rc;
+        return reduce_partials_f64((const float*)ws, sums, rows, 2 * Cout, st);
+    }
+    int rc = stc_conv_fprop(x, wp, bias, nullptr, y, N, H, W, Cin, Cout, R, S, STC_ACT_NONE, dtype, engine, stream);
+    if (rc) return rc;
+    return stc_bn_reduce(y, sums, P, Cout, ws, ws_bytes, dtype, stream);
 }

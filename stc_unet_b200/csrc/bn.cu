@@ -431,6 +431,14 @@ inline int rows_blocks(long long P, int lanes) {
 
 using namespace stc;
 
+namespace stc {
+// sums partial[g][j] over g in fp64 (shared with the conv epilogue statistics, api_dense.cu)
+int reduce_partials_f64(const float* partial, double* out, int G, int len, cudaStream_t st) {
+    reduce_partials_kernel<<<ceil_div((long long)len * 32, 128), 128, 0, st>>>(partial, out, G, len);
+    return check_launch("reduce_partials");
+}
+}  // namespace stc
+
 extern "C" long long stc_bn_ws_bytes(long long P, int C) {
     (void)P;
     return (long long)num_sms() * 4 * 3 * (long long)C * sizeof(float) + 256;

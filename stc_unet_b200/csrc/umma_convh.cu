@@ -35,9 +35,43 @@ struct alignas(64) ConvHParams {
     const float* bias;
     const void* residual;
     int act, Cout;
+    float* stats;  // optional [gridDim.x * 4][2][Cout] fp32: per epilogue-warp column sums / sums of squares of the STORED (bf16) outputs
 };
 
 constexpr int kConvHThreads = 224;
+
+// Column sums of a 32-row x 32-column register tile (one row per lane, v[j] = column j) by recursive halving: after the five
+// exchange steps lane l holds the total of column l.  31 shuffles instead of 32 x 5.
+__device__ __forceinline__ float convh_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float send = up ? v[i] : v[i + off];
+            const float keep = up ? v[i + off] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
+// BatchNorm statistics fused into the conv epilogue ("BN stats = 0 extra if fused"): f[] are this lane's 32 output
+// values of one pixel; they are rounded to bf16 exactly as stored, masked if the pixel is outside the image, and their per-column
+// sum / sum of squares over the warp's 32 pixels is added to the lane's running totals for column chunk `ci` (static indexing).
+__device__ __forceinline__ void convh_stats_add(const float (&f)[32], bool valid, int lane, int ci, float (&sacc)[8], float (&qacc)[8]) {
+    float a[32], b[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const float r = valid ? __bfloat162float(__float2bfloat16_rn(f[j])) : 0.f;
+        a[j] = r;
+        b[j] = r * r;
+    }
+    const float s1 = convh_colsum32(a, lane), s2 = convh_colsum32(b, lane);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (k == ci) { sacc[k] += s1; qacc[k] += s2; }
+}
 constexpr uint32_t kConvHStageBuf = 32 * 128;                   // 32 pixels x 64 bf16 channels, 128B-swizzled
 constexpr uint32_t kConvHStagingBytes = 4 * 2 * kConvHStageBuf;  // two buffers per epilogue warp
 
@@ -236,6 +270,7 @@ __global__ void __launch_bounds__(kConvHThreads, 1) umma_convh_kernel(const __gr
         int acc = 0, stage_buf = 0;
         uint32_t acc_phase[2] = {0, 0};
         const uint32_t stg0 = smem_base + ring_bytes + (uint32_t)q * 2u * kConvHStageBuf;
+        float sacc[8] = {}, qacc[8] = {};   // p.stats: running column sums of this warp (lane l <-> channel chunk*32 + l); num_n_tiles == 1
         for (int st = blockIdx.x; st < p.num_strips; st += gridDim.x) {
             Strip s = decode_strip(p, st);
             const int w = s.w0 + row;
@@ -287,6 +322,7 @@ __global__ void __launch_bounds__(kConvHThreads, 1) umma_convh_kernel(const __gr
 #pragma unroll
                                 for (int j = 0; j < 32; ++j) f[j] = convh_act(f[j], p.act);
                             }
+                            if (p.stats) convh_stats_add(f, valid, lane, (c >> 5) + half, sacc, qacc);
 #pragma unroll
                             for (int g = 0; g < 4; ++g) {
                                 uint4 ov;
@@ -310,7 +346,7 @@ __global__ void __launch_bounds__(kConvHThreads, 1) umma_convh_kernel(const __gr
                     uint32_t v[32];
                     ptx::tmem_ld_32x32(t_addr + c, v);
                     ptx::tmem_ld_wait();
-                    if (!valid) continue;
+                    if (!valid && !p.stats) continue;   // with statistics every lane takes part in the warp-wide column sums
                     float f[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
@@ -319,7 +355,7 @@ __global__ void __launch_bounds__(kConvHThreads, 1) umma_convh_kernel(const __gr
 #pragma unroll
                         for (int j = 0; j < 32; ++j) f[j] += __ldg(b + j);
                     }
-                    if (p.residual) {
+                    if (p.residual && valid) {
                         const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.residual) + off + c);
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
@@ -340,6 +376,10 @@ __global__ void __launch_bounds__(kConvHThreads, 1) umma_convh_kernel(const __gr
 #pragma unroll
                         for (int j = 0; j < 32; ++j) f[j] = convh_act(f[j], p.act);
                     }
+                    if (p.stats) {
+                        convh_stats_add(f, valid, lane, c >> 5, sacc, qacc);
+                        if (!valid) continue;
+                    }
                     uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + off + c);
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
@@ -358,6 +398,12 @@ __global__ void __launch_bounds__(kConvHThreads, 1) umma_convh_kernel(const __gr
             acc ^= 1;
         }
         if (p.staged && lane == 0) ptx::bulk_wait<0>();
+        if (p.stats) {   // one partial row per epilogue warp: [sum | sum of squares] x Cout
+            float* o = p.stats + ((size_t)blockIdx.x * 4 + q) * 2 * p.Cout;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (k * 32 < p.BN) { o[k * 32 + lane] = sacc[k]; o[p.Cout + k * 32 + lane] = qacc[k]; }
+        }
     }
 
     ptx::tc_fence_before();
@@ -411,8 +457,14 @@ bool conv_convh_eligible(int W, int Cin, int Cout, int R, int S, int dtype) {
     return dtype == STC_BF16 && W >= 128 && Cin % 64 == 0 && R == S && (R == 3 || R == 5 || R == 7) && convh_plan(Cout, R, BN, T, a, b, sg);
 }
 
+// stats != nullptr: also writes *stats_rows partial rows of [sum | sumsq] x Cout (fp32) of the stored outputs; needs BN == Cout
+bool conv_convh_stats_ok(int Cout, int R) {
+    int BN, T, a, b, sg;
+    return convh_plan(Cout, R, BN, T, a, b, sg) && BN == Cout;
+}
+
 int conv_fprop_convh(const void* x, const void* wp, const float* bias, const void* residual, void* y, int N, int H, int W, int Cin,
-                     int Cout, int R, int S, int act, cudaStream_t st) {
+                     int Cout, int R, int S, int act, cudaStream_t st, float* stats, int* stats_rows) {
     ConvHParams p;
     memset(&p, 0, sizeof(p));
     STC_REQUIRE(convh_plan(Cout, R, p.BN, p.T, p.a_slots, p.b_stages, p.staged), "conv_fprop_convh: no plan for Cout=%d R=%d", Cout, R);
@@ -466,6 +518,11 @@ int conv_fprop_convh(const void* x, const void* wp, const float* bias, const voi
         attr_set[dev] = true;
     }
     int grid = p.num_strips < num_sms() ? p.num_strips : num_sms();
+    if (stats) {
+        STC_REQUIRE(p.num_n_tiles == 1 && p.BN <= 256, "conv_fprop_convh: fused statistics need one N tile (Cout=%d BN=%d)", Cout, p.BN);
+        p.stats = stats;
+        *stats_rows = grid * 4;
+    }
     if (p.T == 4) umma_convh_kernel<4><<<grid, kConvHThreads, smem, st>>>(p);
     else if (p.T == 2) umma_convh_kernel<2><<<grid, kConvHThreads, smem, st>>>(p);
     else umma_convh_kernel<1><<<grid, kConvHThreads, smem, st>>>(p);

@@ -282,6 +282,18 @@ def conv_fprop(x, wp, bias, residual, Cout: int, R: int, S: int, act: int = 0) -
     return y
 
 
+def conv_fprop_bnstats(x, wp, bias, Cout: int, R: int, S: int):
+    """y = conv(x) + bias and [sum y | sum y^2] over all pixels (fp64, 2*Cout) of the stored outputs (stc_conv_fprop_bnstats)."""
+    N, H, W, Cin = x.shape
+    y = torch.empty((N, H, W, Cout), dtype=x.dtype, device=x.device)
+    sums = torch.empty(2 * Cout, dtype=torch.float64, device=x.device)
+    ws = _workspace(x.device, lib.raw("stc_bn_ws_bytes")(N * H * W, Cout))
+    _dense("conv_fprop", 2.0 * N * H * W * Cin * Cout * R * S,
+           lambda: lib.call("stc_conv_fprop_bnstats", x, wp, bias, y, N, H, W, Cin, Cout, R, S, dtype_code(x.dtype), config.engine, sums, ws,
+                            ws.numel(), stream_ptr()))
+    return y, sums
+
+
 def conv_wgrad(x, dy, R: int, S: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     N, H, W, Cin = x.shape
     Cout = dy.shape[-1]
@@ -358,16 +370,18 @@ class BNState:
         self.sync, self.group = sync, group
 
 
-def _bn_forward_stats(y, P, C, bn: BNState):
+def _bn_forward_stats(y, P, C, bn: BNState, sums=None):
+    """sums: [sum y | sum y^2] (fp64, 2C) when the producing conv already reduced them in its epilogue (conv_fprop_bnstats)."""
     dev = y.device
     mean = torch.empty(C, dtype=torch.float32, device=dev)
     invstd = torch.empty(C, dtype=torch.float32, device=dev)
     count = float(P)
     if bn.training:
-        sums = torch.empty(2 * C, dtype=torch.float64, device=dev)
-        nb = lib.raw("stc_bn_ws_bytes")(P, C)
-        ws = _workspace(dev, nb)
-        lib.call("stc_bn_reduce", y, sums, P, C, ws, ws.numel(), dtype_code(y.dtype), stream_ptr())
+        if sums is None:
+            sums = torch.empty(2 * C, dtype=torch.float64, device=dev)
+            nb = lib.raw("stc_bn_ws_bytes")(P, C)
+            ws = _workspace(dev, nb)
+            lib.call("stc_bn_reduce", y, sums, P, C, ws, ws.numel(), dtype_code(y.dtype), stream_ptr())
         world = _sync_world(bn)
         if world > 1:
             # C1: one all-reduce of [sum, sumsq]; every rank holds the same per-GPU batch (count = P * world)
@@ -436,10 +450,16 @@ class _ConvBnAct(Function):
             x = _im2col(x, R, S)          # (N,H,W,64): saved instead of the 3-channel image for the wgrad GEMM
             wp = pack_weight(weight, x.dtype, im2col_pad=64)
             y = conv_fprop(x, wp, bias, None, Cout, 1, 1)
+            sums = None
+        elif bn.training and lib.raw("stc_conv_bnstats_fused_ok")(W, Cin, Cout, R, S, dtype_code(x.dtype), config.engine):
+            # conv + batch statistics in one pass: the halo kernel's epilogue reduces sum / sum of squares of what it stores
+            wp = pack_weight(weight, x.dtype)
+            y, sums = conv_fprop_bnstats(x, wp, bias, Cout, R, S)
         else:
             wp = pack_weight(weight, x.dtype)
             y = conv_fprop(x, wp, bias, None, Cout, R, S)
-        mean, invstd, count = _bn_forward_stats(y, P, Cout, bn)
+            sums = None
+        mean, invstd, count = _bn_forward_stats(y, P, Cout, bn, sums)
         a = torch.empty_like(y)
         lib.call("stc_bn_apply", y, mean, invstd, gamma, beta, a, P, Cout, act, dtype_code(y.dtype), stream_ptr())
         ctx.save_for_backward(x, y, weight, gamma, beta, mean, invstd)

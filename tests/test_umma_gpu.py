@@ -246,3 +246,33 @@ def test_transformer_block_folded_matches_unfolded(hw):
     assert errs[True]["out"] < 2e-2 and errs[True]["dx"] < 4e-2
     for k in errs[True]:
         assert errs[True][k] <= max(6e-2, 1.5 * errs[False][k]), (k, errs[True][k], errs[False][k])
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 64, 20, 130, 3), (1, 128, 128, 9, 256, 3), (1, 128, 256, 6, 128, 3), (2, 64, 64, 11, 200, 5),
+                                   (1, 64, 64, 13, 128, 7)])
+def test_conv_bnstats_fused_tcgen05(tc, shape):
+    """stc_conv_fprop_bnstats: the batch statistics taken out of the halo kernel's epilogue (staged and direct store variants, ragged
+    widths with masked pixels) equal stc_bn_reduce of the stored output, and the output equals the plain conv's bit for bit."""
+    import stc_unet_b200 as S
+    from stc_unet_b200._lib import lib, stream_ptr
+    N, Cin, Cout, H, W, k = shape
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = (torch.randn(N, H, W, Cin, device=dev(), generator=g) + 0.3).to(BF)
+    w = torch.randn(Cout, Cin, k, k, device=dev(), generator=g) / math.sqrt(Cin * k * k)
+    b = torch.randn(Cout, device=dev(), generator=g)
+    wp = tc.pack_weight(w, BF)
+    # fused where the tile's K = k*k*Cin is long enough to hide the column sums (staged epilogue: 128->128 k3; direct: the others);
+    # the short-K 64-channel 3x3 shape takes the conv + stc_bn_reduce route of the same entry point
+    assert lib.raw("stc_conv_bnstats_fused_ok")(W, Cin, Cout, k, k, 1, S._lib.ENGINE_AUTO) == (1 if k * k * Cin >= 1152 else 0)
+    y, sums = tc.conv_fprop_bnstats(x, wp, b, Cout, k, k)
+    y_plain = tc.conv_fprop(x, wp, b, None, Cout, k, k)
+    assert torch.equal(y, y_plain)
+    P = N * H * W
+    ref = torch.empty(2 * Cout, dtype=torch.float64, device=dev())
+    ws = torch.empty(lib.raw("stc_bn_ws_bytes")(P, Cout), dtype=torch.uint8, device=dev())
+    lib.call("stc_bn_reduce", y, ref, P, Cout, ws, ws.numel(), 1, stream_ptr())
+    yd = y.double().view(P, Cout)
+    exact = torch.cat([yd.sum(0), (yd * yd).sum(0)])
+    assert rel_l2(ref, exact) < 1e-6
+    assert rel_l2(sums, exact) < 1e-5
+    assert float((sums[:Cout] - exact[:Cout]).abs().max()) < 1e-4 * P ** 0.5 * float(yd.abs().max())
