@@ -204,8 +204,8 @@ class Trainer:
         """Captures fwd + loss + bwd + Adam for inputs of this shape/dtype.  Runs the eager warm-up steps the StepCache needs
         first (they are real training steps).  Afterwards step_graph() replays it on new data."""
         if _dist_on():
-            # tried at N=2 (NCCL bucket all-reduces + SyncBN exchanges inside the capture): the capture hangs, so the multi-GPU
-            # step stays on the eager path
+            # tried twice at N=2 (NCCL bucket all-reduces + SyncBN exchanges inside the capture; global and thread-local capture
+            # error modes): the run hangs, so the multi-GPU step stays on the eager path (+3.9 ms/step of launch gaps at N=2)
             raise RuntimeError("Trainer.capture: the captured step is single-GPU only")
         while self.steps_done < 3:                      # StepCache: record, finalize, replay
             self.step(img, gt_semantic_seg)
