@@ -226,7 +226,8 @@ def main():
     if "call" in S._lib.lib.__dict__:
         del S._lib.lib.__dict__["call"]
     launches_per_step = sum(LAUNCHES.get(n, 1) for n in _names)
-    use_graph = world == 1 and not args.no_graph   # multi-GPU capture (NCCL inside the graph) hung when tried: eager there
+    # N > 1: the step is capturable when its exchanges run as our peer-memory kernels (Trainer.peer); with NCCL inside it hung when tried
+    use_graph = not args.no_graph and (world == 1 or trainer.peer is not None)
     if use_graph:   # the whole step (fwd + loss + bwd + Adam, ~1000 launches) captured once and replayed; same kernels, no launch gaps
         trainer.capture(d_img[0], d_gt[0])
 
@@ -386,6 +387,8 @@ def main():
         line = dict(metric=METRIC, value=value, unit="img/s", n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_per_step,
                     higher_is_better=True, scaling="weak", vs_baseline=None, dtype=args.dtype, data="synthetic",
                     config=dict(workload=workload_name(args), parallelism=f"dp{world}", sync_bn=world > 1, cuda_graph=bool(use_graph),
+                                exchange=("none" if world == 1 else ("nvlink peer-memory kernels (SyncBN stats + gradient all-reduce)" if trainer.peer is not None
+                                                                      else "nccl")),
                                 cache="per-step working set (tens of GB of activations) >> 126 MB L2; 2 distinct input batches alternate",
                                 optimizer="fused Adam lr=1e-5", dropout_ratio=0.1),
                     model_tflops_per_s=value * fl / 1e12, model_frac_of_peak=value * fl / 1e12 / world / peaks["tflops_sustained"],

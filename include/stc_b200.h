@@ -310,6 +310,23 @@ int stc_adam_step(float* p, const float* g, float* m, float* v, long long n, flo
 int stc_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, float* dyn, int* step, float beta1, float beta2, float eps,
                       float weight_decay, void* stream);
 
+/* ---------------------------------------------------------------- data-parallel exchanges over NVLink peer memory (C1-C3)
+ * Replace the NCCL calls of the reference's data-parallel step (nn.SyncBatchNorm's statistics all-reduces and
+ * MMDistributedDataParallel's gradient reduction, mmseg/apis/train.py:104-113) by kernels that read / write the peers' buffers
+ * directly, so the whole step can be one CUDA graph.  *_ptrs: `world` device pointers (as integers, HOST array) to every rank's copy of
+ * a symmetric buffer, own rank included.  Control block: stc_peer_ctrl_bytes(max_n, ctas) bytes, zeroed once before the first use.
+ * seq: DEVICE counters (1 for the small exchange, `ctas` for the arena exchange), zero-initialised, private to this rank.
+ * All ranks must issue the same sequence of calls.  A peer that does not arrive within ~2 s makes the kernel trap. */
+#define STC_PEER_MAX 16
+long long stc_peer_ctrl_bytes(int max_n, int ctas);
+/* out[i] = sum over ranks of in[i] (fp64, n <= max_n), summed in rank order: identical on every rank. */
+int stc_peer_allreduce_small_f64(const unsigned long long* ctrl_ptrs, int rank, int world, int max_n, const double* in, double* out, int n,
+                                 unsigned long long* seq, void* stream);
+/* In place on the symmetric fp32 arena: arena[elem_off : elem_off + n) = scale * sum over ranks (two-shot reduce-scatter + all-gather,
+ * `ctas` CTAs, each pairing with the same CTA of the peers). */
+int stc_peer_allreduce_arena_f32(const unsigned long long* arena_ptrs, const unsigned long long* ctrl_ptrs, int rank, int world, int max_n,
+                                 long long elem_off, long long n, float scale, unsigned long long* seq, int ctas, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

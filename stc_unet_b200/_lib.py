@@ -32,7 +32,7 @@ class GemmDesc(ctypes.Structure):
 
 
 _SCALARS = {"int": ctypes.c_int, "long long": ctypes.c_longlong, "float": ctypes.c_float, "double": ctypes.c_double,
-            "int64_t": ctypes.c_int64}
+            "int64_t": ctypes.c_int64, "unsigned long long": ctypes.c_ulonglong}
 
 
 def parse_header(path: str = HEADER_PATH) -> Dict[str, Tuple[object, List[object]]]:

@@ -60,7 +60,7 @@ def _chk(t: torch.Tensor) -> torch.Tensor:
 # (single bucketed NCCL all-reduce + single fused Adam kernel, no per-tensor copies)
 # ---------------------------------------------------------------------------------------------
 class GradArena:
-    def __init__(self, params: Sequence[torch.nn.Parameter]):
+    def __init__(self, params: Sequence[torch.nn.Parameter], alloc=None):
         self.params = [p for p in params if p.requires_grad]
         total = 0
         self.offsets = {}
@@ -68,7 +68,8 @@ class GradArena:
             self.offsets[id(p)] = (total, p.numel())
             total += (p.numel() + 3) // 4 * 4  # keep every slice 16-byte aligned
         dev = self.params[0].device
-        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        # `alloc` lets the trainer place the arena in NVLink symmetric memory (peer.PeerExchange.alloc_arena)
+        self.flat = alloc(total) if alloc is not None else torch.zeros(total, dtype=torch.float32, device=dev)
         self.total = total
         self.prezeroed = False     # Trainer zeroes the whole arena once per step (one memset) and sets this
 
@@ -81,6 +82,20 @@ class GradArena:
 
 
 _ARENA: Optional[GradArena] = None
+_PEER = None    # peer.PeerExchange: SyncBN statistics go through NVLink peer memory (our kernel) instead of NCCL
+
+
+def set_peer_exchange(px):
+    global _PEER
+    _PEER = px
+
+
+def _allreduce_stats(sums: torch.Tensor, bn) -> None:
+    """SUM of the BN statistic vector over the ranks of the SyncBN group (C1 / C2)."""
+    if _PEER is not None and (bn.group is None or bn.group is _PEER.group):
+        _PEER.allreduce_small_(sums)
+    else:
+        dist.all_reduce(sums, group=bn.group)
 
 
 def set_grad_arena(arena: Optional[GradArena]):
@@ -385,7 +400,7 @@ def _bn_forward_stats(y, P, C, bn: BNState, sums=None):
         world = _sync_world(bn)
         if world > 1:
             # C1: one all-reduce of [sum, sumsq]; every rank holds the same per-GPU batch (count = P * world)
-            dist.all_reduce(sums, group=bn.group)
+            _allreduce_stats(sums, bn)
             count = float(P) * world
         lib.call("stc_bn_finalize", sums, count, mean, invstd, bn.running_mean, bn.running_var, bn.nbt,
                  float(bn.momentum), float(bn.eps), C, stream_ptr())
@@ -414,7 +429,7 @@ def _bn_backward(y, dout, mean, invstd, gamma, beta, P, C, act, bn, count, pg, p
     dbeta = _grad_buf(pb, (C,), dev)
     lib.call("stc_bn_param_grads", sums, dgamma, dbeta, C, stream_ptr())
     if training and _sync_world(bn) > 1:
-        dist.all_reduce(sums, group=bn.group)  # C2
+        _allreduce_stats(sums, bn)  # C2
     dy = torch.empty_like(y)
     if aff is not None:
         lib.call("stc_bn_bwd_apply_aff", y, dout, ua, ub, float(ubs), rows_img, n_img, mean, invstd, gamma, beta, sums, float(count), dy, C,

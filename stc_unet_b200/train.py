@@ -22,6 +22,7 @@ import torch
 import torch.distributed as dist
 
 from . import ops
+from . import peer as peer_mod
 from ._lib import lib, stream_ptr
 
 
@@ -72,8 +73,9 @@ class GradReducer:
     """Buckets are contiguous ranges of the arena taken from its END (backward produces the last parameters
     first); a bucket's all-reduce starts on the comm stream as soon as all of its gradients have been written."""
 
-    def __init__(self, arena: ops.GradArena, bucket_mb: float = 25.0):
+    def __init__(self, arena: ops.GradArena, bucket_mb: float = 25.0, peer=None):
         self.arena = arena
+        self.peer = peer          # peer.PeerExchange: the buckets are reduced by our NVLink peer-memory kernel instead of NCCL
         self.comm = torch.cuda.Stream()
         cap = int(bucket_mb * (1 << 20) // 4)
         spans = [arena.offsets[id(p)] for p in arena.params]
@@ -99,7 +101,10 @@ class GradReducer:
             ev.record(torch.cuda.current_stream())
             self.comm.wait_event(ev)
             with torch.cuda.stream(self.comm):
-                self.handles.append(dist.all_reduce(self.arena.flat[start:end], op=dist.ReduceOp.AVG, async_op=True))
+                if self.peer is not None:
+                    self.peer.allreduce_arena_(start, end, average=True)
+                else:
+                    self.handles.append(dist.all_reduce(self.arena.flat[start:end], op=dist.ReduceOp.AVG, async_op=True))
 
     def finish(self):
         if not self.enabled:
@@ -168,8 +173,10 @@ class Trainer:
         params = [p for p in segmentor.parameters() if p.requires_grad]
         self.flat = FlatParams(params)
         self.flat.broadcast(0)
-        self.arena = ops.GradArena(self.flat.params)
-        self.reducer = GradReducer(self.arena, bucket_mb)
+        # N > 1: SyncBN statistics and gradient buckets travel through NVLink peer memory with our own kernels (no NCCL inside the step)
+        self.peer = peer_mod.try_create(self.flat.flat.device) if _dist_on() else None
+        self.arena = ops.GradArena(self.flat.params, alloc=self.peer.alloc_arena if self.peer is not None else None)
+        self.reducer = GradReducer(self.arena, bucket_mb, peer=self.peer)
         self.optim = FusedAdam(self.flat, self.arena, lr=lr, betas=betas)
         self.cache = ops.StepCache()
         self.steps_done = 0
@@ -179,6 +186,7 @@ class Trainer:
         """One training iteration; returns the (device) log-var tensors, no host sync."""
         ops.set_grad_arena(self.arena)
         ops.set_step_cache(self.cache)
+        ops.set_peer_exchange(self.peer)
         try:
             self.optim.zero_grad()
             self.arena.flat.zero_()          # one memset: kernels that accumulate (+=) into their gradient need zeros
@@ -195,6 +203,7 @@ class Trainer:
         finally:
             ops.set_grad_arena(None)
             ops.set_step_cache(None)
+            ops.set_peer_exchange(None)
             self.arena.prezeroed = False
         self.steps_done += 1
         return out["log_vars"]
@@ -203,7 +212,7 @@ class Trainer:
     def capture(self, img: torch.Tensor, gt_semantic_seg: torch.Tensor):
         """Captures fwd + loss + bwd + Adam for inputs of this shape/dtype.  Runs the eager warm-up steps the StepCache needs
         first (they are real training steps).  Afterwards step_graph() replays it on new data."""
-        if _dist_on():
+        if _dist_on() and self.peer is None:
             # tried twice at N=2 (NCCL bucket all-reduces + SyncBN exchanges inside the capture; global and thread-local capture
             # error modes): the run hangs, so the multi-GPU step stays on the eager path (+3.9 ms/step of launch gaps at N=2)
             raise RuntimeError("Trainer.capture: the captured step is single-GPU only")
@@ -221,8 +230,13 @@ class Trainer:
         opt._t_on_dev = opt.t
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        multi = _dist_on()
+        if multi:      # every rank enters the capture from the same state (the peer kernels pair up by ticket number)
+            dist.barrier()
+            torch.cuda.synchronize()
         self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
+        # thread-local capture mode with a live process group: the NCCL watchdog thread's event queries must not invalidate the capture
+        with torch.cuda.graph(self._graph, capture_error_mode="thread_local" if multi else "global"):
             self._static_out = self.step(self._static_img, self._static_gt, _device_adam=True)
         return self
 

@@ -587,3 +587,29 @@ def test_adam_b200_optimizer_matches_torch_adam(S):
         assert not torch.equal(w0, conv.weight.detach())
     finally:
         ops.set_grad_arena(None)
+
+
+def test_peer_exchange_kernels_single_rank(S):
+    """csrc/peer.cu with a one-rank peer table (a plain device buffer): tickets, slots, float4 body + scalar tail, CTA split, scale.
+    The N >= 2 behaviour over NVLink (against NCCL) is tools/peer_test.py, run under torchrun on a multi-GPU box."""
+    import ctypes
+    from stc_unet_b200._lib import lib, stream_ptr
+    max_n, ctas = 256, 8
+    ctrl = torch.zeros((lib.raw("stc_peer_ctrl_bytes")(max_n, ctas) + 7) // 8, dtype=torch.int64, device=dev())
+    cptr = (ctypes.c_ulonglong * 1)(ctrl.data_ptr())
+    seq = torch.zeros(1, dtype=torch.int64, device=dev())
+    for n in (1, 100, 256, 37):
+        t = torch.randn(n, dtype=torch.float64, device=dev()); ref = t.clone()
+        lib.call("stc_peer_allreduce_small_f64", ctypes.addressof(cptr), 0, 1, max_n, t, t, n, seq, stream_ptr())
+        assert torch.equal(t, ref)
+    assert int(seq) == 4
+    with pytest.raises(RuntimeError):
+        lib.call("stc_peer_allreduce_small_f64", ctypes.addressof(cptr), 0, 1, max_n, t, t, max_n + 1, seq, stream_ptr())
+    arena = torch.randn(100_003, device=dev())
+    aptr = (ctypes.c_ulonglong * 1)(arena.data_ptr())
+    seqa = torch.zeros(ctas, dtype=torch.int64, device=dev())
+    for (a, b, scale) in ((0, 100_003, 0.5), (8, 8 + 4099, 1.0), (100, 103, 2.0)):
+        ref = arena.clone(); ref[a:b] *= scale
+        lib.call("stc_peer_allreduce_arena_f32", ctypes.addressof(aptr), ctypes.addressof(cptr), 0, 1, max_n, a, b - a, scale, seqa, ctas, stream_ptr())
+        assert torch.equal(arena, ref)
+    assert seqa.tolist() == [9] * ctas
