@@ -316,7 +316,7 @@ int stc_adam_step_dev(float* p, const float* g, float* m, float* v, long long n,
  * directly, so the whole step can be one CUDA graph.  *_ptrs: `world` device pointers (as integers, HOST array) to every rank's copy of
  * a symmetric buffer, own rank included.  Control block: stc_peer_ctrl_bytes(max_n, ctas) bytes, zeroed once before the first use.
  * seq: DEVICE counters (1 for the small exchange, `ctas` for the arena exchange), zero-initialised, private to this rank.
- * All ranks must issue the same sequence of calls.  A peer that does not arrive within ~2 s makes the kernel trap. */
+ * All ranks must issue the same sequence of calls.  A peer that does not arrive within ~15 s makes the kernel trap. */
 #define STC_PEER_MAX 16
 long long stc_peer_ctrl_bytes(int max_n, int ctas);
 /* out[i] = sum over ranks of in[i] (fp64, n <= max_n), summed in rank order: identical on every rank. */

@@ -3,7 +3,7 @@
 // the kernels below load / store them directly.  Being plain kernels they can be captured in the whole-step CUDA graph.
 //
 // Synchronisation = monotonically increasing 64-bit tickets written with st.release.sys into the CONSUMER's flag array and polled
-// with ld.acquire.sys.  Every wait is bounded (a few seconds of polling) and traps instead of hanging the GPU.
+// with ld.acquire.sys.  Every wait is bounded (~15 s of polling) and traps instead of hanging the GPU.
 //   small all-reduce (fp64, n <= max_n): one CTA; ticket t uses data slot t & 1 (a rank can be at most one call ahead of a peer, so
 //       two slots suffice): publish own values -> ticket to every peer -> wait for every peer's ticket -> sum the W slots in rank order.
 //   arena all-reduce (fp32, in place on the symmetric gradient arena): CTA c of every rank works on the c-th sub-range and only
@@ -27,11 +27,11 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-// bounded poll: ~4e9 cycles (2 s) then trap
+// bounded poll: ~3e10 cycles (~15 s: ranks may enter their first step seconds apart) then trap
 __device__ __forceinline__ void wait_ticket(const unsigned long long* flag, unsigned long long want) {
     const long long t0 = clock64();
     while (ld_acquire_sys(flag) < want) {
-        if (clock64() - t0 > 4000000000LL) {
+        if (clock64() - t0 > 30000000000LL) {
             printf("stc_b200 peer exchange: timed out waiting for a peer (want %llu, have %llu)\n", want, ld_acquire_sys(flag));
             __trap();
         }

@@ -112,7 +112,8 @@ class EncoderDecoder(BaseModule):
 
     def _slide_logits(self, img):
         h_crop, w_crop = self.test_cfg["crop_size"]
-        N, _, H, W = img.shape
+        u8 = img.dtype == torch.uint8          # decoded (N, H, W, C) pixels: normalised on the device by the backbone (ops.image_to_nhwc)
+        N, H, W = (img.shape[0], img.shape[1], img.shape[2]) if u8 else (img.shape[0], img.shape[2], img.shape[3])
         wins = slide_windows(H, W, (h_crop, w_crop), tuple(self.test_cfg["stride"]))
         preds = torch.zeros((N, self.out_channels, H, W), dtype=torch.float32, device=img.device)
         count = torch.zeros((N, H, W), dtype=torch.float32, device=img.device)
@@ -121,7 +122,7 @@ class EncoderDecoder(BaseModule):
         for g0 in range(0, len(wins), group):
             chunk = wins[g0:g0 + group]
             # windows that share a shape are batched along N (all of them do unless the image is smaller than the crop)
-            crops = torch.cat([img[:, :, y1:y2, x1:x2] for (y1, x1, y2, x2) in chunk], dim=0)
+            crops = torch.cat([(img[:, y1:y2, x1:x2] if u8 else img[:, :, y1:y2, x1:x2]) for (y1, x1, y2, x2) in chunk], dim=0)
             logits = self.encode_decode(crops)
             for wi, (y1, x1, y2, x2) in enumerate(chunk):
                 ops.slide_accum(logits[wi * N:(wi + 1) * N], preds, count, y1, x1)

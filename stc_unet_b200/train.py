@@ -181,6 +181,9 @@ class Trainer:
         self.cache = ops.StepCache()
         self.steps_done = 0
         self._graph = None
+        if self.peer is not None:      # ranks leave the constructor together: the first exchange pairs up within the kernels' time-out
+            torch.cuda.synchronize()
+            dist.barrier()
 
     def step(self, img: torch.Tensor, gt_semantic_seg: torch.Tensor, _device_adam: bool = False):
         """One training iteration; returns the (device) log-var tensors, no host sync."""

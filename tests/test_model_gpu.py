@@ -390,6 +390,20 @@ def test_unetpp_config5_parity(dtype):
     assert rel_l2(logits, ref_eval) <= (1e-4 if dtype == "fp32" else 8e-2)
 
 
+def test_uint8_slide_inference_matches_float_path():
+    """Slide-mode inference fed with decoded uint8 HWC slices (windows cropped from the 8-bit volume, normalised on the device) gives
+    the prediction of the float NCHW interface on the same pixel values."""
+    import stc_unet_b200 as S
+    bb, hd = build(True, 3, "bf16")
+    seg = S.EncoderDecoder(bb, hd, test_cfg=dict(mode="slide", crop_size=(64, 64), stride=(42, 42))).cuda().eval()
+    g = torch.Generator().manual_seed(3)
+    u8 = torch.randint(0, 256, (2, 128, 128, 3), dtype=torch.uint8, generator=g).cuda()
+    seg.backbone.img_norm_cfg = dict(mean=[0.0], std=[255.0], to_rgb=False)
+    pred_u8 = seg.inference_device(u8)
+    pred_f = seg.inference_device(u8.permute(0, 3, 1, 2).float() / 255.0)
+    assert pred_u8.shape == (2, 128, 128) and float((pred_u8 == pred_f).float().mean()) >= 0.999
+
+
 def test_uint8_input_pipeline_matches_float_path():
     """decoded uint8 HWC pixels + uint8 labels, normalised on the device, give exactly the losses and gradients of the
     reference interface (float NCHW image normalised on the host, int64 labels)."""
