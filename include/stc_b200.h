@@ -163,6 +163,10 @@ int stc_bn_param_grads(const double* sums, float* dgamma, float* dbeta, int C, v
  * rows_per_image rows each; ReLU, train mode, C/8 a power of two <= 256 - stc_bn_bwd_aff_ok).  KernelSelectAttention
  * (unet_backbone.py:86-98) hands each branch  df_k = softmax-weight_k[n,c] * dout + dS[n,c]/HW ; these entry points consume
  * dout directly so the three df tensors are never written. */
+/* Inference (eval-mode BN, no gradient): Conv2d + BatchNorm folded into one conv, w' = w * s per output channel, b' = (b - running_mean) * s + beta
+ * with s = gamma / sqrt(running_var + eps); b may be NULL.  The activation then runs in the conv epilogue (no BN-apply pass). */
+int stc_bn_fold_conv(const float* w, const float* b, const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                     float eps, float* w_folded, float* b_folded, int Cout, long long per_out, void* stream);
 int stc_bn_bwd_aff_ok(int C);
 int stc_bn_bwd_reduce_aff(const void* y, const void* dout, const float* up_scale, const float* up_shift, float shift_scale,
                           long long rows_per_image, int N, const float* mean, const float* invstd, const float* gamma,

@@ -432,6 +432,31 @@ inline int rows_blocks(long long P, int lanes) {
 using namespace stc;
 
 namespace stc {
+__global__ void bn_fold_conv_kernel(const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, const float* __restrict__ rm, const float* __restrict__ rv, float eps,
+                                    float* __restrict__ wf, float* __restrict__ bf, int Cout, long long per_out) {
+    const long long total = (long long)Cout * per_out;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int co = (int)(i / per_out);
+        const float s = gamma[co] * rsqrtf(rv[co] + eps);
+        wf[i] = w[i] * s;
+        if (i - co * per_out == 0) bf[co] = fmaf((b ? b[co] : 0.f) - rm[co], s, beta[co]);
+    }
+}
+}  // namespace stc
+
+/* Inference: Conv2d followed by an eval-mode BatchNorm is ONE conv with w' = w * s (per output channel), b' = (b - running_mean) * s + beta,
+ * s = gamma / sqrt(running_var + eps); the activation goes into the conv epilogue, so the BN-apply pass over the feature map disappears. */
+extern "C" int stc_bn_fold_conv(const float* w, const float* b, const float* gamma, const float* beta, const float* running_mean,
+                                const float* running_var, float eps, float* w_folded, float* b_folded, int Cout, long long per_out, void* stream) {
+    STC_REQUIRE(w && gamma && beta && running_mean && running_var && w_folded && b_folded && Cout > 0 && per_out > 0, "bn_fold_conv: bad arguments");
+    const long long total = (long long)Cout * per_out;
+    int blocks = (int)min((long long)num_sms() * 8, (long long)ceil_div(total, 256));
+    stc::bn_fold_conv_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, b, gamma, beta, running_mean, running_var, eps, w_folded, b_folded, Cout, per_out);
+    return check_launch("bn_fold_conv");
+}
+
+namespace stc {
 // sums partial[g][j] over g in fp64 (shared with the conv epilogue statistics, api_dense.cu)
 int reduce_partials_f64(const float* partial, double* out, int G, int len, cudaStream_t st) {
     reduce_partials_kernel<<<ceil_div((long long)len * 32, 128), 128, 0, st>>>(partial, out, G, len);

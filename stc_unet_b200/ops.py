@@ -24,6 +24,7 @@ class _Config:
     engine = _lib.ENGINE_AUTO       # dense engine selection passed to stc_conv_* / stc_gemm
     fold_linear_pairs = True        # bf16 + tcgen05: q/k/v + in_proj and fc1 + fc2 of TransformerLayer run as folded GEMMs
     ksa_lazy_df = True              # KSA branch gradients are consumed implicitly by the BN backward kernels (no df tensors)
+    fold_eval_bn = True             # inference: eval-mode BN folded into the conv weights, activation in the conv epilogue
 
 
 config = _Config()
@@ -461,6 +462,15 @@ class _ConvBnAct(Function):
         N, H, W, _ = x.shape
         P = N * H * W
         ctx.im2col = _use_im2col(x, weight)
+        if not bn.training and not torch.is_grad_enabled() and config.fold_eval_bn:
+            # inference: BN folded into the conv's weights / bias, activation in the conv epilogue - one pass instead of three
+            wf = torch.empty_like(weight)
+            bf = torch.empty(Cout, dtype=torch.float32, device=x.device)
+            lib.call("stc_bn_fold_conv", weight, bias, gamma, beta, bn.running_mean, bn.running_var, float(bn.eps), wf, bf, Cout, Cin * R * S,
+                     stream_ptr())
+            if ctx.im2col:
+                return conv_fprop(_im2col(x, R, S), pack_weight(wf, x.dtype, im2col_pad=64, cache=False), bf, None, Cout, 1, 1, act)
+            return conv_fprop(x, pack_weight(wf, x.dtype, cache=False), bf, None, Cout, R, S, act)
         if ctx.im2col:
             x = _im2col(x, R, S)          # (N,H,W,64): saved instead of the 3-channel image for the wgrad GEMM
             wp = pack_weight(weight, x.dtype, im2col_pad=64)

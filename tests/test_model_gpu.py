@@ -458,3 +458,35 @@ def test_trainer_cuda_graph_matches_eager():
     for a, b in zip(losses["eager"], losses["graph"]):
         assert abs(a - b) <= 2e-3 * max(1.0, abs(a)), (losses["eager"], losses["graph"])
     assert losses["graph"][-1] < losses["graph"][0]          # it does train
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_eval_bn_folding_matches_unfolded(dtype):
+    """Inference folds eval-mode BN into the conv (stc_bn_fold_conv + activation in the conv epilogue); logits must agree with the
+    unfolded conv -> BN-apply path (fp32: 1e-5; bf16: the two differ by one rounding of the conv output) and with the fp64 oracle."""
+    import stc_unet_b200 as S
+    from oracle import stc_oracle as O
+    from stc_unet_b200 import ops
+    bb, hd = build(True, 3, dtype)
+    g = torch.Generator().manual_seed(4)
+    for m in list(bb.modules()) + list(hd.modules()):      # non-trivial running statistics
+        if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+            m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.2)
+            m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) + 0.5)
+    bb.eval(); hd.eval()
+    img = torch.rand(2, 3, 64, 64, generator=g).cuda()
+    with torch.no_grad():
+        folded = hd(bb(img))
+        ops.config.fold_eval_bn = False
+        try:
+            plain = hd(bb(img))
+        finally:
+            ops.config.fold_eval_bn = True
+        bsd = {k: v.double() if v.is_floating_point() else v for k, v in bb.state_dict().items()}
+        hsd = {k: v.double() if v.is_floating_point() else v for k, v in hd.state_dict().items()}
+        ref = O.head_forward(hsd, O.backbone_forward(bsd, img.double(), False, None), False, None)
+    if dtype == "fp32":
+        assert rel_l2(folded, plain) <= 1e-5 and rel_l2(folded, ref) <= 1e-4
+    else:
+        assert rel_l2(folded, ref) <= max(2e-2, 1.25 * rel_l2(plain, ref))
+    assert float((folded.argmax(1) == ref.argmax(1)).float().mean()) >= (0.999 if dtype == "fp32" else 0.97)
