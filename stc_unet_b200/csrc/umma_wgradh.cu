@@ -9,7 +9,11 @@
 //       (r, s+1) of the same 64-channel chunk: the second 64-row atom is the same segment shifted by one pixel, i.e.
 //       LBO = 128 bytes (overlapping atoms), and tap s starts s * 128 bytes into the segment.  A segment therefore feeds
 //       all S taps of its filter row, and — rolling down the image — the R-1 following output rows as well.
-//   (for odd S the last pair's second atom is a dummy "tap S"; its rows are dropped by the epilogue)
+//   S is odd: the taps (r, 0..S-2) of a filter row pair up as above (S/2 MMAs per row); the LAST COLUMN s = S-1 pairs ACROSS filter rows:
+//   taps (r, S-1) and (r+1, S-1) read the segments of two consecutive input rows at the same pixel shift, i.e. LBO = one ring slot
+//   (17408 B).  The ring keeps a mirror copy of slot 0 behind its last slot so that "the next slot" is always 17408 B further on.
+//   Only an odd row count leaves one tap paired with a dummy (its 64 rows are dropped by the epilogue): 5 MMAs instead of 6 per pixel
+//   block for 3x3, 13 instead of 15 for 5x5, 25 instead of 28 for 7x7 (Cout = 64).
 // Accumulators (all taps of the CTA's filter-row group x 64 ci x BN co, fp32) stay in TMEM over the CTA's whole pixel
 // range and are red.add-ed into the [tap][ci][co] workspace once at the end.
 // A work item = (filter-row group, ci chunk, co tile, image n, column block, row range).
@@ -26,7 +30,7 @@ namespace stc {
 struct alignas(64) WgradHParams {
     CUtensorMap tmX;   // x  {Cin,  W, H, N}, box {64, 128+S-1, 1, 1}
     CUtensorMap tmDY;  // dy {Cout, W, H, N}, box {64, 128, 1, 1}
-    int H, W, R, S, SP, cin_chunks, BN, num_n_tiles;
+    int H, W, R, S, SPf, cin_chunks, BN, num_n_tiles;   // SPf = S / 2 full tap pairs per filter row
     int RG, num_groups;          // filter rows per group, number of groups
     int blocks_w, row_splits, rows_per_split;
     int num_items;
@@ -61,7 +65,7 @@ __device__ __forceinline__ WItem decode_item(const WgradHParams& p, int idx) {
 __global__ void __launch_bounds__(kWgradHThreads, 1) umma_wgradh_kernel(const __grid_constant__ WgradHParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const uint32_t a_bytes = (uint32_t)p.a_slots * p.a_slot_bytes;
+    const uint32_t a_bytes = (uint32_t)(p.a_slots + 1) * p.a_slot_bytes;   // ring + mirror of slot 0
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a_bytes + (size_t)p.b_stages * p.b_stage_bytes);
     // bars: a_full[a_slots], a_empty[a_slots], b_full[b_stages], b_empty[b_stages], acc_full, acc_empty
     const int nb = 2 * p.a_slots + 2 * p.b_stages + 2;
@@ -111,8 +115,11 @@ __global__ void __launch_bounds__(kWgradHThreads, 1) umma_wgradh_kernel(const __
             for (int e = 0; e < count; ++e) {
                 ptx::mbar_wait(a_empty(slot), phase ^ 1);
                 if (ptx::elect_one_sync()) {
-                    ptx::mbar_arrive_expect_tx(a_full(slot), p.a_box_bytes);
+                    // slot 0 is loaded twice: in place and into the mirror behind the last ring slot (cross-row pairs starting in the last slot)
+                    ptx::mbar_arrive_expect_tx(a_full(slot), slot == 0 ? 2 * p.a_box_bytes : p.a_box_bytes);
                     ptx::tma_load_4d(smem_base + slot * p.a_slot_bytes, &p.tmX, a_full(slot), it.cc * 64, it.w0 - ps, first + e, it.n_img);
+                    if (slot == 0)
+                        ptx::tma_load_4d(smem_base + p.a_slots * p.a_slot_bytes, &p.tmX, a_full(slot), it.cc * 64, it.w0 - ps, first + e, it.n_img);
                 }
                 __syncwarp();
                 if (++slot == p.a_slots) { slot = 0; phase ^= 1; }
@@ -146,6 +153,7 @@ __global__ void __launch_bounds__(kWgradHThreads, 1) umma_wgradh_kernel(const __
         // MN-major SW128 descriptors (16 B units): SBO = 1024 B between 8-pixel groups, version 1, layout 2
         const uint64_t desc_common = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
         const uint64_t a_hi = desc_common | ((uint64_t)(128 >> 4) << 16);     // LBO = 128 B: second atom = next tap (one pixel on)
+        const uint64_t a_hi_row = desc_common | ((uint64_t)(p.a_slot_bytes >> 4) << 16);   // LBO = one slot: second atom = same tap, next input row
         const uint64_t b_hi = desc_common | ((uint64_t)(16384 >> 4) << 16);   // LBO = 16 KB between 64-wide co atoms
         const uint32_t a_slot16 = p.a_slot_bytes >> 4, b_stage16 = p.b_stage_bytes >> 4;
         const uint32_t a_base16 = (smem_base >> 4) & 0x3FFF, b_base16 = (b_base >> 4) & 0x3FFF;
@@ -173,14 +181,27 @@ __global__ void __launch_bounds__(kWgradHThreads, 1) umma_wgradh_kernel(const __
                         int sl = a_head + rr;
                         if (sl >= p.a_slots) sl -= p.a_slots;
                         const uint32_t seg16 = a_base16 + sl * a_slot16;
-                        for (int sp = 0; sp < p.SP; ++sp) {
+                        for (int sp = 0; sp < p.SPf; ++sp) {
                             const uint64_t a_desc0 = a_hi | (uint64_t)(seg16 + sp * 16);   // tap s = 2*sp starts 2*sp*128 B in
-                            const uint32_t d_addr = (uint32_t)((rr * p.SP + sp) * p.BN);
+                            const uint32_t d_addr = (uint32_t)((rr * p.SPf + sp) * p.BN);
                             ptx::mma_bf16_ss(d_addr, a_desc0, b_desc0, p.idesc, acc_flag);
 #pragma unroll
                             for (int ks = 1; ks < 8; ++ks)   // K step = 16 pixels = 2048 B = 128 units
                                 ptx::mma_bf16_ss(d_addr, a_desc0 + (uint64_t)(ks * 128), b_desc0 + (uint64_t)(ks * 128), p.idesc, 1u);
                         }
+                    }
+                    // last filter column: rows (2j, 2j+1) share one MMA (second atom = the next ring slot, or the mirror of slot 0 behind
+                    // the last one); a leftover row pairs with the dummy tap S of its own segment
+                    for (int j = 0; 2 * j < it.rg; ++j) {
+                        int sl = a_head + 2 * j;
+                        if (sl >= p.a_slots) sl -= p.a_slots;
+                        const uint64_t hi = (2 * j + 1 < it.rg) ? a_hi_row : a_hi;
+                        const uint64_t a_desc0 = hi | (uint64_t)(a_base16 + sl * a_slot16 + (p.S - 1) * 8);   // tap S-1 starts (S-1)*128 B in
+                        const uint32_t d_addr = (uint32_t)((it.rg * p.SPf + j) * p.BN);
+                        ptx::mma_bf16_ss(d_addr, a_desc0, b_desc0, p.idesc, acc_flag);
+#pragma unroll
+                        for (int ks = 1; ks < 8; ++ks)
+                            ptx::mma_bf16_ss(d_addr, a_desc0 + (uint64_t)(ks * 128), b_desc0 + (uint64_t)(ks * 128), p.idesc, 1u);
                     }
                     ptx::tc_commit(b_empty(bstage));
                     ptx::tc_commit(a_empty(a_head));   // x row h + r0 - pr is not read by later output rows
@@ -212,13 +233,16 @@ __global__ void __launch_bounds__(kWgradHThreads, 1) umma_wgradh_kernel(const __
             WItem it = decode_item(p, item);
             ptx::mbar_wait(acc_full, acc_phase);
             ptx::tc_fence_after();
-            for (int rr = 0; rr < it.rg; ++rr) {
-                for (int sp = 0; sp < p.SP; ++sp) {
-                    const int s = 2 * sp + (row >> 6);
-                    const bool valid = s < p.S;
-                    const int tap = (it.r0 + rr) * p.S + s;
+            const int n_full = it.rg * p.SPf, n_slots = n_full + (it.rg + 1) / 2;
+            {
+                for (int qs = 0; qs < n_slots; ++qs) {
+                    int rr, s;
+                    if (qs < n_full) { rr = qs / p.SPf; s = 2 * (qs - rr * p.SPf) + (row >> 6); }      // taps (rr, 2sp) | (rr, 2sp+1)
+                    else { rr = 2 * (qs - n_full) + (row >> 6); s = p.S - 1; }                         // taps (2j, S-1) | (2j+1, S-1)
+                    const bool valid = rr < it.rg;
+                    const int tap = (it.r0 + (valid ? rr : 0)) * p.S + s;
                     float* o = p.ws + ((long long)tap * p.Cin + it.cc * 64 + (row & 63)) * p.Cout + it.nt * p.BN;
-                    const uint32_t t_addr = (uint32_t)((rr * p.SP + sp) * p.BN) + ((uint32_t)(q * 32) << 16);
+                    const uint32_t t_addr = (uint32_t)(qs * p.BN) + ((uint32_t)(q * 32) << 16);
                     for (int c = 0; c < p.BN; c += 32) {
                         uint32_t v[32];
                         ptx::tmem_ld_32x32(t_addr + c, v);
@@ -261,9 +285,11 @@ int conv_wgrad_wgradh(const void* x, const void* dy, float* ws, int N, int H, in
     memset(&p, 0, sizeof(p));
     // BN = 128 when possible (measured 5-40 % faster than 64 on the Cout >= 128 layers: fewer, longer MMAs per dy tile)
     { const char* e = getenv("STC_WGRADH_BN"); p.BN = (Cout % 128 == 0 && !(e && atoi(e) == 64)) ? 128 : 64; }
-    p.SP = (S + 1) / 2;
-    p.RG = 512 / (p.SP * p.BN);
-    if (p.RG > R) p.RG = R;
+    p.SPf = S / 2;
+    // rows per group: as many as fit the 512 TMEM columns; a group of rg rows needs rg * (S/2) + ceil(rg / 2) accumulators of BN columns
+    p.RG = 0;
+    for (int rg = R; rg >= 1; --rg)
+        if ((rg * p.SPf + (rg + 1) / 2) * p.BN <= 512) { p.RG = rg; break; }
     STC_REQUIRE(p.RG >= 1, "conv_wgrad_wgradh: no plan");
     p.num_groups = (R + p.RG - 1) / p.RG;
     const int bwh = 128 + S - 1;
@@ -300,7 +326,7 @@ int conv_wgrad_wgradh(const void* x, const void* dy, float* ws, int N, int H, in
     p.b_stages = p.BN == 64 ? 4 : 3;
     p.idesc = make_idesc_bf16(128, p.BN, 1, 1);
     p.ws = ws;
-    size_t smem = (size_t)p.a_slots * p.a_slot_bytes + (size_t)p.b_stages * p.b_stage_bytes + (2 * p.a_slots + 2 * p.b_stages + 2) * 8 + 16 + 1024;
+    size_t smem = (size_t)(p.a_slots + 1) * p.a_slot_bytes + (size_t)p.b_stages * p.b_stage_bytes + (2 * p.a_slots + 2 * p.b_stages + 2) * 8 + 16 + 1024;
     STC_REQUIRE(smem <= 227 * 1024, "conv_wgrad_wgradh: smem %zu", smem);
     static bool attr_set[64] = {false};
     int dev = 0;
