@@ -15,6 +15,15 @@ def conv(ci, co, hw, k, N=16, wgrad=False):
         else: ops.conv_fprop(x, wp, None, None, co, k, k)
     torch.cuda.synchronize()
 conv(64, 64, 512, 7); conv(64, 64, 512, 3); conv(64, 64, 512, 7, wgrad=True); conv(512, 512, 64, 1); conv(512, 512, 64, 1, wgrad=True)
+conv(128, 128, 256, 7); conv(128, 128, 256, 3, wgrad=True)      # level 2: N = 128 (the shared-memory bound of N = 64 is gone)
+def conv_stats(ci, co, hw, k, N=16):                                # conv + BN statistics out of the epilogue (stc_conv_fprop_bnstats)
+    x = torch.randn(N, hw, hw, ci, device=dev).to(BF)
+    w = torch.randn(co, ci, k, k, device=dev) / (ci * k * k) ** 0.5
+    wp = ops.pack_weight(w, BF)
+    for _ in range(2):
+        ops.conv_fprop_bnstats(x, wp, None, co, k, k)
+    torch.cuda.synchronize()
+conv_stats(64, 64, 512, 7)
 L, hd, B = 4096, 256, 32
 q = torch.randn(B, L, hd, device=dev).to(BF); kk = torch.randn(B, L, hd, device=dev).to(BF); sc = torch.empty(B, L, L, device=dev, dtype=BF)
 for _ in range(2):
