@@ -212,6 +212,9 @@ int stc_upcat_apply_bwd(const void* dout, const void* dyhw, void* dskip, void* d
 /* torch.cat([a, b], dim=1) on NHWC rows (UpConvBlock.forward, mmseg/models/utils/up_conv_block.py:99; FCNHead concat_input,
  * fcn_head.py:81) and its adjoint (a or b may be NULL to drop that half). */
 int stc_concat_channels(const void* a, const void* b, void* out, long long P, int Ca, int Cb, int dtype, void* stream);
+/* y[p][0:Cdst) = x[p][0:min(Csrc,Cdst)), zeros beyond Csrc (both multiples of 8): widens the 16 / 32-channel layers of UNet++'s decoder
+ * (smp DecoderBlock, decoder_channels (256,128,64,32,16)) to the tensor-core kernels' 64-channel K chunks, and narrows the result back. */
+int stc_resize_channels(const void* x, void* y, long long P, int Csrc, int Cdst, int dtype, void* stream);
 int stc_split_channels(const void* cat, void* a, void* b, long long P, int Ca, int Cb, int dtype, void* stream);
 
 /* UNet++ DecoderBlock input (segmentation_models_pytorch 0.2.0, used by decode_heads/unetpp_head.py:16): out = cat([in0', in1, .., in4])

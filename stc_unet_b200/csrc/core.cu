@@ -664,6 +664,37 @@ extern "C" int stc_pack_conv_weights_batched(const int64_t* table, const int64_t
 }
 
 // ------------------------------------------------------------------------------------
+// channel padding: y[p][0:Cdst) = x[p][0:min(Csrc, Cdst)), zero beyond Csrc.  Narrow layers (16 / 32 channels: UNet++'s decoder tail)
+// are widened to the 64-channel granularity of the tcgen05 kernels' K chunks instead of falling back to the SIMT engine.
+// ------------------------------------------------------------------------------------
+template <typename T>
+__global__ void resize_channels_kernel(const T* __restrict__ x, T* __restrict__ y, int Csrc, int Cdst, long long total) {
+    const int ld = Cdst >> 3, ls = Csrc >> 3;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        const int lv = (int)(i % ld);
+        const long long p = i / ld;
+        Vec8<T> v;
+        if (lv < ls) v.load(x + p * Csrc + lv * 8);
+        else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v.v[k] = 0.f;
+        }
+        v.store(y + i * 8);
+    }
+}
+
+extern "C" int stc_resize_channels(const void* x, void* y, long long P, int Csrc, int Cdst, int dtype, void* stream) {
+    STC_REQUIRE(Csrc > 0 && Cdst > 0 && Csrc % 8 == 0 && Cdst % 8 == 0, "resize_channels: channel counts must be multiples of 8 (%d -> %d)", Csrc, Cdst);
+    const long long total = P * (Cdst / 8);
+    if (total <= 0) return STC_OK;
+    int blocks = (int)min((long long)num_sms() * 8, (long long)ceil_div(total, 256));
+    STC_DISPATCH_DTYPE(dtype, (resize_channels_kernel<T><<<blocks, 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, Csrc, Cdst, total)));
+    return check_launch("resize_channels");
+}
+
+// ------------------------------------------------------------------------------------
 // channel concat / split on NHWC rows: out[p] = [a[p] (Ca) | b[p] (Cb)]   (UpConvBlock.forward's torch.cat, up_conv_block.py:99)
 // ------------------------------------------------------------------------------------
 template <typename T, bool SPLIT>

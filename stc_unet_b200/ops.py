@@ -25,6 +25,7 @@ class _Config:
     fold_linear_pairs = True        # bf16 + tcgen05: q/k/v + in_proj and fc1 + fc2 of TransformerLayer run as folded GEMMs
     ksa_lazy_df = True              # KSA branch gradients are consumed implicitly by the BN backward kernels (no df tensors)
     fold_eval_bn = True             # inference: eval-mode BN folded into the conv weights, activation in the conv epilogue
+    widen_narrow_convs = True       # bf16: 16 / 32-channel layers are zero-padded to the tcgen05 kernels' channel granularity
 
 
 config = _Config()
@@ -289,8 +290,41 @@ def _wgrad_ws(n, device):
     return torch.zeros(n, dtype=torch.float32, device=device)
 
 
+def _resize_c(x: torch.Tensor, C: int) -> torch.Tensor:
+    """(..., Cx) -> (..., C): zero-padded or truncated along the channel dimension (stc_resize_channels)."""
+    Cx = x.shape[-1]
+    if Cx == C:
+        return x
+    y = torch.empty((*x.shape[:-1], C), dtype=x.dtype, device=x.device)
+    lib.call("stc_resize_channels", x, y, x.numel() // Cx, Cx, C, dtype_code(x.dtype), stream_ptr())
+    return y
+
+
+def _widen(Cin: int, Cout: int, dtype, wgrad: bool, macs: float = 0.0):
+    """Channel counts the tcgen05 kernels take (K chunks of 64 input channels; 32-multiples of output channels, 64 for wgrad) when a narrow
+    bf16 layer (>= 8 channels, at most 4x padding, at least 1 GMAC - the tiny CoordAtt convs stay on the SIMT engine) would otherwise
+    run on the SIMT engine; None if no widening applies."""
+    if dtype != torch.bfloat16 or config.engine == _lib.ENGINE_SIMT or not config.widen_narrow_convs or macs < 1e9:
+        return None
+    co_q = 64 if wgrad else 32
+    Cip, Cop = (Cin + 63) // 64 * 64, (Cout + co_q - 1) // co_q * co_q
+    if (Cip == Cin and Cop == Cout) or Cin % 8 or Cout % 8 or Cip > 4 * Cin or Cop > 4 * Cout:
+        return None
+    return Cip, Cop
+
+
 def conv_fprop(x, wp, bias, residual, Cout: int, R: int, S: int, act: int = 0) -> torch.Tensor:
     N, H, W, Cin = x.shape
+    wide = _widen(Cin, Cout, x.dtype, False, float(N) * H * W * Cin * Cout * R * S) if residual is None else None
+    if wide is not None:     # zero-padded channels change nothing in the sums; the padded outputs are dropped again
+        Cip, Cop = wide
+        wpp = torch.zeros((R * S, Cop, Cip), dtype=wp.dtype, device=wp.device)
+        wpp[:, :Cout, :Cin] = wp.view(R * S, Cout, Cin)
+        bp = None
+        if bias is not None:
+            bp = torch.zeros(Cop, dtype=torch.float32, device=x.device)
+            bp[:Cout] = bias
+        return _resize_c(conv_fprop(_resize_c(x, Cip), wpp, bp, None, Cop, R, S, act), Cout)
     y = torch.empty((N, H, W, Cout), dtype=x.dtype, device=x.device)
     _dense("conv_fprop", 2.0 * N * H * W * Cin * Cout * R * S,
            lambda: lib.call("stc_conv_fprop", x, wp, bias, residual, y, N, H, W, Cin, Cout, R, S, act, dtype_code(x.dtype),
@@ -313,6 +347,14 @@ def conv_fprop_bnstats(x, wp, bias, Cout: int, R: int, S: int):
 def conv_wgrad(x, dy, R: int, S: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     N, H, W, Cin = x.shape
     Cout = dy.shape[-1]
+    wide = _widen(Cin, Cout, x.dtype, True, float(N) * H * W * Cin * Cout * R * S)
+    if wide is not None:
+        Cip, Cop = wide
+        full = conv_wgrad(_resize_c(x, Cip), _resize_c(dy, Cop), R, S)          # (Cop, Cip, R, S)
+        if out is None:
+            out = torch.empty((Cout, Cin, R, S), dtype=torch.float32, device=x.device)
+        out.copy_(full[:Cout, :Cin])
+        return out
     ws = _wgrad_ws(R * S * Cin * Cout, x.device)
     _dense("conv_wgrad", 2.0 * N * H * W * Cin * Cout * R * S,
            lambda: lib.call("stc_conv_wgrad", x, dy, ws, N, H, W, Cin, Cout, R, S, dtype_code(x.dtype), config.engine, stream_ptr()))

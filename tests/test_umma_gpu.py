@@ -276,3 +276,28 @@ def test_conv_bnstats_fused_tcgen05(tc, shape):
     assert rel_l2(ref, exact) < 1e-6
     assert rel_l2(sums, exact) < 1e-5
     assert float((sums[:Cout] - exact[:Cout]).abs().max()) < 1e-4 * P ** 0.5 * float(yd.abs().max())
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16, 512, 512, 3), (1, 32, 16, 500, 520, 3), (1, 64, 16, 256, 512, 3), (1, 16, 64, 250, 520, 3), (2, 32, 160, 128, 128, 3),
+                                   (2, 32, 32, 200, 128, 5)])    # >= 1 GMAC each (smaller layers stay on the SIMT engine by design)
+def test_narrow_convs_widened_onto_tcgen05(shape):
+    """16 / 32-channel layers (UNet++ decoder tail) run on the tcgen05 kernels through zero-padded channels: fprop, dgrad and wgrad
+    against fp64 on the bf16-rounded operands, and the engine really is a tensor-core one."""
+    import stc_unet_b200 as S
+    from stc_unet_b200 import ops
+    N, Cin, Cout, H, W, k = shape
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = bf16_round(torch.randn(N, Cin, H, W, device=dev(), generator=g)).requires_grad_(True)
+    w = bf16_round(torch.randn(Cout, Cin, k, k, device=dev(), generator=g) / math.sqrt(Cin * k * k)).requires_grad_(True)
+    b = torch.randn(Cout, device=dev(), generator=g)
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=k // 2)
+    dy = bf16_round(torch.randn(N, Cout, H, W, device=dev(), generator=g))
+    ref.backward(dy.double())
+    y = ops.conv_fprop(nhwc(x.detach()).to(BF), ops.pack_weight(w.detach(), BF), b, None, Cout, k, k)
+    assert S._lib.lib.raw("stc_dense_last_engine")() in (2, 3)          # tcgen05 per-tap or halo kernel, not SIMT
+    assert y.shape == (N, H, W, Cout) and rel_l2(nchw(y.float()), ref) < 6e-3
+    dx = ops.conv_fprop(nhwc(dy).to(BF), ops.pack_weight(w.detach(), BF, transpose_flip=True), None, None, Cin, k, k)
+    assert rel_l2(nchw(dx.float()), x.grad) < 6e-3
+    dw = ops.conv_wgrad(nhwc(x.detach()).to(BF), nhwc(dy).to(BF), k, k)
+    assert S._lib.lib.raw("stc_dense_last_engine")() in (2, 4)
+    assert dw.shape == (Cout, Cin, k, k) and rel_l2(dw, w.grad) < 3e-3
