@@ -59,6 +59,14 @@ int stc_nchw_to_nhwc(const float* src, void* dst, int N, int C, int H, int W, in
 int stc_image_u8_to_nhwc(const uint8_t* src, void* dst, const float* mean, const float* inv_std, long long P, int C, int Cpad, int swap_rb,
                          int dtype, void* stream);
 int stc_widen_u8_i64(const uint8_t* src, int64_t* dst, long long n, void* stream);
+/* The geometric part of the training pipeline on the device as well (my_config/STC-UNet.py:31-37: RandomCrop -> RandomFlip(horizontal) ->
+ * Normalize -> Pad; transforms.py RandomCrop :599-614, RandomFlip :347-380): src = N decoded 8-bit images (Hs x Ws x C), geom = N x {y0, x0,
+ * flip} (int32, device; drawn on the host exactly like RandomCrop.get_crop_bbox / RandomFlip), dst = N x H x W x Cpad normalised
+ * activations; output pixels beyond the cropped source get pad_val (images) / seg_pad_val (labels). */
+int stc_image_u8_crop_flip_to_nhwc(const uint8_t* src, void* dst, const int* geom, const float* mean, const float* inv_std, int N, int Hs, int Ws,
+                                   int H, int W, int C, int Cpad, int swap_rb, float pad_val, int dtype, void* stream);
+int stc_label_u8_crop_flip_i64(const uint8_t* src, int64_t* dst, const int* geom, int N, int Hs, int Ws, int H, int W, int seg_pad_val,
+                               void* stream);
 /* Conv2d.weight (Cout,Cin,R,S) fp32 -> packed [R*S][Cout][CinPad] `dtype` (K-major per tap).
  * transpose_flip != 0 packs the dgrad operand: [(R-1-r)*S+(S-1-s)][Cin][CoutPad] = W[co][ci][r][s]. */
 int stc_pack_conv_weight(const float* w, void* dst, int Cout, int Cin, int R, int S, int inner_pad,

@@ -103,6 +103,67 @@ extern "C" int stc_image_u8_to_nhwc(const uint8_t* src, void* dst, const float* 
     return check_launch("image_u8_to_nhwc");
 }
 
+// RandomCrop -> RandomFlip(horizontal) -> Normalize(to_rgb) -> Pad of the training pipeline (my_config/STC-UNet.py:31-37;
+// mmseg/datasets/pipelines/transforms.py RandomCrop.crop :610-614, RandomFlip :347-380, Normalize, Pad) on the device, for a batch of
+// decoded 8-bit HWC images.  geom[n] = {y0, x0, flip}: the crop window starts at (y0, x0) of source image n (the host draws the offsets
+// exactly as RandomCrop.get_crop_bbox does), is then mirrored horizontally when flip != 0; pixels of the H x W output that fall outside
+// the source (the Pad step) get pad_val.  One thread per output pixel.
+template <typename T>
+__global__ void image_u8_crop_flip_kernel(const uint8_t* __restrict__ src, T* __restrict__ dst, const int* __restrict__ geom,
+                                          const float* __restrict__ mean, const float* __restrict__ inv_std, int Hs, int Ws, int H, int W, int C,
+                                          int Cpad, int swap_rb, float pad_val, long long total) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int x = (int)(i % W);
+        const int y = (int)((i / W) % H);
+        const long long n = i / ((long long)W * H);
+        const int y0 = geom[3 * n], x0 = geom[3 * n + 1], flip = geom[3 * n + 2];
+        const int ch = min(H, Hs - y0), cw = min(W, Ws - x0);          // size of the cropped image (before the Pad step)
+        const int xs = flip ? cw - 1 - x : x;                          // the flip mirrors the CROPPED image
+        const bool inside = y < ch && x < cw;
+        const uint8_t* sp = src + ((n * Hs + (y0 + y)) * (long long)Ws + (x0 + xs)) * C;
+        for (int c = 0; c < Cpad; ++c) {
+            float v = 0.f;
+            if (c < C) v = inside ? ((float)sp[swap_rb ? C - 1 - c : c] - mean[c]) * inv_std[c] : pad_val;   // Pad comes AFTER Normalize
+            stf(dst + i * Cpad + c, v);
+        }
+    }
+}
+
+__global__ void label_u8_crop_flip_kernel(const uint8_t* __restrict__ src, int64_t* __restrict__ dst, const int* __restrict__ geom, int Hs, int Ws,
+                                          int H, int W, int seg_pad_val, long long total) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int x = (int)(i % W);
+        const int y = (int)((i / W) % H);
+        const long long n = i / ((long long)W * H);
+        const int y0 = geom[3 * n], x0 = geom[3 * n + 1], flip = geom[3 * n + 2];
+        const int ch = min(H, Hs - y0), cw = min(W, Ws - x0);
+        const int xs = flip ? cw - 1 - x : x;
+        dst[i] = (y < ch && x < cw) ? (int64_t)src[(n * Hs + (y0 + y)) * (long long)Ws + (x0 + xs)] : (int64_t)seg_pad_val;
+    }
+}
+
+extern "C" int stc_image_u8_crop_flip_to_nhwc(const uint8_t* src, void* dst, const int* geom, const float* mean, const float* inv_std, int N, int Hs,
+                                              int Ws, int H, int W, int C, int Cpad, int swap_rb, float pad_val, int dtype, void* stream) {
+    STC_REQUIRE(src && dst && geom && mean && inv_std && C >= 1 && C <= 4 && Cpad >= C && N > 0 && Hs > 0 && Ws > 0 && H > 0 && W > 0,
+                "image_u8_crop_flip_to_nhwc: bad arguments");
+    const long long total = (long long)N * H * W;
+    int blocks = (int)min((long long)num_sms() * 16, (long long)ceil_div(total, 256));
+    STC_DISPATCH_DTYPE(dtype, (image_u8_crop_flip_kernel<T><<<blocks, 256, 0, (cudaStream_t)stream>>>(src, (T*)dst, geom, mean, inv_std, Hs, Ws, H, W, C,
+                                                                                                    Cpad, swap_rb, pad_val, total)));
+    return check_launch("image_u8_crop_flip_to_nhwc");
+}
+
+extern "C" int stc_label_u8_crop_flip_i64(const uint8_t* src, int64_t* dst, const int* geom, int N, int Hs, int Ws, int H, int W, int seg_pad_val,
+                                          void* stream) {
+    STC_REQUIRE(src && dst && geom && N > 0 && Hs > 0 && Ws > 0 && H > 0 && W > 0, "label_u8_crop_flip_i64: bad arguments");
+    const long long total = (long long)N * H * W;
+    int blocks = (int)min((long long)num_sms() * 16, (long long)ceil_div(total, 256));
+    label_u8_crop_flip_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, geom, Hs, Ws, H, W, seg_pad_val, total);
+    return check_launch("label_u8_crop_flip_i64");
+}
+
 // 8-bit label maps (as stored in the annotation PNGs) -> the int64 maps the loss / histogram kernels index with
 __global__ void widen_u8_i64_kernel(const uint8_t* __restrict__ src, int64_t* __restrict__ dst, long long n) {
     const long long stride = (long long)gridDim.x * blockDim.x;

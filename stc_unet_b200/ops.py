@@ -1296,6 +1296,8 @@ def image_to_nhwc(img: torch.Tensor, dtype: torch.dtype, norm_cfg: Optional[dict
     """Module input -> NHWC activations.  float (N,C,H,W): the reference's interface (already normalised by its CPU pipeline).
     uint8 (N,H,W,C): decoded pixels straight from the loader; `norm_cfg = dict(mean, std, to_rgb)` (the config's img_norm_cfg,
     my_config/STC-UNet.py:35) is applied on the device."""
+    if getattr(img, "_stc_nhwc", False):     # already normalised NHWC activations (augment_batch_u8)
+        return _chk(img) if img.dtype == dtype else _chk(img.to(dtype))
     if img.dtype == torch.uint8:
         img = _chk(img)
         if img.dim() != 4 or img.shape[-1] > 4:
@@ -1312,6 +1314,43 @@ def image_to_nhwc(img: torch.Tensor, dtype: torch.dtype, norm_cfg: Optional[dict
     out = torch.empty((N, H, W, C), dtype=dtype, device=img.device)
     lib.call("stc_nchw_to_nhwc", img, out, N, C, H, W, C, dtype_code(dtype), stream_ptr())
     return out
+
+
+def draw_crop_flip(n: int, src_hw, crop_hw, flip_prob: float = 0.5, rng=None) -> torch.Tensor:
+    """(n, 3) int32 {y0, x0, flip} drawn on the host the way the reference pipeline does it per image: RandomCrop.get_crop_bbox
+    (transforms.py:599-608: offsets uniform in [0, margin]) and RandomFlip (`np.random.rand() < prob`, :358-360)."""
+    import numpy as np
+    rng = rng or np.random
+    mh, mw = max(src_hw[0] - crop_hw[0], 0), max(src_hw[1] - crop_hw[1], 0)
+    g = np.empty((n, 3), dtype=np.int32)
+    for i in range(n):
+        g[i, 0] = rng.randint(0, mh + 1)
+        g[i, 1] = rng.randint(0, mw + 1)
+        g[i, 2] = 1 if rng.rand() < flip_prob else 0
+    return torch.from_numpy(g)
+
+
+def augment_batch_u8(img_u8: torch.Tensor, label_u8: Optional[torch.Tensor], geom: torch.Tensor, crop_hw, dtype: torch.dtype,
+                     norm_cfg: Optional[dict] = None, pad_val: float = 0.0, seg_pad_val: int = 255):
+    """RandomCrop -> RandomFlip -> Normalize -> Pad of the training pipeline on the device.  img_u8 (N, Hs, Ws, C) uint8,
+    label_u8 (N, Hs, Ws) uint8 or None, geom (N, 3) int32 from draw_crop_flip.  Returns NHWC activations (N, H, W, C) in `dtype` - which the
+    backbone takes as they are - and int64 labels (N, 1, H, W)."""
+    img_u8 = _chk(img_u8)
+    N, Hs, Ws, C = img_u8.shape
+    H, W = crop_hw
+    geom = geom.to(device=img_u8.device, dtype=torch.int32).contiguous()
+    cfg = norm_cfg or {}
+    mean, inv_std = _norm_vectors(img_u8.device, C, cfg.get("mean", [0.0]), cfg.get("std", [1.0]))
+    out = torch.empty((N, H, W, C), dtype=dtype, device=img_u8.device)
+    lib.call("stc_image_u8_crop_flip_to_nhwc", img_u8, out, geom, mean, inv_std, N, Hs, Ws, H, W, C, C, int(bool(cfg.get("to_rgb", False))),
+             float(pad_val), dtype_code(dtype), stream_ptr())
+    out._stc_nhwc = True        # image_to_nhwc (the backbones' first step) passes it through
+    lab = None
+    if label_u8 is not None:
+        label_u8 = _chk(label_u8)
+        lab = torch.empty((N, 1, H, W), dtype=torch.int64, device=img_u8.device)
+        lib.call("stc_label_u8_crop_flip_i64", label_u8, lab, geom, N, Hs, Ws, H, W, int(seg_pad_val), stream_ptr())
+    return out, lab
 
 
 def labels_to_int64(label: torch.Tensor) -> torch.Tensor:

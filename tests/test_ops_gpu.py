@@ -613,3 +613,39 @@ def test_peer_exchange_kernels_single_rank(S):
         lib.call("stc_peer_allreduce_arena_f32", ctypes.addressof(aptr), ctypes.addressof(cptr), 0, 1, max_n, a, b - a, scale, seqa, ctas, stream_ptr())
         assert torch.equal(arena, ref)
     assert seqa.tolist() == [9] * ctas
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_device_crop_flip_pad_matches_numpy_pipeline(S, dt):
+    """RandomCrop -> RandomFlip(horizontal) -> Normalize(to_rgb) -> Pad(pad_val=0, seg_pad_val=255) on the device against the same steps in
+    numpy (the reference pipeline's arithmetic, transforms.py:599-614 / :347-380), with source images both larger (600x600, as
+    Resize(img_scale=(600,600)) gives) and smaller than the 512x512 crop (so the Pad step matters); labels bit-exact."""
+    import numpy as np
+    from stc_unet_b200 import ops
+    rng = np.random.RandomState(0)
+    for (Hs, Ws), (H, W) in (((600, 600), (512, 512)), ((40, 70), (64, 64)), ((64, 64), (64, 64))):
+        N = 3
+        img = rng.randint(0, 256, (N, Hs, Ws, 3)).astype(np.uint8)
+        lab = rng.randint(0, 3, (N, Hs, Ws)).astype(np.uint8)
+        geom = ops.draw_crop_flip(N, (Hs, Ws), (H, W), 0.5, rng)
+        geom[0, 2], geom[1, 2] = 1, 0        # both flip states present
+        mean, std = np.array([10.0, 20.0, 30.0]), np.array([50.0, 60.0, 70.0])
+        out, lb = ops.augment_batch_u8(torch.from_numpy(img).cuda(), torch.from_numpy(lab).cuda(), geom, (H, W), dt,
+                                       dict(mean=mean.tolist(), std=std.tolist(), to_rgb=True), pad_val=0, seg_pad_val=255)
+        assert out.shape == (N, H, W, 3) and lb.shape == (N, 1, H, W) and lb.dtype == torch.int64
+        for n in range(N):
+            y0, x0, flip = (int(v) for v in geom[n])
+            ci, cl = img[n, y0:y0 + H, x0:x0 + W], lab[n, y0:y0 + H, x0:x0 + W]          # RandomCrop.crop
+            if flip:
+                ci, cl = ci[:, ::-1], cl[:, ::-1]                                            # mmcv.imflip horizontal
+            ci = (ci[..., ::-1].astype(np.float64) - mean) / std                             # Normalize with to_rgb
+            pi = np.zeros((H, W, 3))                          # Pad(pad_val=0) comes AFTER Normalize in the reference: padded pixels are exactly 0
+            pl = np.full((H, W), 255, dtype=np.int64)
+            pi[:ci.shape[0], :ci.shape[1]] = ci
+            pl[:cl.shape[0], :cl.shape[1]] = cl
+            got = out[n].float().cpu().numpy()
+            inside = np.zeros((H, W), dtype=bool); inside[:ci.shape[0], :ci.shape[1]] = True
+            tol_ = 1e-5 if dt == torch.float32 else 2e-2
+            assert np.abs(got[inside] - pi[inside]).max() <= tol_ * max(1.0, np.abs(pi).max())
+            assert not (~inside).any() or np.abs(got[~inside]).max() == 0.0
+            assert np.array_equal(lb[n, 0].cpu().numpy(), pl)
