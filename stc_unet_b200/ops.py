@@ -26,6 +26,10 @@ class _Config:
     ksa_lazy_df = True              # KSA branch gradients are consumed implicitly by the BN backward kernels (no df tensors)
     fold_eval_bn = True             # inference: eval-mode BN folded into the conv weights, activation in the conv epilogue
     widen_narrow_convs = True       # bf16: 16 / 32-channel layers are zero-padded to the tcgen05 kernels' channel granularity
+    # Inference with FROZEN weights (a deployed checkpoint): keep the folded / packed bf16 operands between forwards instead of rebuilding
+    # them every call.  Opt-in, because nothing can observe a raw-pointer update of a parameter (our fused Adam, load_checkpoint's in-place
+    # copy through .data): call ops.invalidate_weight_caches() after changing weights, or leave this off.
+    cache_eval_weights = False
 
 
 config = _Config()
@@ -265,6 +269,15 @@ def set_step_cache(c: Optional[StepCache]):
     _STEP_CACHE = c
 
 
+_INFER_PACK_CACHE: dict = {}
+
+
+def invalidate_weight_caches():
+    """Drops the inference-time operand caches (config.cache_eval_weights)."""
+    _INFER_PACK_CACHE.clear()
+    _EVAL_FOLD_CACHE.clear()
+
+
 def pack_weight(w: torch.Tensor, dtype: torch.dtype, transpose_flip: bool = False, im2col_pad: int = 0, cache: bool = True) -> torch.Tensor:
     """Conv2d.weight (Cout,Cin,R,S) fp32 -> packed `dtype` operand: [R*S][Cout][Cin] (fprop), [R*S][Cin][Cout] with flipped
     taps (dgrad, transpose_flip) or [1][Cout][im2col_pad] with k = tap*Cin + ci (im2col)."""
@@ -279,8 +292,18 @@ def pack_weight(w: torch.Tensor, dtype: torch.dtype, transpose_flip: bool = Fals
         hit = _STEP_CACHE.pack(w, dtype, mode, inner, shape_out)
         if hit is not None:
             return hit
+    infer_key = None
+    if cache and config.cache_eval_weights and not torch.is_grad_enabled():   # opt-in: the caller promises frozen weights (see _Config)
+        infer_key = (w.data_ptr(), w._version, tuple(w.shape), dtype, mode, inner)
+        hit = _INFER_PACK_CACHE.get(infer_key)
+        if hit is not None:
+            return hit
     out = torch.empty(shape_out, dtype=dtype, device=w.device)
     lib.call("stc_pack_conv_weight", w, out, Cout, Cin, R, S, inner, mode, dtype_code(dtype), stream_ptr())
+    if infer_key is not None:
+        if len(_INFER_PACK_CACHE) >= 2048:
+            _INFER_PACK_CACHE.clear()
+        _INFER_PACK_CACHE[infer_key] = out
     return out
 
 
@@ -496,6 +519,9 @@ def _im2col(x, R, S, Kpad=64):
     return out
 
 
+_EVAL_FOLD_CACHE: dict = {}     # (dtype, im2col, eps, (data_ptr, version) of every tensor involved) -> (packed folded weight, folded bias)
+
+
 class _ConvBnAct(Function):
     @staticmethod
     def forward(ctx, x, weight, bias, gamma, beta, bn: BNState, act: int, pobjs):
@@ -506,13 +532,25 @@ class _ConvBnAct(Function):
         ctx.im2col = _use_im2col(x, weight)
         if not bn.training and not torch.is_grad_enabled() and config.fold_eval_bn:
             # inference: BN folded into the conv's weights / bias, activation in the conv epilogue - one pass instead of three
-            wf = torch.empty_like(weight)
-            bf = torch.empty(Cout, dtype=torch.float32, device=x.device)
-            lib.call("stc_bn_fold_conv", weight, bias, gamma, beta, bn.running_mean, bn.running_var, float(bn.eps), wf, bf, Cout, Cin * R * S,
-                     stream_ptr())
+            # the folded + packed operand only changes when a parameter / running statistic does: cached on their version counters
+            ts = (weight, gamma, beta, bn.running_mean, bn.running_var) + ((bias,) if bias is not None else ())
+            key = (x.dtype, ctx.im2col, float(bn.eps)) + tuple((t.data_ptr(), t._version) for t in ts)
+            hit = _EVAL_FOLD_CACHE.get(key) if config.cache_eval_weights else None
+            if hit is None:
+                wf = torch.empty_like(weight)
+                bf = torch.empty(Cout, dtype=torch.float32, device=x.device)
+                lib.call("stc_bn_fold_conv", weight, bias, gamma, beta, bn.running_mean, bn.running_var, float(bn.eps), wf, bf, Cout, Cin * R * S,
+                         stream_ptr())
+                wp = pack_weight(wf, x.dtype, im2col_pad=64, cache=False) if ctx.im2col else pack_weight(wf, x.dtype, cache=False)
+                hit = (wp, bf)
+                if config.cache_eval_weights:
+                    if len(_EVAL_FOLD_CACHE) >= 1024:
+                        _EVAL_FOLD_CACHE.clear()
+                    _EVAL_FOLD_CACHE[key] = hit
+            wp, bf = hit
             if ctx.im2col:
-                return conv_fprop(_im2col(x, R, S), pack_weight(wf, x.dtype, im2col_pad=64, cache=False), bf, None, Cout, 1, 1, act)
-            return conv_fprop(x, pack_weight(wf, x.dtype, cache=False), bf, None, Cout, R, S, act)
+                return conv_fprop(_im2col(x, R, S), wp, bf, None, Cout, 1, 1, act)
+            return conv_fprop(x, wp, bf, None, Cout, R, S, act)
         if ctx.im2col:
             x = _im2col(x, R, S)          # (N,H,W,64): saved instead of the 3-channel image for the wgrad GEMM
             wp = pack_weight(weight, x.dtype, im2col_pad=64)

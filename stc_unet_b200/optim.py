@@ -81,6 +81,7 @@ class AdamB200(torch.optim.Optimizer):
         for a, b, t in runs:
             lib.call("stc_adam_step", self.flat.flat[a:], self.arena.flat[a:], self.exp_avg[a:], self.exp_avg_sq[a:], b - a, float(g["lr"]),
                      float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]), t, stream_ptr())
+        ops.invalidate_weight_caches()
         return loss
 
     def state_dict(self):
@@ -188,4 +189,5 @@ def load_checkpoint(model, filename: str, map_location="cpu", strict: bool = Fal
         for k, v in sd.items():
             if k in own and k not in mismatched:
                 own[k].copy_(v)
+    ops.invalidate_weight_caches()
     return ckpt

@@ -209,6 +209,7 @@ class Trainer:
             ops.set_peer_exchange(None)
             self.arena.prezeroed = False
         self.steps_done += 1
+        ops.invalidate_weight_caches()      # the fused Adam moved the weights through raw pointers
         return out["log_vars"]
 
     # ---- whole-step CUDA graph: ~1000 launches replayed as one graph (no tracing compiler involved: the kernels are ours) ----
@@ -254,4 +255,5 @@ class Trainer:
         self.optim.t += 1
         self.optim._t_on_dev = self.optim.t
         self.steps_done += 1
+        ops.invalidate_weight_caches()
         return self._static_out

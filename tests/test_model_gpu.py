@@ -490,3 +490,27 @@ def test_eval_bn_folding_matches_unfolded(dtype):
     else:
         assert rel_l2(folded, ref) <= max(2e-2, 1.25 * rel_l2(plain, ref))
     assert float((folded.argmax(1) == ref.argmax(1)).float().mean()) >= (0.999 if dtype == "fp32" else 0.97)
+
+
+def test_eval_weight_cache_is_opt_in_and_invalidated():
+    """config.cache_eval_weights keeps folded / packed operands between no-grad forwards (frozen weights); it is off by default, and
+    after a weight change + ops.invalidate_weight_caches() the next forward sees the new weights."""
+    import stc_unet_b200 as S
+    from stc_unet_b200 import ops
+    assert ops.config.cache_eval_weights is False
+    bb, hd = build(True, 3, "bf16")      # STC-UNet: conv+BN layers (fold cache) and Linear / attention projections (pack cache)
+    bb.eval(); hd.eval()
+    img = torch.rand(1, 3, 64, 64, generator=torch.Generator().manual_seed(2)).cuda()
+    ops.config.cache_eval_weights = True
+    try:
+        with torch.no_grad():
+            a = hd(bb(img))
+            b = hd(bb(img))                       # served from the caches
+            assert torch.equal(a, b) and len(ops._EVAL_FOLD_CACHE) > 0 and len(ops._INFER_PACK_CACHE) > 0
+            bb.inc.conv.conv[0].weight.data.mul_(1.5)     # raw .data update: invisible to version counters
+            ops.invalidate_weight_caches()
+            c = hd(bb(img))
+            assert not torch.equal(a, c)
+    finally:
+        ops.config.cache_eval_weights = False
+        ops.invalidate_weight_caches()

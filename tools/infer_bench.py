@@ -22,6 +22,7 @@ tcfg = dict(mode="slide", crop_size=(256, 256), stride=(170, 170), max_windows_p
 seg = S.EncoderDecoder(bcfg, hcfg, test_cfg=tcfg).to(dev)
 seg.backbone.init_weights(); seg.decode_head.init_weights()
 seg.eval()
+S.ops.config.cache_eval_weights = True      # deployed checkpoint: weights are frozen, keep the folded / packed operands between forwards
 seg.backbone.img_norm_cfg = dict(mean=[0.0], std=[255.0], to_rgb=False)     # uint8 HWC slices, normalised on the device
 g = torch.Generator().manual_seed(5)
 h_vol = torch.randint(0, 256, (args.slices, 512, 512, 3), dtype=torch.uint8, generator=g).pin_memory()
