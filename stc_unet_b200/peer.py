@@ -85,3 +85,11 @@ def try_create(device: torch.device, group=None) -> Optional[PeerExchange]:
         import sys
         print(f"stc_unet_b200: peer-memory exchange unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
         return None
+
+
+def agree(px, device: torch.device, group=None):
+    """All ranks use the peer-memory exchanges or none does: a rank whose rendezvous failed would otherwise issue NCCL calls that its
+    peers never match.  One small all-reduce at start-up; returns `px` when every rank has one, else None."""
+    flag = torch.tensor([1 if px is not None else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    return px if int(flag) == 1 else None

@@ -174,7 +174,7 @@ class Trainer:
         self.flat = FlatParams(params)
         self.flat.broadcast(0)
         # N > 1: SyncBN statistics and gradient buckets travel through NVLink peer memory with our own kernels (no NCCL inside the step)
-        self.peer = peer_mod.try_create(self.flat.flat.device) if _dist_on() else None
+        self.peer = peer_mod.agree(peer_mod.try_create(self.flat.flat.device), self.flat.flat.device) if _dist_on() else None
         self.arena = ops.GradArena(self.flat.params, alloc=self.peer.alloc_arena if self.peer is not None else None)
         self.reducer = GradReducer(self.arena, bucket_mb, peer=self.peer)
         self.optim = FusedAdam(self.flat, self.arena, lr=lr, betas=betas)

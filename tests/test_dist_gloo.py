@@ -50,7 +50,12 @@ def _worker(rank, world, port, q):
         for (a, b, _) in buckets:
             dist.all_reduce(flat[a:b]); flat[a:b] /= world
         ok_ar = torch.allclose(flat, torch.full((tot,), (1 + world) / 2))
-        q.put((rank, bool(ok_bn), bool(ok_bwd), bool(ok_lv), bool(ok_ar)))
+        # peer-exchange agreement: all ranks or none (a CPU "device" can never rendezvous symmetric memory -> try_create gives None)
+        from stc_unet_b200 import peer as peer_mod
+        cpu = torch.device("cpu")
+        ok_peer = peer_mod.agree(object() if rank == 0 else None, cpu) is None and peer_mod.agree(object(), cpu) is not None \
+            and peer_mod.try_create(cpu) is None
+        q.put((rank, bool(ok_bn), bool(ok_bwd), bool(ok_lv), bool(ok_ar), bool(ok_peer)))
     finally:
         dist.destroy_process_group()
 

@@ -1,4 +1,6 @@
-"""Times individual bandwidth-bound C-ABI calls at their heaviest in-step shapes (STC-UNet, N=16, 512x512, bf16): CUDA events, 5 reps
+"""ncu: BW_MICRO_REPS=1 ncu --set full --clock-control none -k regex:"bn_|softmax|add_n|ksa_|cls_|colsum" -c 40 ... (bound the launch count: a
+full replay of every repetition does not fit a few GPU-minutes).
+Times individual bandwidth-bound C-ABI calls at their heaviest in-step shapes (STC-UNet, N=16, 512x512, bf16): CUDA events, 5 reps
 after warm-up, a 512 MB write between reps so nothing is served from L2.  Prints ms and algorithmic GB/s per call."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -12,7 +14,11 @@ flush = torch.empty(256 << 20, dtype=torch.float32, device=dev)
 only = os.environ.get("ONLY")
 
 
-def timeit(name, gbytes, fn, reps=5):
+REPS = int(os.environ.get("BW_MICRO_REPS", "5"))     # under `ncu --set full` use BW_MICRO_REPS=1 (every launch is replayed ~40 times)
+
+
+def timeit(name, gbytes, fn, reps=None):
+    reps = reps or REPS
     if only and only not in name:
         return
     fn(); torch.cuda.synchronize()
