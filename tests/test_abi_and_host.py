@@ -164,3 +164,33 @@ def test_checkpoint_round_trip_uses_the_reference_layout(tmp_path):
 def OrderedDictPrefix(sd, prefix):
     from collections import OrderedDict
     return OrderedDict((prefix + k, v) for k, v in sd.items())
+
+
+def test_step_cache_record_finalize_layout_on_cpu():
+    """StepCache host logic without a GPU: a recorded step's packs get 16-byte aligned slots in ONE arena in first-use order (so q/k/v packs
+    are equally spaced - what the batched folded-weight products rely on), the batched-pack table carries {src ptr, dst offset, shape, mode},
+    work-item prefix sums are dense, and wgrad workspaces are handed out in recorded order from one zero-able arena."""
+    from stc_unet_b200 import ops
+    c = ops.StepCache()
+    c.begin_step()
+    assert c.mode == "record"
+    ws_ = [torch.randn(512, 512, 1, 1) for _ in range(3)] + [torch.randn(64, 3, 3, 3), torch.randn(30, 64, 3, 3)]
+    shapes = []
+    for w in ws_[:3]:
+        assert c.pack(w, torch.bfloat16, 0, 512, (1, 512, 512)) is None
+        shapes.append((1, 512, 512))
+    assert c.pack(ws_[3], torch.bfloat16, 2, 64, (1, 64, 64)) is None            # im2col pack of the image conv
+    assert c.pack(ws_[4], torch.bfloat16, 1, 30, (9, 64, 30)) is None            # dgrad orientation, odd Cout
+    assert c.pack(ws_[0], torch.bfloat16, 0, 512, (1, 512, 512)) is None and len(c.order) == 5   # asked twice, recorded once
+    for n in (9 * 64 * 30, 512 * 1536, 7):
+        assert c.workspace(n, torch.device("cpu")).numel() == n
+    c.mode = "record"
+    c._finalize()
+    table, prefix = c.table.tolist(), c.prefix.tolist()
+    assert [r[0] for r in table] == [w.data_ptr() for w in ws_]
+    offs = [r[1] for r in table]
+    assert all(o % 8 == 0 for o in offs) and offs[1] - offs[0] == offs[2] - offs[1] == 512 * 512      # 16 B aligned, q/k/v equally spaced
+    assert [r[7] for r in table] == [0, 0, 0, 2, 1]
+    assert prefix == [0, 262144, 524288, 786432, 786432 + 64 * 64, 786432 + 64 * 64 + 30 * 64] and c.total == prefix[-1]
+    assert c.ws_off == [0, 9 * 64 * 30, 9 * 64 * 30 + 512 * 1536, 9 * 64 * 30 + 512 * 1536 + 8]
+    assert c.arena.numel() >= offs[-1] + 9 * 64 * 30 and c.ws_arena.numel() == c.ws_off[-1]
