@@ -194,3 +194,27 @@ def test_step_cache_record_finalize_layout_on_cpu():
     assert prefix == [0, 262144, 524288, 786432, 786432 + 64 * 64, 786432 + 64 * 64 + 30 * 64] and c.total == prefix[-1]
     assert c.ws_off == [0, 9 * 64 * 30, 9 * 64 * 30 + 512 * 1536, 9 * 64 * 30 + 512 * 1536 + 8]
     assert c.arena.numel() >= offs[-1] + 9 * 64 * 30 and c.ws_arena.numel() == c.ws_off[-1]
+
+
+def test_widen_rule_and_crop_flip_draws():
+    """Pure host logic: (1) which narrow bf16 convs are zero-padded onto the tensor-core kernels (ops._widen), (2) draw_crop_flip consumes the
+    random stream exactly like the reference pipeline does per image - RandomCrop.get_crop_bbox (transforms.py:599-608: randint(0, margin_h+1),
+    randint(0, margin_w+1)) followed by RandomFlip (np.random.rand() < prob)."""
+    import numpy as np
+    from stc_unet_b200 import ops
+    bf, G = torch.bfloat16, 2e9
+    assert ops._widen(16, 16, bf, False, G) == (64, 32)            # UNet++ x_0_4: K chunk of 64 input channels, N tile of 32
+    assert ops._widen(576, 32, bf, True, G) == (576, 64)           # wgrad needs 64-multiples on both sides
+    assert ops._widen(32, 576, bf, False, G) == (64, 576)
+    assert ops._widen(64, 64, bf, False, G) is None                # already eligible
+    assert ops._widen(16, 16, bf, False, 1e8) is None              # tiny layers (CoordAtt) stay on the SIMT engine
+    assert ops._widen(16, 16, torch.float32, False, G) is None     # fp32 parity path is never touched
+    assert ops._widen(8, 64, bf, False, G) is None                 # > 4x padding
+    assert ops._widen(20, 64, bf, False, G) is None                # not a multiple of 8
+    rs_a, rs_b = np.random.RandomState(7), np.random.RandomState(7)
+    g = ops.draw_crop_flip(5, (600, 600), (512, 512), 0.5, rs_a).numpy()
+    for i in range(5):
+        assert g[i, 0] == rs_b.randint(0, 89) and g[i, 1] == rs_b.randint(0, 89) and g[i, 2] == int(rs_b.rand() < 0.5)
+    assert g[:, :2].min() >= 0 and g[:, :2].max() <= 88
+    small = ops.draw_crop_flip(4, (40, 70), (64, 64), 1.0, np.random.RandomState(1)).numpy()
+    assert (small[:, 0] == 0).all() and (small[:, 1] <= 6).all() and (small[:, 2] == 1).all()      # no vertical margin; always flipped
