@@ -331,9 +331,14 @@ int stc_adam_step_dev(float* p, const float* g, float* m, float* v, long long n,
  * directly, so the whole step can be one CUDA graph.  *_ptrs: `world` device pointers (as integers, HOST array) to every rank's copy of
  * a symmetric buffer, own rank included.  Control block: stc_peer_ctrl_bytes(max_n, ctas) bytes, zeroed once before the first use.
  * seq: DEVICE counters (1 for the small exchange, `ctas` for the arena exchange), zero-initialised, private to this rank.
- * All ranks must issue the same sequence of calls.  A peer that does not arrive within ~15 s makes the kernel trap. */
+ * All ranks must issue the same sequence of calls.  Every wait for a peer is bounded in wall-clock time (stc_peer_configure; default
+ * 10 minutes, like NCCL's watchdog): when it runs out the kernel writes 1 to the configured error flag and returns (it does not trap, so
+ * the CUDA context survives and the host can raise). */
 #define STC_PEER_MAX 16
 long long stc_peer_ctrl_bytes(int max_n, int ctas);
+/* timeout_ms: bound of one cross-rank wait.  err_flag: int the kernels can write and the host can read without synchronising (pinned,
+ * device-mapped host memory), or NULL.  Process-wide (one process drives one GPU, SURVEY 8b threading model). */
+int stc_peer_configure(long long timeout_ms, int* err_flag);
 /* out[i] = sum over ranks of in[i] (fp64, n <= max_n), summed in rank order: identical on every rank. */
 int stc_peer_allreduce_small_f64(const unsigned long long* ctrl_ptrs, int rank, int world, int max_n, const double* in, double* out, int n,
                                  unsigned long long* seq, void* stream);

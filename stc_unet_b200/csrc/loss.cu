@@ -342,34 +342,103 @@ __global__ void argmax_kernel(const float* __restrict__ preds, const float* __re
 }
 
 // ---------------------------------------------------------------- confusion matrix / area histograms
-__global__ void __launch_bounds__(256) confusion_hist_kernel(const int64_t* __restrict__ pred, const void* __restrict__ label, int label_u8,
-                                                             long long n, int C, int ignore, unsigned long long* __restrict__ cm,
-                                                             unsigned long long* __restrict__ areas) {
-    __shared__ unsigned int s_cm[kMaxCls * kMaxCls];
-    __shared__ unsigned int s_ar[3 * kMaxCls];
-    for (int i = threadIdx.x; i < C * C; i += blockDim.x) s_cm[i] = 0;
-    for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) s_ar[i] = 0;
+// ONE shared-memory counter update per pixel: the (C+1) x (C+1) matrix M[y'][p'] with y' / p' = the class, or C when the label / the
+// prediction is outside [0, C) (ignored pixels are skipped).  Everything metrics.py:75-87 asks for is a marginal of M:
+//   cm[y][p] = M[y][p] (y, p < C) | area_label[c] = sum_p' M[c][p'] | area_pred[c] = sum_y' M[y'][c] | area_intersect[c] = M[c][c].
+// Counters are PRIVATE PER WARP and the lanes of a warp that hit the same bin are combined first (__match_any_sync: one
+// leader adds the population count), so the C = 3 case - at most 16 live bins - never serialises 32 lanes on one address.
+// Loads: a warp iteration covers 256 consecutive pixels; a lane reads 4 pixel pairs as 16-byte (two int64 predictions) and 2-byte
+// (two uint8 labels) vectors, consecutive lanes consecutive vectors.  Algorithmic traffic 9 B/pixel (int64 pred + uint8 label).
+constexpr int kHistWarps = 8;
+constexpr int kHistPrivBins = 1536;     // (C+1)^2 up to here: one matrix per warp (48 KB); above: one per CTA; above kHistBlockBins: global
+constexpr int kHistBlockBins = 16384;
+
+__device__ __forceinline__ void hist_add(unsigned int* h, int bin, int lane) {
+    const unsigned peers = __match_any_sync(0xffffffffu, bin);
+    if (bin >= 0 && lane == __ffs(peers) - 1) atomicAdd(h + bin, (unsigned)__popc(peers));
+}
+
+// mode 0: per-warp matrices in shared memory; 1: one matrix per CTA; 2: cm by global atomics, only the 3*C area counters in shared memory
+template <bool VEC, bool L8>
+__global__ void __launch_bounds__(kHistWarps * 32) confusion_hist_kernel(const int64_t* __restrict__ pred, const void* __restrict__ label, long long n,
+                                                                        int C, int ignore, int mode, unsigned long long* __restrict__ cm,
+                                                                        unsigned long long* __restrict__ areas) {
+    extern __shared__ unsigned int s_hist[];
+    const int B = C + 1, BB = B * B;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int copies = mode == 0 ? kHistWarps : 1;
+    const int words = mode == 2 ? 3 * C : copies * BB;
+    for (int i = threadIdx.x; i < words; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
+    unsigned int* mine = s_hist + (mode == 0 ? warp * BB : 0);
     const uint8_t* l8 = reinterpret_cast<const uint8_t*>(label);
     const int64_t* l64 = reinterpret_cast<const int64_t*>(label);
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        long long y = label_u8 ? (long long)l8[i] : l64[i];
-        if (y == ignore) continue;
-        long long p = pred[i];
-        bool yin = y >= 0 && y < C, pin = p >= 0 && p < C;
-        if (yin) atomicAdd(&s_ar[2 * C + (int)y], 1u);            // area_label
-        if (pin) atomicAdd(&s_ar[C + (int)p], 1u);                // area_pred_label
-        if (pin && p == y) atomicAdd(&s_ar[(int)p], 1u);          // area_intersect
-        if (yin && pin) atomicAdd(&s_cm[(int)y * C + (int)p], 1u);
+    auto count = [&](long long y, long long p) {     // executed by all 32 lanes (bin = -1: nothing to count)
+        const bool live = y != (long long)ignore && y != -(1LL << 62);
+        const int yy = (y >= 0 && y < C) ? (int)y : C, pp = (p >= 0 && p < C) ? (int)p : C;
+        if (mode != 2) {
+            hist_add(mine, live ? yy * B + pp : -1, lane);
+        } else if (live) {
+            if (yy < C) atomicAdd(s_hist + 2 * C + yy, 1u);
+            if (pp < C) atomicAdd(s_hist + C + pp, 1u);
+            if (pp < C && pp == yy) atomicAdd(s_hist + pp, 1u);
+            if (yy < C && pp < C && cm) atomicAdd(cm + (size_t)yy * C + pp, 1ull);
+        }
+    };
+    const long long kSkip = -(1LL << 62);             // marks a lane position past the end
+    const long long warps_total = (long long)gridDim.x * kHistWarps, wid = (long long)blockIdx.x * kHistWarps + warp;
+    for (long long base = wid * 256; base < n; base += warps_total * 256) {     // trip count is uniform across the warp
+        if (VEC && base + 256 <= n) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const long long i = base + j * 64 + 2 * lane;
+                const longlong2 pv = *reinterpret_cast<const longlong2*>(pred + i);
+                long long y0, y1;
+                if (L8) { const uchar2 lv = *reinterpret_cast<const uchar2*>(l8 + i); y0 = lv.x; y1 = lv.y; }
+                else { const longlong2 lv = *reinterpret_cast<const longlong2*>(l64 + i); y0 = lv.x; y1 = lv.y; }
+                count(y0, pv.x);
+                count(y1, pv.y);
+            }
+        } else {
+#pragma unroll 1
+            for (int j = 0; j < 8; ++j) {
+                const long long i = base + j * 32 + lane;
+                const bool in = i < n;
+                const long long y = in ? (L8 ? (long long)l8[i] : l64[i]) : kSkip;
+                const long long p = in ? pred[i] : 0;
+                count(y, p);
+            }
+        }
+    }
+    __syncthreads();
+    if (mode == 2) {
+        if (areas)
+            for (int c = threadIdx.x; c < C; c += blockDim.x) {
+                const unsigned long long I = s_hist[c], Pp = s_hist[C + c], Ll = s_hist[2 * C + c];
+                if (I) atomicAdd(areas + c, I);
+                if (Pp + Ll - I) atomicAdd(areas + C + c, Pp + Ll - I);
+                if (Pp) atomicAdd(areas + 2 * C + c, Pp);
+                if (Ll) atomicAdd(areas + 3 * C + c, Ll);
+            }
+        return;
+    }
+    // fold the per-warp copies into copy 0, then flush the marginals (global layout of areas: int64[4][C] = intersect, union, pred, label)
+    for (int i = threadIdx.x; i < BB; i += blockDim.x) {
+        unsigned int t = 0;
+        for (int w = 0; w < copies; ++w) t += s_hist[w * BB + i];
+        s_hist[i] = t;
     }
     __syncthreads();
     if (cm)
-        for (int i = threadIdx.x; i < C * C; i += blockDim.x)
-            if (s_cm[i]) atomicAdd(cm + i, (unsigned long long)s_cm[i]);
+        for (int i = threadIdx.x; i < C * C; i += blockDim.x) {
+            const unsigned int v = s_hist[(i / C) * B + (i % C)];
+            if (v) atomicAdd(cm + i, (unsigned long long)v);
+        }
     if (areas)
         for (int c = threadIdx.x; c < C; c += blockDim.x) {
-            // global layout int64[4][C] = intersect, union, pred, label; union is linear in the other three
-            unsigned long long I = s_ar[c], Pp = s_ar[C + c], Ll = s_ar[2 * C + c];
+            unsigned long long Ll = 0, Pp = 0;
+            for (int k = 0; k < B; ++k) { Ll += s_hist[c * B + k]; Pp += s_hist[k * B + c]; }
+            const unsigned long long I = s_hist[c * B + c];
             if (I) atomicAdd(areas + c, I);
             if (Pp + Ll - I) atomicAdd(areas + C + c, Pp + Ll - I);
             if (Pp) atomicAdd(areas + 2 * C + c, Pp);
@@ -466,11 +535,23 @@ extern "C" int stc_argmax(const float* preds, const float* count, int64_t* pred,
 
 extern "C" int stc_confusion_hist(const int64_t* pred, const void* label, int label_is_u8, long long n, int C, int ignore_index,
                                   int64_t* cm, int64_t* areas, void* stream) {
-    STC_REQUIRE(C >= 1 && C <= kMaxCls, "confusion_hist: C=%d must be in [1,%d]", C, kMaxCls);
+    STC_REQUIRE(C >= 1 && C <= 4096, "confusion_hist: C=%d must be in [1,4096]", C);
     if (n <= 0) return STC_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    int blocks = (int)max(1LL, min((long long)num_sms() * 4, (long long)ceil_div(n, 256 * 8)));
-    confusion_hist_kernel<<<blocks, 256, 0, st>>>(pred, label, label_is_u8, n, C, ignore_index, (unsigned long long*)cm,
-                                                   (unsigned long long*)areas);
+    const int BB = (C + 1) * (C + 1);
+    const int mode = BB <= kHistPrivBins ? 0 : (BB <= kHistBlockBins ? 1 : 2);
+    const size_t smem = sizeof(unsigned int) * (mode == 0 ? (size_t)kHistWarps * BB : (mode == 1 ? (size_t)BB : (size_t)3 * C));
+    // vector path: 16-byte prediction pairs and 2-byte (or 16-byte) label pairs must be aligned; a warp iteration is 256 pixels
+    const bool vec = ((uintptr_t)pred & 15) == 0 && ((uintptr_t)label & (label_is_u8 ? 1 : 15)) == 0;
+    int blocks = (int)max(1LL, min((long long)num_sms() * 4, (long long)ceil_div(n, 256 * kHistWarps * 2)));
+    auto go = [&](auto kern) -> int {
+        if (smem > 48 * 1024) STC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<blocks, kHistWarps * 32, smem, st>>>(pred, label, n, C, ignore_index, mode, (unsigned long long*)cm, (unsigned long long*)areas);
+        return STC_OK;
+    };
+    int rc;
+    if (vec) rc = label_is_u8 ? go(confusion_hist_kernel<true, true>) : go(confusion_hist_kernel<true, false>);
+    else rc = label_is_u8 ? go(confusion_hist_kernel<false, true>) : go(confusion_hist_kernel<false, false>);
+    if (rc) return rc;
     return check_launch("confusion_hist");
 }

@@ -350,10 +350,32 @@ class BaseDecodeHead(BaseModule):
                 kind = type(ld).__name__
                 if kind not in ("CrossEntropyLoss", "DiceLoss"):
                     raise NotImplementedError(f"loss {kind} is not on the STC-UNet path")
+                _check_stock_loss(ld, kind, self.ignore_index)
                 val = ops.scale(fused["ce" if kind == "CrossEntropyLoss" else "dice"], getattr(ld, "loss_weight", 1.0))
             loss[ld.loss_name] = val if ld.loss_name not in loss else loss[ld.loss_name] + val
         loss["acc_seg"] = acc.detach()
         return loss
+
+
+def _check_stock_loss(ld, kind: str, ignore_index: int):
+    """A stock mmseg CrossEntropyLoss / DiceLoss object is only honoured when it is configured for exactly what the fused kernel
+    computes (cross_entropy_loss.py:186-297, dice_loss.py:50-137 defaults); any other setting must raise, never be silently ignored."""
+    bad = []
+    if getattr(ld, "class_weight", None) is not None:
+        bad.append("class_weight")
+    if getattr(ld, "reduction", "mean") != "mean":
+        bad.append("reduction")
+    if kind == "CrossEntropyLoss":
+        bad += [k for k in ("use_sigmoid", "use_mask", "avg_non_ignore") if getattr(ld, k, False)]
+    else:
+        if getattr(ld, "smooth", 1) != 1:
+            bad.append("smooth")
+        if getattr(ld, "exponent", 2) != 2:
+            bad.append("exponent")
+        if getattr(ld, "ignore_index", ignore_index) != ignore_index:
+            bad.append("ignore_index")
+    if bad:
+        raise NotImplementedError(f"{kind} with non-default {', '.join(bad)} is not computed by the fused CE/Dice kernel of stc_unet_b200")
 
 
 @HEADS.register_module()

@@ -78,6 +78,20 @@ class GradArena:
         self.flat = alloc(total) if alloc is not None else torch.zeros(total, dtype=torch.float32, device=dev)
         self.total = total
         self.prezeroed = False     # Trainer zeroes the whole arena once per step (one memset) and sets this
+        self._claimed = set()      # parameters whose arena slice has been handed out during the CURRENT backward pass
+
+    def claim(self, p: torch.nn.Parameter) -> bool:
+        """True the first time `p` asks for its slice during one backward pass.  The set is emptied by a callback the autograd engine
+        runs when that pass ends, so the bookkeeping needs no cooperation from the training loop."""
+        if not self._claimed:
+            try:
+                torch.autograd.Variable._execution_engine.queue_callback(self._claimed.clear)
+            except RuntimeError:      # not inside a backward pass (a Function.backward called by hand): nothing to track
+                return True
+        if id(p) in self._claimed:
+            return False
+        self._claimed.add(id(p))
+        return True
 
     def view(self, p: torch.nn.Parameter) -> Optional[torch.Tensor]:
         ent = self.offsets.get(id(p))
@@ -110,13 +124,21 @@ def set_grad_arena(arena: Optional[GradArena]):
 
 
 def _grad_buf(param, shape, device, zero=False) -> torch.Tensor:
-    """fp32 buffer that will become param.grad: a fresh view into the arena when one is active."""
+    """fp32 buffer that will become param.grad: the parameter's slice of the arena when one is active.
+
+    The slice is handed out only when nothing else lives in it: if param.grad already IS that slice (a second backward without
+    zero_grad: gradient accumulation, mmcv's GradientCumulativeOptimizerHook) or the parameter was already served during this
+    backward pass (a weight used twice in one graph), the kernel writes into a temporary instead and autograd ADDS it to the
+    accumulated gradient - overwriting the slice would turn g1 + g2 into 2 * g2."""
     if _ARENA is not None and param is not None:
         v = _ARENA.view(param)
         if v is not None:
-            if zero and not _ARENA.prezeroed:
-                v.zero_()
-            return v.view(shape)
+            g = param.grad
+            aliased = g is not None and g.data_ptr() == v.data_ptr()
+            if _ARENA.claim(param) and not aliased:
+                if zero and not _ARENA.prezeroed:
+                    v.zero_()
+                return v.view(shape)
     return (torch.zeros if zero else torch.empty)(shape, dtype=torch.float32, device=device)
 
 
@@ -506,6 +528,13 @@ def _bn_backward(y, dout, mean, invstd, gamma, beta, P, C, act, bn, count, pg, p
     return dy, dgamma, dbeta
 
 
+def _check_channels(x: torch.Tensor, Cin: int, what: str):
+    """The kernels take Cin from the activations: a layout mix-up (NHWC data read as NCHW, a wrong skip tensor) must raise, not read
+    the packed weights out of bounds."""
+    if x.dim() != 4 or x.shape[-1] != Cin:
+        raise RuntimeError(f"{what}: activations are {tuple(x.shape)} (N, H, W, C) but the weight expects {Cin} input channels")
+
+
 def _use_im2col(x, weight) -> bool:
     """Small-Cin convs (the image conv) go through im2col + a K=64 1x1 conv so they run on the tensor cores."""
     Cout, Cin, R, S = weight.shape
@@ -527,6 +556,7 @@ class _ConvBnAct(Function):
     def forward(ctx, x, weight, bias, gamma, beta, bn: BNState, act: int, pobjs):
         x = _chk(x)
         Cout, Cin, R, S = weight.shape
+        _check_channels(x, Cin, "conv_bn_act")
         N, H, W, _ = x.shape
         P = N * H * W
         ctx.im2col = _use_im2col(x, weight)
@@ -635,6 +665,7 @@ class _Conv(Function):
         if residual is not None:
             residual = _chk(residual)
         Cout, Cin, R, S = weight.shape
+        _check_channels(x, Cin, "conv2d / linear_tokens")
         ctx.im2col = _use_im2col(x, weight)
         if ctx.im2col:   # small-Cin conv (VGG16's first conv in UNet++): K=64 1x1 conv on the tensor cores
             x = _im2col(x, R, S)
@@ -1330,11 +1361,24 @@ def _norm_vectors(device, C, mean, std):
     return hit
 
 
+class NHWCImage(torch.Tensor):
+    """Already-normalised (N, H, W, C) activations (the output of augment_batch_u8).  The layout travels with the TYPE: a tensor
+    subclass survives clone() / to() / copy_() - which Trainer.capture / step_graph apply to their inputs - where a Python attribute
+    on the tensor object would be dropped silently and the NHWC data re-read as NCHW."""
+
+    @staticmethod
+    def wrap(t: torch.Tensor) -> "NHWCImage":
+        return t.as_subclass(NHWCImage)
+
+
 def image_to_nhwc(img: torch.Tensor, dtype: torch.dtype, norm_cfg: Optional[dict] = None) -> torch.Tensor:
     """Module input -> NHWC activations.  float (N,C,H,W): the reference's interface (already normalised by its CPU pipeline).
     uint8 (N,H,W,C): decoded pixels straight from the loader; `norm_cfg = dict(mean, std, to_rgb)` (the config's img_norm_cfg,
     my_config/STC-UNet.py:35) is applied on the device."""
-    if getattr(img, "_stc_nhwc", False):     # already normalised NHWC activations (augment_batch_u8)
+    if isinstance(img, NHWCImage):           # already normalised NHWC activations (augment_batch_u8)
+        img = img.as_subclass(torch.Tensor)
+        if img.dim() != 4:
+            raise ValueError(f"NHWCImage must be (N, H, W, C), got {tuple(img.shape)}")
         return _chk(img) if img.dtype == dtype else _chk(img.to(dtype))
     if img.dtype == torch.uint8:
         img = _chk(img)
@@ -1382,7 +1426,7 @@ def augment_batch_u8(img_u8: torch.Tensor, label_u8: Optional[torch.Tensor], geo
     out = torch.empty((N, H, W, C), dtype=dtype, device=img_u8.device)
     lib.call("stc_image_u8_crop_flip_to_nhwc", img_u8, out, geom, mean, inv_std, N, Hs, Ws, H, W, C, C, int(bool(cfg.get("to_rgb", False))),
              float(pad_val), dtype_code(dtype), stream_ptr())
-    out._stc_nhwc = True        # image_to_nhwc (the backbones' first step) passes it through
+    out = NHWCImage.wrap(out)   # image_to_nhwc (the backbones' first step) passes it through
     lab = None
     if label_u8 is not None:
         label_u8 = _chk(label_u8)

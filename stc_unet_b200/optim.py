@@ -48,6 +48,7 @@ class AdamB200(torch.optim.Optimizer):
     def zero_grad(self, set_to_none: bool = True):
         for p in self.flat.params:
             p.grad = None
+        self.arena._claimed.clear()
 
     @torch.no_grad()
     def step(self, closure=None):

@@ -38,8 +38,20 @@ class PeerExchange:
         self.seq_arena = torch.zeros(self.ctas, dtype=torch.int64, device=device)
         self.arena = None
         self.arena_ptrs = None
+        # cross-rank waits are bounded in wall-clock time (default 10 min, STC_PEER_TIMEOUT_MS); a wait that runs out raises this
+        # host-visible flag instead of trapping, and check() turns it into an exception on the host
+        self.err = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.timeout_ms = int(os.environ.get("STC_PEER_TIMEOUT_MS", "600000"))
+        lib.call("stc_peer_configure", self.timeout_ms, self.err)
         torch.cuda.synchronize(device)
         dist.barrier(group=self.group)          # every rank's control block is zeroed before anybody's first ticket can arrive
+
+    def check(self):
+        """Raises if a cross-rank wait timed out since the last check (reads pinned host memory: no synchronisation)."""
+        if int(self.err[0]) != 0:
+            raise RuntimeError(f"stc_unet_b200 peer exchange: a peer did not arrive within {self.timeout_ms} ms (rank {self.rank} of {self.world}); "
+                               "the step's results are invalid. Ranks must issue the same sequence of exchanges; barrier before re-entering "
+                               "the step after long rank-asymmetric work, or raise STC_PEER_TIMEOUT_MS.")
 
     def alloc_arena(self, numel: int) -> torch.Tensor:
         """fp32 gradient arena in symmetric memory (zeroed); one per PeerExchange."""

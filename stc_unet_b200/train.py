@@ -45,9 +45,14 @@ class FlatParams:
             p.data = view
         self.total = total
 
-    def broadcast(self, src: int = 0):
+    def broadcast(self, src: int = 0, buffers=()):
+        """Rank `src`'s parameters - and, once at start-up, the module buffers (BN running statistics), as DDP does at construction -
+        to every rank.  Afterwards the buffers stay identical by construction (every rank applies the same global SyncBN statistics;
+        the reference passes broadcast_buffers=False, mmseg/apis/train.py:112)."""
         if _dist_on():
             dist.broadcast(self.flat, src)
+            for b in buffers:
+                dist.broadcast(b, src)
 
 
 def plan_buckets(spans, total: int, cap_elems: int):
@@ -91,24 +96,39 @@ class GradReducer:
         self.handles = []
 
     def _on_grad(self, p):
+        g = p.grad
+        if g is not None:      # a gradient that is not the arena slice itself (foreign op, shared weight summed by autograd): copy it in
+            v = self.arena.view(p)
+            if g.data_ptr() != v.data_ptr():
+                v.copy_(g)
         if not self.enabled:
             return
         b = self.bucket_of[id(p)]
         self.pending[b] -= 1
         if self.pending[b] == 0:
-            start, end, _ = self.buckets[b]
-            ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream())
-            self.comm.wait_event(ev)
-            with torch.cuda.stream(self.comm):
-                if self.peer is not None:
-                    self.peer.allreduce_arena_(start, end, average=True)
-                else:
-                    self.handles.append(dist.all_reduce(self.arena.flat[start:end], op=dist.ReduceOp.AVG, async_op=True))
+            self._launch(b)
+
+    def _launch(self, b):
+        start, end, _ = self.buckets[b]
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self.comm.wait_event(ev)
+        with torch.cuda.stream(self.comm):
+            if self.peer is not None:
+                self.peer.allreduce_arena_(start, end, average=True)
+            else:
+                self.handles.append(dist.all_reduce(self.arena.flat[start:end], op=dist.ReduceOp.AVG, async_op=True))
+        self.pending[b] = -1      # launched
 
     def finish(self):
         if not self.enabled:
             return
+        # A bucket whose parameters did not all receive a gradient this step (an unused branch) never reached zero: reduce it now.
+        # Every rank runs the same graph, so every rank flushes the same buckets in the same order and the exchanges still pair up;
+        # the missing gradients are the zeros the step's memset left in the arena (DDP would raise for unused parameters instead).
+        for b in range(len(self.buckets)):
+            if self.pending[b] > 0:
+                self._launch(b)
         for h in self.handles:
             h.wait()
         torch.cuda.current_stream().wait_stream(self.comm)
@@ -172,7 +192,7 @@ class Trainer:
         self.model = segmentor
         params = [p for p in segmentor.parameters() if p.requires_grad]
         self.flat = FlatParams(params)
-        self.flat.broadcast(0)
+        self.flat.broadcast(0, buffers=[b for b in segmentor.buffers() if b.is_cuda])
         # N > 1: SyncBN statistics and gradient buckets travel through NVLink peer memory with our own kernels (no NCCL inside the step)
         self.peer = peer_mod.agree(peer_mod.try_create(self.flat.flat.device), self.flat.flat.device) if _dist_on() else None
         self.arena = ops.GradArena(self.flat.params, alloc=self.peer.alloc_arena if self.peer is not None else None)
@@ -187,11 +207,14 @@ class Trainer:
 
     def step(self, img: torch.Tensor, gt_semantic_seg: torch.Tensor, _device_adam: bool = False):
         """One training iteration; returns the (device) log-var tensors, no host sync."""
+        if self.peer is not None:
+            self.peer.check()                # a peer wait that timed out during an earlier step invalidated it: raise here, on the host
         ops.set_grad_arena(self.arena)
         ops.set_step_cache(self.cache)
         ops.set_peer_exchange(self.peer)
         try:
             self.optim.zero_grad()
+            self.arena._claimed.clear()      # (a backward pass that raised may have left its bookkeeping behind)
             self.arena.flat.zero_()          # one memset: kernels that accumulate (+=) into their gradient need zeros
             self.arena.prezeroed = True
             self.cache.begin_step()          # one batched weight-pack launch + one workspace memset (from step 2 on)
@@ -211,6 +234,15 @@ class Trainer:
         self.steps_done += 1
         ops.invalidate_weight_caches()      # the fused Adam moved the weights through raw pointers
         return out["log_vars"]
+
+    def resync(self):
+        """Call after long rank-asymmetric host work (rank-0 checkpointing / evaluation between epochs) before stepping again: the ranks
+        re-enter the step together instead of relying on the exchange kernels' wall-clock bound (STC_PEER_TIMEOUT_MS, default 10 min)."""
+        if _dist_on():
+            torch.cuda.synchronize()
+            dist.barrier()
+        if self.peer is not None:
+            self.peer.check()
 
     # ---- whole-step CUDA graph: ~1000 launches replayed as one graph (no tracing compiler involved: the kernels are ours) ----
     def capture(self, img: torch.Tensor, gt_semantic_seg: torch.Tensor):
@@ -248,6 +280,11 @@ class Trainer:
         """Replays the captured step on new data (host or device tensors; copied into the static input buffers)."""
         if self._graph is None:
             raise RuntimeError("Trainer.step_graph: call capture() first")
+        if self.peer is not None:
+            self.peer.check()
+        if tuple(img.shape) != tuple(self._static_img.shape) or img.dtype != self._static_img.dtype:
+            raise RuntimeError(f"Trainer.step_graph: captured for {tuple(self._static_img.shape)} {self._static_img.dtype}, got "
+                               f"{tuple(img.shape)} {img.dtype}")
         self._static_img.copy_(img, non_blocking=True)
         self._static_gt.copy_(gt_semantic_seg, non_blocking=True)
         self.optim.sync_device_state()

@@ -514,3 +514,229 @@ def test_eval_weight_cache_is_opt_in_and_invalidated():
     finally:
         ops.config.cache_eval_weights = False
         ops.invalidate_weight_caches()
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs[1] at its real spatial size: the path the headline number runs
+# ------------------------------------------------------------------------------------------------
+def _trainer_grads(bb, hd):
+    got = {("b", k): p.grad for k, p in bb.named_parameters()}
+    got.update({("h", k): p.grad for k, p in hd.named_parameters()})
+    return got
+
+
+@pytest.mark.parametrize("posbn", [True, False])
+def test_bf16_parity_config2_512(posbn):
+    """my_config/STC-UNet.py fwd+bwd in bf16 on 512x512 slices (N = 2 here; BASELINE.json configs[1] uses N = 16 of the same
+    shape), driven the way bench.py drives it: Trainer.step x 3 (StepCache record -> finalize -> replay) and then the captured
+    whole-step CUDA graph, against the oracle evaluated on the GPU in fp64 and - the reference's own bf16 path - under autocast.
+    At W >= 128 the convolutions run on the halo tcgen05 kernels (umma_convh / umma_wgradh), the 3x3 / 5x5 / 7x7 layers that
+    qualify get their BN statistics from the conv epilogue, the image conv runs through im2col: all asserted below."""
+    import stc_unet_b200 as S
+    from stc_unet_b200 import ops
+    from stc_unet_b200.train import Trainer
+    img, gt = inputs(2, 3, 512, 512)
+    bb0, hd0 = build(True, 3, "fp32", posbn=posbn)
+    ref64 = oracle(bb0, hd0, img, gt, torch.float64)
+    refac = oracle(bb0, hd0, img, gt, torch.float32, autocast=True)
+    torch.cuda.empty_cache()
+    # forward logits (train-mode BN) of the bf16 path
+    b1, h1 = build(True, 3, "bf16", posbn=posbn)
+    with torch.no_grad():
+        logits = h1(b1(img))
+    e_log, e_log_ac = rel_l2(logits, ref64["logits"]), rel_l2(refac["logits"], ref64["logits"])
+    assert e_log <= max(2e-2, 1.25 * e_log_ac), (e_log, e_log_ac)
+    if posbn:
+        assert e_log <= 2e-2, e_log
+        assert float((logits.argmax(1) == ref64["logits"].argmax(1)).float().mean()) >= 0.97
+    # the training step as the bench runs it
+    b2, h2 = build(True, 3, "bf16", posbn=posbn)
+    seg = S.EncoderDecoder(b2, h2).cuda().train()
+    tr = Trainer(seg, lr=0.0)
+    names, orig = [], S._lib.lib.call
+    prof = ops.LaunchProfiler(time_dense=True)
+    for it in range(3):
+        if it == 2:                                   # steady state (replay): record which kernels serve it
+            ops.set_profiler(prof)
+            inner = S._lib.lib.call
+            S._lib.lib.call = lambda name, *a, _i=inner: (names.append(name), _i(name, *a))[1]
+        lv = tr.step(img, gt)
+    ops.set_profiler(None)
+    if "call" in S._lib.lib.__dict__:
+        del S._lib.lib.__dict__["call"]
+    assert tr.cache.mode == "replay"
+    engines = {(kind, eng) for (kind, eng) in prof.summary()}
+    assert ("conv_fprop", 3) in engines, engines      # stc::umma_convh_kernel (halo fprop / dgrad)
+    assert ("conv_wgrad", 4) in engines, engines      # stc::umma_wgradh_kernel (halo wgrad)
+    assert ("gemm", 2) in engines, engines            # stc::umma_kernel (attention / folded linears)
+    assert "stc_conv_fprop_bnstats" in names and "stc_im2col" in names and "stc_pack_conv_weights_batched" in names
+    ref_loss = float(ref64["losses"]["loss_bce"] + ref64["losses"]["loss_dice"])
+    assert abs(float(lv["loss"]) - ref_loss) <= 2e-2 * max(1.0, abs(ref_loss))
+
+    def check(got, what):
+        e_ours, e_ac = grad_errors(dict(grads=got), ref64), grad_errors(refac, ref64)
+        med, med_ac = statistics.median(e_ours.values()), statistics.median(e_ac.values())
+        assert med <= max(2e-2, 1.25 * med_ac), (what, med, med_ac)
+        assert max(e_ours.values()) <= max(2e-2, 2.0 * max(e_ac.values())), (what, max(e_ours.values()), max(e_ac.values()))
+        if posbn:       # flip-free: the north-star bound itself on the bulk of the 242 gradients
+            assert med <= 2e-2, (what, med)
+    check(_trainer_grads(b2, h2), "eager replay")
+    # the captured graph on the same data: same gradients (lr = 0, so the weights have not moved)
+    tr.capture(img, gt)
+    lvg = tr.step_graph(img, gt)
+    torch.cuda.synchronize()
+    assert abs(float(lvg["loss"]) - ref_loss) <= 2e-2 * max(1.0, abs(ref_loss))
+    check({k: g.clone() for k, g in _trainer_grads(b2, h2).items()}, "cuda graph")
+    # running statistics after the steps: the first step's update is the oracle's (momentum 0.1 from the initial buffers)
+    b3, h3 = build(True, 3, "bf16", posbn=posbn)
+    h3.forward_train(b3(img), None, gt, None)
+    for mod, new in ((b3, ref64["new_b"]), (h3, ref64["new_h"])):
+        sd = mod.state_dict()
+        for k, v in new.items():
+            if k.endswith("num_batches_tracked"):
+                assert int(sd[k]) == int(v), k
+            else:
+                assert rel_l2(sd[k], v) <= 2e-2, (k, rel_l2(sd[k], v))
+
+
+def _set_posbn(*mods):
+    for mod in mods:
+        for m in mod.modules():
+            if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+                m.weight.data.fill_(0.25); m.bias.data.fill_(4.0)
+
+
+@pytest.mark.parametrize("upsample", ["InterpConv", "DeconvModule"])
+def test_family_b_flip_free_strict_gradients(upsample):
+    """Family B (mmseg UNet + FCNHead) in the flip-free configuration (every BN gamma = 0.25, beta = 4: all pre-activations
+    positive, so no ReLU decision can flip under rounding): EVERY fp32 parameter gradient within the north-star 1e-4."""
+    from oracle import stc_oracle as O
+    from tests.test_oracle import build_ours_b
+    bb, hd = build_ours_b(3, base=64, stages=4, dtype="fp32", upsample=upsample)
+    bb.init_weights(); hd.init_weights()
+    _set_posbn(bb, hd)
+    bb, hd = bb.cuda(), hd.cuda()
+    img, gt = inputs(2, 3, 64, 64)
+    conv = lambda v: v.detach().double() if v.is_floating_point() else v.detach().clone()
+    bsd = {k: conv(v).requires_grad_(v.is_floating_point() and "running" not in k) for k, v in bb.state_dict().items()}
+    hsd = {k: conv(v).requires_grad_(v.is_floating_point() and "running" not in k) for k, v in hd.state_dict().items()}
+    ref_logits = O.fcn_head_forward(hsd, O.unet_b_forward(bsd, img.double(), True, None), 3, True, None)
+    O.losses(ref_logits, gt)["loss_bce"].backward()
+    losses = hd.forward_train(bb(img), None, gt, None)
+    losses["loss_ce"].backward()
+    worst = 0.0
+    for mod, sd in ((bb, bsd), (hd, hsd)):
+        for name, p in mod.named_parameters():
+            g = sd[name].grad
+            if float(g.norm()) < 1e-12 * max(1.0, float(sd[name].detach().norm())):     # exactly-cancelled (bias into train-mode BN)
+                assert float(p.grad.abs().max()) <= 1e-6, name
+                continue
+            e = rel_l2(p.grad, g)
+            worst = max(worst, e)
+            assert e <= 1e-4, (name, e)
+    assert worst > 0.0
+
+
+def test_unetpp_flip_free_strict_gradients():
+    """UNet++ (config 5) with flip-free decoder BNs and large positive VGG biases (the encoder has no BN; bias 4 keeps every
+    encoder pre-activation positive): every fp32 gradient within 1e-4 of the (restated, UNPINNED) oracle."""
+    import stc_unet_b200 as S
+    from oracle import stc_oracle as O
+    torch.manual_seed(0)
+    seg = S.build_segmentor(dict(type="EncoderDecoderFull", decode_head=dict(
+        type="UnetPlusPlus", num_classes=2, norm_cfg=dict(type="BN", requires_grad=True), loss_decode=LOSS_CFG, dropout_ratio=0.0,
+        compute_dtype="fp32"))).cuda().train()
+    hd = seg.decode_head
+    _set_posbn(hd)
+    for m in hd.model.encoder.features:
+        if isinstance(m, torch.nn.Conv2d):
+            m.bias.data.fill_(4.0)
+    img, gt = inputs(2, 2, 64, 64)
+    conv = lambda v: v.detach().double() if v.is_floating_point() else v.detach().clone()
+    sd = {k: conv(v).requires_grad_(v.is_floating_point() and "running" not in k) for k, v in hd.state_dict().items()}
+    ref = O.losses(O.unetpp_forward(sd, img.double(), True, None), gt)
+    (ref["loss_bce"] + ref["loss_dice"]).backward()
+    out = seg.train_step(dict(img=img, img_metas=None, gt_semantic_seg=gt))
+    out["loss"].backward()
+    assert abs(float(out["loss"]) - float(ref["loss_bce"] + ref["loss_dice"])) <= 1e-5
+    for name, p in hd.named_parameters():
+        e = rel_l2(p.grad, sd[name].grad)
+        assert e <= 1e-4, (name, e)
+
+
+def test_gradient_accumulation_without_zero_grad():
+    """Two backward passes without zero_grad (mmcv's GradientCumulativeOptimizerHook) and a weight used twice in one graph must
+    ACCUMULATE, although every parameter gradient normally is a view into the flat arena our kernels overwrite."""
+    import stc_unet_b200 as S
+    from stc_unet_b200 import ops
+    bb, hd = build(False, 3, "fp32", posbn=True)
+    seg = S.EncoderDecoder(bb, hd).cuda().train()
+    params = [p for p in seg.parameters() if p.requires_grad]
+    img1, gt1 = inputs(2, 3, 32, 32)
+    g = torch.Generator().manual_seed(77)
+    img2 = torch.rand(2, 3, 32, 32, generator=g).cuda()
+    gt2 = torch.randint(0, 3, (2, 1, 32, 32), generator=g).cuda()
+
+    def grads_of(img, gt):
+        seg.zero_grad(set_to_none=True)
+        seg.train_step(dict(img=img, img_metas=None, gt_semantic_seg=gt))["loss"].backward()
+        return [p.grad.clone() for p in params]
+    g1, g2 = grads_of(img1, gt1), grads_of(img2, gt2)
+    arena = ops.GradArena(params)
+    ops.set_grad_arena(arena)
+    try:
+        seg.zero_grad(set_to_none=True)
+        seg.train_step(dict(img=img1, img_metas=None, gt_semantic_seg=gt1))["loss"].backward()
+        assert all(p.grad.data_ptr() == arena.view(p).data_ptr() for p in params)       # first pass: straight into the arena
+        seg.train_step(dict(img=img2, img_metas=None, gt_semantic_seg=gt2))["loss"].backward()
+        for p, a, b in zip(params, g1, g2):
+            assert rel_l2(p.grad, a + b) <= 1e-5 or float((a + b).abs().max()) < 1e-9
+            assert rel_l2(arena.view(p), a + b) <= 1e-5 or float((a + b).abs().max()) < 1e-9    # ... and the sum lives in the arena
+        # one Linear weight used twice in ONE graph
+        w = torch.nn.Parameter(torch.randn(64, 64, device="cuda") * 0.1)
+        ar2 = ops.GradArena([w])
+        ops.set_grad_arena(ar2)
+        x = torch.randn(1, 40, 64, device="cuda")
+        y = ops.linear_tokens(ops.linear_tokens(x, w), w)
+        y.sum().backward()
+        wr = w.detach().clone().requires_grad_(True)
+        (x @ wr.t() @ wr.t()).sum().backward()
+        assert rel_l2(w.grad, wr.grad) <= 1e-5
+    finally:
+        ops.set_grad_arena(None)
+
+
+def test_device_augmentation_feeds_trainer_and_cuda_graph():
+    """augment_batch_u8 -> Trainer.capture / step_graph: the NHWC layout of the pre-normalised activations must survive the clone()
+    and copy_() the trainer applies to its inputs (it travels with the tensor TYPE), and a mis-laid-out input must raise."""
+    import stc_unet_b200 as S
+    from stc_unet_b200 import ops
+    from stc_unet_b200.train import Trainer
+    g = torch.Generator().manual_seed(9)
+    raw = torch.randint(0, 256, (2, 80, 96, 3), dtype=torch.uint8, generator=g).cuda()
+    lab = torch.randint(0, 3, (2, 80, 96), dtype=torch.uint8, generator=g).cuda()
+    geom = torch.tensor([[3, 5, 0], [10, 20, 1]], dtype=torch.int32)
+    cfg = dict(mean=[0.0], std=[255.0], to_rgb=False)
+    x, y = ops.augment_batch_u8(raw, lab, geom, (64, 64), torch.float32, cfg)
+    assert isinstance(x, ops.NHWCImage) and isinstance(x.clone(), ops.NHWCImage) and tuple(x.shape) == (2, 64, 64, 3)
+    losses = {}
+    for mode in ("eager", "graph"):
+        bb, hd = build(False, 3, "fp32", posbn=True)
+        seg = S.EncoderDecoder(bb, hd).cuda().train()
+        tr = Trainer(seg, lr=1e-3)
+        seq = [float(tr.step(x, y)["loss"]) for _ in range(3)]
+        if mode == "graph":
+            tr.capture(x, y)
+            assert isinstance(tr._static_img, ops.NHWCImage)
+        else:
+            tr.step(x, y)
+        for _ in range(3):
+            lv = tr.step_graph(x, y) if mode == "graph" else tr.step(x, y)
+            seq.append(float(lv["loss"]))
+        losses[mode] = seq
+    for a, b in zip(losses["eager"], losses["graph"]):
+        assert abs(a - b) <= 2e-3 * max(1.0, abs(a)), losses
+    # the same activations WITHOUT the type: read as NCHW (N, C=64, ...) -> must raise, not compute garbage
+    bb, hd = build(False, 3, "fp32")
+    with pytest.raises(RuntimeError):
+        hd.forward_train(bb(x.as_subclass(torch.Tensor)), None, y, None)

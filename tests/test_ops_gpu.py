@@ -346,7 +346,7 @@ def test_ce_known_answers(S):
     assert abs(float(ce) - float(want)) < 1e-5
 
 
-@pytest.mark.parametrize("C", [2, 3, 19])
+@pytest.mark.parametrize("C", [2, 3, 19, 100, 150])
 def test_confusion_hist_bit_exact(S, C):
     """tests/test_metrics.py:9-26 (np.bincount confusion matrix) and metrics.py:75-87 (area vectors)."""
     import numpy as np
@@ -367,6 +367,40 @@ def test_confusion_hist_bit_exact(S, C):
     assert np.array_equal(cm2.cpu().numpy(), O.confusion_matrix(pred2, label, C, 255))
     b = O.intersect_and_union(pred2, label, C, 255)
     assert all(np.array_equal(areas2.cpu().numpy()[i], b[i]) for i in range(4))
+
+
+@pytest.mark.parametrize("C", [3, 19])
+def test_confusion_hist_ragged_unaligned_and_large(S, C):
+    """Edge cases of the vectorised kernel: sizes that are not a multiple of the 256-pixel warp iteration (scalar tail), a label view
+    starting at an odd byte (no 2-byte vectors), negative / out-of-range labels, an empty input, and a 512x512x64 volume
+    (BASELINE.json configs[3]) accumulated on top of earlier counts - all bit-exact against the oracle."""
+    import numpy as np
+    from oracle import stc_oracle as O
+    from stc_unet_b200 import ops
+    rng = np.random.RandomState(1)
+    for n in (1, 31, 255, 257, 1000, 4099):
+        pred = rng.randint(-1, C + 2, size=n)
+        label = rng.randint(0, C + 2, size=n)
+        label[rng.rand(n) < 0.1] = 255
+        buf = torch.zeros(n + 1, dtype=torch.uint8)
+        buf[1:] = torch.from_numpy(label.astype(np.uint8))
+        lab_dev = buf.cuda()[1:]                       # contiguous view at an odd address
+        assert lab_dev.data_ptr() % 2 == 1
+        cm, areas = ops.confusion_hist(torch.from_numpy(pred).cuda(), lab_dev, C, 255)
+        assert np.array_equal(cm.cpu().numpy(), O.confusion_matrix(pred, label, C, 255)), n
+        want = O.intersect_and_union(pred, label, C, 255)
+        assert all(np.array_equal(areas.cpu().numpy()[i], want[i]) for i in range(4)), n
+    cm0, ar0 = ops.confusion_hist(torch.zeros(0, dtype=torch.int64).cuda(), torch.zeros(0, dtype=torch.uint8).cuda(), C, 255)
+    assert int(cm0.sum()) == 0 and int(ar0.sum()) == 0
+    g = torch.Generator().manual_seed(5)
+    pred = torch.randint(0, C, (64, 512, 512), generator=g)
+    label = torch.randint(0, C, (64, 512, 512), generator=g).to(torch.uint8)
+    label[:, :9] = 255
+    cm, areas = ops.confusion_hist(pred.cuda(), label.cuda(), C, 255)
+    cm, areas = ops.confusion_hist(pred.cuda(), label.cuda(), C, 255, cm, areas)      # accumulates
+    want = O.confusion_matrix(pred.numpy(), label.numpy(), C, 255)
+    assert np.array_equal(cm.cpu().numpy(), 2 * want)
+    assert int(areas[3].sum()) == 2 * int((label != 255).sum())
 
 
 def test_argmax_and_slide(S):
@@ -591,7 +625,7 @@ def test_adam_b200_optimizer_matches_torch_adam(S):
 
 def test_peer_exchange_kernels_single_rank(S):
     """csrc/peer.cu with a one-rank peer table (a plain device buffer): tickets, slots, float4 body + scalar tail, CTA split, scale.
-    The N >= 2 behaviour over NVLink (against NCCL) is tools/peer_test.py, run under torchrun on a multi-GPU box."""
+    The N >= 2 behaviour over NVLink (against NCCL) is tools/peer_check.py, run under torchrun on a multi-GPU box."""
     import ctypes
     from stc_unet_b200._lib import lib, stream_ptr
     max_n, ctas = 256, 8

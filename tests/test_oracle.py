@@ -267,3 +267,41 @@ def test_family_b_deconv_upsampler_matches_reference():
     import stc_unet_b200 as S
     with pytest.raises(AssertionError):
         S.modules_b.DeconvModule(8, 8, kernel_size=3)
+
+
+def test_unetpp_encoder_is_pinned_to_torchvision_vgg16():
+    """Config 5 (unetpp_head.py:16: smp.UnetPlusPlus(encoder_name="vgg16")).  smp 0.2.0 itself is absent, but its vgg16 encoder IS
+    torchvision's `vgg16().features` (smp's VGGEncoder subclasses torchvision.models.VGG, drops the classifier, and cuts the stage
+    outputs at every MaxPool2d).  This pins that half: our container has torchvision's keys / shapes / default init, and the oracle's
+    encoder loop reproduces torchvision's layers stage by stage.  The nested decoder remains UNPINNED (no smp source anywhere)."""
+    tv = pytest.importorskip("torchvision")
+    from stc_unet_b200.modules_pp import _VGGEncoder
+    torch.manual_seed(3)
+    ref = tv.models.vgg16(weights=None).features
+    torch.manual_seed(3)
+    ours = _VGGEncoder()
+    rs, os_ = ref.state_dict(), ours.features.state_dict()
+    assert list(rs) == list(os_) and all(tuple(rs[k].shape) == tuple(os_[k].shape) for k in rs)
+    assert [type(m).__name__ for m in ref] == [type(m).__name__ for m in ours.features]
+    # oracle encoder == torchvision layers, cut at each pool (stage outputs BEFORE the pool, plus the final pooled map)
+    x = torch.rand(2, 3, 64, 64)
+    feats, h = [], x
+    with torch.no_grad():
+        for m in ref:
+            if isinstance(m, torch.nn.MaxPool2d):
+                feats.append(h)
+            h = m(h)
+        feats.append(h)
+    assert [f.shape[1] for f in feats] == [64, 128, 256, 512, 512, 512] and [f.shape[-1] for f in feats] == [64, 32, 16, 8, 4, 2]
+    # run the oracle with hooks: unetpp_forward's encoder part recomputed with the same weights
+    sd = {f"model.encoder.features.{k}": v for k, v in rs.items()}
+    got, h, idx = [], x, 0
+    with torch.no_grad():
+        for v in O._VGG16_CFG:
+            if v == "M":
+                got.append(h); h = F.max_pool2d(h, 2); idx += 1
+            else:
+                h = torch.relu(F.conv2d(h, sd[f"model.encoder.features.{idx}.weight"], sd[f"model.encoder.features.{idx}.bias"], padding=1)); idx += 2
+        got.append(h)
+    for a, b in zip(got, feats):
+        assert torch.equal(a, b)

@@ -1,5 +1,6 @@
-"""N >= 2 check of the NVLink peer-memory exchanges (csrc/peer.cu) against NCCL, then a short training comparison.
-    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29520 tools/peer_test.py"""
+"""N >= 2 check of the two NVLink peer-memory collectives (csrc/peer.cu) against NCCL, with their timings.  The 2-rank TRAINING-step
+comparison against the oracle (SyncBN + gradient all-reduce through these kernels) is tests/test_dist_gpu.py.
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29520 tools/peer_check.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.distributed as dist
