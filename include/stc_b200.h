@@ -107,6 +107,22 @@ int stc_conv_fprop_bnstats(const void* x, const void* wp, const float* bias, voi
  * += sum_pixels x[p+(r,s)][ci] * dy[p][co].  Then stc_unpack_conv_wgrad -> OIHW. */
 int stc_conv_wgrad(const void* x, const void* dy, float* dw_ws, int N, int H, int W, int Cin, int Cout,
                    int R, int S, int dtype, int engine, void* stream);
+/* Virtual channel concat: the conv that consumes `torch.cat([x2, x1], dim=1)` (Up.forward, unet_head.py:54-55;
+ * UpConvBlock.forward, up_conv_block.py:99; the smp UNet++ decoder blocks behind unetpp_head.py:16) reads its up-to-5 NHWC sources
+ * directly - the K loop walks the sources' 64-channel chunks through one TMA descriptor each - so the concatenated tensor is never
+ * written; its dgrad stores every 64-channel chunk straight into the gradient tensor of the source that owns it, and its wgrad
+ * reads the sources the same way.  Parts: pointers x0.. with channel counts c0.. (multiples of 64, unused = NULL / 0, packed to the
+ * front), all (N,H,W,c_i) bf16; wp / the wgrad workspace use the CONCATENATED channel order.  tcgen05 engine only
+ * (stc_conv_cat_ok tells; otherwise the caller materialises the concat with stc_upcat_fwd / stc_concat_channels / stc_catn_fwd). */
+int stc_conv_cat_ok(int c0, int c1, int c2, int c3, int c4, int Cother, int dtype, int engine);
+int stc_conv_fprop_cat(const void* x0, const void* x1, const void* x2, const void* x3, const void* x4, int c0, int c1, int c2, int c3, int c4,
+                       const void* wp, const float* bias, void* y, int N, int H, int W, int Cout, int R, int S, int act, int dtype,
+                       int engine, void* stream);
+/* dx_i = the i-th channel block of conv_transpose(dy): dy (N,H,W,Cdy), wpt = the transpose_flip pack [taps][sum c_i][Cdy]. */
+int stc_conv_dgrad_split(const void* dy, const void* wpt, void* dx0, void* dx1, void* dx2, void* dx3, void* dx4, int c0, int c1, int c2, int c3,
+                         int c4, int N, int H, int W, int Cdy, int R, int S, int dtype, int engine, void* stream);
+int stc_conv_wgrad_cat(const void* x0, const void* x1, const void* x2, const void* x3, const void* x4, int c0, int c1, int c2, int c3, int c4,
+                       const void* dy, float* dw_ws, int N, int H, int W, int Cout, int R, int S, int dtype, int engine, void* stream);
 /* column sums: out[c] (+)= sum_p x[p][c]  (Conv2d/Linear bias gradients). */
 int stc_colsum(const void* x, float* out, long long P, int C, int accumulate, int dtype, void* stream);
 

@@ -11,14 +11,14 @@ int conv_wgrad_simt(const void*, const void*, float*, int, int, int, int, int, i
 int gemm_simt(const void*, const void*, void*, const stc_gemm_desc*, int, cudaStream_t);
 bool conv_umma_eligible(int Cin, int Cout, int dtype);
 int conv_fprop_umma(const void*, const void*, const float*, const void*, void*, int, int, int, int, int, int, int, int,
-                    cudaStream_t);
-int conv_wgrad_umma(const void*, const void*, float*, int, int, int, int, int, int, int, cudaStream_t);
+                    cudaStream_t, const ChanCat* src = nullptr, const ChanCat* dst = nullptr);
+int conv_wgrad_umma(const void*, const void*, float*, int, int, int, int, int, int, int, cudaStream_t, const ChanCat* src = nullptr);
 bool gemm_umma_eligible(const stc_gemm_desc*, int dtype);
 bool conv_convh_eligible(int W, int Cin, int Cout, int R, int S, int dtype);
 bool conv_wgradh_eligible(int W, int Cin, int Cout, int R, int S, int dtype);
-int conv_wgrad_wgradh(const void*, const void*, float*, int, int, int, int, int, int, int, cudaStream_t);
+int conv_wgrad_wgradh(const void*, const void*, float*, int, int, int, int, int, int, int, cudaStream_t, const ChanCat* src = nullptr);
 int conv_fprop_convh(const void*, const void*, const float*, const void*, void*, int, int, int, int, int, int, int, int, cudaStream_t, float* stats = nullptr,
-                     int* stats_rows = nullptr);
+                     int* stats_rows = nullptr, const ChanCat* src = nullptr, const ChanCat* dst = nullptr);
 bool conv_convh_stats_ok(int Cout, int R);
 int gemm_umma(const void*, const void*, void*, const stc_gemm_desc*, int, cudaStream_t);
 }  // namespace stc
@@ -72,6 +72,92 @@ extern "C" int stc_conv_wgrad(const void* x, const void* dy, float* dw_ws, int N
     }
     g_last_engine = STC_ENGINE_SIMT;
     return conv_wgrad_simt(x, dy, dw_ws, N, H, W, Cin, Cout, R, S, dtype, st);
+}
+
+// ---- virtual channel concat (K9: the torch.cat of Up.forward / UpConvBlock.forward / UNet++ decoder blocks is never written) ----
+static int make_cat(ChanCat& c, const void* p0, const void* p1, const void* p2, const void* p3, const void* p4, int c0, int c1, int c2, int c3,
+                    int c4, const char* what) {
+    const void* ps[kMaxCat] = {p0, p1, p2, p3, p4};
+    const int cs[kMaxCat] = {c0, c1, c2, c3, c4};
+    c.n = 0;
+    for (int i = 0; i < kMaxCat; ++i) {
+        if (cs[i] == 0) {
+            for (int k = i; k < kMaxCat; ++k) STC_REQUIRE(cs[k] == 0, "%s: channel counts must be packed to the front", what);
+            break;
+        }
+        STC_REQUIRE(cs[i] > 0 && cs[i] % 64 == 0 && ps[i] && ((uintptr_t)ps[i] & 15) == 0,
+                    "%s: part %d needs a 16-byte aligned pointer and a multiple of 64 channels (has %d)", what, i, cs[i]);
+        c.ptr[c.n] = ps[i];
+        c.c[c.n++] = cs[i];
+    }
+    STC_REQUIRE(c.n >= 1, "%s: no parts", what);
+    return STC_OK;
+}
+
+extern "C" int stc_conv_cat_ok(int c0, int c1, int c2, int c3, int c4, int Cother, int dtype, int engine) {
+    static int off = -1;
+    if (off < 0) { const char* e = getenv("STC_VCAT"); off = (e && e[0] == '0') ? 1 : 0; }
+    const int cs[kMaxCat] = {c0, c1, c2, c3, c4};
+    int total = 0;
+    for (int c : cs) {
+        if (c < 0 || c % 64) return 0;
+        total += c;
+    }
+    // the concatenated side is Cin of fprop / wgrad and Cout of dgrad; Cother is the conv's other channel count
+    return (!off && dtype == STC_BF16 && engine != STC_ENGINE_SIMT && total > 0 && conv_umma_eligible(total, Cother, dtype) &&
+            conv_umma_eligible(Cother, total, dtype) && Cother % 64 == 0) ? 1 : 0;
+}
+
+extern "C" int stc_conv_fprop_cat(const void* x0, const void* x1, const void* x2, const void* x3, const void* x4, int c0, int c1, int c2, int c3,
+                                  int c4, const void* wp, const float* bias, void* y, int N, int H, int W, int Cout, int R, int S, int act,
+                                  int dtype, int engine, void* stream) {
+    ChanCat src;
+    if (int rc = make_cat(src, x0, x1, x2, x3, x4, c0, c1, c2, c3, c4, "conv_fprop_cat")) return rc;
+    const int Cin = src.total();
+    STC_REQUIRE(N > 0 && H > 0 && W > 0 && Cout > 0 && (R & 1) && (S & 1), "conv_fprop_cat: bad shape");
+    STC_REQUIRE(dtype == STC_BF16 && engine != STC_ENGINE_SIMT && conv_umma_eligible(Cin, Cout, dtype),
+                "conv_fprop_cat: tcgen05 engine only (bf16, Cin=%d, Cout=%d); materialise the concat otherwise", Cin, Cout);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (conv_convh_eligible(W, Cin, Cout, R, S, dtype)) {
+        g_last_engine = STC_KERNEL_CONVH;
+        return conv_fprop_convh(nullptr, wp, bias, nullptr, y, N, H, W, Cin, Cout, R, S, act, st, nullptr, nullptr, &src, nullptr);
+    }
+    g_last_engine = STC_ENGINE_TCGEN05;
+    return conv_fprop_umma(nullptr, wp, bias, nullptr, y, N, H, W, Cin, Cout, R, S, act, st, &src, nullptr);
+}
+
+extern "C" int stc_conv_dgrad_split(const void* dy, const void* wpt, void* dx0, void* dx1, void* dx2, void* dx3, void* dx4, int c0, int c1, int c2,
+                                    int c3, int c4, int N, int H, int W, int Cdy, int R, int S, int dtype, int engine, void* stream) {
+    ChanCat dst;
+    if (int rc = make_cat(dst, dx0, dx1, dx2, dx3, dx4, c0, c1, c2, c3, c4, "conv_dgrad_split")) return rc;
+    const int Cdx = dst.total();
+    STC_REQUIRE(N > 0 && H > 0 && W > 0 && Cdy > 0 && (R & 1) && (S & 1), "conv_dgrad_split: bad shape");
+    STC_REQUIRE(dtype == STC_BF16 && engine != STC_ENGINE_SIMT && conv_umma_eligible(Cdy, Cdx, dtype),
+                "conv_dgrad_split: tcgen05 engine only (bf16, Cdy=%d, Cdx=%d)", Cdy, Cdx);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (conv_convh_eligible(W, Cdy, Cdx, R, S, dtype)) {
+        g_last_engine = STC_KERNEL_CONVH;
+        return conv_fprop_convh(dy, wpt, nullptr, nullptr, nullptr, N, H, W, Cdy, Cdx, R, S, STC_ACT_NONE, st, nullptr, nullptr, nullptr, &dst);
+    }
+    g_last_engine = STC_ENGINE_TCGEN05;
+    return conv_fprop_umma(dy, wpt, nullptr, nullptr, nullptr, N, H, W, Cdy, Cdx, R, S, STC_ACT_NONE, st, nullptr, &dst);
+}
+
+extern "C" int stc_conv_wgrad_cat(const void* x0, const void* x1, const void* x2, const void* x3, const void* x4, int c0, int c1, int c2, int c3,
+                                  int c4, const void* dy, float* dw_ws, int N, int H, int W, int Cout, int R, int S, int dtype, int engine,
+                                  void* stream) {
+    ChanCat src;
+    if (int rc = make_cat(src, x0, x1, x2, x3, x4, c0, c1, c2, c3, c4, "conv_wgrad_cat")) return rc;
+    const int Cin = src.total();
+    STC_REQUIRE(N > 0 && H > 0 && W > 0 && Cout > 0 && (R & 1) && (S & 1), "conv_wgrad_cat: bad shape");
+    STC_REQUIRE(dtype == STC_BF16 && engine != STC_ENGINE_SIMT && Cout % 64 == 0, "conv_wgrad_cat: tcgen05 engine only (bf16, Cout=%d)", Cout);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (conv_wgradh_eligible(W, Cin, Cout, R, S, dtype)) {
+        g_last_engine = STC_KERNEL_WGRADH;
+        return conv_wgrad_wgradh(nullptr, dy, dw_ws, N, H, W, Cin, Cout, R, S, st, &src);
+    }
+    g_last_engine = STC_ENGINE_TCGEN05;
+    return conv_wgrad_umma(nullptr, dy, dw_ws, N, H, W, Cin, Cout, R, S, st, &src);
 }
 
 extern "C" int stc_gemm(const void* A, const void* B, void* C, const stc_gemm_desc* d, int dtype, int engine, void* stream) {

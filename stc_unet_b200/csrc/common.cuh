@@ -84,6 +84,18 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// Virtual channel concatenation (torch.cat([skip, up]) of Up.forward / UpConvBlock.forward / the UNet++ decoder blocks is never
+// materialised): up to 5 NHWC tensors that share (N, H, W) act as ONE tensor whose channel axis is their concatenation.  As a conv INPUT
+// the K loop walks the sources' 64-channel chunks through one TMA descriptor per source; as a dgrad OUTPUT every 64-channel chunk of the
+// result is stored through the descriptor of the tensor that owns it.  n == 0 / nullptr = a plain single tensor.
+constexpr int kMaxCat = 5;
+struct ChanCat {
+    int n;
+    const void* ptr[kMaxCat];
+    int c[kMaxCat];
+    int total() const { int t = 0; for (int i = 0; i < n; ++i) t += c[i]; return t; }
+};
+
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 int num_sms();
 

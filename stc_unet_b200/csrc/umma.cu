@@ -24,6 +24,12 @@ struct alignas(64) UmmaParams {
     CUtensorMap tmA;
     CUtensorMap tmB;
     CUtensorMap tmC;   // output map for the staged (shared memory + TMA store) epilogue, see store_tma
+    // virtual channel concat (common.cuh ChanCat): extra A sources (CONV / WGRAD) and extra outputs (CONV = dgrad of a concat conv)
+    CUtensorMap tmA2[kMaxCat - 1];
+    CUtensorMap tmC2[kMaxCat - 1];
+    int n_src, src_chunk_end[kMaxCat];     // cumulative 64-channel chunk counts of the A sources
+    int n_out, out_ch_end[kMaxCat];        // cumulative channel counts of the outputs
+    void* out2[kMaxCat - 1];
     int mode;
     int num_tiles, num_n_tiles, num_m_tiles;
     int num_k_iters;  // conv/gemm: k iterations per tile; wgrad: total pixel tiles
@@ -95,6 +101,24 @@ __device__ __forceinline__ TileInfo decode_tile(const UmmaParams& p, int tile) {
     return t;
 }
 
+// chunk index (64 channels) within the virtual concat -> source index and chunk inside that source
+__device__ __forceinline__ int cat_source(const UmmaParams& p, int cc, int& local) {
+    int j = 0;
+    while (j + 1 < p.n_src && cc >= p.src_chunk_end[j]) ++j;
+    local = cc - (j ? p.src_chunk_end[j - 1] : 0);
+    return j;
+}
+__device__ __forceinline__ const CUtensorMap* cat_map_a(const UmmaParams& p, int j) { return j ? &p.tmA2[j - 1] : &p.tmA; }
+// global output channel -> output tensor index, channel inside it and its channel count
+__device__ __forceinline__ int cat_output(const UmmaParams& p, int gch, int& local, int& width) {
+    int j = 0;
+    while (j + 1 < p.n_out && gch >= p.out_ch_end[j]) ++j;
+    const int start = j ? p.out_ch_end[j - 1] : 0;
+    local = gch - start;
+    width = p.out_ch_end[j] - start;
+    return j;
+}
+
 __device__ __forceinline__ float epi_act(float v, int act) {
     if (act == STC_ACT_RELU) return fmaxf(v, 0.f);
     if (act == STC_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
@@ -127,6 +151,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_cons
         ptx::prefetch_tensormap(&p.tmA);
         ptx::prefetch_tensormap(&p.tmB);
         if (p.store_tma) ptx::prefetch_tensormap(&p.tmC);
+        for (int j = 1; j < p.n_src; ++j) ptx::prefetch_tensormap(&p.tmA2[j - 1]);
+        if (p.store_tma) for (int j = 1; j < p.n_out; ++j) ptx::prefetch_tensormap(&p.tmC2[j - 1]);
         for (int s = 0; s < p.stages; ++s) {
             ptx::mbar_init(full_bar(s), 1);
             ptx::mbar_init(empty_bar(s), 1);
@@ -167,7 +193,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_cons
                     if (p.mode == MODE_CONV) {
                         int tap = kt / p.cin_chunks, cc = kt - tap * p.cin_chunks;
                         int r = tap / p.S, s = tap - r * p.S;
-                        ptx::tma_load_4d(a_dst, &p.tmA, fb, cc * 64, t.w0 + s - p.S / 2, t.h0 + r - p.R / 2, t.n_img);
+                        int lc = cc;
+                        const CUtensorMap* ma = p.n_src > 1 ? cat_map_a(p, cat_source(p, cc, lc)) : &p.tmA;
+                        ptx::tma_load_4d(a_dst, ma, fb, lc * 64, t.w0 + s - p.S / 2, t.h0 + r - p.R / 2, t.n_img);
                         ptx::tma_load_3d(b_dst, &p.tmB, fb, cc * 64, t.nt * p.BN, tap);
                     } else if (p.mode == MODE_GEMM) {
                         if (!p.a_mn_major) {
@@ -190,7 +218,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_cons
                             if (atom >= p.num_atoms) atom = 0;  // dummy rows, dropped by the epilogue
                             int tap = atom / p.cin_chunks, cc = atom - tap * p.cin_chunks;
                             int r = tap / p.S, s = tap - r * p.S;
-                            ptx::tma_load_4d(a_dst + j * p.a_box_bytes, &p.tmA, fb, cc * 64, w0 + s - p.S / 2, h0 + r - p.R / 2, n_img);
+                            int lc = cc;
+                            const CUtensorMap* ma = p.n_src > 1 ? cat_map_a(p, cat_source(p, cc, lc)) : &p.tmA;
+                            ptx::tma_load_4d(a_dst + j * p.a_box_bytes, ma, fb, lc * 64, w0 + s - p.S / 2, h0 + r - p.R / 2, n_img);
                         }
                         for (int j = 0; j < p.b_boxes; ++j)
                             ptx::tma_load_4d(b_dst + j * p.b_box_bytes, &p.tmB, fb, t.nt * p.BN + j * 64, w0, h0, n_img);
@@ -332,7 +362,10 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_cons
                     ptx::fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
-                        ptx::tma_store_4d(&p.tmC, stg, t.nt * p.BN + c, c1, c2, c3);
+                        int oc = t.nt * p.BN + c, ow;
+                        const CUtensorMap* mc = &p.tmC;
+                        if (p.n_out > 1) { const int j = cat_output(p, oc, oc, ow); if (j) mc = &p.tmC2[j - 1]; }
+                        ptx::tma_store_4d(mc, stg, oc, c1, c2, c3);
                         ptx::bulk_commit();
                     }
                     stage_buf ^= 1;
@@ -395,6 +428,12 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_cons
                 }
                 if (p.out_dtype == STC_BF16) {
                     uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + off + c);
+                    if (p.n_out > 1) {   // dgrad of a virtual concat: this 32-channel chunk belongs to one of the outputs
+                        int lc, ow;
+                        const int j = cat_output(p, t.nt * p.BN + c, lc, ow);
+                        const long long pix = (off - (long long)t.nt * p.BN) / p.Cout;
+                        o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(j ? p.out2[j - 1] : p.out) + pix * ow + lc);
+                    }
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         uint4 ov;
@@ -533,20 +572,53 @@ static int pick_stages(uint32_t stage_bytes, bool staged_epilogue = false) {
 
 bool conv_umma_eligible(int Cin, int Cout, int dtype) { return dtype == STC_BF16 && Cin % 64 == 0 && pick_bn(Cout) != 0; }
 
+// NHWC activation map {C, W, H, N} with the given box
+static int encode_nhwc(CUtensorMap* m, const void* base, int N, int H, int W, int C, uint32_t bc, uint32_t bw, uint32_t bh) {
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    uint64_t str[4] = {2, (uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+    uint32_t box[4] = {bc, bw, bh, 1};
+    return encode_map(m, base, 4, dims, str, box);
+}
+
+// checks a ChanCat (every part a non-null 16-byte aligned pointer with a multiple of 64 channels, sum = total)
+int check_cat(const ChanCat* c, int total, const char* what) {
+    if (!c) return STC_OK;
+    STC_REQUIRE(c->n >= 1 && c->n <= kMaxCat && c->total() == total, "%s: %d parts do not add up to %d channels", what, c->n, total);
+    for (int i = 0; i < c->n; ++i)
+        STC_REQUIRE(c->ptr[i] && ((uintptr_t)c->ptr[i] & 15) == 0 && c->c[i] > 0 && c->c[i] % 64 == 0,
+                    "%s: part %d must be a 16-byte aligned tensor with a multiple of 64 channels (has %d)", what, i, c->c[i]);
+    return STC_OK;
+}
+
+// src: the input is a virtual concat (x ignored); dst: the output is split over several tensors (y ignored; no bias / residual / act)
 int conv_fprop_umma(const void* x, const void* wp, const float* bias, const void* residual, void* y, int N, int H, int W,
-                    int Cin, int Cout, int R, int S, int act, cudaStream_t st) {
+                    int Cin, int Cout, int R, int S, int act, cudaStream_t st, const ChanCat* src, const ChanCat* dst) {
     STC_REQUIRE(conv_umma_eligible(Cin, Cout, STC_BF16), "conv_fprop_umma: shape Cin=%d Cout=%d not eligible", Cin, Cout);
+    if (src && src->n == 1) { x = src->ptr[0]; src = nullptr; }
+    if (dst && dst->n == 1) { y = const_cast<void*>(dst->ptr[0]); dst = nullptr; }
+    if (int rc = check_cat(src, Cin, "conv_fprop_umma input")) return rc;
+    if (int rc = check_cat(dst, Cout, "conv_fprop_umma output")) return rc;
+    STC_REQUIRE(!dst || (!bias && !residual && act == STC_ACT_NONE), "conv_fprop_umma: a split output takes no bias / residual / activation");
+    if (src) x = src->ptr[0];
+    if (dst) y = const_cast<void*>(dst->ptr[0]);
     STC_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)wp & 15) == 0 && ((uintptr_t)y & 15) == 0, "conv_fprop_umma: unaligned pointer");
     UmmaParams p;
     memset(&p, 0, sizeof(p));
     p.mode = MODE_CONV;
     conv_geometry(p, H, W, R, S, Cin);
     p.BN = pick_bn(Cout);
-    {
-        uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-        uint64_t str[4] = {2, (uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
-        uint32_t box[4] = {64, (uint32_t)p.BW, (uint32_t)p.BH, 1};
-        int rc = encode_map(&p.tmA, x, 4, dims, str, box);
+    p.n_src = 1; p.n_out = 1;
+    if (src) {
+        p.n_src = src->n;
+        int acc = 0;
+        for (int j = 0; j < src->n; ++j) {
+            int rc = encode_nhwc(j ? &p.tmA2[j - 1] : &p.tmA, src->ptr[j], N, H, W, src->c[j], 64, (uint32_t)p.BW, (uint32_t)p.BH);
+            if (rc) return rc;
+            acc += src->c[j] / 64;
+            p.src_chunk_end[j] = acc;
+        }
+    } else {
+        int rc = encode_nhwc(&p.tmA, x, N, H, W, Cin, 64, (uint32_t)p.BW, (uint32_t)p.BH);
         if (rc) return rc;
     }
     {
@@ -568,13 +640,21 @@ int conv_fprop_umma(const void* x, const void* wp, const float* bias, const void
     p.b_lbo = 0; p.b_sbo = 1024; p.b_kstep_bytes = 32;
     p.idesc = make_idesc_bf16(128, p.BN, 0, 0);
     p.store_tma = (p.BN % 64 == 0 && !getenv_off("STC_TMA_STORE")) ? 1 : 0;
+    if (dst) {
+        p.n_out = dst->n;
+        int acc = 0;
+        for (int j = 0; j < dst->n; ++j) {
+            acc += dst->c[j];
+            p.out_ch_end[j] = acc;
+            if (j) p.out2[j - 1] = const_cast<void*>(dst->ptr[j]);
+        }
+    }
     if (p.store_tma) {   // per epilogue warp: 32 tile rows = a (bw32 x 32/bw32) pixel patch, 64 channels
         const uint32_t bw32 = (uint32_t)(p.BW < 32 ? p.BW : 32);
-        uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-        uint64_t str[4] = {2, (uint64_t)Cout * 2, (uint64_t)W * Cout * 2, (uint64_t)H * W * Cout * 2};
-        uint32_t box[4] = {64, bw32, 32 / bw32, 1};
-        int rc = encode_map(&p.tmC, y, 4, dims, str, box);
-        if (rc) return rc;
+        for (int j = 0; j < p.n_out; ++j) {
+            int rc = encode_nhwc(j ? &p.tmC2[j - 1] : &p.tmC, dst ? dst->ptr[j] : y, N, H, W, dst ? dst->c[j] : Cout, 64, bw32, 32 / bw32);
+            if (rc) return rc;
+        }
     }
     p.stages = pick_stages(p.a_stage_bytes + p.b_stage_bytes, p.store_tma);
     p.out = y; p.bias = bias; p.residual = residual; p.act = act; p.out_dtype = STC_BF16; p.Cout = Cout;
@@ -583,18 +663,27 @@ int conv_fprop_umma(const void* x, const void* wp, const float* bias, const void
 }
 
 int conv_wgrad_umma(const void* x, const void* dy, float* ws, int N, int H, int W, int Cin, int Cout, int R, int S,
-                    cudaStream_t st) {
+                    cudaStream_t st, const ChanCat* src) {
     STC_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "conv_wgrad_umma: Cin=%d Cout=%d must be multiples of 64", Cin, Cout);
+    if (src && src->n == 1) { x = src->ptr[0]; src = nullptr; }
+    if (int rc = check_cat(src, Cin, "conv_wgrad_umma input")) return rc;
     UmmaParams p;
     memset(&p, 0, sizeof(p));
     p.mode = MODE_WGRAD;
     conv_geometry(p, H, W, R, S, Cin);
     p.BN = Cout % 128 == 0 ? 128 : 64;
-    {
-        uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-        uint64_t str[4] = {2, (uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
-        uint32_t box[4] = {64, (uint32_t)p.BW, (uint32_t)p.BH, 1};
-        int rc = encode_map(&p.tmA, x, 4, dims, str, box);
+    p.n_src = 1; p.n_out = 1;
+    if (src) {
+        p.n_src = src->n;
+        int acc = 0;
+        for (int j = 0; j < src->n; ++j) {
+            int rc = encode_nhwc(j ? &p.tmA2[j - 1] : &p.tmA, src->ptr[j], N, H, W, src->c[j], 64, (uint32_t)p.BW, (uint32_t)p.BH);
+            if (rc) return rc;
+            acc += src->c[j] / 64;
+            p.src_chunk_end[j] = acc;
+        }
+    } else {
+        int rc = encode_nhwc(&p.tmA, x, N, H, W, Cin, 64, (uint32_t)p.BW, (uint32_t)p.BH);
         if (rc) return rc;
     }
     {
@@ -655,6 +744,7 @@ int gemm_umma(const void* A, const void* B, void* C, const stc_gemm_desc* d, int
     UmmaParams p;
     memset(&p, 0, sizeof(p));
     p.mode = MODE_GEMM;
+    p.n_src = 1; p.n_out = 1;
     p.BN = pick_bn(d->N);
     p.a_mn_major = (d->sAk != 1);
     p.b_mn_major = (d->sBk != 1);

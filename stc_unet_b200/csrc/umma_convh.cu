@@ -24,6 +24,12 @@ struct alignas(64) ConvHParams {
     CUtensorMap tmA;  // NHWC activations {C, W, H, N}, box {64, 128+S-1, 1, 1}
     CUtensorMap tmB;  // packed weights {Cin, Cout, taps}, box {64, BN, 1}
     CUtensorMap tmC;  // output {Cout, W, H, N}, box {64, 32, 1, 1}: staged epilogue (see umma.cu), used when `staged`
+    // virtual channel concat (common.cuh ChanCat): extra input sources / extra outputs (dgrad of a concat conv)
+    CUtensorMap tmA2[kMaxCat - 1];
+    CUtensorMap tmC2[kMaxCat - 1];
+    int n_src, src_chunk_end[kMaxCat];
+    int n_out, out_ch_end[kMaxCat];
+    void* out2[kMaxCat - 1];
     int staged;
     int H, W, R, S, cin_chunks, T, BN, num_n_tiles;
     int strips_h, strips_w, num_strips;
@@ -85,6 +91,20 @@ __device__ __forceinline__ float convh_act(float v, int act) {
 struct Strip {
     int nt, n_img, h0, w0;
 };
+__device__ __forceinline__ const CUtensorMap* convh_map_a(const ConvHParams& p, int cc, int& local) {
+    int j = 0;
+    while (j + 1 < p.n_src && cc >= p.src_chunk_end[j]) ++j;
+    local = cc - (j ? p.src_chunk_end[j - 1] : 0);
+    return j ? &p.tmA2[j - 1] : &p.tmA;
+}
+__device__ __forceinline__ int convh_output(const ConvHParams& p, int gch, int& local, int& width) {
+    int j = 0;
+    while (j + 1 < p.n_out && gch >= p.out_ch_end[j]) ++j;
+    const int start = j ? p.out_ch_end[j - 1] : 0;
+    local = gch - start;
+    width = p.out_ch_end[j] - start;
+    return j;
+}
 __device__ __forceinline__ Strip decode_strip(const ConvHParams& p, int idx) {
     Strip s;
     s.nt = idx % p.num_n_tiles;
@@ -123,6 +143,7 @@ __global__ void __launch_bounds__(kConvHThreads, 1) umma_convh_kernel(const __gr
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&p.tmA);
         ptx::prefetch_tensormap(&p.tmB);
+        for (int j = 1; j < p.n_src; ++j) ptx::prefetch_tensormap(&p.tmA2[j - 1]);
         for (int s = 0; s < p.a_slots; ++s) { ptx::mbar_init(a_full(s), 1); ptx::mbar_init(a_empty(s), 1); }
         for (int s = 0; s < p.b_stages; ++s) { ptx::mbar_init(b_full(s), 1); ptx::mbar_init(b_empty(s), 1); }
         for (int s = 0; s < 2; ++s) { ptx::mbar_init(tfull(s), 1); ptx::mbar_init(tempty(s), 4); }
@@ -151,11 +172,13 @@ __global__ void __launch_bounds__(kConvHThreads, 1) umma_convh_kernel(const __gr
             for (int st = blockIdx.x; st < p.num_strips; st += gridDim.x) {
                 Strip s = decode_strip(p, st);
                 for (int cc = 0; cc < p.cin_chunks; ++cc) {
+                    int lc = cc;
+                    const CUtensorMap* ma = p.n_src > 1 ? convh_map_a(p, cc, lc) : &p.tmA;
                     for (int i = 0; i < segs_per_chunk; ++i) {
                         ptx::mbar_wait(a_empty(slot), phase ^ 1);
                         if (ptx::elect_one_sync()) {
                             ptx::mbar_arrive_expect_tx(a_full(slot), p.a_box_bytes);
-                            ptx::tma_load_4d(smem_base + slot * p.a_slot_bytes, &p.tmA, a_full(slot), cc * 64, s.w0 - ps, s.h0 + i - pr, s.n_img);
+                            ptx::tma_load_4d(smem_base + slot * p.a_slot_bytes, ma, a_full(slot), lc * 64, s.w0 - ps, s.h0 + i - pr, s.n_img);
                         }
                         __syncwarp();
                         if (++slot == p.a_slots) { slot = 0; phase ^= 1; }
@@ -335,7 +358,10 @@ __global__ void __launch_bounds__(kConvHThreads, 1) umma_convh_kernel(const __gr
                         ptx::fence_proxy_async();
                         __syncwarp();
                         if (lane == 0) {
-                            ptx::tma_store_4d(&p.tmC, stg, s.nt * p.BN + c, s.w0 + q * 32, h, s.n_img);
+                            int oc = s.nt * p.BN + c, ow;
+                            const CUtensorMap* mc = &p.tmC;
+                            if (p.n_out > 1) { const int j = convh_output(p, oc, oc, ow); if (j) mc = &p.tmC2[j - 1]; }
+                            ptx::tma_store_4d(mc, stg, oc, s.w0 + q * 32, h, s.n_img);
                             ptx::bulk_commit();
                         }
                         stage_buf ^= 1;
@@ -381,6 +407,12 @@ __global__ void __launch_bounds__(kConvHThreads, 1) umma_convh_kernel(const __gr
                         if (!valid) continue;
                     }
                     uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + off + c);
+                    if (p.n_out > 1) {   // dgrad of a virtual concat: this 32-channel chunk belongs to one of the outputs
+                        int lc, ow;
+                        const int j = convh_output(p, s.nt * p.BN + c, lc, ow);
+                        const long long pix = ((long long)s.n_img * p.H + h) * p.W + w;
+                        o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(j ? p.out2[j - 1] : p.out) + pix * ow + lc);
+                    }
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         uint4 ov;
@@ -463,19 +495,51 @@ bool conv_convh_stats_ok(int Cout, int R) {
     return convh_plan(Cout, R, BN, T, a, b, sg) && BN == Cout;
 }
 
+int check_cat(const ChanCat* c, int total, const char* what);
+
+static int convh_encode_nhwc(CUtensorMap* m, const void* base, int N, int H, int W, int C, uint32_t bw) {
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    uint64_t str[4] = {2, (uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+    uint32_t box[4] = {64, bw, 1, 1};
+    return encode_map_bf16(m, base, 4, dims, str, box);
+}
+
 int conv_fprop_convh(const void* x, const void* wp, const float* bias, const void* residual, void* y, int N, int H, int W, int Cin,
-                     int Cout, int R, int S, int act, cudaStream_t st, float* stats, int* stats_rows) {
+                     int Cout, int R, int S, int act, cudaStream_t st, float* stats, int* stats_rows, const ChanCat* src, const ChanCat* dst) {
     ConvHParams p;
     memset(&p, 0, sizeof(p));
     STC_REQUIRE(convh_plan(Cout, R, p.BN, p.T, p.a_slots, p.b_stages, p.staged), "conv_fprop_convh: no plan for Cout=%d R=%d", Cout, R);
+    if (src && src->n == 1) { x = src->ptr[0]; src = nullptr; }
+    if (dst && dst->n == 1) { y = const_cast<void*>(dst->ptr[0]); dst = nullptr; }
+    if (int rc = check_cat(src, Cin, "conv_fprop_convh input")) return rc;
+    if (int rc = check_cat(dst, Cout, "conv_fprop_convh output")) return rc;
+    STC_REQUIRE(!dst || (!bias && !residual && act == STC_ACT_NONE && !stats), "conv_fprop_convh: a split output takes no bias / residual / activation / statistics");
+    if (src) x = src->ptr[0];
+    if (dst) y = const_cast<void*>(dst->ptr[0]);
     STC_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)wp & 15) == 0 && ((uintptr_t)y & 15) == 0, "conv_fprop_convh: unaligned pointer");
     const int bwh = 128 + S - 1;
-    {
-        uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-        uint64_t str[4] = {2, (uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
-        uint32_t box[4] = {64, (uint32_t)bwh, 1, 1};
-        int rc = encode_map_bf16(&p.tmA, x, 4, dims, str, box);
+    p.n_src = 1; p.n_out = 1;
+    if (src) {
+        p.n_src = src->n;
+        int acc = 0;
+        for (int j = 0; j < src->n; ++j) {
+            int rc = convh_encode_nhwc(j ? &p.tmA2[j - 1] : &p.tmA, src->ptr[j], N, H, W, src->c[j], (uint32_t)bwh);
+            if (rc) return rc;
+            acc += src->c[j] / 64;
+            p.src_chunk_end[j] = acc;
+        }
+    } else {
+        int rc = convh_encode_nhwc(&p.tmA, x, N, H, W, Cin, (uint32_t)bwh);
         if (rc) return rc;
+    }
+    if (dst) {
+        p.n_out = dst->n;
+        int acc = 0;
+        for (int j = 0; j < dst->n; ++j) {
+            acc += dst->c[j];
+            p.out_ch_end[j] = acc;
+            if (j) p.out2[j - 1] = const_cast<void*>(dst->ptr[j]);
+        }
     }
     {
         uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)(R * S)};
@@ -485,11 +549,10 @@ int conv_fprop_convh(const void* x, const void* wp, const float* bias, const voi
         if (rc) return rc;
     }
     if (p.staged) {
-        uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-        uint64_t str[4] = {2, (uint64_t)Cout * 2, (uint64_t)W * Cout * 2, (uint64_t)H * W * Cout * 2};
-        uint32_t box[4] = {64, 32, 1, 1};
-        int rc = encode_map_bf16(&p.tmC, y, 4, dims, str, box);
-        if (rc) return rc;
+        for (int j = 0; j < p.n_out; ++j) {
+            int rc = convh_encode_nhwc(j ? &p.tmC2[j - 1] : &p.tmC, dst ? dst->ptr[j] : y, N, H, W, dst ? dst->c[j] : Cout, 32);
+            if (rc) return rc;
+        }
     }
     p.H = H; p.W = W; p.R = R; p.S = S; p.cin_chunks = Cin / 64;
     p.num_n_tiles = Cout / p.BN;

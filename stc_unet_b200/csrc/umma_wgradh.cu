@@ -30,6 +30,8 @@ namespace stc {
 struct alignas(64) WgradHParams {
     CUtensorMap tmX;   // x  {Cin,  W, H, N}, box {64, 128+S-1, 1, 1}
     CUtensorMap tmDY;  // dy {Cout, W, H, N}, box {64, 128, 1, 1}
+    CUtensorMap tmX2[kMaxCat - 1];   // virtual channel concat of the input (common.cuh ChanCat): sources 1..n_src-1
+    int n_src, src_chunk_end[kMaxCat];
     int H, W, R, S, SPf, cin_chunks, BN, num_n_tiles;   // SPf = S / 2 full tap pairs per filter row
     int RG, num_groups;          // filter rows per group, number of groups
     int blocks_w, row_splits, rows_per_split;
@@ -85,6 +87,7 @@ __global__ void __launch_bounds__(kWgradHThreads, 1) umma_wgradh_kernel(const __
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&p.tmX);
         ptx::prefetch_tensormap(&p.tmDY);
+        for (int j = 1; j < p.n_src; ++j) ptx::prefetch_tensormap(&p.tmX2[j - 1]);
         for (int s = 0; s < p.a_slots; ++s) { ptx::mbar_init(a_full(s), 1); ptx::mbar_init(a_empty(s), 1); }
         for (int s = 0; s < p.b_stages; ++s) { ptx::mbar_init(b_full(s), 1); ptx::mbar_init(b_empty(s), 1); }
         ptx::mbar_init(acc_full, 1);
@@ -112,14 +115,22 @@ __global__ void __launch_bounds__(kWgradHThreads, 1) umma_wgradh_kernel(const __
         for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
             WItem it = decode_item(p, item);
             const int first = it.h_a + it.r0 - pr, count = (it.h_b - it.h_a) + it.rg - 1;
+            int lc = it.cc;
+            const CUtensorMap* mx = &p.tmX;
+            if (p.n_src > 1) {
+                int j = 0;
+                while (j + 1 < p.n_src && it.cc >= p.src_chunk_end[j]) ++j;
+                lc = it.cc - (j ? p.src_chunk_end[j - 1] : 0);
+                if (j) mx = &p.tmX2[j - 1];
+            }
             for (int e = 0; e < count; ++e) {
                 ptx::mbar_wait(a_empty(slot), phase ^ 1);
                 if (ptx::elect_one_sync()) {
                     // slot 0 is loaded twice: in place and into the mirror behind the last ring slot (cross-row pairs starting in the last slot)
                     ptx::mbar_arrive_expect_tx(a_full(slot), slot == 0 ? 2 * p.a_box_bytes : p.a_box_bytes);
-                    ptx::tma_load_4d(smem_base + slot * p.a_slot_bytes, &p.tmX, a_full(slot), it.cc * 64, it.w0 - ps, first + e, it.n_img);
+                    ptx::tma_load_4d(smem_base + slot * p.a_slot_bytes, mx, a_full(slot), lc * 64, it.w0 - ps, first + e, it.n_img);
                     if (slot == 0)
-                        ptx::tma_load_4d(smem_base + p.a_slots * p.a_slot_bytes, &p.tmX, a_full(slot), it.cc * 64, it.w0 - ps, first + e, it.n_img);
+                        ptx::tma_load_4d(smem_base + p.a_slots * p.a_slot_bytes, mx, a_full(slot), lc * 64, it.w0 - ps, first + e, it.n_img);
                 }
                 __syncwarp();
                 if (++slot == p.a_slots) { slot = 0; phase ^= 1; }
@@ -280,9 +291,14 @@ bool conv_wgradh_eligible(int W, int Cin, int Cout, int R, int S, int dtype) {
     return dtype == STC_BF16 && W >= 128 && Cin % 64 == 0 && Cout % 64 == 0 && R == S && (R == 3 || R == 5 || R == 7);
 }
 
-int conv_wgrad_wgradh(const void* x, const void* dy, float* ws, int N, int H, int W, int Cin, int Cout, int R, int S, cudaStream_t st) {
+int check_cat(const ChanCat* c, int total, const char* what);
+
+int conv_wgrad_wgradh(const void* x, const void* dy, float* ws, int N, int H, int W, int Cin, int Cout, int R, int S, cudaStream_t st,
+                      const ChanCat* src) {
     WgradHParams p;
     memset(&p, 0, sizeof(p));
+    if (src && src->n == 1) { x = src->ptr[0]; src = nullptr; }
+    if (int rc = check_cat(src, Cin, "conv_wgrad_wgradh input")) return rc;
     // BN = 128 when possible (measured 5-40 % faster than 64 on the Cout >= 128 layers: fewer, longer MMAs per dy tile)
     { const char* e = getenv("STC_WGRADH_BN"); p.BN = (Cout % 128 == 0 && !(e && atoi(e) == 64)) ? 128 : 64; }
     p.SPf = S / 2;
@@ -293,12 +309,16 @@ int conv_wgrad_wgradh(const void* x, const void* dy, float* ws, int N, int H, in
     STC_REQUIRE(p.RG >= 1, "conv_wgrad_wgradh: no plan");
     p.num_groups = (R + p.RG - 1) / p.RG;
     const int bwh = 128 + S - 1;
-    {
-        uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-        uint64_t str[4] = {2, (uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+    p.n_src = src ? src->n : 1;
+    for (int j = 0, acc = 0; j < p.n_src; ++j) {
+        const int cj = src ? src->c[j] : Cin;
+        uint64_t dims[4] = {(uint64_t)cj, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+        uint64_t str[4] = {2, (uint64_t)cj * 2, (uint64_t)W * cj * 2, (uint64_t)H * W * cj * 2};
         uint32_t box[4] = {64, (uint32_t)bwh, 1, 1};
-        int rc = encode_map_bf16(&p.tmX, x, 4, dims, str, box);
+        int rc = encode_map_bf16(j ? &p.tmX2[j - 1] : &p.tmX, src ? src->ptr[j] : x, 4, dims, str, box);
         if (rc) return rc;
+        acc += cj / 64;
+        p.src_chunk_end[j] = acc;
     }
     {
         uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)N};

@@ -54,6 +54,11 @@ class DoubleConv(nn.Module):
         x = ops.conv_bn_act(x, self.conv[0], self.conv[1], ACT_RELU, self.training)
         return ops.conv_bn_act(x, self.conv[3], self.conv[4], ACT_RELU, self.training)
 
+    def forward_cat(self, xs):
+        """DoubleConv(torch.cat(xs, dim=1)) with the first conv reading its sources directly (virtual concat)."""
+        x = ops.conv_bn_act_cat(xs, self.conv[0], self.conv[1], ACT_RELU, self.training)
+        return ops.conv_bn_act(x, self.conv[3], self.conv[4], ACT_RELU, self.training)
+
 
 class InConv(nn.Module):
     def __init__(self, in_ch, out_ch):
@@ -259,11 +264,14 @@ class Up(nn.Module):
         self.conv = DoubleConv(in_ch, out_ch)
 
     def forward(self, x1, x2):  # both NHWC; x2 = skip
-        if self.se:   # cat, CoordAtt pooling and `ca(x) + x` without ever writing the concatenated tensor
+        if self.se:   # cat, CoordAtt pooling and `ca(x) + x` in one fused write of cat + a_h * a_w
             x = ops.upcat_coordatt(x2, x1, True, self.ca.attention)
-        else:
-            x = ops.upcat(x2, x1, align_corners=True)
-        return self.conv(x)
+            return self.conv(x)
+        same = x2.shape[1] == 2 * x1.shape[1] and x2.shape[2] == 2 * x1.shape[2]       # no F.pad needed (unet_head.py:52-54)
+        if same and ops.cat_ok([x2.shape[-1], x1.shape[-1]], self.conv.conv[0].weight.shape[0], x1.dtype):
+            # virtual concat: the up-sampled map is written once, the skip is read in place by the conv's K loop; cat never exists
+            return self.conv.forward_cat([x2, ops.upsample2x(x1, align_corners=True)])
+        return self.conv(ops.upcat(x2, x1, align_corners=True))
 
 
 class BaseDecodeHead(BaseModule):

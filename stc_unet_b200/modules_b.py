@@ -60,6 +60,13 @@ class ConvModule(nn.Module):
             return ops.conv_bn_act(x, self.conv, self.bn, act, self.bn.training)
         return ops.conv2d(x, self.conv.weight, self.conv.bias, act=act)
 
+    def forward_cat(self, a, b):
+        """forward(torch.cat([a, b], dim=1)): the conv reads both tensors in place when the tcgen05 kernels take them (virtual concat)."""
+        if self.with_norm:
+            act = ACT_RELU if self.with_activation else ACT_NONE
+            return ops.conv_bn_act_cat([a, b], self.conv, self.bn, act, self.bn.training, materialise=lambda xs: ops.concat_channels(*xs))
+        return self.forward(ops.concat_channels(a, b))
+
 
 class BasicConvBlock(nn.Module):
     def __init__(self, in_channels, out_channels, num_convs=2, stride=1, dilation=1, with_cp=False, conv_cfg=None,
@@ -77,6 +84,12 @@ class BasicConvBlock(nn.Module):
 
     def forward(self, x):
         for m in self.convs:
+            x = m(x)
+        return x
+
+    def forward_cat(self, a, b):
+        x = self.convs[0].forward_cat(a, b)
+        for m in list(self.convs)[1:]:
             x = m(x)
         return x
 
@@ -157,7 +170,7 @@ class UpConvBlock(nn.Module):
 
     def forward(self, skip, x):
         x = self.upsample(x)
-        return self.conv_block(ops.concat_channels(skip, x))
+        return self.conv_block.forward_cat(skip, x)      # up_conv_block.py:99 torch.cat([skip, x], dim=1), never materialised
 
 
 @BACKBONES.register_module()
@@ -278,10 +291,10 @@ class FCNHead(BaseDecodeHead):
             for m in self.convs:
                 feats = m(feats)
             if self.concat_input:
-                feats = self.conv_cat(ops.concat_channels(xb, feats))
+                feats = self.conv_cat.forward_cat(xb, feats)
         elif self.concat_input:
             xa, xb = ops.fanout(x, 2)
-            feats = self.conv_cat(ops.concat_channels(xb, xa))
+            feats = self.conv_cat.forward_cat(xb, xa)
         return feats
 
     def forward(self, inputs):

@@ -67,6 +67,13 @@ class _DecoderBlock(nn.Module):
         self.attention2 = nn.Identity()
 
     def forward(self, x, skips=()):
+        skips = list(skips)
+        chs = [x.shape[-1]] + [t.shape[-1] for t in skips]
+        if skips and ops.cat_ok(chs, self.conv1[0].weight.shape[0], x.dtype):
+            # virtual concat: only the nearest-x2 map is written; the dense skips are read in place by conv1's K loop
+            xu = ops.cat_channels_n([x], up0=True)
+            y = ops.conv_bn_act_cat([xu, *skips], self.conv1[0], self.conv1[1], ACT_RELU, self.conv1[1].training)
+            return self.conv2(y)
         x = ops.cat_channels_n([x, *skips], up0=True)
         return self.conv2(self.conv1(x))
 

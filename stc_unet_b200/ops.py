@@ -551,6 +551,27 @@ def _im2col(x, R, S, Kpad=64):
 _EVAL_FOLD_CACHE: dict = {}     # (dtype, im2col, eps, (data_ptr, version) of every tensor involved) -> (packed folded weight, folded bias)
 
 
+def _folded_eval_operands(weight, bias, gamma, beta, bn: BNState, dtype, im2col: bool):
+    """(packed weight, bias) of the conv with the eval-mode BN folded in.  The folded + packed operand only changes when a parameter /
+    running statistic does: cached on their version counters when config.cache_eval_weights."""
+    Cout, Cin, R, S = weight.shape
+    ts = (weight, gamma, beta, bn.running_mean, bn.running_var) + ((bias,) if bias is not None else ())
+    key = (dtype, im2col, float(bn.eps)) + tuple((t.data_ptr(), t._version) for t in ts)
+    hit = _EVAL_FOLD_CACHE.get(key) if config.cache_eval_weights else None
+    if hit is None:
+        wf = torch.empty_like(weight)
+        bf = torch.empty(Cout, dtype=torch.float32, device=weight.device)
+        lib.call("stc_bn_fold_conv", weight, bias, gamma, beta, bn.running_mean, bn.running_var, float(bn.eps), wf, bf, Cout, Cin * R * S,
+                 stream_ptr())
+        wp = pack_weight(wf, dtype, im2col_pad=64, cache=False) if im2col else pack_weight(wf, dtype, cache=False)
+        hit = (wp, bf)
+        if config.cache_eval_weights:
+            if len(_EVAL_FOLD_CACHE) >= 1024:
+                _EVAL_FOLD_CACHE.clear()
+            _EVAL_FOLD_CACHE[key] = hit
+    return hit
+
+
 class _ConvBnAct(Function):
     @staticmethod
     def forward(ctx, x, weight, bias, gamma, beta, bn: BNState, act: int, pobjs):
@@ -563,20 +584,7 @@ class _ConvBnAct(Function):
         if not bn.training and not torch.is_grad_enabled() and config.fold_eval_bn:
             # inference: BN folded into the conv's weights / bias, activation in the conv epilogue - one pass instead of three
             # the folded + packed operand only changes when a parameter / running statistic does: cached on their version counters
-            ts = (weight, gamma, beta, bn.running_mean, bn.running_var) + ((bias,) if bias is not None else ())
-            key = (x.dtype, ctx.im2col, float(bn.eps)) + tuple((t.data_ptr(), t._version) for t in ts)
-            hit = _EVAL_FOLD_CACHE.get(key) if config.cache_eval_weights else None
-            if hit is None:
-                wf = torch.empty_like(weight)
-                bf = torch.empty(Cout, dtype=torch.float32, device=x.device)
-                lib.call("stc_bn_fold_conv", weight, bias, gamma, beta, bn.running_mean, bn.running_var, float(bn.eps), wf, bf, Cout, Cin * R * S,
-                         stream_ptr())
-                wp = pack_weight(wf, x.dtype, im2col_pad=64, cache=False) if ctx.im2col else pack_weight(wf, x.dtype, cache=False)
-                hit = (wp, bf)
-                if config.cache_eval_weights:
-                    if len(_EVAL_FOLD_CACHE) >= 1024:
-                        _EVAL_FOLD_CACHE.clear()
-                    _EVAL_FOLD_CACHE[key] = hit
+            hit = _folded_eval_operands(weight, bias, gamma, beta, bn, x.dtype, ctx.im2col)
             wp, bf = hit
             if ctx.im2col:
                 return conv_fprop(_im2col(x, R, S), wp, bf, None, Cout, 1, 1, act)
@@ -644,6 +652,117 @@ class _ConvBnAct(Function):
             wpt = pack_weight(weight, dy.dtype, transpose_flip=True)
             dx = conv_fprop(dy, wpt, None, None, weight.shape[1], R, S)
         return dx, dw, dbias, dgamma, dbeta, None, None, None
+
+
+def _bn_state(bn, training: bool) -> BNState:
+    sync = isinstance(bn, torch.nn.SyncBatchNorm)
+    return BNState(bn.running_mean, bn.running_var, bn.num_batches_tracked, 0.1 if bn.momentum is None else bn.momentum, bn.eps,
+                   training or not bn.track_running_stats, sync=sync, group=getattr(bn, "process_group", None) if sync else None)
+
+
+# ---------------------------------------------------------------------------------------------
+# Conv + BN + activation over a VIRTUAL channel concat: the conv reads its sources directly, the concatenated
+# tensor of Up.forward (unet_head.py:54-55) / UpConvBlock.forward (up_conv_block.py:99) / the UNet++ decoder blocks is never written
+# ---------------------------------------------------------------------------------------------
+def _pad5(vals, fill):
+    vals = list(vals)
+    return vals + [fill] * (5 - len(vals))
+
+
+def cat_ok(cins, Cout: int, dtype, needs_dgrad: bool = True) -> bool:
+    """True when the tcgen05 kernels take this list of sources as a virtual concat (bf16, every part a multiple of 64 channels)."""
+    if dtype != torch.bfloat16 or not 2 <= len(cins) <= 5:
+        return False
+    return bool(lib.raw("stc_conv_cat_ok")(*_pad5(cins, 0), int(Cout), dtype_code(dtype), config.engine))
+
+
+def conv_fprop_cat(xs, wp, bias, Cout: int, R: int, S: int, act: int = 0) -> torch.Tensor:
+    N, H, W, _ = xs[0].shape
+    cins = [x.shape[-1] for x in xs]
+    y = torch.empty((N, H, W, Cout), dtype=xs[0].dtype, device=xs[0].device)
+    _dense("conv_fprop", 2.0 * N * H * W * sum(cins) * Cout * R * S,
+           lambda: lib.call("stc_conv_fprop_cat", *_pad5(xs, None), *_pad5(cins, 0), wp, bias, y, N, H, W, Cout, R, S, act, dtype_code(y.dtype),
+                            config.engine, stream_ptr()))
+    return y
+
+
+def conv_wgrad_cat(xs, dy, R: int, S: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    N, H, W, _ = xs[0].shape
+    cins = [x.shape[-1] for x in xs]
+    Cin, Cout = sum(cins), dy.shape[-1]
+    ws = _wgrad_ws(R * S * Cin * Cout, dy.device)
+    _dense("conv_wgrad", 2.0 * N * H * W * Cin * Cout * R * S,
+           lambda: lib.call("stc_conv_wgrad_cat", *_pad5(xs, None), *_pad5(cins, 0), dy, ws, N, H, W, Cout, R, S, dtype_code(dy.dtype),
+                            config.engine, stream_ptr()))
+    if out is None:
+        out = torch.empty((Cout, Cin, R, S), dtype=torch.float32, device=dy.device)
+    lib.call("stc_unpack_conv_wgrad", ws, out, Cout, Cin, R, S, 0, stream_ptr())
+    return out
+
+
+def conv_dgrad_split(dy, wpt, cins, R: int, S: int):
+    """Input gradients of a conv over a virtual concat: one tensor per source, written by ONE dgrad launch."""
+    N, H, W, Cdy = dy.shape
+    dxs = [torch.empty((N, H, W, c), dtype=dy.dtype, device=dy.device) for c in cins]
+    _dense("conv_fprop", 2.0 * N * H * W * sum(cins) * Cdy * R * S,
+           lambda: lib.call("stc_conv_dgrad_split", dy, wpt, *_pad5(dxs, None), *_pad5(cins, 0), N, H, W, Cdy, R, S, dtype_code(dy.dtype),
+                            config.engine, stream_ptr()))
+    return dxs
+
+
+class _ConvBnActCat(Function):
+    @staticmethod
+    def forward(ctx, weight, bias, gamma, beta, bn: BNState, act: int, pobjs, *xs):
+        xs = [_chk(x) for x in xs]
+        Cout, Cin, R, S = weight.shape
+        cins = [x.shape[-1] for x in xs]
+        if sum(cins) != Cin or any(x.shape[:3] != xs[0].shape[:3] for x in xs):
+            raise RuntimeError(f"conv_bn_act_cat: sources {[tuple(x.shape) for x in xs]} do not concatenate to {Cin} input channels")
+        N, H, W, _ = xs[0].shape
+        P = N * H * W
+        if not bn.training and not torch.is_grad_enabled() and config.fold_eval_bn:
+            wp, bf = _folded_eval_operands(weight, bias, gamma, beta, bn, xs[0].dtype, False)
+            return conv_fprop_cat(xs, wp, bf, Cout, R, S, act)
+        wp = pack_weight(weight, xs[0].dtype)
+        y = conv_fprop_cat(xs, wp, bias, Cout, R, S)
+        mean, invstd, count = _bn_forward_stats(y, P, Cout, bn, None)
+        a = torch.empty_like(y)
+        lib.call("stc_bn_apply", y, mean, invstd, gamma, beta, a, P, Cout, act, dtype_code(y.dtype), stream_ptr())
+        ctx.save_for_backward(y, weight, gamma, beta, mean, invstd, *xs)
+        ctx.meta = (act, bn, count, R, S, pobjs, bias is not None, cins)
+        return a
+
+    @staticmethod
+    def backward(ctx, da):
+        y, weight, gamma, beta, mean, invstd, *xs = ctx.saved_tensors
+        act, bn, count, R, S, pobjs, has_bias, cins = ctx.meta
+        pw, pbias, pg, pb = pobjs
+        da = _chk(da)
+        N, H, W, Cout = y.shape
+        P = N * H * W
+        dy, dgamma, dbeta = _bn_backward(y, da, mean, invstd, gamma, beta, P, Cout, act, bn, count, pg, pb, None)
+        dbias = None
+        if has_bias:
+            dbias = _grad_buf(pbias, (Cout,), dy.device, zero=True) if bn.training else colsum(P, Cout, dy, _grad_buf(pbias, (Cout,), dy.device))
+        dw = conv_wgrad_cat(xs, dy, R, S, _grad_buf(pw, weight.shape, dy.device))
+        dxs = [None] * len(xs)
+        if any(ctx.needs_input_grad[7:]):
+            wpt = pack_weight(weight, dy.dtype, transpose_flip=True)
+            got = conv_dgrad_split(dy, wpt, cins, R, S)
+            dxs = [g if need else None for g, need in zip(got, ctx.needs_input_grad[7:])]
+        return (dw, dbias, dgamma, dbeta, None, None, None, *dxs)
+
+
+def conv_bn_act_cat(xs, conv: torch.nn.Conv2d, bn: torch.nn.modules.batchnorm._BatchNorm, act: int, training: bool, materialise=None):
+    """conv_bn_act(cat(xs, channels)) without writing the concatenation when the tcgen05 kernels take the sources directly; otherwise
+    `materialise(xs)` (default: ops.cat_channels_n) builds the concatenated tensor for the ordinary path."""
+    xs = list(xs)
+    Cout = conv.weight.shape[0]
+    if len(xs) >= 2 and cat_ok([x.shape[-1] for x in xs], Cout, xs[0].dtype) and all(x.shape[:3] == xs[0].shape[:3] for x in xs):
+        return _ConvBnActCat.apply(conv.weight, conv.bias, bn.weight, bn.bias, _bn_state(bn, training), act,
+                                   (conv.weight, conv.bias, bn.weight, bn.bias), *xs)
+    x = xs[0] if len(xs) == 1 else (materialise(xs) if materialise is not None else cat_channels_n(xs))
+    return conv_bn_act(x, conv, bn, act, training)
 
 
 def conv_bn_act(x, conv: torch.nn.Conv2d, bn: torch.nn.modules.batchnorm._BatchNorm, act: int, training: bool):

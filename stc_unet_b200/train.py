@@ -233,7 +233,9 @@ class Trainer:
             self.arena.prezeroed = False
         self.steps_done += 1
         ops.invalidate_weight_caches()      # the fused Adam moved the weights through raw pointers
-        return out["log_vars"]
+        # detached: a caller holding on to the log vars must not keep this step's autograd graph (and its AccumulateGrad nodes, which
+        # remember the stream they were created on) alive into a later CUDA-graph capture on another stream
+        return type(out["log_vars"])((k, v.detach()) for k, v in out["log_vars"].items())
 
     def resync(self):
         """Call after long rank-asymmetric host work (rank-0 checkpointing / evaluation between epochs) before stepping again: the ranks

