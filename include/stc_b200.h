@@ -318,6 +318,16 @@ int stc_seg_loss_fwd(const float* logits, const int64_t* label, double* stats, f
 int stc_seg_loss_bwd(const float* logits, const int64_t* label, const double* stats, const float* g_ce, const float* g_dice,
                      float* dlogits, int N, long long HW, int C, int ignore_index, float smooth, void* stream);
 
+/* Softmax backward inside the dP product of nn.MultiheadAttention's backward (unet_backbone.py:202,207): C = alpha * P .* (A * B - D[row])
+ * with A = dO, B = V^T, P = the stored probabilities (bf16, laid out like C) and D[b1, b2, m] = rowsum(dO * O) (fp32, stc_rowdot_heads):
+ * dS = scale * P * (dP - D) leaves the GEMM's epilogue directly - the L x L dP tensor and the separate softmax-backward pass
+ * (read P, read dP, write dS) disappear.  tcgen05 engine only; stc_gemm_dsoftmax_ok tells. */
+int stc_gemm_dsoftmax_ok(const stc_gemm_desc* d, int dtype, int engine);
+int stc_gemm_dsoftmax(const void* A, const void* B, const void* P, const float* D, void* C, const stc_gemm_desc* d, int dtype, int engine,
+                      void* stream);
+/* out[n, h, i] = sum_d a[n, i, h*hd + d] * b[n, i, h*hd + d] for (N, L, heads*hd) token tensors (fp32 out, (N, heads, L)). */
+int stc_rowdot_heads(const void* a, const void* b, float* out, int N, int L, int heads, int hd, int dtype, void* stream);
+
 /* ---------------------------------------------------------------- inference post-processing (K17; encoder_decoder.py:157-203,253,272) */
 /* preds[:, :, y1:y1+hc, x1:x1+wc] += crop ; count[:, y1.., x1..] += 1  (NCHW fp32; count (N,H,W)) */
 int stc_slide_accum(const float* crop, float* preds, float* count, int N, int C, int H, int W, int hc, int wc, int y1,

@@ -14,13 +14,14 @@ int conv_fprop_umma(const void*, const void*, const float*, const void*, void*, 
                     cudaStream_t, const ChanCat* src = nullptr, const ChanCat* dst = nullptr);
 int conv_wgrad_umma(const void*, const void*, float*, int, int, int, int, int, int, int, cudaStream_t, const ChanCat* src = nullptr);
 bool gemm_umma_eligible(const stc_gemm_desc*, int dtype);
+bool umma_staged_ok(int N);
 bool conv_convh_eligible(int W, int Cin, int Cout, int R, int S, int dtype);
 bool conv_wgradh_eligible(int W, int Cin, int Cout, int R, int S, int dtype);
 int conv_wgrad_wgradh(const void*, const void*, float*, int, int, int, int, int, int, int, cudaStream_t, const ChanCat* src = nullptr);
 int conv_fprop_convh(const void*, const void*, const float*, const void*, void*, int, int, int, int, int, int, int, int, cudaStream_t, float* stats = nullptr,
                      int* stats_rows = nullptr, const ChanCat* src = nullptr, const ChanCat* dst = nullptr);
 bool conv_convh_stats_ok(int Cout, int R);
-int gemm_umma(const void*, const void*, void*, const stc_gemm_desc*, int, cudaStream_t);
+int gemm_umma(const void*, const void*, void*, const stc_gemm_desc*, int, cudaStream_t, const void* mul_residual = nullptr, const float* rowvec = nullptr);
 }  // namespace stc
 
 using namespace stc;
@@ -175,6 +176,62 @@ extern "C" int stc_gemm(const void* A, const void* B, void* C, const stc_gemm_de
     }
     g_last_engine = STC_ENGINE_SIMT;
     return gemm_simt(A, B, C, d, dtype, st);
+}
+
+/* Softmax backward inside the dP product (K4): C = alpha * P .* (A * B - D[row]) with P laid out like C (bf16) and D fp32 indexed
+ * (batch1, batch2, m): dS = scale * P * (dO V^T - rowsum(dO * O)).  tcgen05 engine only (the caller keeps the separate softmax pass else). */
+extern "C" int stc_gemm_dsoftmax(const void* A, const void* B, const void* P, const float* D, void* C, const stc_gemm_desc* d, int dtype,
+                                 int engine, void* stream) {
+    STC_REQUIRE(d && d->M > 0 && d->N > 0 && d->K > 0 && d->batch1 > 0 && d->batch2 > 0 && P && D, "gemm_dsoftmax: bad arguments");
+    STC_REQUIRE(dtype == STC_BF16 && engine != STC_ENGINE_SIMT && gemm_umma_eligible(d, dtype), "gemm_dsoftmax: tcgen05 engine only (bf16, eligible strides)");
+    g_last_engine = STC_ENGINE_TCGEN05;
+    return gemm_umma(A, B, C, d, dtype, (cudaStream_t)stream, P, D);
+}
+extern "C" int stc_gemm_dsoftmax_ok(const stc_gemm_desc* d, int dtype, int engine) {
+    // OPT-IN (STC_DSOFTMAX_FUSED=1).  Measured on the STC-UNet step (N=16, 512x512, same box A/B): 75.1 -> 74.5-75.0 ms, but D taken from the
+    // bf16-rounded O does not cancel the tokens' common component exactly (the separate pass divides by the ACTUAL row sum of the stored
+    // probabilities, so sum_j dS_ij = 0): the worst q / k gradient error of the flip-free 512x512 parity run rises from 2.6 to 11 (the
+    // reference's own autocast path: 4.8), so the default keeps the separate softmax-backward pass.
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("STC_DSOFTMAX_FUSED"); on = (e && e[0] == '1') ? 1 : 0; }
+    const int off = !on;
+    return (!off && d && dtype == STC_BF16 && engine != STC_ENGINE_SIMT && gemm_umma_eligible(d, dtype) && umma_staged_ok(d->N)) ? 1 : 0;
+}
+
+namespace stc {
+// D[n, h, i] = sum_d a[n, i, h*hd + d] * b[n, i, h*hd + d]: one warp per (n, i, h), 8-element vectors, fp32 accumulation
+template <typename T>
+__global__ void __launch_bounds__(256) rowdot_heads_kernel(const T* __restrict__ a, const T* __restrict__ b, float* __restrict__ out, long long rows,
+                                                           int L, int heads, int hd) {
+    const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wid >= rows * heads) return;
+    const long long r = wid / heads;          // n * L + i
+    const int h = (int)(wid - r * heads);
+    const T* pa = a + (r * heads + h) * (long long)hd;
+    const T* pb = b + (r * heads + h) * (long long)hd;
+    float acc = 0.f;
+    for (int c = lane * 8; c < hd; c += 256) {
+        Vec8<T> x, y;
+        x.load(pa + c);
+        y.load(pb + c);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc = fmaf(x.v[k], y.v[k], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+        const long long n = r / L, i = r - n * L;
+        out[(n * heads + h) * (long long)L + i] = acc;
+    }
+}
+}  // namespace stc
+
+extern "C" int stc_rowdot_heads(const void* a, const void* b, float* out, int N, int L, int heads, int hd, int dtype, void* stream) {
+    STC_REQUIRE(a && b && out && N > 0 && L > 0 && heads > 0 && hd > 0 && hd % 8 == 0, "rowdot_heads: bad arguments (hd=%d must be a multiple of 8)", hd);
+    const long long warps = (long long)N * L * heads;
+    STC_DISPATCH_DTYPE(dtype, (rowdot_heads_kernel<T><<<ceil_div(warps * 32, 256), 256, 0, (cudaStream_t)stream>>>((const T*)a, (const T*)b, out,
+                                                                                                                  (long long)N * L, L, heads, hd)));
+    return check_launch("rowdot_heads");
 }
 
 /* bf16 operands, fp32 result: tcgen05 engine only (small weight-gradient products of a folded Linear pair). */

@@ -24,12 +24,7 @@ struct alignas(64) UmmaParams {
     CUtensorMap tmA;
     CUtensorMap tmB;
     CUtensorMap tmC;   // output map for the staged (shared memory + TMA store) epilogue, see store_tma
-    // virtual channel concat (common.cuh ChanCat): extra A sources (CONV / WGRAD) and extra outputs (CONV = dgrad of a concat conv)
-    CUtensorMap tmA2[kMaxCat - 1];
-    CUtensorMap tmC2[kMaxCat - 1];
-    int n_src, src_chunk_end[kMaxCat];     // cumulative 64-channel chunk counts of the A sources
-    int n_out, out_ch_end[kMaxCat];        // cumulative channel counts of the outputs
-    void* out2[kMaxCat - 1];
+    int n_src, n_out;   // virtual channel concat: number of A sources / outputs (1 = plain); the descriptors live at the END of the struct
     int mode;
     int num_tiles, num_n_tiles, num_m_tiles;
     int num_k_iters;  // conv/gemm: k iterations per tile; wgrad: total pixel tiles
@@ -56,6 +51,21 @@ struct alignas(64) UmmaParams {
     // store_tma: each epilogue warp stages 32 rows x 64 bf16 columns in a 128B-swizzled 4 KB buffer (two per warp) and one lane
     // issues a TMA store of that box -> full 128-byte lines instead of 32 scattered 16-byte row segments per instruction
     int store_tma;
+    // epi_mode 1 (GEMM, bf16 out): out = alpha * residual * (acc - rowvec[row]) - the softmax backward dS = scale * P * (dP - D) applied in
+    // the epilogue of the dP = dO V^T product (residual = P, rowvec = D = rowsum(dO * O)); rowvec index = b1 * rv_s1 + b2 * rv_s2 + m
+    int epi_mode;
+    const float* rowvec;
+    long long rv_s1, rv_s2;
+    // cta_group::2 variant (umma2_kernel): a CTA pair computes a 256 x BN tile; num_tiles counts PAIR tiles, b_* describe ONE CTA's half of B
+    int cta2;
+    // ---- cold tail (virtual channel concat, common.cuh ChanCat): extra A sources (CONV / WGRAD) and extra outputs (CONV = dgrad of a concat
+    // conv).  Kept BEHIND the hot fields: the roles read this struct through the small constant cache, and 1 KB of descriptors in front of
+    // the per-iteration scalars cost the per-tap wgrad 25 % (measured: 0.297 -> 0.390 ms on 512->512 3x3 @64x64)
+    int src_chunk_end[kMaxCat];            // cumulative 64-channel chunk counts of the A sources
+    int out_ch_end[kMaxCat];               // cumulative channel counts of the outputs
+    void* out2[kMaxCat - 1];
+    CUtensorMap tmA2[kMaxCat - 1];
+    CUtensorMap tmC2[kMaxCat - 1];
 };
 
 constexpr uint32_t kStageBufBytes = 32 * 128;   // 32 rows x 64 bf16
@@ -77,7 +87,9 @@ __device__ __forceinline__ void pixel_tile_origin(const UmmaParams& p, int pt, i
     w0 = (rem - th * p.tiles_w) * p.BW;
 }
 
-__device__ __forceinline__ TileInfo decode_tile(const UmmaParams& p, int tile) {
+// rank: this CTA's rank in its pair (CTA2), which owns M tile 2 * (pair tile) + rank
+template <bool CTA2>
+__device__ __forceinline__ TileInfo decode_tile(const UmmaParams& p, int tile, int rank) {
     TileInfo t;
     t.nt = tile % p.num_n_tiles;
     int t2 = tile / p.num_n_tiles;
@@ -85,11 +97,13 @@ __device__ __forceinline__ TileInfo decode_tile(const UmmaParams& p, int tile) {
     t.k0 = 0;
     t.k1 = p.num_k_iters;
     if (p.mode == MODE_CONV) {
-        t.mt = t2;
-        pixel_tile_origin(p, t2, t.n_img, t.h0, t.w0);
+        t.mt = CTA2 ? 2 * t2 + rank : t2;
+        pixel_tile_origin(p, t.mt, t.n_img, t.h0, t.w0);
     } else if (p.mode == MODE_GEMM) {
-        t.mt = t2 % p.num_m_tiles;
-        int b = t2 / p.num_m_tiles;
+        const int mts = CTA2 ? p.num_m_tiles / 2 : p.num_m_tiles;
+        t.mt = t2 % mts;
+        int b = t2 / mts;
+        if (CTA2) t.mt = 2 * t.mt + rank;
         t.b1 = b / p.batch2;
         t.b2 = b - t.b1 * p.batch2;
     } else {
@@ -129,7 +143,8 @@ __device__ __forceinline__ float epi_act(float v, int act) {
 constexpr int kUmmaThreads = 192;
 constexpr int kAccCols = 256;
 
-__global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_constant__ UmmaParams p) {
+template <bool CTA2>
+__device__ __forceinline__ void umma_body(const UmmaParams& p) {
     extern __shared__ uint8_t smem_raw[];
     // 1024B alignment for the 128B swizzle atoms
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -142,6 +157,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_cons
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = ptx::smem_u32(smem);
     const uint32_t bar_base = ptx::smem_u32(bars);
+    const int rank = CTA2 ? (int)ptx::cluster_ctarank() : 0;                 // 0 = leader of the pair
+    const int tile0 = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;        // persistent loop: pair (or CTA) index and stride
+    const int tstep = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * p.stages + s); };
@@ -159,16 +177,16 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_cons
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(tfull_bar(s), 1);
-            ptx::mbar_init(tempty_bar(s), 4);
+            ptx::mbar_init(tempty_bar(s), CTA2 ? 8 : 4);   // cta2: the epilogue warps of BOTH CTAs arrive on the leader's barrier
         }
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
-        ptx::tmem_relinquish();
+        if (CTA2) { ptx::tmem_alloc2(ptx::smem_u32(tmem_slot), 512); ptx::tmem_relinquish2(); }
+        else { ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512); ptx::tmem_relinquish(); }
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    if (CTA2) ptx::cluster_sync_all(); else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (tmem_base != 0) {  // we allocate all 512 columns, so the base must be column 0 / lane 0
@@ -178,68 +196,108 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_cons
 
     if (warp == 0) {
         // ===================== TMA producer (warp-uniform; one elected lane issues) =====================
+        // The k loop carries its coordinates incrementally: no integer division per iteration.  (With the tap / chunk / pixel-tile
+        // decompositions recomputed every iteration the two dependent division chains of the per-tap wgrad took longer than the 8 MMAs of
+        // a k iteration - the producer, not the tensor pipe, paced that kernel.)
         {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                TileInfo t = decode_tile(p, tile);
+            const int bn_off = CTA2 ? rank * (p.BN / 2) : 0;   // cta2: this CTA stages its half of the N columns of B
+            const int pw_end = p.tiles_w * p.BW, ph_end = p.tiles_h * p.BH;
+            for (int tile = tile0; tile < p.num_tiles; tile += tstep) {
+                TileInfo t = decode_tile<CTA2>(p, tile, rank);
+                int cc = 0, r = 0, s = 0, tap = 0;            // CONV: k iteration = (tap = r * S + s, 64-channel chunk cc)
+                int pn = 0, ph0 = 0, pw0 = 0;                 // WGRAD: k iteration = pixel tile (image pn, origin ph0 / pw0)
+                int a_cc[2] = {0, 0}, a_r[2] = {0, 0}, a_s[2] = {0, 0};   // WGRAD: (chunk, tap row, tap column) of the tile's two 64-row atoms
+                if (p.mode == MODE_WGRAD) {
+                    pixel_tile_origin(p, t.k0, pn, ph0, pw0);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        int atom = 2 * t.mt + j;
+                        if (atom >= p.num_atoms) atom = 0;  // dummy rows, dropped by the epilogue
+                        const int atap = atom / p.cin_chunks;
+                        a_cc[j] = atom - atap * p.cin_chunks;
+                        a_r[j] = atap / p.S;
+                        a_s[j] = atap - a_r[j] * p.S;
+                    }
+                }
                 for (int kt = t.k0; kt < t.k1; ++kt) {
                     ptx::mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t a_dst = smem_base + stage * stage_bytes;
                     const uint32_t b_dst = a_dst + p.a_stage_bytes;
-                    const uint32_t fb = full_bar(stage);
+                    // cta2: the TMA bytes of both CTAs complete on the LEADER's full barrier, which the leader arms for 2 x stage_bytes
+                    const uint32_t fb = CTA2 ? ptx::mapa_shared(full_bar(stage), 0) : full_bar(stage);
+                    auto ld4 = [&](uint32_t dst, const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+                        if (CTA2) ptx::tma_load_4d_2sm(dst, m, fb, c0, c1, c2, c3);
+                        else ptx::tma_load_4d(dst, m, fb, c0, c1, c2, c3);
+                    };
                     if (ptx::elect_one_sync()) {
-                    ptx::mbar_arrive_expect_tx(fb, stage_bytes);
-                    if (p.mode == MODE_CONV) {
-                        int tap = kt / p.cin_chunks, cc = kt - tap * p.cin_chunks;
-                        int r = tap / p.S, s = tap - r * p.S;
-                        int lc = cc;
-                        const CUtensorMap* ma = p.n_src > 1 ? cat_map_a(p, cat_source(p, cc, lc)) : &p.tmA;
-                        ptx::tma_load_4d(a_dst, ma, fb, lc * 64, t.w0 + s - p.S / 2, t.h0 + r - p.R / 2, t.n_img);
-                        ptx::tma_load_3d(b_dst, &p.tmB, fb, cc * 64, t.nt * p.BN, tap);
-                    } else if (p.mode == MODE_GEMM) {
-                        if (!p.a_mn_major) {
-                            ptx::tma_load_4d(a_dst, &p.tmA, fb, kt * 64, t.mt * 128, t.b2, t.b1);
+                        if (!CTA2) ptx::mbar_arrive_expect_tx(fb, stage_bytes);
+                        else if (rank == 0) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * stage_bytes);
+                        if (p.mode == MODE_CONV) {
+                            if (p.n_src > 1) {   // virtual concat: the chunk's source tensor has its own descriptor
+                                int lc;
+                                const CUtensorMap* ma = cat_map_a(p, cat_source(p, cc, lc));
+                                ld4(a_dst, ma, lc * 64, t.w0 + s - p.S / 2, t.h0 + r - p.R / 2, t.n_img);
+                            } else {
+                                ld4(a_dst, &p.tmA, cc * 64, t.w0 + s - p.S / 2, t.h0 + r - p.R / 2, t.n_img);
+                            }
+                            if (CTA2) ptx::tma_load_3d_2sm(b_dst, &p.tmB, fb, cc * 64, t.nt * p.BN + bn_off, tap);
+                            else ptx::tma_load_3d(b_dst, &p.tmB, fb, cc * 64, t.nt * p.BN, tap);
+                        } else if (p.mode == MODE_GEMM) {
+                            if (!p.a_mn_major) {
+                                ld4(a_dst, &p.tmA, kt * 64, t.mt * 128, t.b2, t.b1);
+                            } else {
+                                for (int j = 0; j < p.a_boxes; ++j) ld4(a_dst + j * p.a_box_bytes, &p.tmA, t.mt * 128 + j * 64, kt * 64, t.b2, t.b1);
+                            }
+                            if (!p.b_mn_major) {
+                                ld4(b_dst, &p.tmB, kt * 64, t.nt * p.BN + bn_off, t.b2, t.b1);
+                            } else {
+                                for (int j = 0; j < p.b_boxes; ++j)
+                                    ld4(b_dst + j * p.b_box_bytes, &p.tmB, t.nt * p.BN + bn_off + j * 64, kt * 64, t.b2, t.b1);
+                            }
                         } else {
-                            for (int j = 0; j < p.a_boxes; ++j)
-                                ptx::tma_load_4d(a_dst + j * p.a_box_bytes, &p.tmA, fb, t.mt * 128 + j * 64, kt * 64, t.b2, t.b1);
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                if (p.n_src > 1) {
+                                    int lc;
+                                    const CUtensorMap* ma = cat_map_a(p, cat_source(p, a_cc[j], lc));
+                                    ld4(a_dst + j * p.a_box_bytes, ma, lc * 64, pw0 + a_s[j] - p.S / 2, ph0 + a_r[j] - p.R / 2, pn);
+                                } else {
+                                    ld4(a_dst + j * p.a_box_bytes, &p.tmA, a_cc[j] * 64, pw0 + a_s[j] - p.S / 2, ph0 + a_r[j] - p.R / 2, pn);
+                                }
+                            }
+                            for (int j = 0; j < p.b_boxes; ++j) ld4(b_dst + j * p.b_box_bytes, &p.tmB, t.nt * p.BN + j * 64, pw0, ph0, pn);
                         }
-                        if (!p.b_mn_major) {
-                            ptx::tma_load_4d(b_dst, &p.tmB, fb, kt * 64, t.nt * p.BN, t.b2, t.b1);
-                        } else {
-                            for (int j = 0; j < p.b_boxes; ++j)
-                                ptx::tma_load_4d(b_dst + j * p.b_box_bytes, &p.tmB, fb, t.nt * p.BN + j * 64, kt * 64, t.b2, t.b1);
-                        }
-                    } else {
-                        int n_img, h0, w0;
-                        pixel_tile_origin(p, kt, n_img, h0, w0);
-                        for (int j = 0; j < 2; ++j) {
-                            int atom = 2 * t.mt + j;
-                            if (atom >= p.num_atoms) atom = 0;  // dummy rows, dropped by the epilogue
-                            int tap = atom / p.cin_chunks, cc = atom - tap * p.cin_chunks;
-                            int r = tap / p.S, s = tap - r * p.S;
-                            int lc = cc;
-                            const CUtensorMap* ma = p.n_src > 1 ? cat_map_a(p, cat_source(p, cc, lc)) : &p.tmA;
-                            ptx::tma_load_4d(a_dst + j * p.a_box_bytes, ma, fb, lc * 64, w0 + s - p.S / 2, h0 + r - p.R / 2, n_img);
-                        }
-                        for (int j = 0; j < p.b_boxes; ++j)
-                            ptx::tma_load_4d(b_dst + j * p.b_box_bytes, &p.tmB, fb, t.nt * p.BN + j * 64, w0, h0, n_img);
-                    }
                     }
                     __syncwarp();
+                    if (p.mode == MODE_CONV) {
+                        if (++cc == p.cin_chunks) {
+                            cc = 0;
+                            ++tap;
+                            if (++s == p.S) { s = 0; ++r; }
+                        }
+                    } else if (p.mode == MODE_WGRAD) {
+                        pw0 += p.BW;
+                        if (pw0 >= pw_end) {
+                            pw0 = 0;
+                            ph0 += p.BH;
+                            if (ph0 >= ph_end) { ph0 = 0; ++pn; }
+                        }
+                    }
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (warp-uniform; one elected lane issues) =====================
-        {
+        // ===================== MMA issuer (warp-uniform; one elected lane issues; cta2: the leader CTA only) =====================
+        if (!CTA2 || rank == 0) {
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase[2] = {0, 0};
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                TileInfo t = decode_tile(p, tile);
+            for (int tile = tile0; tile < p.num_tiles; tile += tstep) {
+                TileInfo t = decode_tile<CTA2>(p, tile, rank);
                 if (t.k1 <= t.k0) continue;
                 ptx::mbar_wait(tempty_bar(acc), acc_phase[acc] ^ 1);
                 ptx::tc_fence_after();
@@ -256,14 +314,18 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_cons
                             // advancing the 14-bit start-address field (16B units); never carries out of it (smem < 256 KB)
                             uint64_t a_desc = a_desc0 + (uint64_t)((ks * p.a_kstep_bytes) >> 4);
                             uint64_t b_desc = b_desc0 + (uint64_t)((ks * p.b_kstep_bytes) >> 4);
-                            ptx::mma_bf16_ss(d_tmem, a_desc, b_desc, p.idesc, (kt > t.k0 || ks > 0) ? 1u : 0u);
+                            if (CTA2) ptx::mma_bf16_ss2(d_tmem, a_desc, b_desc, p.idesc, (kt > t.k0 || ks > 0) ? 1u : 0u);
+                            else ptx::mma_bf16_ss(d_tmem, a_desc, b_desc, p.idesc, (kt > t.k0 || ks > 0) ? 1u : 0u);
                         }
-                        ptx::tc_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+                        // frees the smem slot (cta2: in both CTAs) once these MMAs retire
+                        if (CTA2) ptx::tc_commit2(empty_bar(stage), 3); else ptx::tc_commit(empty_bar(stage));
                     }
                     __syncwarp();
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
-                if (ptx::elect_one_sync()) ptx::tc_commit(tfull_bar(acc));  // accumulator ready for the epilogue
+                if (ptx::elect_one_sync()) {   // accumulator ready for the epilogue (cta2: of both CTAs)
+                    if (CTA2) ptx::tc_commit2(tfull_bar(acc), 3); else ptx::tc_commit(tfull_bar(acc));
+                }
                 __syncwarp();
                 acc_phase[acc] ^= 1;
                 acc ^= 1;
@@ -275,8 +337,13 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_cons
         const int row = q * 32 + lane;
         int acc = 0, stage_buf = 0;
         uint32_t acc_phase[2] = {0, 0};
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-            TileInfo t = decode_tile(p, tile);
+        const uint32_t tempty_leader0 = CTA2 ? ptx::mapa_shared(tempty_bar(0), 0) : 0u, tempty_leader1 = CTA2 ? ptx::mapa_shared(tempty_bar(1), 0) : 0u;
+        auto release_acc = [&](int a) {
+            if (CTA2) ptx::mbar_arrive_cluster(a ? tempty_leader1 : tempty_leader0);
+            else ptx::mbar_arrive(tempty_bar(a));
+        };
+        for (int tile = tile0; tile < p.num_tiles; tile += tstep) {
+            TileInfo t = decode_tile<CTA2>(p, tile, rank);
             if (t.k1 <= t.k0) continue;
             bool valid;
             long long off;
@@ -294,6 +361,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_cons
                 valid = atom < p.num_atoms;
                 off = ((long long)atom * 64 + (row & 63)) * p.Cout + (long long)t.nt * p.BN;
             }
+            // epi_mode 1: alpha * D[row], subtracted from alpha * acc before the product with the residual (P)
+            const float dsub = (p.epi_mode && valid) ? p.alpha * __ldg(p.rowvec + t.b1 * p.rv_s1 + t.b2 * p.rv_s2 + (t.mt * 128 + row)) : 0.f;
             ptx::mbar_wait(tfull_bar(acc), acc_phase[acc]);
             ptx::tc_fence_after();
             const uint32_t t_addr = tmem_base + acc * kAccCols + ((uint32_t)(q * 32) << 16);
@@ -330,16 +399,24 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_cons
                         }
                         if (p.residual && valid) {
                             const uint4* r = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.residual) + off + c + half * 32);
+                            float x[32];
 #pragma unroll
                             for (int g = 0; g < 4; ++g) {
                                 uint4 rv = __ldg(r + g);
                                 const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) {
-                                    float2 x = __bfloat1622float2(h[e]);
-                                    f[g * 8 + 2 * e] += x.x;
-                                    f[g * 8 + 2 * e + 1] += x.y;
+                                    const float2 xx = __bfloat1622float2(h[e]);
+                                    x[g * 8 + 2 * e] = xx.x;
+                                    x[g * 8 + 2 * e + 1] = xx.y;
                                 }
+                            }
+                            if (p.epi_mode) {   // softmax backward: (alpha * acc - alpha * D[row]) * P
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) f[j] = (f[j] - dsub) * x[j];
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) f[j] += x[j];
                             }
                         }
                         if (p.act == STC_ACT_RELU) {   // uniform branch per chunk: a per-element switch compiles to a jump table
@@ -372,7 +449,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_cons
                 }
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+                if (lane == 0) release_acc(acc);
                 acc_phase[acc] ^= 1;
                 acc ^= 1;
                 continue;
@@ -409,8 +486,13 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_cons
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 float2 x = __bfloat1622float2(h[e]);
-                                f[g * 8 + 2 * e] += x.x;
-                                f[g * 8 + 2 * e + 1] += x.y;
+                                if (p.epi_mode) {
+                                    f[g * 8 + 2 * e] = (f[g * 8 + 2 * e] - dsub) * x.x;
+                                    f[g * 8 + 2 * e + 1] = (f[g * 8 + 2 * e + 1] - dsub) * x.y;
+                                } else {
+                                    f[g * 8 + 2 * e] += x.x;
+                                    f[g * 8 + 2 * e + 1] += x.y;
+                                }
                             }
                         }
                     } else {
@@ -450,7 +532,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_cons
             }
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+            if (lane == 0) release_acc(acc);
             acc_phase[acc] ^= 1;
             acc ^= 1;
         }
@@ -458,12 +540,16 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_cons
     }
 
     ptx::tc_fence_before();
-    __syncthreads();
+    if (CTA2) ptx::cluster_sync_all(); else __syncthreads();   // cta2: the peer's shared memory / barriers stay alive until both are done
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, 512);
+        if (CTA2) ptx::tmem_dealloc2(tmem_base, 512); else ptx::tmem_dealloc(tmem_base, 512);
     }
 }
+
+__global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_constant__ UmmaParams p) { umma_body<false>(p); }
+// the cta_group::2 variant: CTA pairs (cluster of 2 = the two SMs of a TPC) computing 256 x BN tiles
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1) umma2_kernel(const __grid_constant__ UmmaParams p) { umma_body<true>(p); }
 
 // ------------------------------------------------------------------------------------------------
 // host side
@@ -542,10 +628,35 @@ static int launch(UmmaParams& p, cudaStream_t st) {
         set_error("umma: smem %zu too large", smem);
         return STC_ERR_INVALID;
     }
+    if (p.cta2) {
+        static bool attr2[64] = {false};
+        if (dev >= 0 && dev < 64 && !attr2[dev]) {
+            STC_CUDA(cudaFuncSetAttribute(umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr2[dev] = true;
+        }
+        int pairs = num_sms() / 2;
+        if (p.num_tiles < pairs) pairs = p.num_tiles;
+        if (pairs <= 0) return STC_OK;
+        umma2_kernel<<<2 * pairs, kUmmaThreads, smem, st>>>(p);
+        return check_launch("umma2_kernel");
+    }
     int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
     if (grid <= 0) return STC_OK;
     umma_kernel<<<grid, kUmmaThreads, smem, st>>>(p);
     return check_launch("umma_kernel");
+}
+
+// cta_group::2 is used when the M tiles pair up and each CTA's half of B keeps the layout rules (K-major: BN/2 rows, a multiple of 16;
+// MN-major: whole 64-column atoms).  STC_CTA2=0 switches it off (the 1-CTA kernel is the reference for the tests).
+// Measured (profiles/r2_gemm_probe.txt): the pair wins where the main loop dominates (PV / dV / dQ / dK with K = 4096: +6 %, the W < 128
+// 3x3 convolutions: +2-3 %) and loses on short-K tiles, which are bound by the accumulator read-out of the epilogue (QK^T, K = 256: -13 %),
+// so it is taken from 16 k-iterations (K >= 1024) on.  STC_CTA2=0 never, STC_CTA2=2 whenever the shapes allow (tests).
+static bool use_cta2(int num_m_tiles_per_batch, int BN, bool b_mn_major, int k_iters) {
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("STC_CTA2"); mode = e ? atoi(e) : 1; }
+    if (mode == 0 || num_m_tiles_per_batch % 2 != 0 || BN % 32 != 0) return false;
+    if (b_mn_major && BN % 128 != 0) return false;
+    return mode == 2 || k_iters >= 16;
 }
 
 static void conv_geometry(UmmaParams& p, int H, int W, int R, int S, int Cin) {
@@ -608,6 +719,10 @@ int conv_fprop_umma(const void* x, const void* wp, const float* bias, const void
     conv_geometry(p, H, W, R, S, Cin);
     p.BN = pick_bn(Cout);
     p.n_src = 1; p.n_out = 1;
+    p.num_n_tiles = Cout / p.BN;
+    p.num_m_tiles = N * p.tiles_h * p.tiles_w;
+    p.cta2 = use_cta2(p.num_m_tiles, p.BN, false, R * S * p.cin_chunks) ? 1 : 0;
+    const int bn_cta = p.cta2 ? p.BN / 2 : p.BN;          // rows of B (output channels) staged by one CTA
     if (src) {
         p.n_src = src->n;
         int acc = 0;
@@ -624,21 +739,19 @@ int conv_fprop_umma(const void* x, const void* wp, const float* bias, const void
     {
         uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)(R * S)};
         uint64_t str[3] = {2, (uint64_t)Cin * 2, (uint64_t)Cout * Cin * 2};
-        uint32_t box[3] = {64, (uint32_t)p.BN, 1};
+        uint32_t box[3] = {64, (uint32_t)bn_cta, 1};
         int rc = encode_map(&p.tmB, wp, 3, dims, str, box);
         if (rc) return rc;
     }
-    p.num_n_tiles = Cout / p.BN;
-    p.num_m_tiles = N * p.tiles_h * p.tiles_w;
-    p.num_tiles = p.num_m_tiles * p.num_n_tiles;
+    p.num_tiles = (p.cta2 ? p.num_m_tiles / 2 : p.num_m_tiles) * p.num_n_tiles;
     p.num_k_iters = R * S * p.cin_chunks;
     p.ksteps = 4;
     p.a_boxes = p.b_boxes = 1;
     p.a_stage_bytes = p.a_box_bytes = 128 * 128;
-    p.b_stage_bytes = p.b_box_bytes = (uint32_t)p.BN * 128;
+    p.b_stage_bytes = p.b_box_bytes = (uint32_t)bn_cta * 128;
     p.a_lbo = 0; p.a_sbo = 1024; p.a_kstep_bytes = 32;
     p.b_lbo = 0; p.b_sbo = 1024; p.b_kstep_bytes = 32;
-    p.idesc = make_idesc_bf16(128, p.BN, 0, 0);
+    p.idesc = make_idesc_bf16(p.cta2 ? 256 : 128, p.BN, 0, 0);
     p.store_tma = (p.BN % 64 == 0 && !getenv_off("STC_TMA_STORE")) ? 1 : 0;
     if (dst) {
         p.n_out = dst->n;
@@ -725,6 +838,9 @@ int conv_wgrad_umma(const void* x, const void* dy, float* ws, int N, int H, int 
 
 // Batched GEMM on the tensor cores.  Supported operand layouts (element strides):
 //   A: K-major (sAk == 1) or M-major (sAm == 1);  B: K-major (sBk == 1) or N-major (sBn == 1).
+// the epilogue modes that live in the staged (TMA store) path need BN % 64 == 0
+bool umma_staged_ok(int N) { const int bn = pick_bn(N); return bn != 0 && bn % 64 == 0 && !getenv_off("STC_TMA_STORE"); }
+
 bool gemm_umma_eligible(const stc_gemm_desc* d, int dtype) {
     if (dtype != STC_BF16 || d->beta != 0.f) return false;
     if (!(d->sAk == 1 || d->sAm == 1) || !(d->sBk == 1 || d->sBn == 1)) return false;
@@ -739,8 +855,11 @@ bool gemm_umma_eligible(const stc_gemm_desc* d, int dtype) {
     return true;
 }
 
-int gemm_umma(const void* A, const void* B, void* C, const stc_gemm_desc* d, int out_dtype, cudaStream_t st) {
+int gemm_umma(const void* A, const void* B, void* C, const stc_gemm_desc* d, int out_dtype, cudaStream_t st, const void* mul_residual,
+              const float* rowvec) {
     STC_REQUIRE(gemm_umma_eligible(d, STC_BF16), "gemm_umma: descriptor not eligible");
+    STC_REQUIRE((mul_residual == nullptr) == (rowvec == nullptr) && (!mul_residual || (out_dtype == STC_BF16 && ((uintptr_t)mul_residual & 15) == 0)),
+                "gemm_umma: the softmax-backward epilogue needs P (bf16, 16-byte aligned, laid out like C) and D together");
     UmmaParams p;
     memset(&p, 0, sizeof(p));
     p.mode = MODE_GEMM;
@@ -748,6 +867,8 @@ int gemm_umma(const void* A, const void* B, void* C, const stc_gemm_desc* d, int
     p.BN = pick_bn(d->N);
     p.a_mn_major = (d->sAk != 1);
     p.b_mn_major = (d->sBk != 1);
+    p.cta2 = (d->M % 128 == 0 && use_cta2(d->M / 128, p.BN, p.b_mn_major, (d->K + 63) / 64)) ? 1 : 0;
+    const int bn_cta = p.cta2 ? p.BN / 2 : p.BN;          // columns of B staged by one CTA
     uint64_t b1 = (uint64_t)d->batch1, b2 = (uint64_t)d->batch2;
     {
         // inner dim is the unit-stride one
@@ -764,7 +885,7 @@ int gemm_umma(const void* A, const void* B, void* C, const stc_gemm_desc* d, int
         uint64_t ld = p.b_mn_major ? d->sBk : d->sBn;
         uint64_t dims[4] = {inner, outer, b2, b1};
         uint64_t str[4] = {2, ld * 2, (uint64_t)(d->sB2 ? d->sB2 : 8) * 2, (uint64_t)(d->sB1 ? d->sB1 : 8) * 2};
-        uint32_t box[4] = {64, (uint32_t)(p.b_mn_major ? 64 : p.BN), 1, 1};
+        uint32_t box[4] = {64, (uint32_t)(p.b_mn_major ? 64 : bn_cta), 1, 1};
         int rc = encode_map(&p.tmB, B, 4, dims, str, box);
         if (rc) return rc;
     }
@@ -772,7 +893,7 @@ int gemm_umma(const void* A, const void* B, void* C, const stc_gemm_desc* d, int
     p.batch2 = d->batch2;
     p.num_m_tiles = (d->M + 127) / 128;
     p.num_n_tiles = d->N / p.BN;
-    p.num_tiles = p.num_m_tiles * p.num_n_tiles * d->batch1 * d->batch2;
+    p.num_tiles = (p.cta2 ? p.num_m_tiles / 2 : p.num_m_tiles) * p.num_n_tiles * d->batch1 * d->batch2;
     p.num_k_iters = (d->K + 63) / 64;
     p.ksteps = 4;
     if (!p.a_mn_major) {
@@ -782,12 +903,12 @@ int gemm_umma(const void* A, const void* B, void* C, const stc_gemm_desc* d, int
     }
     p.a_stage_bytes = 128 * 128;
     if (!p.b_mn_major) {
-        p.b_boxes = 1; p.b_box_bytes = (uint32_t)p.BN * 128; p.b_lbo = 0; p.b_sbo = 1024; p.b_kstep_bytes = 32;
+        p.b_boxes = 1; p.b_box_bytes = (uint32_t)bn_cta * 128; p.b_lbo = 0; p.b_sbo = 1024; p.b_kstep_bytes = 32;
     } else {
-        p.b_boxes = p.BN / 64; p.b_box_bytes = 64 * 128; p.b_lbo = p.b_box_bytes; p.b_sbo = 1024; p.b_kstep_bytes = 16 * 128;
+        p.b_boxes = bn_cta / 64; p.b_box_bytes = 64 * 128; p.b_lbo = p.b_box_bytes; p.b_sbo = 1024; p.b_kstep_bytes = 16 * 128;
     }
-    p.b_stage_bytes = (uint32_t)p.BN * 128;
-    p.idesc = make_idesc_bf16(128, p.BN, p.a_mn_major, p.b_mn_major);
+    p.b_stage_bytes = (uint32_t)bn_cta * 128;
+    p.idesc = make_idesc_bf16(p.cta2 ? 256 : 128, p.BN, p.a_mn_major, p.b_mn_major);
     p.store_tma = (out_dtype == STC_BF16 && p.BN % 64 == 0 && ((uintptr_t)C & 15) == 0 && !getenv_off("STC_TMA_STORE")) ? 1 : 0;
     if (p.store_tma) {
         uint64_t dims[4] = {(uint64_t)d->N, (uint64_t)d->M, b2, b1};
@@ -799,6 +920,13 @@ int gemm_umma(const void* A, const void* B, void* C, const stc_gemm_desc* d, int
     p.stages = pick_stages(p.a_stage_bytes + p.b_stage_bytes, p.store_tma);
     p.out = C; p.out_dtype = out_dtype; p.Cout = d->N;
     p.ldc = d->sCm; p.sC1 = d->sC1; p.sC2 = d->sC2; p.alpha = d->alpha;
+    if (mul_residual) {
+        p.epi_mode = 1;
+        p.residual = mul_residual;
+        p.rowvec = rowvec;
+        p.rv_s1 = (long long)d->batch2 * d->M;
+        p.rv_s2 = d->M;
+    }
     return launch(p, st);
 }
 

@@ -30,17 +30,27 @@ namespace stc {
 struct alignas(64) WgradHParams {
     CUtensorMap tmX;   // x  {Cin,  W, H, N}, box {64, 128+S-1, 1, 1}
     CUtensorMap tmDY;  // dy {Cout, W, H, N}, box {64, 128, 1, 1}
-    CUtensorMap tmX2[kMaxCat - 1];   // virtual channel concat of the input (common.cuh ChanCat): sources 1..n_src-1
-    int n_src, src_chunk_end[kMaxCat];
+    int n_src;                       // virtual channel concat of the input: number of sources (descriptors at the end of the struct)
     int H, W, R, S, SPf, cin_chunks, BN, num_n_tiles;   // SPf = S / 2 full tap pairs per filter row
     int RG, num_groups;          // filter rows per group, number of groups
-    int blocks_w, row_splits, rows_per_split;
-    int num_items;
+    int blocks_w;
+    // Work = (filter-row group g, base item b = (image, column block, ci chunk, co tile), output row h).  It is laid out on ONE cost axis -
+    // group after group, base item after base item, row after row, a row of group g weighing w[g] (its MMA count + a fixed per-row
+    // share) - and CTA k takes the k-th of gridDim.x EQUAL slices of that axis, cut at row granularity.  A CTA's slice is a handful of
+    // contiguous row ranges ("pieces"); every role walks the same pieces.  (Round-robin over ~2 unequal items per SM left the SMs idle
+    // 22-27 % of the launch: ncu sm__cycles_active / sm__cycles_elapsed = 0.78 / 0.73 on the 64->64 7x7 / 128->128 3x3 layers.)
+    long long bases;             // base items per group
+    long long group_cost[8];     // bases * H * w[g]
+    long long total_cost;
+    int w[8];
     int a_slots, b_stages;
     uint32_t a_slot_bytes, a_box_bytes, b_stage_bytes;
     uint32_t idesc;
     float* ws;
     int Cin, Cout;
+    // cold tail (virtual channel concat of the input, common.cuh ChanCat): sources 1..n_src-1
+    int src_chunk_end[kMaxCat];
+    CUtensorMap tmX2[kMaxCat - 1];
 };
 
 constexpr int kWgradHThreads = 224;
@@ -48,21 +58,42 @@ constexpr int kWgradHThreads = 224;
 struct WItem {
     int g, cc, nt, n_img, w0, h_a, h_b, r0, rg;
 };
-__device__ __forceinline__ WItem decode_item(const WgradHParams& p, int idx) {
-    WItem it;
-    it.nt = idx % p.num_n_tiles; idx /= p.num_n_tiles;
-    it.cc = idx % p.cin_chunks; idx /= p.cin_chunks;
-    it.g = idx % p.num_groups; idx /= p.num_groups;
-    int sp = idx % p.row_splits; idx /= p.row_splits;
-    int wb = idx % p.blocks_w;
-    it.n_img = idx / p.blocks_w;
-    it.w0 = wb * 128;
-    it.h_a = sp * p.rows_per_split;
-    it.h_b = min(p.H, it.h_a + p.rows_per_split);
-    it.r0 = it.g * p.RG;
-    it.rg = min(p.RG, p.R - it.r0);
-    return it;
-}
+struct WSched {
+    const WgradHParams& p;
+    long long pos, end;
+    __device__ __forceinline__ WSched(const WgradHParams& p_, int cta, int ctas) : p(p_) {
+        pos = p.total_cost * cta / ctas;
+        end = p.total_cost * (cta + 1) / ctas;
+    }
+    // next non-empty piece of this CTA's slice; false when the slice is exhausted
+    __device__ __forceinline__ bool next(WItem& it) {
+        while (pos < end) {
+            long long q = pos, gstart = 0;
+            int g = 0;
+            while (g + 1 < p.num_groups && q >= p.group_cost[g]) { q -= p.group_cost[g]; gstart += p.group_cost[g]; ++g; }
+            const long long per_base = (long long)p.H * p.w[g];
+            const long long b = q / per_base;
+            const long long base_start = gstart + b * per_base, base_end = base_start + per_base;
+            const int h_a = (int)((pos - base_start) / p.w[g]);
+            const long long pend = end < base_end ? end : base_end;
+            const int h_b = pend == base_end ? p.H : (int)((pend - base_start) / p.w[g]);
+            pos = pend;
+            if (h_b <= h_a) continue;
+            long long idx = b;
+            it.nt = (int)(idx % p.num_n_tiles); idx /= p.num_n_tiles;
+            it.cc = (int)(idx % p.cin_chunks); idx /= p.cin_chunks;
+            it.w0 = (int)(idx % p.blocks_w) * 128;
+            it.n_img = (int)(idx / p.blocks_w);
+            it.g = g;
+            it.h_a = h_a;
+            it.h_b = h_b;
+            it.r0 = g * p.RG;
+            it.rg = min(p.RG, p.R - it.r0);
+            return true;
+        }
+        return false;
+    }
+};
 
 __global__ void __launch_bounds__(kWgradHThreads, 1) umma_wgradh_kernel(const __grid_constant__ WgradHParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -112,11 +143,12 @@ __global__ void __launch_bounds__(kWgradHThreads, 1) umma_wgradh_kernel(const __
         // ===================== x-segment producer: input rows h_a + r0 - pr ... h_b - 1 + r0 + rg - 1 - pr =====================
         int slot = 0;
         uint32_t phase = 0;
-        for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-            WItem it = decode_item(p, item);
+        WSched sched(p, blockIdx.x, gridDim.x);
+        WItem it;
+        while (sched.next(it)) {
             const int first = it.h_a + it.r0 - pr, count = (it.h_b - it.h_a) + it.rg - 1;
             int lc = it.cc;
-            const CUtensorMap* mx = &p.tmX;
+            const CUtensorMap* mx = nullptr;      // non-null: a source of a virtual concat other than the first
             if (p.n_src > 1) {
                 int j = 0;
                 while (j + 1 < p.n_src && it.cc >= p.src_chunk_end[j]) ++j;
@@ -128,9 +160,15 @@ __global__ void __launch_bounds__(kWgradHThreads, 1) umma_wgradh_kernel(const __
                 if (ptx::elect_one_sync()) {
                     // slot 0 is loaded twice: in place and into the mirror behind the last ring slot (cross-row pairs starting in the last slot)
                     ptx::mbar_arrive_expect_tx(a_full(slot), slot == 0 ? 2 * p.a_box_bytes : p.a_box_bytes);
-                    ptx::tma_load_4d(smem_base + slot * p.a_slot_bytes, mx, a_full(slot), lc * 64, it.w0 - ps, first + e, it.n_img);
-                    if (slot == 0)
-                        ptx::tma_load_4d(smem_base + p.a_slots * p.a_slot_bytes, mx, a_full(slot), lc * 64, it.w0 - ps, first + e, it.n_img);
+                    if (mx) {
+                        ptx::tma_load_4d(smem_base + slot * p.a_slot_bytes, mx, a_full(slot), lc * 64, it.w0 - ps, first + e, it.n_img);
+                        if (slot == 0)
+                            ptx::tma_load_4d(smem_base + p.a_slots * p.a_slot_bytes, mx, a_full(slot), lc * 64, it.w0 - ps, first + e, it.n_img);
+                    } else {
+                        ptx::tma_load_4d(smem_base + slot * p.a_slot_bytes, &p.tmX, a_full(slot), lc * 64, it.w0 - ps, first + e, it.n_img);
+                        if (slot == 0)
+                            ptx::tma_load_4d(smem_base + p.a_slots * p.a_slot_bytes, &p.tmX, a_full(slot), lc * 64, it.w0 - ps, first + e, it.n_img);
+                    }
                 }
                 __syncwarp();
                 if (++slot == p.a_slots) { slot = 0; phase ^= 1; }
@@ -141,8 +179,9 @@ __global__ void __launch_bounds__(kWgradHThreads, 1) umma_wgradh_kernel(const __
         int stage = 0;
         uint32_t phase = 0;
         const int nbox = p.BN / 64;
-        for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-            WItem it = decode_item(p, item);
+        WSched sched(p, blockIdx.x, gridDim.x);
+        WItem it;
+        while (sched.next(it)) {
             for (int h = it.h_a; h < it.h_b; ++h) {
                 ptx::mbar_wait(b_empty(stage), phase ^ 1);
                 if (ptx::elect_one_sync()) {
@@ -168,8 +207,9 @@ __global__ void __launch_bounds__(kWgradHThreads, 1) umma_wgradh_kernel(const __
         const uint64_t b_hi = desc_common | ((uint64_t)(16384 >> 4) << 16);   // LBO = 16 KB between 64-wide co atoms
         const uint32_t a_slot16 = p.a_slot_bytes >> 4, b_stage16 = p.b_stage_bytes >> 4;
         const uint32_t a_base16 = (smem_base >> 4) & 0x3FFF, b_base16 = (b_base >> 4) & 0x3FFF;
-        for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-            WItem it = decode_item(p, item);
+        WSched sched(p, blockIdx.x, gridDim.x);
+        WItem it;
+        while (sched.next(it)) {
             ptx::mbar_wait(acc_empty, acc_phase ^ 1);
             ptx::tc_fence_after();
             int ready = 0;  // segments of this item observed full (relative to a_head at item start -> tracked via `seen`)
@@ -240,8 +280,9 @@ __global__ void __launch_bounds__(kWgradHThreads, 1) umma_wgradh_kernel(const __
         const int q = warp & 3;
         const int row = q * 32 + lane;
         uint32_t acc_phase = 0;
-        for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-            WItem it = decode_item(p, item);
+        WSched sched(p, blockIdx.x, gridDim.x);
+        WItem it;
+        while (sched.next(it)) {
             ptx::mbar_wait(acc_full, acc_phase);
             ptx::tc_fence_after();
             const int n_full = it.rg * p.SPf, n_slots = n_full + (it.rg + 1) / 2;
@@ -331,14 +372,17 @@ int conv_wgrad_wgradh(const void* x, const void* dy, float* ws, int N, int H, in
     p.cin_chunks = Cin / 64;
     p.num_n_tiles = Cout / p.BN;
     p.blocks_w = (W + 127) / 128;
-    // row splits: enough work items for ~2 per SM, at least 16 rows each so the R-1 warm-up segments amortise
-    long long base = (long long)p.num_n_tiles * p.cin_chunks * p.num_groups * p.blocks_w * N;
-    int want = (int)((2LL * num_sms() + base - 1) / base);
-    int max_splits = H / 16 > 0 ? H / 16 : 1;
-    p.row_splits = want < 1 ? 1 : (want > max_splits ? max_splits : want);
-    p.rows_per_split = (H + p.row_splits - 1) / p.row_splits;
-    p.row_splits = (H + p.rows_per_split - 1) / p.rows_per_split;
-    p.num_items = (int)(base * p.row_splits);
+    STC_REQUIRE(p.num_groups <= 8, "conv_wgrad_wgradh: too many filter-row groups");
+    p.bases = (long long)p.num_n_tiles * p.cin_chunks * p.blocks_w * N;
+    p.total_cost = 0;
+    static int row_overhead = -1;   // fixed per-row share (TMA issue, barrier round trips) in MMA units; STC_WGRADH_ROWCOST
+    if (row_overhead < 0) { const char* e = getenv("STC_WGRADH_ROWCOST"); row_overhead = e ? atoi(e) : 16; }
+    for (int g = 0; g < p.num_groups; ++g) {
+        const int rg = (R - g * p.RG) < p.RG ? (R - g * p.RG) : p.RG;
+        p.w[g] = (rg * p.SPf + (rg + 1) / 2) * 8 + row_overhead;
+        p.group_cost[g] = p.bases * H * p.w[g];
+        p.total_cost += p.group_cost[g];
+    }
     p.a_slot_bytes = 17408;
     p.a_box_bytes = (uint32_t)bwh * 128;
     p.b_stage_bytes = (uint32_t)p.BN * 256;
@@ -355,7 +399,8 @@ int conv_wgrad_wgradh(const void* x, const void* dy, float* ws, int N, int H, in
         STC_CUDA(cudaFuncSetAttribute(umma_wgradh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set[dev] = true;
     }
-    int grid = p.num_items < num_sms() ? p.num_items : num_sms();
+    const long long rows_total = p.bases * H * p.num_groups;
+    int grid = rows_total < num_sms() ? (int)rows_total : num_sms();
     umma_wgradh_kernel<<<grid, kWgradHThreads, smem, st>>>(p);
     return check_launch("umma_wgradh_kernel");
 }

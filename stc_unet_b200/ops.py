@@ -7,6 +7,7 @@ reference's layouts (Conv2d OIHW, Linear (out,in)).
 """
 from __future__ import annotations
 
+import ctypes
 import math
 from typing import Optional, Sequence
 
@@ -1152,6 +1153,19 @@ def ksa_fuse(x, f0, f1, f2, fc, fcs):
 # ---------------------------------------------------------------------------------------------
 # Multi-head attention core: softmax(Q K^T / sqrt(hd)) V on (N, L, E) token tensors
 # ---------------------------------------------------------------------------------------------
+def _dsoftmax_gemm(do, v, P, o, dS, L, hd, N, heads, sA, sB, sC, scale) -> bool:
+    """dS = scale * P * (dO V^T - rowsum(dO * O)) out of the dP product's epilogue (stc_gemm_dsoftmax); False when the tcgen05 engine
+    does not take it (the caller then runs the product and the softmax-backward pass separately)."""
+    d = GemmDesc(L, L, hd, N, heads, sA[0], sA[1], sA[2], sA[3], sB[0], sB[1], sB[2], sB[3], sC[0], sC[1], sC[2], float(scale), 0.0)
+    if not lib.raw("stc_gemm_dsoftmax_ok")(ctypes.byref(d), dtype_code(do.dtype), config.engine):
+        return False
+    D = torch.empty((N, heads, L), dtype=torch.float32, device=do.device)
+    lib.call("stc_rowdot_heads", do, o, D, N, L, heads, hd, dtype_code(do.dtype), stream_ptr())
+    _dense("gemm", 2.0 * L * L * hd * N * heads,
+           lambda: lib.call("stc_gemm_dsoftmax", do, v, P, D, dS, d, dtype_code(do.dtype), config.engine, stream_ptr()))
+    return True
+
+
 def _center_tokens(x: torch.Tensor) -> torch.Tensor:
     """x (N, L, E) -> x - mean over the L tokens (stc_center_tokens)."""
     N, L, E = x.shape
@@ -1177,13 +1191,13 @@ class _Attention(Function):
         lib.call("stc_softmax_rows_fwd", P, P, N * heads * L, L, scale, dtype_code(q.dtype), stream_ptr())
         o = torch.empty_like(q)
         gemm(P, v, o, L, hd, L, N, heads, (heads * L * L, L * L, L, 1), (*tok, E, 1), (L * E, hd, E))
-        ctx.save_for_backward(q, k, v, P)
+        ctx.save_for_backward(q, k, v, P, o)
         ctx.heads = heads
         return o
 
     @staticmethod
     def backward(ctx, do):
-        q, k, v, P = ctx.saved_tensors
+        q, k, v, P, o = ctx.saved_tensors
         heads = ctx.heads
         do = _chk(do)
         N, L, E = q.shape
@@ -1195,8 +1209,9 @@ class _Attention(Function):
         gemm(P, do, dv, L, hd, L, N, heads, (*pb, 1, L), (*tok, E, 1), (L * E, hd, E))            # dV = P^T dO
         dP = torch.empty_like(P)
         vc = _center_tokens(v) if v.dtype == torch.float32 else v   # dS is invariant under a common shift of the values
-        gemm(do, vc, dP, L, L, hd, N, heads, (*tok, E, 1), (*tok, 1, E), (*pb, L))                  # dP = dO V^T
-        lib.call("stc_softmax_rows_bwd", P, dP, dP, N * heads * L, L, scale, dtype_code(q.dtype), stream_ptr())
+        if not _dsoftmax_gemm(do, vc, P, o, dP, L, hd, N, heads, (*tok, E, 1), (*tok, 1, E), (*pb, L), scale):   # dS from the dP epilogue
+            gemm(do, vc, dP, L, L, hd, N, heads, (*tok, E, 1), (*tok, 1, E), (*pb, L))              # dP = dO V^T
+            lib.call("stc_softmax_rows_bwd", P, dP, dP, N * heads * L, L, scale, dtype_code(q.dtype), stream_ptr())
         dq = torch.empty_like(q)
         gemm(dP, k, dq, L, hd, L, N, heads, (*pb, L, 1), (*tok, E, 1), (L * E, hd, E))             # dQ = dS K
         dk = torch.empty_like(k)
@@ -1357,13 +1372,13 @@ class _AttentionPacked(Function):
         lib.call("stc_softmax_rows_fwd", P, P, N * heads * L, L, scale, dtype_code(qkv.dtype), stream_ptr())
         o = torch.empty((N, L, E), dtype=qkv.dtype, device=dev)
         gemm(P, v, o, L, hd, L, N, heads, (heads * L * L, L * L, L, 1), (*pk, E3, 1), (L * E, hd, E))
-        ctx.save_for_backward(qkv, P)
+        ctx.save_for_backward(qkv, P, o)
         ctx.heads = heads
         return o
 
     @staticmethod
     def backward(ctx, do):
-        qkv, P = ctx.saved_tensors
+        qkv, P, o = ctx.saved_tensors
         heads = ctx.heads
         do = _chk(do)
         N, L, E3 = qkv.shape
@@ -1378,8 +1393,9 @@ class _AttentionPacked(Function):
         dq, dk, dv = dqkv[..., :E], dqkv[..., E:2 * E], dqkv[..., 2 * E:]
         gemm(P, do, dv, L, hd, L, N, heads, (*pb, 1, L), (*tok, E, 1), (*pk, E3))                   # dV = P^T dO
         dP = torch.empty_like(P)
-        gemm(do, v, dP, L, L, hd, N, heads, (*tok, E, 1), (*pk, 1, E3), (*pb, L))                   # dP = dO V^T
-        lib.call("stc_softmax_rows_bwd", P, dP, dP, N * heads * L, L, scale, dtype_code(qkv.dtype), stream_ptr())
+        if not _dsoftmax_gemm(do, v, P, o, dP, L, hd, N, heads, (*tok, E, 1), (*pk, 1, E3), (*pb, L), scale):   # dS from the dP epilogue
+            gemm(do, v, dP, L, L, hd, N, heads, (*tok, E, 1), (*pk, 1, E3), (*pb, L))               # dP = dO V^T
+            lib.call("stc_softmax_rows_bwd", P, dP, dP, N * heads * L, L, scale, dtype_code(qkv.dtype), stream_ptr())
         gemm(dP, k, dq, L, hd, L, N, heads, (*pb, L, 1), (*pk, E3, 1), (*pk, E3))                   # dQ = dS K
         gemm(dP, q, dk, L, hd, L, N, heads, (*pb, 1, L), (*pk, E3, 1), (*pk, E3))                   # dK = dS^T Q
         return dqkv, None

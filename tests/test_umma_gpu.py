@@ -383,3 +383,85 @@ def test_virtual_concat_modules_never_materialise(tc):
     assert "stc_conv_fprop_cat" not in m[4]
     for a, b, tol in ((v[0], m[0], 2e-2), (v[1], m[1], 3e-2), (v[2], m[2], 3e-2), (v[3], m[3], 3e-2)):
         assert rel_l2(a, b) < tol
+
+
+def test_cta_group2_pairs_match_single_cta(tc):
+    """umma2_kernel (cta_group::2: a CTA pair computes a 256 x BN tile, each CTA staging its own rows of A and half of B) against the
+    1-CTA kernel on the same operands - bit-identical (same K order, same fp32 accumulation) - for a per-tap conv, the four GEMM
+    operand-layout combinations of attention, and a split-output dgrad."""
+    import os
+    import subprocess, sys
+    code = r'''
+import os, sys, math, torch
+sys.path.insert(0, os.getcwd())
+import stc_unet_b200 as S
+from stc_unet_b200 import ops
+ops.config.engine = S._lib.ENGINE_TCGEN05
+BF = torch.bfloat16; dev = torch.device("cuda:0")
+g = torch.Generator(device="cuda").manual_seed(1)
+out = {}
+x = torch.randn(2, 32, 64, 128, device=dev, generator=g).to(BF)
+w = torch.randn(256, 128, 3, 3, device=dev, generator=g) / math.sqrt(128 * 9)
+b = torch.randn(256, device=dev, generator=g)
+out["conv"] = ops.conv_fprop(x, ops.pack_weight(w, BF), b, None, 256, 3, 3, act=1)
+L, hd, B = 512, 256, 4
+q = torch.randn(B, L, hd, device=dev, generator=g).to(BF); k = torch.randn(B, L, hd, device=dev, generator=g).to(BF)
+v = torch.randn(B, L, hd, device=dev, generator=g).to(BF)
+sc = torch.empty(B, L, L, device=dev, dtype=BF); o = torch.empty(B, L, hd, device=dev, dtype=BF); dv = torch.empty(B, L, hd, device=dev, dtype=BF)
+ops.gemm(q, k, sc, L, L, hd, B, 1, (L * hd, 0, hd, 1), (L * hd, 0, 1, hd), (L * L, 0, L)); out["qk"] = sc.clone()
+ops.gemm(sc, v, o, L, hd, L, B, 1, (L * L, 0, L, 1), (L * hd, 0, hd, 1), (L * hd, 0, hd)); out["pv"] = o.clone()
+ops.gemm(sc, v, dv, L, hd, L, B, 1, (L * L, 0, 1, L), (L * hd, 0, hd, 1), (L * hd, 0, hd)); out["ptv"] = dv.clone()
+dy = torch.randn(2, 32, 64, 256, device=dev, generator=g).to(BF)
+dxs = ops.conv_dgrad_split(dy, ops.pack_weight(w, BF, transpose_flip=True), [64, 64], 3, 3)
+out["dx0"], out["dx1"] = dxs
+torch.save({k_: t.cpu() for k_, t in out.items()}, sys.argv[1])
+'''
+    import tempfile
+    res = {}
+    with tempfile.TemporaryDirectory() as d:
+        for mode in ("0", "2"):
+            path = os.path.join(d, f"o{mode}.pt")
+            r = subprocess.run([sys.executable, "-c", code, path], env=dict(os.environ, STC_CTA2=mode), capture_output=True, text=True,
+                               cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), timeout=300)
+            assert r.returncode == 0, r.stderr[-2000:]
+            res[mode] = torch.load(path)
+    for k in res["0"]:
+        assert torch.equal(res["0"][k], res["2"][k]), k
+
+
+def test_softmax_backward_in_the_dP_epilogue(tc):
+    """stc_gemm_dsoftmax (opt-in, STC_DSOFTMAX_FUSED=1): dS = scale * P * (dO V^T - rowsum(dO * O)) out of the GEMM epilogue equals the
+    separate product + softmax-backward pass up to bf16 rounding on well-conditioned inputs (no large common token component)."""
+    import ctypes
+    from stc_unet_b200._lib import GemmDesc, dtype_code, lib, stream_ptr
+    N, heads, L, hd = 2, 2, 256, 256
+    E = heads * hd
+    g = torch.Generator(device="cuda").manual_seed(21)
+    q = (torch.randn(N, L, E, device=dev(), generator=g) * 0.5).to(BF)
+    k = (torch.randn(N, L, E, device=dev(), generator=g) * 0.5).to(BF)
+    v = torch.randn(N, L, E, device=dev(), generator=g).to(BF)
+    do = torch.randn(N, L, E, device=dev(), generator=g).to(BF)
+    scale = 1.0 / math.sqrt(hd)
+    tok, pb = (L * E, hd), (heads * L * L, L * L)
+    P = torch.empty(N, heads, L, L, device=dev(), dtype=BF)
+    tc.gemm(q, k, P, L, L, hd, N, heads, (*tok, E, 1), (*tok, 1, E), (*pb, L))
+    lib.call("stc_softmax_rows_fwd", P, P, N * heads * L, L, scale, dtype_code(BF), stream_ptr())
+    o = torch.empty(N, L, E, device=dev(), dtype=BF)
+    tc.gemm(P, v, o, L, hd, L, N, heads, (*pb, L, 1), (*tok, E, 1), (L * E, hd, E))
+    # separate path
+    dS_ref = torch.empty_like(P)
+    tc.gemm(do, v, dS_ref, L, L, hd, N, heads, (*tok, E, 1), (*tok, 1, E), (*pb, L))
+    lib.call("stc_softmax_rows_bwd", P, dS_ref, dS_ref, N * heads * L, L, scale, dtype_code(BF), stream_ptr())
+    # fused
+    D = torch.empty(N, heads, L, device=dev(), dtype=torch.float32)
+    lib.call("stc_rowdot_heads", do, o, D, N, L, heads, hd, dtype_code(BF), stream_ptr())
+    want_D = (do.float() * o.float()).view(N, L, heads, hd).sum(-1).permute(0, 2, 1)
+    assert rel_l2(D, want_D) < 1e-5
+    d = GemmDesc(L, L, hd, N, heads, tok[0], tok[1], E, 1, tok[0], tok[1], 1, E, pb[0], pb[1], L, float(scale), 0.0)
+    dS = torch.empty_like(P)
+    lib.call("stc_gemm_dsoftmax", do, v, P, D, dS, d, dtype_code(BF), 2, stream_ptr())
+    # fp32 reference from the same stored P
+    Pf = P.float()
+    dP = torch.einsum("nihd,njhd->nhij", do.float().view(N, L, heads, hd), v.float().view(N, L, heads, hd))
+    ref = scale * Pf * (dP - (Pf * dP).sum(-1, keepdim=True))
+    assert rel_l2(dS.float(), ref) < 3e-2 and rel_l2(dS_ref.float(), ref) < 3e-2
