@@ -34,15 +34,14 @@ struct alignas(64) WgradHParams {
     int H, W, R, S, SPf, cin_chunks, BN, num_n_tiles;   // SPf = S / 2 full tap pairs per filter row
     int RG, num_groups;          // filter rows per group, number of groups
     int blocks_w;
-    // Work = (filter-row group g, base item b = (image, column block, ci chunk, co tile), output row h).  It is laid out on ONE cost axis -
-    // group after group, base item after base item, row after row, a row of group g weighing w[g] (its MMA count + a fixed per-row
-    // share) - and CTA k takes the k-th of gridDim.x EQUAL slices of that axis, cut at row granularity.  A CTA's slice is a handful of
-    // contiguous row ranges ("pieces"); every role walks the same pieces.  (Round-robin over ~2 unequal items per SM left the SMs idle
-    // 22-27 % of the launch: ncu sm__cycles_active / sm__cycles_elapsed = 0.78 / 0.73 on the 64->64 7x7 / 128->128 3x3 layers.)
-    long long bases;             // base items per group
-    long long group_cost[8];     // bases * H * w[g]
-    long long total_cost;
-    int w[8];
+    // Work = (filter-row group g, base item b = (image, column block, ci chunk, co tile), output row h).  The CTAs are divided among the
+    // groups in proportion to a group's cost per row (its MMA count + a fixed per-row share), and the CTAs of one group split the
+    // (base item, row) axis into equal contiguous slices.  Every CTA therefore finishes at the same time (round-robin over ~2 unequal
+    // items per SM had left the SMs idle 22-27 % of the launch), AND the CTAs of different groups sweep the (base, row) axis in
+    // step - the same x / dy rows at about the same time - so the re-reads of the later groups hit L2 instead of DRAM (laying the groups
+    // out one after the other on a single cost axis read x and dy once per group from DRAM: 4.2 GB for a 1.07 GB request).
+    long long rows_total;        // base items * H
+    int grp_cta_begin[9];        // CTAs [grp_cta_begin[g], grp_cta_begin[g+1]) work on group g
     int a_slots, b_stages;
     uint32_t a_slot_bytes, a_box_bytes, b_stage_bytes;
     uint32_t idesc;
@@ -61,37 +60,33 @@ struct WItem {
 struct WSched {
     const WgradHParams& p;
     long long pos, end;
-    __device__ __forceinline__ WSched(const WgradHParams& p_, int cta, int ctas) : p(p_) {
-        pos = p.total_cost * cta / ctas;
-        end = p.total_cost * (cta + 1) / ctas;
+    int g;
+    __device__ __forceinline__ WSched(const WgradHParams& p_, int cta) : p(p_) {
+        g = 0;
+        while (g + 1 < p.num_groups && cta >= p.grp_cta_begin[g + 1]) ++g;
+        const int j = cta - p.grp_cta_begin[g], n = p.grp_cta_begin[g + 1] - p.grp_cta_begin[g];
+        pos = p.rows_total * j / n;
+        end = p.rows_total * (j + 1) / n;
     }
-    // next non-empty piece of this CTA's slice; false when the slice is exhausted
+    // next piece (a row range of one base item) of this CTA's slice; false when the slice is exhausted
     __device__ __forceinline__ bool next(WItem& it) {
-        while (pos < end) {
-            long long q = pos, gstart = 0;
-            int g = 0;
-            while (g + 1 < p.num_groups && q >= p.group_cost[g]) { q -= p.group_cost[g]; gstart += p.group_cost[g]; ++g; }
-            const long long per_base = (long long)p.H * p.w[g];
-            const long long b = q / per_base;
-            const long long base_start = gstart + b * per_base, base_end = base_start + per_base;
-            const int h_a = (int)((pos - base_start) / p.w[g]);
-            const long long pend = end < base_end ? end : base_end;
-            const int h_b = pend == base_end ? p.H : (int)((pend - base_start) / p.w[g]);
-            pos = pend;
-            if (h_b <= h_a) continue;
-            long long idx = b;
-            it.nt = (int)(idx % p.num_n_tiles); idx /= p.num_n_tiles;
-            it.cc = (int)(idx % p.cin_chunks); idx /= p.cin_chunks;
-            it.w0 = (int)(idx % p.blocks_w) * 128;
-            it.n_img = (int)(idx / p.blocks_w);
-            it.g = g;
-            it.h_a = h_a;
-            it.h_b = h_b;
-            it.r0 = g * p.RG;
-            it.rg = min(p.RG, p.R - it.r0);
-            return true;
-        }
-        return false;
+        if (pos >= end) return false;
+        const long long b = pos / p.H;
+        const int h_a = (int)(pos - b * p.H);
+        const long long left = end - pos;
+        const int h_b = left < (long long)(p.H - h_a) ? h_a + (int)left : p.H;
+        pos += h_b - h_a;
+        long long idx = b;
+        it.nt = (int)(idx % p.num_n_tiles); idx /= p.num_n_tiles;
+        it.cc = (int)(idx % p.cin_chunks); idx /= p.cin_chunks;
+        it.w0 = (int)(idx % p.blocks_w) * 128;
+        it.n_img = (int)(idx / p.blocks_w);
+        it.g = g;
+        it.h_a = h_a;
+        it.h_b = h_b;
+        it.r0 = g * p.RG;
+        it.rg = min(p.RG, p.R - it.r0);
+        return true;
     }
 };
 
@@ -143,7 +138,7 @@ __global__ void __launch_bounds__(kWgradHThreads, 1) umma_wgradh_kernel(const __
         // ===================== x-segment producer: input rows h_a + r0 - pr ... h_b - 1 + r0 + rg - 1 - pr =====================
         int slot = 0;
         uint32_t phase = 0;
-        WSched sched(p, blockIdx.x, gridDim.x);
+        WSched sched(p, blockIdx.x);
         WItem it;
         while (sched.next(it)) {
             const int first = it.h_a + it.r0 - pr, count = (it.h_b - it.h_a) + it.rg - 1;
@@ -179,7 +174,7 @@ __global__ void __launch_bounds__(kWgradHThreads, 1) umma_wgradh_kernel(const __
         int stage = 0;
         uint32_t phase = 0;
         const int nbox = p.BN / 64;
-        WSched sched(p, blockIdx.x, gridDim.x);
+        WSched sched(p, blockIdx.x);
         WItem it;
         while (sched.next(it)) {
             for (int h = it.h_a; h < it.h_b; ++h) {
@@ -207,7 +202,7 @@ __global__ void __launch_bounds__(kWgradHThreads, 1) umma_wgradh_kernel(const __
         const uint64_t b_hi = desc_common | ((uint64_t)(16384 >> 4) << 16);   // LBO = 16 KB between 64-wide co atoms
         const uint32_t a_slot16 = p.a_slot_bytes >> 4, b_stage16 = p.b_stage_bytes >> 4;
         const uint32_t a_base16 = (smem_base >> 4) & 0x3FFF, b_base16 = (b_base >> 4) & 0x3FFF;
-        WSched sched(p, blockIdx.x, gridDim.x);
+        WSched sched(p, blockIdx.x);
         WItem it;
         while (sched.next(it)) {
             ptx::mbar_wait(acc_empty, acc_phase ^ 1);
@@ -280,7 +275,7 @@ __global__ void __launch_bounds__(kWgradHThreads, 1) umma_wgradh_kernel(const __
         const int q = warp & 3;
         const int row = q * 32 + lane;
         uint32_t acc_phase = 0;
-        WSched sched(p, blockIdx.x, gridDim.x);
+        WSched sched(p, blockIdx.x);
         WItem it;
         while (sched.next(it)) {
             ptx::mbar_wait(acc_full, acc_phase);
@@ -373,15 +368,29 @@ int conv_wgrad_wgradh(const void* x, const void* dy, float* ws, int N, int H, in
     p.num_n_tiles = Cout / p.BN;
     p.blocks_w = (W + 127) / 128;
     STC_REQUIRE(p.num_groups <= 8, "conv_wgrad_wgradh: too many filter-row groups");
-    p.bases = (long long)p.num_n_tiles * p.cin_chunks * p.blocks_w * N;
-    p.total_cost = 0;
+    p.rows_total = (long long)p.num_n_tiles * p.cin_chunks * p.blocks_w * N * H;
     static int row_overhead = -1;   // fixed per-row share (TMA issue, barrier round trips) in MMA units; STC_WGRADH_ROWCOST
     if (row_overhead < 0) { const char* e = getenv("STC_WGRADH_ROWCOST"); row_overhead = e ? atoi(e) : 16; }
-    for (int g = 0; g < p.num_groups; ++g) {
-        const int rg = (R - g * p.RG) < p.RG ? (R - g * p.RG) : p.RG;
-        p.w[g] = (rg * p.SPf + (rg + 1) / 2) * 8 + row_overhead;
-        p.group_cost[g] = p.bases * H * p.w[g];
-        p.total_cost += p.group_cost[g];
+    int grid = p.rows_total * p.num_groups < num_sms() ? (int)(p.rows_total * p.num_groups) : num_sms();
+    {   // CTAs per group in proportion to the group's cost per row; every group gets at least one, the counts sum to the grid
+        int wgt[8], wsum = 0;
+        for (int g = 0; g < p.num_groups; ++g) {
+            const int rg = (R - g * p.RG) < p.RG ? (R - g * p.RG) : p.RG;
+            wgt[g] = (rg * p.SPf + (rg + 1) / 2) * 8 + row_overhead;
+            wsum += wgt[g];
+        }
+        if (grid < p.num_groups) grid = p.num_groups;
+        int cnt[8], used = 0;
+        for (int g = 0; g < p.num_groups; ++g) {
+            cnt[g] = (int)((long long)grid * wgt[g] / wsum);
+            if (cnt[g] < 1) cnt[g] = 1;
+            used += cnt[g];
+        }
+        for (int g = 0; used < grid; g = (g + 1) % p.num_groups) { ++cnt[g]; ++used; }          // leftovers: one each, heaviest groups first
+        for (int g = p.num_groups - 1; used > grid; g = (g + p.num_groups - 1) % p.num_groups)
+            if (cnt[g] > 1) { --cnt[g]; --used; }
+        p.grp_cta_begin[0] = 0;
+        for (int g = 0; g < p.num_groups; ++g) p.grp_cta_begin[g + 1] = p.grp_cta_begin[g] + cnt[g];
     }
     p.a_slot_bytes = 17408;
     p.a_box_bytes = (uint32_t)bwh * 128;
@@ -399,8 +408,6 @@ int conv_wgrad_wgradh(const void* x, const void* dy, float* ws, int N, int H, in
         STC_CUDA(cudaFuncSetAttribute(umma_wgradh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set[dev] = true;
     }
-    const long long rows_total = p.bases * H * p.num_groups;
-    int grid = rows_total < num_sms() ? (int)rows_total : num_sms();
     umma_wgradh_kernel<<<grid, kWgradHThreads, smem, st>>>(p);
     return check_launch("umma_wgradh_kernel");
 }

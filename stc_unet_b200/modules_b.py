@@ -223,7 +223,9 @@ class UNet(BaseModule):
                 nn.init.constant_(m.bias, 0)
 
     def _check_input_divisible(self, x):
-        h, w = x.shape[-2:]
+        # decoded uint8 pixels and pre-normalised device batches arrive as (N, H, W, C); the reference interface is (N, C, H, W)
+        nhwc = x.dtype == torch.uint8 or isinstance(x, ops.NHWCImage)
+        h, w = (x.shape[1], x.shape[2]) if nhwc else x.shape[-2:]
         rate = 1
         for i in range(1, self.num_stages):
             if self.strides[i] == 2 or self.downsamples[i - 1]:

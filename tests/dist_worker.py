@@ -94,7 +94,10 @@ def main():
         if dtype == "fp32":
             tol_g, tol_s, tol_l = (1e-4, 1e-5, 1e-5) if posbn else (5e-2, 1e-5, 1e-5)
         else:
-            tol_g, tol_s, tol_l = 0.5, 2e-2, 3e-2       # bf16: bulk checked through the median below
+            # bf16: the bulk is checked through the median below; the WORST gradient (a BN bias of the last decoder level, whose true
+            # gradient nearly cancels) sits at 2.0 here and at 2.6 on one GPU, where the reference's own autocast path is at 4.8
+            # (profiles/r2_parity_config2_512_flipfree.json), hence the loose bound on the maximum
+            tol_g, tol_s, tol_l = 5.0, 2e-2, 3e-2
         # CoordAtt's conv1 feeds a BN whose sum(dy) vanishes only GLOBALLY under SyncBN, so the single-rank centring trick
         # does not apply per rank: its weight gradient is as ill-conditioned as in torch's own fp32 path (1-3e-4 there) -> 1e-3
         loose = {k: e for k, e in errs.items() if "ca.conv1" in k}

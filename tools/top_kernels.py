@@ -1,5 +1,6 @@
 """One launch of each dominant tcgen05 kernel at its heaviest in-step shape (for `ncu --set full`): halo fprop L1 64->64 k7 and k3,
-halo wgrad L1 64->64 k7, Linear 512x512 @65536 rows (fprop + wgrad), QK^T."""
+halo wgrad L1 64->64 k7, Linear 512x512 @65536 rows (fprop + wgrad), level-2 128->128 (N = 128: no shared-memory bound), conv + BN
+statistics, QK^T (K = 256: epilogue / TMEM read-out bound) and PV (K = 4096: the cta_group::2 pair kernel)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -25,7 +26,11 @@ def conv_stats(ci, co, hw, k, N=16):                                # conv + BN 
     torch.cuda.synchronize()
 conv_stats(64, 64, 512, 7)
 L, hd, B = 4096, 256, 32
-q = torch.randn(B, L, hd, device=dev).to(BF); kk = torch.randn(B, L, hd, device=dev).to(BF); sc = torch.empty(B, L, L, device=dev, dtype=BF)
+q = torch.randn(B, L, hd, device=dev).to(BF); kk = torch.randn(B, L, hd, device=dev).to(BF); v = torch.randn(B, L, hd, device=dev).to(BF)
+sc = torch.empty(B, L, L, device=dev, dtype=BF); o = torch.empty(B, L, hd, device=dev, dtype=BF)
 for _ in range(2):
     ops.gemm(q, kk, sc, L, L, hd, B, 1, (L * hd, 0, hd, 1), (L * hd, 0, 1, hd), (L * L, 0, L))
+for _ in range(2):
+    ops.gemm(sc, v, o, L, hd, L, B, 1, (L * L, 0, L, 1), (L * hd, 0, hd, 1), (L * hd, 0, hd))
+conv(512, 512, 64, 3, wgrad=True)                                   # per-tap wgrad (W < 128), division-free producer
 torch.cuda.synchronize(); print("ok")
