@@ -150,6 +150,10 @@ int stc_gemm_f32out(const void* A, const void* B, float* C, const stc_gemm_desc*
 #define STC_KERNEL_CONVH 3
 #define STC_KERNEL_WGRADH 4
 int stc_dense_last_engine(void);
+/* Diagnostics: a device buffer of at least 148 * 16 int64 into which the tcgen05 kernels of the NEXT launches write per-CTA clock
+ * counters (time the MMA issuer / epilogue / producers spent waiting on each barrier; layout in tools/convh_prof.py); NULL = off
+ * (the default; the kernels then only test one pointer). */
+int stc_debug_profile(void* counters);
 
 /* row softmax over the last dim: P = softmax(scale * S) ; rows x L (MHA, L = H*W tokens). */
 int stc_softmax_rows_fwd(const void* S, void* P, long long rows, int L, float scale, int dtype, void* stream);

@@ -30,6 +30,10 @@ static thread_local int g_last_engine = 0;
 /* engine actually used by the last stc_conv_fprop / stc_conv_wgrad / stc_gemm call on this thread */
 extern "C" int stc_dense_last_engine(void) { return g_last_engine; }
 
+static long long* g_debug_profile = nullptr;
+namespace stc { long long* debug_profile_buffer() { return g_debug_profile; } }
+extern "C" int stc_debug_profile(void* counters) { g_debug_profile = static_cast<long long*>(counters); return STC_OK; }
+
 extern "C" int stc_conv_fprop(const void* x, const void* wp, const float* bias, const void* residual, void* y, int N, int H,
                               int W, int Cin, int Cout, int R, int S, int act, int dtype, int engine, void* stream) {
     STC_REQUIRE(N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && (R & 1) && (S & 1), "conv_fprop: bad shape N=%d H=%d W=%d Cin=%d Cout=%d R=%d S=%d",

@@ -18,6 +18,8 @@
 
 namespace stc {
 
+long long* debug_profile_buffer();
+
 enum { MODE_CONV = 0, MODE_GEMM = 1, MODE_WGRAD = 2 };
 
 struct alignas(64) UmmaParams {
@@ -58,6 +60,7 @@ struct alignas(64) UmmaParams {
     long long rv_s1, rv_s2;
     // cta_group::2 variant (umma2_kernel): a CTA pair computes a 256 x BN tile; num_tiles counts PAIR tiles, b_* describe ONE CTA's half of B
     int cta2;
+    long long* prof;   // diagnostics (stc_debug_profile): 16 clock counters per CTA; nullptr = off
     // ---- cold tail (virtual channel concat, common.cuh ChanCat): extra A sources (CONV / WGRAD) and extra outputs (CONV = dgrad of a concat
     // conv).  Kept BEHIND the hot fields: the roles read this struct through the small constant cache, and 1 KB of descriptors in front of
     // the per-iteration scalars cost the per-tap wgrad 25 % (measured: 0.297 -> 0.390 ms on 512->512 3x3 @64x64)
@@ -296,14 +299,20 @@ __device__ __forceinline__ void umma_body(const UmmaParams& p) {
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase[2] = {0, 0};
+            long long w_te = 0, w_f = 0, n_t = 0;
+            const long long t_begin = p.prof ? clock64() : 0;
             for (int tile = tile0; tile < p.num_tiles; tile += tstep) {
                 TileInfo t = decode_tile<CTA2>(p, tile, rank);
                 if (t.k1 <= t.k0) continue;
+                long long t0 = p.prof ? clock64() : 0;
                 ptx::mbar_wait(tempty_bar(acc), acc_phase[acc] ^ 1);
+                if (p.prof) { w_te += clock64() - t0; ++n_t; }
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = acc * kAccCols;  // TMEM base is 0: the CTA owns all 512 columns (checked above)
                 for (int kt = t.k0; kt < t.k1; ++kt) {
+                    t0 = p.prof ? clock64() : 0;
                     ptx::mbar_wait(full_bar(stage), phase);
+                    if (p.prof) w_f += clock64() - t0;
                     ptx::tc_fence_after();
                     const uint32_t a_addr = smem_base + stage * stage_bytes;
                     const uint32_t b_addr = a_addr + p.a_stage_bytes;
@@ -330,6 +339,10 @@ __device__ __forceinline__ void umma_body(const UmmaParams& p) {
                 acc_phase[acc] ^= 1;
                 acc ^= 1;
             }
+            if (p.prof && lane == 0) {
+                long long* o = p.prof + (blockIdx.x % 148) * 16;
+                o[0] = clock64() - t_begin; o[1] = w_te; o[2] = w_f; o[4] = n_t;
+            }
         }
     } else {
         // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
@@ -338,6 +351,7 @@ __device__ __forceinline__ void umma_body(const UmmaParams& p) {
         int acc = 0, stage_buf = 0;
         uint32_t acc_phase[2] = {0, 0};
         const uint32_t tempty_leader0 = CTA2 ? ptx::mapa_shared(tempty_bar(0), 0) : 0u, tempty_leader1 = CTA2 ? ptx::mapa_shared(tempty_bar(1), 0) : 0u;
+        long long w_tf = 0, t_work = 0;
         auto release_acc = [&](int a) {
             if (CTA2) ptx::mbar_arrive_cluster(a ? tempty_leader1 : tempty_leader0);
             else ptx::mbar_arrive(tempty_bar(a));
@@ -363,7 +377,10 @@ __device__ __forceinline__ void umma_body(const UmmaParams& p) {
             }
             // epi_mode 1: alpha * D[row], subtracted from alpha * acc before the product with the residual (P)
             const float dsub = (p.epi_mode && valid) ? p.alpha * __ldg(p.rowvec + t.b1 * p.rv_s1 + t.b2 * p.rv_s2 + (t.mt * 128 + row)) : 0.f;
+            const long long pt0 = p.prof ? clock64() : 0;
             ptx::mbar_wait(tfull_bar(acc), acc_phase[acc]);
+            const long long pt1 = p.prof ? clock64() : 0;
+            w_tf += pt1 - pt0;
             ptx::tc_fence_after();
             const uint32_t t_addr = tmem_base + acc * kAccCols + ((uint32_t)(q * 32) << 16);
             if (p.store_tma) {
@@ -452,6 +469,7 @@ __device__ __forceinline__ void umma_body(const UmmaParams& p) {
                 if (lane == 0) release_acc(acc);
                 acc_phase[acc] ^= 1;
                 acc ^= 1;
+                if (p.prof) t_work += clock64() - pt1;
                 continue;
             }
             for (int c = 0; c < p.BN; c += 32) {
@@ -535,7 +553,9 @@ __device__ __forceinline__ void umma_body(const UmmaParams& p) {
             if (lane == 0) release_acc(acc);
             acc_phase[acc] ^= 1;
             acc ^= 1;
+            if (p.prof) t_work += clock64() - pt1;
         }
+        if (p.prof && q == 0 && lane == 0) { p.prof[(blockIdx.x % 148) * 16 + 5] = w_tf; p.prof[(blockIdx.x % 148) * 16 + 6] = t_work; }
         if (p.store_tma && lane == 0) ptx::bulk_wait<0>();   // all output boxes written before the CTA retires
     }
 
@@ -628,6 +648,7 @@ static int launch(UmmaParams& p, cudaStream_t st) {
         set_error("umma: smem %zu too large", smem);
         return STC_ERR_INVALID;
     }
+    p.prof = debug_profile_buffer();
     if (p.cta2) {
         static bool attr2[64] = {false};
         if (dev >= 0 && dev < 64 && !attr2[dev]) {

@@ -12,6 +12,13 @@
 //     A traffic per output tile:  R*S*16 KB  ->  (T+R-1)/T * 17 KB   (3x3, T=4: 144 KB -> 26 KB)
 // Loop order inside a strip: for cin-chunk { for r { for s { B(r,s,chunk) once; for t: acc[t] += seg[t+r](+s) * B } } }.
 // Warps: 0 = A (segment) producer, 1 = MMA issuer + TMEM owner, 2..5 = epilogue, 6 = B (weight) producer.
+//
+// CTA2 variant (cta_group::2): two CTAs of a cluster (one TPC) work on two strips of the SAME N tile with ONE tcgen05.mma of M = 256 per
+// (segment, tap, k step): each CTA stages its own input segments and only HALF of the weight tile's output channels; the leader's MMA reads A
+// from both shared memories and the two B halves, accumulator rows 0-127 in the leader's TMEM (its strip), 128-255 in the peer's.  The SS-mode
+// MMA is paced by shared-memory operand reads (~90 B/clk/SM measured: 128x64 47 %, 128x128 68 % of the tensor peak, profiles/r2_convh_roles.txt);
+// the pair form cuts them from A + B to A + B/2 per CTA.  Protocol as in umma.cu: `full` barriers in the leader receive the TMA bytes of both
+// CTAs, `empty` / `tmem_full` are signalled in both CTAs by multicast commits, both epilogues release the leader's `tmem_empty`.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -42,6 +49,7 @@ struct alignas(64) ConvHParams {
     const void* residual;
     int act, Cout;
     float* stats;  // optional [gridDim.x * 4][2][Cout] fp32: per epilogue-warp column sums / sums of squares of the STORED (bf16) outputs
+    long long* prof;  // diagnostics (stc_debug_profile): 16 clock counters per CTA, see tools/convh_prof.py; nullptr = off
 };
 
 constexpr int kConvHThreads = 224;
@@ -105,10 +113,13 @@ __device__ __forceinline__ int convh_output(const ConvHParams& p, int gch, int& 
     width = p.out_ch_end[j] - start;
     return j;
 }
-__device__ __forceinline__ Strip decode_strip(const ConvHParams& p, int idx) {
+// CTA2: idx counts strip PAIRS; the pair's two CTAs take spatially consecutive strips of the same N tile
+template <bool CTA2>
+__device__ __forceinline__ Strip decode_strip(const ConvHParams& p, int idx, int rank) {
     Strip s;
     s.nt = idx % p.num_n_tiles;
     int r = idx / p.num_n_tiles;
+    if (CTA2) r = 2 * r + rank;
     int sw = r % p.strips_w;
     r /= p.strips_w;
     int sh = r % p.strips_h;
@@ -118,7 +129,7 @@ __device__ __forceinline__ Strip decode_strip(const ConvHParams& p, int idx) {
     return s;
 }
 
-template <int T>
+template <int T, bool CTA2>
 __global__ void __launch_bounds__(kConvHThreads, 1) umma_convh_kernel(const __grid_constant__ ConvHParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -130,6 +141,9 @@ __global__ void __launch_bounds__(kConvHThreads, 1) umma_convh_kernel(const __gr
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + nb);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = CTA2 ? (int)ptx::cluster_ctarank() : 0;              // 0 = leader of the pair
+    const int item0 = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;     // persistent loop over strips (CTA2: strip pairs)
+    const int istep = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const uint32_t smem_base = ptx::smem_u32(smem);
     const uint32_t b_base = smem_base + a_bytes;
     const uint32_t bar_base = ptx::smem_u32(bars);
@@ -146,15 +160,15 @@ __global__ void __launch_bounds__(kConvHThreads, 1) umma_convh_kernel(const __gr
         for (int j = 1; j < p.n_src; ++j) ptx::prefetch_tensormap(&p.tmA2[j - 1]);
         for (int s = 0; s < p.a_slots; ++s) { ptx::mbar_init(a_full(s), 1); ptx::mbar_init(a_empty(s), 1); }
         for (int s = 0; s < p.b_stages; ++s) { ptx::mbar_init(b_full(s), 1); ptx::mbar_init(b_empty(s), 1); }
-        for (int s = 0; s < 2; ++s) { ptx::mbar_init(tfull(s), 1); ptx::mbar_init(tempty(s), 4); }
+        for (int s = 0; s < 2; ++s) { ptx::mbar_init(tfull(s), 1); ptx::mbar_init(tempty(s), CTA2 ? 8 : 4); }
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
-        ptx::tmem_relinquish();
+        if (CTA2) { ptx::tmem_alloc2(ptx::smem_u32(tmem_slot), 512); ptx::tmem_relinquish2(); }
+        else { ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512); ptx::tmem_relinquish(); }
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    if (CTA2) ptx::cluster_sync_all(); else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (tmem_base != 0) {
@@ -169,46 +183,64 @@ __global__ void __launch_bounds__(kConvHThreads, 1) umma_convh_kernel(const __gr
         {
             int slot = 0;          // ring position of the next segment
             uint32_t phase = 0;    // flips every time the ring wraps
-            for (int st = blockIdx.x; st < p.num_strips; st += gridDim.x) {
-                Strip s = decode_strip(p, st);
+            long long w_ae = 0;
+            for (int st = item0; st < p.num_strips; st += istep) {
+                Strip s = decode_strip<CTA2>(p, st, rank);
                 for (int cc = 0; cc < p.cin_chunks; ++cc) {
                     int lc = cc;
                     const CUtensorMap* ma = p.n_src > 1 ? convh_map_a(p, cc, lc) : &p.tmA;
                     for (int i = 0; i < segs_per_chunk; ++i) {
+                        const long long t0 = p.prof ? clock64() : 0;
                         ptx::mbar_wait(a_empty(slot), phase ^ 1);
+                        if (p.prof) w_ae += clock64() - t0;
                         if (ptx::elect_one_sync()) {
-                            ptx::mbar_arrive_expect_tx(a_full(slot), p.a_box_bytes);
-                            ptx::tma_load_4d(smem_base + slot * p.a_slot_bytes, ma, a_full(slot), lc * 64, s.w0 - ps, s.h0 + i - pr, s.n_img);
+                            if (CTA2) {   // both CTAs' bytes complete on the leader's barrier, which the leader arms for 2 boxes
+                                if (rank == 0) ptx::mbar_arrive_expect_tx(a_full(slot), 2 * p.a_box_bytes);
+                                ptx::tma_load_4d_2sm(smem_base + slot * p.a_slot_bytes, ma, ptx::mapa_shared(a_full(slot), 0), lc * 64, s.w0 - ps, s.h0 + i - pr, s.n_img);
+                            } else {
+                                ptx::mbar_arrive_expect_tx(a_full(slot), p.a_box_bytes);
+                                ptx::tma_load_4d(smem_base + slot * p.a_slot_bytes, ma, a_full(slot), lc * 64, s.w0 - ps, s.h0 + i - pr, s.n_img);
+                            }
                         }
                         __syncwarp();
                         if (++slot == p.a_slots) { slot = 0; phase ^= 1; }
                     }
                 }
             }
+            if (p.prof && lane == 0) p.prof[blockIdx.x * 16 + 8] = w_ae;
         }
     } else if (warp == 6) {
         // ===================== B producer: one weight tile per (chunk, tap) =====================
         {
             int stage = 0;
             uint32_t phase = 0;
-            for (int st = blockIdx.x; st < p.num_strips; st += gridDim.x) {
-                Strip s = decode_strip(p, st);
+            long long w_be = 0;
+            for (int st = item0; st < p.num_strips; st += istep) {
+                Strip s = decode_strip<CTA2>(p, st, rank);
                 for (int cc = 0; cc < p.cin_chunks; ++cc) {
                     for (int tap = 0; tap < p.R * p.S; ++tap) {
+                        const long long t0 = p.prof ? clock64() : 0;
                         ptx::mbar_wait(b_empty(stage), phase ^ 1);
+                        if (p.prof) w_be += clock64() - t0;
                         if (ptx::elect_one_sync()) {
-                            ptx::mbar_arrive_expect_tx(b_full(stage), p.b_stage_bytes);
-                            ptx::tma_load_3d(b_base + stage * p.b_stage_bytes, &p.tmB, b_full(stage), cc * 64, s.nt * p.BN, tap);
+                            if (CTA2) {   // this CTA stages its half of the tile's output channels (b_stage_bytes = the half)
+                                if (rank == 0) ptx::mbar_arrive_expect_tx(b_full(stage), 2 * p.b_stage_bytes);
+                                ptx::tma_load_3d_2sm(b_base + stage * p.b_stage_bytes, &p.tmB, ptx::mapa_shared(b_full(stage), 0), cc * 64, s.nt * p.BN + rank * (p.BN / 2), tap);
+                            } else {
+                                ptx::mbar_arrive_expect_tx(b_full(stage), p.b_stage_bytes);
+                                ptx::tma_load_3d(b_base + stage * p.b_stage_bytes, &p.tmB, b_full(stage), cc * 64, s.nt * p.BN, tap);
+                            }
                         }
                         __syncwarp();
                         if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
+            if (p.prof && lane == 0) p.prof[blockIdx.x * 16 + 9] = w_be;
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (warp-uniform; elected lane issues) =====================
-        {
+        // ===================== MMA issuer (warp-uniform; elected lane issues; CTA2: the leader only) =====================
+        if (!CTA2 || rank == 0) {
             int a_head = 0;            // ring slot of segment 0 of the current chunk
             uint32_t a_phase = 0;      // parity of the ring pass that a_head belongs to
             int bstage = 0;
@@ -219,8 +251,14 @@ __global__ void __launch_bounds__(kConvHThreads, 1) umma_convh_kernel(const __gr
             const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
             const uint32_t a_slot16 = p.a_slot_bytes >> 4, b_stage16 = p.b_stage_bytes >> 4;
             const uint32_t a_base16 = (smem_base >> 4) & 0x3FFF, b_base16 = (b_base >> 4) & 0x3FFF;
-            for (int st = blockIdx.x; st < p.num_strips; st += gridDim.x) {
+            // arrives once the MMAs issued so far have retired (CTA2: on the barrier at this offset in BOTH CTAs)
+            auto commit = [&](uint32_t bar) { if (CTA2) ptx::tc_commit2(bar, 3); else ptx::tc_commit(bar); };
+            long long w_te = 0, w_af = 0, w_bf = 0, n_st = 0;
+            const long long t_begin = p.prof ? clock64() : 0;
+            for (int st = item0; st < p.num_strips; st += istep) {
+                long long t0 = p.prof ? clock64() : 0;
                 ptx::mbar_wait(tempty(acc), (acc ? acc_phase1 : acc_phase0) ^ 1);
+                if (p.prof) { w_te += clock64() - t0; ++n_st; }
                 ptx::tc_fence_after();
                 const uint32_t d_base = acc * 256;  // TMEM base is 0 (all 512 columns are ours; checked after the allocation)
                 for (int cc = 0; cc < p.cin_chunks; ++cc) {
@@ -231,7 +269,9 @@ __global__ void __launch_bounds__(kConvHThreads, 1) umma_convh_kernel(const __gr
                             int sl = a_head + ready;
                             uint32_t ph = a_phase;
                             if (sl >= p.a_slots) { sl -= p.a_slots; ph ^= 1; }
+                            t0 = p.prof ? clock64() : 0;
                             ptx::mbar_wait(a_full(sl), ph);
+                            if (p.prof) w_af += clock64() - t0;
                             ++ready;
                         }
                         uint32_t a16[T];  // start-address fields (16 B units) of the T segments this row reads
@@ -242,7 +282,9 @@ __global__ void __launch_bounds__(kConvHThreads, 1) umma_convh_kernel(const __gr
                             a16[t] = a_base16 + sl * a_slot16;
                         }
                         for (int s = 0; s < p.S; ++s) {
+                            t0 = p.prof ? clock64() : 0;
                             ptx::mbar_wait(b_full(bstage), bphase);
+                            if (p.prof) w_bf += clock64() - t0;
                             ptx::tc_fence_after();
                             const uint64_t b_desc0 = desc_hi | (uint64_t)(b_base16 + bstage * b_stage16);
                             const uint32_t acc_flag = (cc | r | s) ? 1u : 0u;
@@ -251,12 +293,19 @@ __global__ void __launch_bounds__(kConvHThreads, 1) umma_convh_kernel(const __gr
                                 for (int t = 0; t < T; ++t) {
                                     const uint64_t a_desc0 = desc_hi | (uint64_t)(a16[t] + s * 8);
                                     const uint32_t d_addr = d_base + t * p.BN;
-                                    ptx::mma_bf16_ss(d_addr, a_desc0, b_desc0, p.idesc, acc_flag);
-                                    ptx::mma_bf16_ss(d_addr, a_desc0 + 2, b_desc0 + 2, p.idesc, 1u);
-                                    ptx::mma_bf16_ss(d_addr, a_desc0 + 4, b_desc0 + 4, p.idesc, 1u);
-                                    ptx::mma_bf16_ss(d_addr, a_desc0 + 6, b_desc0 + 6, p.idesc, 1u);
+                                    if (CTA2) {
+                                        ptx::mma_bf16_ss2(d_addr, a_desc0, b_desc0, p.idesc, acc_flag);
+                                        ptx::mma_bf16_ss2(d_addr, a_desc0 + 2, b_desc0 + 2, p.idesc, 1u);
+                                        ptx::mma_bf16_ss2(d_addr, a_desc0 + 4, b_desc0 + 4, p.idesc, 1u);
+                                        ptx::mma_bf16_ss2(d_addr, a_desc0 + 6, b_desc0 + 6, p.idesc, 1u);
+                                    } else {
+                                        ptx::mma_bf16_ss(d_addr, a_desc0, b_desc0, p.idesc, acc_flag);
+                                        ptx::mma_bf16_ss(d_addr, a_desc0 + 2, b_desc0 + 2, p.idesc, 1u);
+                                        ptx::mma_bf16_ss(d_addr, a_desc0 + 4, b_desc0 + 4, p.idesc, 1u);
+                                        ptx::mma_bf16_ss(d_addr, a_desc0 + 6, b_desc0 + 6, p.idesc, 1u);
+                                    }
                                 }
-                                ptx::tc_commit(b_empty(bstage));
+                                commit(b_empty(bstage));
                             }
                             __syncwarp();
                             if (++bstage == p.b_stages) { bstage = 0; bphase ^= 1; }
@@ -266,12 +315,12 @@ __global__ void __launch_bounds__(kConvHThreads, 1) umma_convh_kernel(const __gr
                             if (r < p.R - 1) {
                                 int sl = a_head + r;
                                 if (sl >= p.a_slots) sl -= p.a_slots;
-                                ptx::tc_commit(a_empty(sl));
+                                commit(a_empty(sl));
                             } else {
                                 for (int i = p.R - 1; i < segs_per_chunk; ++i) {
                                     int sl = a_head + i;
                                     if (sl >= p.a_slots) sl -= p.a_slots;
-                                    ptx::tc_commit(a_empty(sl));
+                                    commit(a_empty(sl));
                                 }
                             }
                         }
@@ -280,10 +329,14 @@ __global__ void __launch_bounds__(kConvHThreads, 1) umma_convh_kernel(const __gr
                     a_head += segs_per_chunk;
                     if (a_head >= p.a_slots) { a_head -= p.a_slots; a_phase ^= 1; }
                 }
-                if (ptx::elect_one_sync()) ptx::tc_commit(tfull(acc));
+                if (ptx::elect_one_sync()) commit(tfull(acc));
                 __syncwarp();
                 if (acc) acc_phase1 ^= 1; else acc_phase0 ^= 1;
                 acc ^= 1;
+            }
+            if (p.prof && lane == 0) {
+                long long* o = p.prof + blockIdx.x * 16;
+                o[0] = clock64() - t_begin; o[1] = w_te; o[2] = w_af; o[3] = w_bf; o[4] = n_st;
             }
         }
     } else if (warp >= 2 && warp <= 5) {
@@ -294,10 +347,14 @@ __global__ void __launch_bounds__(kConvHThreads, 1) umma_convh_kernel(const __gr
         uint32_t acc_phase[2] = {0, 0};
         const uint32_t stg0 = smem_base + ring_bytes + (uint32_t)q * 2u * kConvHStageBuf;
         float sacc[8] = {}, qacc[8] = {};   // p.stats: running column sums of this warp (lane l <-> channel chunk*32 + l); num_n_tiles == 1
-        for (int st = blockIdx.x; st < p.num_strips; st += gridDim.x) {
-            Strip s = decode_strip(p, st);
+        long long w_tf = 0, t_work = 0;
+        for (int st = item0; st < p.num_strips; st += istep) {
+            Strip s = decode_strip<CTA2>(p, st, rank);
             const int w = s.w0 + row;
+            const long long t0 = p.prof ? clock64() : 0;
             ptx::mbar_wait(tfull(acc), acc_phase[acc]);
+            const long long t1 = p.prof ? clock64() : 0;
+            w_tf += t1 - t0;
             ptx::tc_fence_after();
             for (int t = 0; t < T; ++t) {
                 const int h = s.h0 + t;
@@ -425,10 +482,15 @@ __global__ void __launch_bounds__(kConvHThreads, 1) umma_convh_kernel(const __gr
             }
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(tempty(acc));
+            if (lane == 0) {
+                if (CTA2) ptx::mbar_arrive_cluster(ptx::mapa_shared(tempty(acc), 0));
+                else ptx::mbar_arrive(tempty(acc));
+            }
             acc_phase[acc] ^= 1;
             acc ^= 1;
+            if (p.prof) t_work += clock64() - t1;
         }
+        if (p.prof && q == 0 && lane == 0) { p.prof[blockIdx.x * 16 + 5] = w_tf; p.prof[blockIdx.x * 16 + 6] = t_work; }
         if (p.staged && lane == 0) ptx::bulk_wait<0>();
         if (p.stats) {   // one partial row per epilogue warp: [sum | sum of squares] x Cout
             float* o = p.stats + ((size_t)blockIdx.x * 4 + q) * 2 * p.Cout;
@@ -439,10 +501,10 @@ __global__ void __launch_bounds__(kConvHThreads, 1) umma_convh_kernel(const __gr
     }
 
     ptx::tc_fence_before();
-    __syncthreads();
+    if (CTA2) ptx::cluster_sync_all(); else __syncthreads();   // CTA2: the peer's shared memory / barriers stay alive until both are done
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, 512);
+        if (CTA2) ptx::tmem_dealloc2(tmem_base, 512); else ptx::tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -458,7 +520,14 @@ static int convh_staged_max_r() {
     return v;
 }
 
-static int convh_plan(int Cout, int R, int& BN, int& T, int& a_slots, int& b_stages, int& staged) {
+// STC_CONVH_CTA2=0 keeps every halo conv on single CTAs
+static bool convh_cta2_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("STC_CONVH_CTA2"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v != 0;
+}
+
+static int convh_plan(int Cout, int R, int& BN, int& T, int& a_slots, int& b_stages, int& staged, bool cta2 = false) {
     BN = umma_pick_bn(Cout);
     if (BN == 0 || BN > 256) return 0;
     staged = (BN % 64 == 0 && BN <= 128 && R <= convh_staged_max_r()) ? 1 : 0;   // BN = 256 needs the smem for its weight ring
@@ -470,7 +539,7 @@ static int convh_plan(int Cout, int R, int& BN, int& T, int& a_slots, int& b_sta
         for (int extra = 3; extra >= 1; --extra) {
             for (int bs = 4; bs >= 2; --bs) {
                 int slots = t + R - 1 + extra;
-                size_t smem = (size_t)slots * 17408 + (size_t)bs * BN * 128 + staging + (2 * slots + 2 * bs + 4) * 8 + 16 + 1024;
+                size_t smem = (size_t)slots * 17408 + (size_t)bs * (cta2 ? BN / 2 : BN) * 128 + staging + (2 * slots + 2 * bs + 4) * 8 + 16 + 1024;
                 if (smem <= 225 * 1024) {
                     T = t; a_slots = slots; b_stages = bs;
                     return 1;
@@ -496,6 +565,7 @@ bool conv_convh_stats_ok(int Cout, int R) {
 }
 
 int check_cat(const ChanCat* c, int total, const char* what);
+long long* debug_profile_buffer();
 
 static int convh_encode_nhwc(CUtensorMap* m, const void* base, int N, int H, int W, int C, uint32_t bw) {
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
@@ -509,6 +579,13 @@ int conv_fprop_convh(const void* x, const void* wp, const float* bias, const voi
     ConvHParams p;
     memset(&p, 0, sizeof(p));
     STC_REQUIRE(convh_plan(Cout, R, p.BN, p.T, p.a_slots, p.b_stages, p.staged), "conv_fprop_convh: no plan for Cout=%d R=%d", Cout, R);
+    // CTA pairs need an even number of spatial strips (the two CTAs of a pair always work on two real strips of one N tile)
+    bool cta2 = convh_cta2_enabled() && ((long long)N * ((H + p.T - 1) / p.T) * ((W + 127) / 128)) % 2 == 0 && p.BN % 32 == 0;
+    if (cta2) {
+        int bn2, t2;
+        cta2 = convh_plan(Cout, R, bn2, t2, p.a_slots, p.b_stages, p.staged, true) && bn2 == p.BN && t2 == p.T;
+        if (!cta2) convh_plan(Cout, R, p.BN, p.T, p.a_slots, p.b_stages, p.staged);
+    }
     if (src && src->n == 1) { x = src->ptr[0]; src = nullptr; }
     if (dst && dst->n == 1) { y = const_cast<void*>(dst->ptr[0]); dst = nullptr; }
     if (int rc = check_cat(src, Cin, "conv_fprop_convh input")) return rc;
@@ -544,7 +621,7 @@ int conv_fprop_convh(const void* x, const void* wp, const float* bias, const voi
     {
         uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)(R * S)};
         uint64_t str[3] = {2, (uint64_t)Cin * 2, (uint64_t)Cout * Cin * 2};
-        uint32_t box[3] = {64, (uint32_t)p.BN, 1};
+        uint32_t box[3] = {64, (uint32_t)(cta2 ? p.BN / 2 : p.BN), 1};
         int rc = encode_map_bf16(&p.tmB, wp, 3, dims, str, box);
         if (rc) return rc;
     }
@@ -558,37 +635,60 @@ int conv_fprop_convh(const void* x, const void* wp, const float* bias, const voi
     p.num_n_tiles = Cout / p.BN;
     p.strips_h = (H + p.T - 1) / p.T;
     p.strips_w = (W + 127) / 128;
-    p.num_strips = N * p.strips_h * p.strips_w * p.num_n_tiles;
+    p.num_strips = N * p.strips_h * p.strips_w * p.num_n_tiles;   // work items of the persistent loop: strips, or (cta2) strip pairs
+    if (cta2) p.num_strips /= 2;
     p.a_slot_bytes = 17408;
     p.a_box_bytes = (uint32_t)bwh * 128;
-    p.b_stage_bytes = (uint32_t)p.BN * 128;
-    p.idesc = make_idesc_bf16(128, p.BN, 0, 0);
+    p.b_stage_bytes = (uint32_t)(cta2 ? p.BN / 2 : p.BN) * 128;
+    p.idesc = make_idesc_bf16(cta2 ? 256 : 128, p.BN, 0, 0);
     {
         static int bo = -1;
         if (bo < 0) { const char* e = getenv("STC_CONVH_BO"); bo = e ? atoi(e) : 1; }
         p.bo_mode = bo;
     }
     p.out = y; p.bias = bias; p.residual = residual; p.act = act; p.Cout = Cout;
+    p.prof = debug_profile_buffer();
     size_t smem = (size_t)p.a_slots * p.a_slot_bytes + (size_t)p.b_stages * p.b_stage_bytes + (p.staged ? kConvHStagingBytes : 0) +
                   (2 * p.a_slots + 2 * p.b_stages + 4) * 8 + 16 + 1024;
     static bool attr_set[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        STC_CUDA(cudaFuncSetAttribute(umma_convh_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        STC_CUDA(cudaFuncSetAttribute(umma_convh_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        STC_CUDA(cudaFuncSetAttribute(umma_convh_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        STC_CUDA(cudaFuncSetAttribute(umma_convh_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        STC_CUDA(cudaFuncSetAttribute(umma_convh_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        STC_CUDA(cudaFuncSetAttribute(umma_convh_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        STC_CUDA(cudaFuncSetAttribute(umma_convh_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        STC_CUDA(cudaFuncSetAttribute(umma_convh_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        STC_CUDA(cudaFuncSetAttribute(umma_convh_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set[dev] = true;
     }
     int grid = p.num_strips < num_sms() ? p.num_strips : num_sms();
+    if (cta2) {
+        int pairs = num_sms() / 2;
+        if (p.num_strips < pairs) pairs = p.num_strips;
+        grid = 2 * pairs;
+    }
     if (stats) {
         STC_REQUIRE(p.num_n_tiles == 1 && p.BN <= 256, "conv_fprop_convh: fused statistics need one N tile (Cout=%d BN=%d)", Cout, p.BN);
         p.stats = stats;
         *stats_rows = grid * 4;
     }
-    if (p.T == 4) umma_convh_kernel<4><<<grid, kConvHThreads, smem, st>>>(p);
-    else if (p.T == 2) umma_convh_kernel<2><<<grid, kConvHThreads, smem, st>>>(p);
-    else umma_convh_kernel<1><<<grid, kConvHThreads, smem, st>>>(p);
+    if (cta2) {   // clusters of two CTAs (the two SMs of a TPC)
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kConvHThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (p.T == 4) STC_CUDA(cudaLaunchKernelEx(&cfg, umma_convh_kernel<4, true>, p));
+        else if (p.T == 2) STC_CUDA(cudaLaunchKernelEx(&cfg, umma_convh_kernel<2, true>, p));
+        else STC_CUDA(cudaLaunchKernelEx(&cfg, umma_convh_kernel<1, true>, p));
+        return check_launch("umma_convh_kernel (cta_group::2)");
+    }
+    if (p.T == 4) umma_convh_kernel<4, false><<<grid, kConvHThreads, smem, st>>>(p);
+    else if (p.T == 2) umma_convh_kernel<2, false><<<grid, kConvHThreads, smem, st>>>(p);
+    else umma_convh_kernel<1, false><<<grid, kConvHThreads, smem, st>>>(p);
     return check_launch("umma_convh_kernel");
 }
 

@@ -25,3 +25,26 @@ timeit(lambda: ops.conv_fprop(x, wp, None, None, 512, 1, 1), 2.0 * 65536 * 512 *
 w3 = torch.randn(1536, 512, 1, 1, device=dev) / 512 ** 0.5
 wp3 = ops.pack_weight(w3, BF)
 timeit(lambda: ops.conv_fprop(x, wp3, None, None, 1536, 1, 1), 2.0 * 65536 * 512 * 1536, "Linear 65536x1536x512")
+if os.environ.get("PROBE_CUBLAS", "0") == "1":
+    # library yardstick (torch.matmul -> cuBLASLt) on the same shapes, plus cuDNN on the conv shapes that bound the step: measurement only
+    timeit(lambda: torch.bmm(q, kk.transpose(1, 2), out=sc), 2.0 * B * L * L * hd, "cuBLAS QK^T 32x4096x4096x256")
+    timeit(lambda: torch.bmm(sc, v, out=o), 2.0 * B * L * L * hd, "cuBLAS PV   32x4096x256x4096")
+    x2 = x.view(65536, 512); w2 = torch.randn(512, 512, device=dev).to(BF); y2 = torch.empty(65536, 512, device=dev, dtype=BF)
+    timeit(lambda: torch.mm(x2, w2, out=y2), 2.0 * 65536 * 512 * 512, "cuBLAS Linear 65536x512x512")
+    w23 = torch.randn(512, 1536, device=dev).to(BF); y23 = torch.empty(65536, 1536, device=dev, dtype=BF)
+    timeit(lambda: torch.mm(x2, w23, out=y23), 2.0 * 65536 * 512 * 1536, "cuBLAS Linear 65536x1536x512")
+    for (M, N, K) in ((4194304, 64, 576), (4194304, 64, 3136), (1048576, 128, 1152), (1048576, 128, 6272), (4194304, 64, 64), (4194304, 128, 128)):
+        a = torch.randn(M, K, device=dev).to(BF); b = torch.randn(K, N, device=dev).to(BF); c = torch.empty(M, N, device=dev, dtype=BF)
+        timeit(lambda: torch.mm(a, b, out=c), 2.0 * M * N * K, f"cuBLAS GEMM {M}x{N}x{K}")
+        del a, b, c
+    import torch.nn.functional as F
+    torch.backends.cudnn.benchmark = True
+    for (C, Co, k, HW) in ((64, 64, 3, 512), (64, 64, 7, 512), (128, 128, 3, 256), (128, 128, 7, 256), (256, 256, 3, 128)):
+        xi = torch.randn(16, C, HW, HW, device=dev).to(BF).contiguous(memory_format=torch.channels_last)
+        wi = torch.randn(Co, C, k, k, device=dev).to(BF).contiguous(memory_format=torch.channels_last)
+        fl = 2.0 * 16 * HW * HW * C * Co * k * k
+        timeit(lambda: F.conv2d(xi, wi, padding=k // 2), fl, f"cuDNN fprop {C}->{Co} k{k} @{HW}")
+        yi = F.conv2d(xi, wi, padding=k // 2)
+        timeit(lambda: torch.ops.aten.convolution_backward(yi, xi, wi, None, (1, 1), (k // 2, k // 2), (1, 1), False, (0, 0), 1, (False, True, False)), fl, f"cuDNN wgrad {C}->{Co} k{k} @{HW}")
+        timeit(lambda: torch.ops.aten.convolution_backward(yi, xi, wi, None, (1, 1), (k // 2, k // 2), (1, 1), False, (0, 0), 1, (True, False, False)), fl, f"cuDNN dgrad {C}->{Co} k{k} @{HW}")
+        del xi, wi, yi
