@@ -19,6 +19,10 @@
 // A work item = (filter-row group, ci chunk, co tile, image n, column block, row range).
 // Traffic per output row and CTA: one new x segment (17 KB) + one dy tile (BN*256 B) for rg*ceil(S/2)*8 MMAs.
 // Warps: 0 = x-segment producer, 1 = MMA issuer + TMEM owner, 2..5 = epilogue, 6 = dy producer.
+//
+// CTA2 variant (cta_group::2, Cin % 128 == 0, BN = 128): the two CTAs of a cluster take two consecutive 64-channel ci chunks of the SAME
+// (filter-row group, co tile, pixels): one M = 256 MMA per tap pair, rows 0-127 = the leader's chunk, 128-255 = the peer's.  Each CTA stages
+// its own x segments and only ONE of the dy tile's two 64-channel atoms (dy traffic per pair halves); barrier protocol as in umma_convh.cu.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -47,6 +51,7 @@ struct alignas(64) WgradHParams {
     uint32_t idesc;
     float* ws;
     int Cin, Cout;
+    int cta2;                    // CTA pairs: `cin_chunks` counts PAIRS of chunks in the work decomposition below
     // cold tail (virtual channel concat of the input, common.cuh ChanCat): sources 1..n_src-1
     int src_chunk_end[kMaxCat];
     CUtensorMap tmX2[kMaxCat - 1];
@@ -61,7 +66,8 @@ struct WSched {
     const WgradHParams& p;
     long long pos, end;
     int g;
-    __device__ __forceinline__ WSched(const WgradHParams& p_, int cta) : p(p_) {
+    int rank;
+    __device__ __forceinline__ WSched(const WgradHParams& p_, int cta, int rank_ = 0) : p(p_), rank(rank_) {
         g = 0;
         while (g + 1 < p.num_groups && cta >= p.grp_cta_begin[g + 1]) ++g;
         const int j = cta - p.grp_cta_begin[g], n = p.grp_cta_begin[g + 1] - p.grp_cta_begin[g];
@@ -79,6 +85,7 @@ struct WSched {
         long long idx = b;
         it.nt = (int)(idx % p.num_n_tiles); idx /= p.num_n_tiles;
         it.cc = (int)(idx % p.cin_chunks); idx /= p.cin_chunks;
+        if (p.cta2) it.cc = 2 * it.cc + rank;
         it.w0 = (int)(idx % p.blocks_w) * 128;
         it.n_img = (int)(idx / p.blocks_w);
         it.g = g;
@@ -90,6 +97,7 @@ struct WSched {
     }
 };
 
+template <bool CTA2>
 __global__ void __launch_bounds__(kWgradHThreads, 1) umma_wgradh_kernel(const __grid_constant__ WgradHParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -100,6 +108,8 @@ __global__ void __launch_bounds__(kWgradHThreads, 1) umma_wgradh_kernel(const __
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + nb);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = CTA2 ? (int)ptx::cluster_ctarank() : 0;          // 0 = leader of the pair
+    const int unit = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;  // scheduling unit: CTA, or CTA pair
     const uint32_t smem_base = ptx::smem_u32(smem);
     const uint32_t b_base = smem_base + a_bytes;
     const uint32_t bar_base = ptx::smem_u32(bars);
@@ -117,15 +127,15 @@ __global__ void __launch_bounds__(kWgradHThreads, 1) umma_wgradh_kernel(const __
         for (int s = 0; s < p.a_slots; ++s) { ptx::mbar_init(a_full(s), 1); ptx::mbar_init(a_empty(s), 1); }
         for (int s = 0; s < p.b_stages; ++s) { ptx::mbar_init(b_full(s), 1); ptx::mbar_init(b_empty(s), 1); }
         ptx::mbar_init(acc_full, 1);
-        ptx::mbar_init(acc_empty, 4);
+        ptx::mbar_init(acc_empty, CTA2 ? 8 : 4);
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
-        ptx::tmem_relinquish();
+        if (CTA2) { ptx::tmem_alloc2(ptx::smem_u32(tmem_slot), 512); ptx::tmem_relinquish2(); }
+        else { ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512); ptx::tmem_relinquish(); }
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    if (CTA2) ptx::cluster_sync_all(); else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (tmem_base != 0) {
@@ -138,7 +148,7 @@ __global__ void __launch_bounds__(kWgradHThreads, 1) umma_wgradh_kernel(const __
         // ===================== x-segment producer: input rows h_a + r0 - pr ... h_b - 1 + r0 + rg - 1 - pr =====================
         int slot = 0;
         uint32_t phase = 0;
-        WSched sched(p, blockIdx.x);
+        WSched sched(p, unit, rank);
         WItem it;
         while (sched.next(it)) {
             const int first = it.h_a + it.r0 - pr, count = (it.h_b - it.h_a) + it.rg - 1;
@@ -154,15 +164,17 @@ __global__ void __launch_bounds__(kWgradHThreads, 1) umma_wgradh_kernel(const __
                 ptx::mbar_wait(a_empty(slot), phase ^ 1);
                 if (ptx::elect_one_sync()) {
                     // slot 0 is loaded twice: in place and into the mirror behind the last ring slot (cross-row pairs starting in the last slot)
-                    ptx::mbar_arrive_expect_tx(a_full(slot), slot == 0 ? 2 * p.a_box_bytes : p.a_box_bytes);
-                    if (mx) {
-                        ptx::tma_load_4d(smem_base + slot * p.a_slot_bytes, mx, a_full(slot), lc * 64, it.w0 - ps, first + e, it.n_img);
-                        if (slot == 0)
-                            ptx::tma_load_4d(smem_base + p.a_slots * p.a_slot_bytes, mx, a_full(slot), lc * 64, it.w0 - ps, first + e, it.n_img);
+                    const uint32_t bytes = slot == 0 ? 2 * p.a_box_bytes : p.a_box_bytes;
+                    const CUtensorMap* m = mx ? mx : &p.tmX;
+                    if (CTA2) {   // both CTAs' bytes complete on the leader's barrier
+                        const uint32_t fb = ptx::mapa_shared(a_full(slot), 0);
+                        if (rank == 0) ptx::mbar_arrive_expect_tx(a_full(slot), 2 * bytes);
+                        ptx::tma_load_4d_2sm(smem_base + slot * p.a_slot_bytes, m, fb, lc * 64, it.w0 - ps, first + e, it.n_img);
+                        if (slot == 0) ptx::tma_load_4d_2sm(smem_base + p.a_slots * p.a_slot_bytes, m, fb, lc * 64, it.w0 - ps, first + e, it.n_img);
                     } else {
-                        ptx::tma_load_4d(smem_base + slot * p.a_slot_bytes, &p.tmX, a_full(slot), lc * 64, it.w0 - ps, first + e, it.n_img);
-                        if (slot == 0)
-                            ptx::tma_load_4d(smem_base + p.a_slots * p.a_slot_bytes, &p.tmX, a_full(slot), lc * 64, it.w0 - ps, first + e, it.n_img);
+                        ptx::mbar_arrive_expect_tx(a_full(slot), bytes);
+                        ptx::tma_load_4d(smem_base + slot * p.a_slot_bytes, m, a_full(slot), lc * 64, it.w0 - ps, first + e, it.n_img);
+                        if (slot == 0) ptx::tma_load_4d(smem_base + p.a_slots * p.a_slot_bytes, m, a_full(slot), lc * 64, it.w0 - ps, first + e, it.n_img);
                     }
                 }
                 __syncwarp();
@@ -174,22 +186,28 @@ __global__ void __launch_bounds__(kWgradHThreads, 1) umma_wgradh_kernel(const __
         int stage = 0;
         uint32_t phase = 0;
         const int nbox = p.BN / 64;
-        WSched sched(p, blockIdx.x);
+        WSched sched(p, unit, rank);
         WItem it;
         while (sched.next(it)) {
             for (int h = it.h_a; h < it.h_b; ++h) {
                 ptx::mbar_wait(b_empty(stage), phase ^ 1);
                 if (ptx::elect_one_sync()) {
-                    ptx::mbar_arrive_expect_tx(b_full(stage), p.b_stage_bytes);
-                    for (int j = 0; j < nbox; ++j)
-                        ptx::tma_load_4d(b_base + stage * p.b_stage_bytes + j * 16384, &p.tmDY, b_full(stage), it.nt * p.BN + j * 64, it.w0, h, it.n_img);
+                    if (CTA2) {   // BN = 128: this CTA stages the 64-channel atom `rank` of the tile (b_stage_bytes = one atom)
+                        if (rank == 0) ptx::mbar_arrive_expect_tx(b_full(stage), 2 * p.b_stage_bytes);
+                        ptx::tma_load_4d_2sm(b_base + stage * p.b_stage_bytes, &p.tmDY, ptx::mapa_shared(b_full(stage), 0), it.nt * p.BN + rank * 64, it.w0, h, it.n_img);
+                    } else {
+                        ptx::mbar_arrive_expect_tx(b_full(stage), p.b_stage_bytes);
+                        for (int j = 0; j < nbox; ++j)
+                            ptx::tma_load_4d(b_base + stage * p.b_stage_bytes + j * 16384, &p.tmDY, b_full(stage), it.nt * p.BN + j * 64, it.w0, h, it.n_img);
+                    }
                 }
                 __syncwarp();
                 if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (warp-uniform; elected lane issues) =====================
+        // ===================== MMA issuer (warp-uniform; elected lane issues; CTA2: the leader only) =====================
+        if (!CTA2 || rank == 0) {
         int a_head = 0;          // ring slot of the oldest live segment (x row h + r0 - pr)
         uint32_t a_phase = 0;
         int bstage = 0;
@@ -202,7 +220,12 @@ __global__ void __launch_bounds__(kWgradHThreads, 1) umma_wgradh_kernel(const __
         const uint64_t b_hi = desc_common | ((uint64_t)(16384 >> 4) << 16);   // LBO = 16 KB between 64-wide co atoms
         const uint32_t a_slot16 = p.a_slot_bytes >> 4, b_stage16 = p.b_stage_bytes >> 4;
         const uint32_t a_base16 = (smem_base >> 4) & 0x3FFF, b_base16 = (b_base >> 4) & 0x3FFF;
-        WSched sched(p, blockIdx.x);
+        auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t flag) {
+            if (CTA2) ptx::mma_bf16_ss2(d, a, b, p.idesc, flag); else ptx::mma_bf16_ss(d, a, b, p.idesc, flag);
+        };
+        // arrives once the MMAs issued so far have retired (CTA2: on the barrier at this offset in BOTH CTAs)
+        auto commit = [&](uint32_t bar) { if (CTA2) ptx::tc_commit2(bar, 3); else ptx::tc_commit(bar); };
+        WSched sched(p, unit, rank);
         WItem it;
         while (sched.next(it)) {
             ptx::mbar_wait(acc_empty, acc_phase ^ 1);
@@ -230,10 +253,10 @@ __global__ void __launch_bounds__(kWgradHThreads, 1) umma_wgradh_kernel(const __
                         for (int sp = 0; sp < p.SPf; ++sp) {
                             const uint64_t a_desc0 = a_hi | (uint64_t)(seg16 + sp * 16);   // tap s = 2*sp starts 2*sp*128 B in
                             const uint32_t d_addr = (uint32_t)((rr * p.SPf + sp) * p.BN);
-                            ptx::mma_bf16_ss(d_addr, a_desc0, b_desc0, p.idesc, acc_flag);
+                            mma(d_addr, a_desc0, b_desc0, acc_flag);
 #pragma unroll
                             for (int ks = 1; ks < 8; ++ks)   // K step = 16 pixels = 2048 B = 128 units
-                                ptx::mma_bf16_ss(d_addr, a_desc0 + (uint64_t)(ks * 128), b_desc0 + (uint64_t)(ks * 128), p.idesc, 1u);
+                                mma(d_addr, a_desc0 + (uint64_t)(ks * 128), b_desc0 + (uint64_t)(ks * 128), 1u);
                         }
                     }
                     // last filter column: rows (2j, 2j+1) share one MMA (second atom = the next ring slot, or the mirror of slot 0 behind
@@ -244,13 +267,13 @@ __global__ void __launch_bounds__(kWgradHThreads, 1) umma_wgradh_kernel(const __
                         const uint64_t hi = (2 * j + 1 < it.rg) ? a_hi_row : a_hi;
                         const uint64_t a_desc0 = hi | (uint64_t)(a_base16 + sl * a_slot16 + (p.S - 1) * 8);   // tap S-1 starts (S-1)*128 B in
                         const uint32_t d_addr = (uint32_t)((it.rg * p.SPf + j) * p.BN);
-                        ptx::mma_bf16_ss(d_addr, a_desc0, b_desc0, p.idesc, acc_flag);
+                        mma(d_addr, a_desc0, b_desc0, acc_flag);
 #pragma unroll
                         for (int ks = 1; ks < 8; ++ks)
-                            ptx::mma_bf16_ss(d_addr, a_desc0 + (uint64_t)(ks * 128), b_desc0 + (uint64_t)(ks * 128), p.idesc, 1u);
+                            mma(d_addr, a_desc0 + (uint64_t)(ks * 128), b_desc0 + (uint64_t)(ks * 128), 1u);
                     }
-                    ptx::tc_commit(b_empty(bstage));
-                    ptx::tc_commit(a_empty(a_head));   // x row h + r0 - pr is not read by later output rows
+                    commit(b_empty(bstage));
+                    commit(a_empty(a_head));   // x row h + r0 - pr is not read by later output rows
                 }
                 __syncwarp();
                 if (++bstage == p.b_stages) { bstage = 0; bphase ^= 1; }
@@ -261,21 +284,22 @@ __global__ void __launch_bounds__(kWgradHThreads, 1) umma_wgradh_kernel(const __
                 for (int k = 0; k < it.rg - 1; ++k) {
                     int sl = a_head + k;
                     if (sl >= p.a_slots) sl -= p.a_slots;
-                    ptx::tc_commit(a_empty(sl));
+                    commit(a_empty(sl));
                 }
-                ptx::tc_commit(acc_full);
+                commit(acc_full);
             }
             __syncwarp();
             a_head += it.rg - 1;
             if (a_head >= p.a_slots) { a_head -= p.a_slots; a_phase ^= 1; }
             acc_phase ^= 1;
         }
+        }
     } else if (warp >= 2 && warp <= 5) {
         // ===================== epilogue: TMEM -> red.add into ws[tap][ci][co] =====================
         const int q = warp & 3;
         const int row = q * 32 + lane;
         uint32_t acc_phase = 0;
-        WSched sched(p, blockIdx.x);
+        WSched sched(p, unit, rank);
         WItem it;
         while (sched.next(it)) {
             ptx::mbar_wait(acc_full, acc_phase);
@@ -305,16 +329,18 @@ __global__ void __launch_bounds__(kWgradHThreads, 1) umma_wgradh_kernel(const __
             }
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(acc_empty);
+            if (lane == 0) {
+                if (CTA2) ptx::mbar_arrive_cluster(ptx::mapa_shared(acc_empty, 0)); else ptx::mbar_arrive(acc_empty);
+            }
             acc_phase ^= 1;
         }
     }
 
     ptx::tc_fence_before();
-    __syncthreads();
+    if (CTA2) ptx::cluster_sync_all(); else __syncthreads();   // CTA2: the peer's shared memory / barriers stay alive until both are done
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, 512);
+        if (CTA2) ptx::tmem_dealloc2(tmem_base, 512); else ptx::tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -365,13 +391,23 @@ int conv_wgrad_wgradh(const void* x, const void* dy, float* ws, int N, int H, in
     }
     p.H = H; p.W = W; p.R = R; p.S = S; p.Cin = Cin; p.Cout = Cout;
     p.cin_chunks = Cin / 64;
+    {   // CTA pairs over two consecutive ci chunks (STC_WGRADH_CTA2=0 disables)
+        static int en = -1;
+        if (en < 0) { const char* e = getenv("STC_WGRADH_CTA2"); en = (e && e[0] == '0') ? 0 : 1; }
+        bool ok = en && p.BN == 128 && p.cin_chunks % 2 == 0;
+        if (ok && src)   // a pair's two chunks may come from different sources, but every source must hold whole chunks (it does: c % 64 == 0)
+            ok = true;
+        p.cta2 = ok ? 1 : 0;
+        if (p.cta2) p.cin_chunks /= 2;
+    }
     p.num_n_tiles = Cout / p.BN;
     p.blocks_w = (W + 127) / 128;
     STC_REQUIRE(p.num_groups <= 8, "conv_wgrad_wgradh: too many filter-row groups");
     p.rows_total = (long long)p.num_n_tiles * p.cin_chunks * p.blocks_w * N * H;
     static int row_overhead = -1;   // fixed per-row share (TMA issue, barrier round trips) in MMA units; STC_WGRADH_ROWCOST
     if (row_overhead < 0) { const char* e = getenv("STC_WGRADH_ROWCOST"); row_overhead = e ? atoi(e) : 16; }
-    int grid = p.rows_total * p.num_groups < num_sms() ? (int)(p.rows_total * p.num_groups) : num_sms();
+    const int units = p.cta2 ? num_sms() / 2 : num_sms();   // scheduling units: CTAs, or CTA pairs
+    int grid = p.rows_total * p.num_groups < units ? (int)(p.rows_total * p.num_groups) : units;
     {   // CTAs per group in proportion to the group's cost per row; every group gets at least one, the counts sum to the grid
         int wgt[8], wsum = 0;
         for (int g = 0; g < p.num_groups; ++g) {
@@ -394,10 +430,10 @@ int conv_wgrad_wgradh(const void* x, const void* dy, float* ws, int N, int H, in
     }
     p.a_slot_bytes = 17408;
     p.a_box_bytes = (uint32_t)bwh * 128;
-    p.b_stage_bytes = (uint32_t)p.BN * 256;
+    p.b_stage_bytes = (uint32_t)(p.cta2 ? p.BN / 2 : p.BN) * 256;
     p.a_slots = p.RG + 3;
-    p.b_stages = p.BN == 64 ? 4 : 3;
-    p.idesc = make_idesc_bf16(128, p.BN, 1, 1);
+    p.b_stages = (p.BN == 64 || p.cta2) ? 4 : 3;
+    p.idesc = make_idesc_bf16(p.cta2 ? 256 : 128, p.BN, 1, 1);
     p.ws = ws;
     size_t smem = (size_t)(p.a_slots + 1) * p.a_slot_bytes + (size_t)p.b_stages * p.b_stage_bytes + (2 * p.a_slots + 2 * p.b_stages + 2) * 8 + 16 + 1024;
     STC_REQUIRE(smem <= 227 * 1024, "conv_wgrad_wgradh: smem %zu", smem);
@@ -405,10 +441,22 @@ int conv_wgrad_wgradh(const void* x, const void* dy, float* ws, int N, int H, in
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        STC_CUDA(cudaFuncSetAttribute(umma_wgradh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        STC_CUDA(cudaFuncSetAttribute(umma_wgradh_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        STC_CUDA(cudaFuncSetAttribute(umma_wgradh_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set[dev] = true;
     }
-    umma_wgradh_kernel<<<grid, kWgradHThreads, smem, st>>>(p);
+    if (p.cta2) {   // `grid` counted pairs: clusters of two CTAs (the two SMs of a TPC)
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)(2 * grid)); cfg.blockDim = dim3(kWgradHThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        STC_CUDA(cudaLaunchKernelEx(&cfg, umma_wgradh_kernel<true>, p));
+        return check_launch("umma_wgradh_kernel (cta_group::2)");
+    }
+    umma_wgradh_kernel<false><<<grid, kWgradHThreads, smem, st>>>(p);
     return check_launch("umma_wgradh_kernel");
 }
 

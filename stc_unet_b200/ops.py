@@ -153,6 +153,7 @@ class LaunchProfiler:
         self.time_all = time_all  # CUDA events around EVERY C-ABI call (tools/step_profile.py)
         self.records = []       # (kind, engine, flops, start_event, end_event)
         self.all_records = []   # (entry point, bytes of the tensor arguments, start_event, end_event)
+        self.all_sigs = []      # the small integer arguments of the same calls (shape signature; tools/step_profile.py --dense)
         self.calls = 0
 
     def dense(self, kind, flops, fn):
@@ -193,6 +194,7 @@ def set_profiler(p: Optional[LaunchProfiler]):
             _o(self_, name, *args)
             e.record()
             p.all_records.append((name, sum(a.numel() * a.element_size() for a in args if isinstance(a, torch.Tensor)), s, e))
+            p.all_sigs.append(tuple(a for a in args if isinstance(a, int) and not isinstance(a, bool) and abs(a) < (1 << 20)))
         lib.call = counting_call.__get__(lib, type(lib))
     elif "call" in lib.__dict__:
         del lib.__dict__["call"]

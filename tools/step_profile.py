@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--classes", type=int, default=3)
     ap.add_argument("--dtype", default="bf16")
     ap.add_argument("--detail", default="")
+    ap.add_argument("--dense", action="store_true", help="list the dense calls (conv / gemm entry points) grouped by their integer arguments")
     args = ap.parse_args()
     import stc_unet_b200 as S
     from stc_unet_b200 import ops
@@ -57,6 +58,16 @@ def main():
     print(f"{'entry point':34s} {'calls':>5s} {'ms':>8s} {'GB touched':>10s} {'GB/s':>8s}")
     for name, (n, ms, nb) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print(f"{name:34s} {n:5d} {ms:8.3f} {nb / 1e9:10.3f} {nb / 1e6 / max(ms, 1e-6):8.0f}")
+    if args.dense:
+        grp = collections.OrderedDict()
+        for (name, nbytes, s, e), sig in zip(prof.all_records, prof.all_sigs):
+            if not (name.startswith("stc_conv_") or name.startswith("stc_gemm")):
+                continue
+            d = grp.setdefault((name, sig), [0, 0.0])
+            d[0] += 1; d[1] += s.elapsed_time(e)
+        print("--- dense calls by (entry point, integer arguments): calls, total ms")
+        for (name, sig), (n, ms) in sorted(grp.items(), key=lambda kv: -kv[1][1]):
+            print(f"    {ms:8.3f} ms {n:3d} x {name} {sig}")
     for name in filter(None, args.detail.split(",")):
         print(f"--- {name}")
         for ms, nb in per[name]:
