@@ -592,7 +592,7 @@ static EncodeTiledFn get_encode_fn() {
 
 // rank-`rank` bf16 tensor map with 128B swizzle; dims/strides innermost first; strides[0] is implicit (2 bytes)
 static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                      const uint32_t* box) {
+                      const uint32_t* box, bool swizzle64 = false) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled entry point unavailable");
@@ -607,7 +607,7 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t
         if (i > 0) gstr[i - 1] = strides_bytes[i];
     }
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr, gbox, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu] box [%u %u %u %u] base %p", (int)r, rank,
@@ -632,6 +632,10 @@ static int pick_bn(int n) {
 
 int encode_map_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
     return encode_map(m, base, rank, dims, strides_bytes, box);
+}
+// 64-byte swizzle (inner box = 32 bf16): the half-width dy tiles of the paired halo wgrad
+int encode_map_bf16_sw64(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+    return encode_map(m, base, rank, dims, strides_bytes, box, true);
 }
 int umma_pick_bn(int n) { return pick_bn(n); }
 

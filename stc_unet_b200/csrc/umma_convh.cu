@@ -534,10 +534,13 @@ static int convh_plan(int Cout, int R, int& BN, int& T, int& a_slots, int& b_sta
     const size_t staging = staged ? kConvHStagingBytes : 0;
     const int tmax = 256 / BN;  // two accumulator stages of 256 TMEM columns
     const int cands[] = {4, 2, 1};
+    static int bs_max = -1, extra_max = -1;   // experiment knobs: STC_CONVH_BS (weight-ring depth), STC_CONVH_EXTRA (spare segment slots)
+    if (bs_max < 0) { const char* e = getenv("STC_CONVH_BS"); bs_max = e ? atoi(e) : 4; }
+    if (extra_max < 0) { const char* e = getenv("STC_CONVH_EXTRA"); extra_max = e ? atoi(e) : 3; }
     for (int t : cands) {
         if (t > tmax) continue;
-        for (int extra = 3; extra >= 1; --extra) {
-            for (int bs = 4; bs >= 2; --bs) {
+        for (int extra = extra_max; extra >= 1; --extra) {
+            for (int bs = bs_max; bs >= 2; --bs) {
                 int slots = t + R - 1 + extra;
                 size_t smem = (size_t)slots * 17408 + (size_t)bs * (cta2 ? BN / 2 : BN) * 128 + staging + (2 * slots + 2 * bs + 4) * 8 + 16 + 1024;
                 if (smem <= 225 * 1024) {

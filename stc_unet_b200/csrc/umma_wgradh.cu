@@ -20,9 +20,12 @@
 // Traffic per output row and CTA: one new x segment (17 KB) + one dy tile (BN*256 B) for rg*ceil(S/2)*8 MMAs.
 // Warps: 0 = x-segment producer, 1 = MMA issuer + TMEM owner, 2..5 = epilogue, 6 = dy producer.
 //
-// CTA2 variant (cta_group::2, Cin % 128 == 0, BN = 128): the two CTAs of a cluster take two consecutive 64-channel ci chunks of the SAME
-// (filter-row group, co tile, pixels): one M = 256 MMA per tap pair, rows 0-127 = the leader's chunk, 128-255 = the peer's.  Each CTA stages
-// its own x segments and only ONE of the dy tile's two 64-channel atoms (dy traffic per pair halves); barrier protocol as in umma_convh.cu.
+// CTA2 variant (cta_group::2): the two CTAs of a cluster work on the SAME (co tile, pixels) with one M = 256 MMA per tap pair, rows 0-127
+// from the leader's x segments, 128-255 from the peer's.  What differs between the two is either the 64-channel ci chunk (pair_mode 0:
+// two consecutive chunks, Cin % 128 == 0) or the filter-row group (pair_mode 1, Cin = 64 layers: the peer's ring holds the input rows RG
+// further down, so the same descriptors address the next group's taps; a group that sticks out of the filter is computed and dropped).
+// Each CTA stages only HALF of the dy tile's channels (dy traffic per pair halves): one 64-channel SW128 atom for BN = 128, a 32-channel
+// tile in the 64-byte swizzle for BN = 64 (MN-major SW64: 64 B per pixel row, SBO = 512 B).  Barrier protocol as in umma_convh.cu.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -51,7 +54,9 @@ struct alignas(64) WgradHParams {
     uint32_t idesc;
     float* ws;
     int Cin, Cout;
-    int cta2;                    // CTA pairs: `cin_chunks` counts PAIRS of chunks in the work decomposition below
+    int cta2;                    // CTA pairs
+    int pair_mode;               // 0: the pair splits two ci chunks (`cin_chunks` counts PAIRS of chunks); 1: it splits two filter-row groups (`num_groups` counts PAIRS)
+    int b_kstep16;               // descriptor advance of the dy tile per 16-pixel K step, 16 B units (128: SW128 atom, 64: SW64 half tile)
     // cold tail (virtual channel concat of the input, common.cuh ChanCat): sources 1..n_src-1
     int src_chunk_end[kMaxCat];
     CUtensorMap tmX2[kMaxCat - 1];
@@ -85,14 +90,19 @@ struct WSched {
         long long idx = b;
         it.nt = (int)(idx % p.num_n_tiles); idx /= p.num_n_tiles;
         it.cc = (int)(idx % p.cin_chunks); idx /= p.cin_chunks;
-        if (p.cta2) it.cc = 2 * it.cc + rank;
+        if (p.cta2 && p.pair_mode == 0) it.cc = 2 * it.cc + rank;
         it.w0 = (int)(idx % p.blocks_w) * 128;
         it.n_img = (int)(idx / p.blocks_w);
         it.g = g;
         it.h_a = h_a;
         it.h_b = h_b;
-        it.r0 = g * p.RG;
-        it.rg = min(p.RG, p.R - it.r0);
+        if (p.cta2 && p.pair_mode == 1) {   // both CTAs run the leader group's row count; rows >= R are dropped by the epilogue
+            it.rg = min(p.RG, p.R - 2 * g * p.RG);
+            it.r0 = (2 * g + rank) * p.RG;
+        } else {
+            it.r0 = g * p.RG;
+            it.rg = min(p.RG, p.R - it.r0);
+        }
         return true;
     }
 };
@@ -192,9 +202,9 @@ __global__ void __launch_bounds__(kWgradHThreads, 1) umma_wgradh_kernel(const __
             for (int h = it.h_a; h < it.h_b; ++h) {
                 ptx::mbar_wait(b_empty(stage), phase ^ 1);
                 if (ptx::elect_one_sync()) {
-                    if (CTA2) {   // BN = 128: this CTA stages the 64-channel atom `rank` of the tile (b_stage_bytes = one atom)
+                    if (CTA2) {   // this CTA stages half `rank` of the tile's channels (b_stage_bytes = that half)
                         if (rank == 0) ptx::mbar_arrive_expect_tx(b_full(stage), 2 * p.b_stage_bytes);
-                        ptx::tma_load_4d_2sm(b_base + stage * p.b_stage_bytes, &p.tmDY, ptx::mapa_shared(b_full(stage), 0), it.nt * p.BN + rank * 64, it.w0, h, it.n_img);
+                        ptx::tma_load_4d_2sm(b_base + stage * p.b_stage_bytes, &p.tmDY, ptx::mapa_shared(b_full(stage), 0), it.nt * p.BN + rank * (p.BN / 2), it.w0, h, it.n_img);
                     } else {
                         ptx::mbar_arrive_expect_tx(b_full(stage), p.b_stage_bytes);
                         for (int j = 0; j < nbox; ++j)
@@ -217,7 +227,10 @@ __global__ void __launch_bounds__(kWgradHThreads, 1) umma_wgradh_kernel(const __
         const uint64_t desc_common = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
         const uint64_t a_hi = desc_common | ((uint64_t)(128 >> 4) << 16);     // LBO = 128 B: second atom = next tap (one pixel on)
         const uint64_t a_hi_row = desc_common | ((uint64_t)(p.a_slot_bytes >> 4) << 16);   // LBO = one slot: second atom = same tap, next input row
-        const uint64_t b_hi = desc_common | ((uint64_t)(16384 >> 4) << 16);   // LBO = 16 KB between 64-wide co atoms
+        // dy tile: LBO = 16 KB between 64-wide co atoms; the 32-channel half tile (b_kstep16 == 64) is MN-major SW64: SBO = 512 B, layout 4
+        const uint64_t b_hi = p.b_kstep16 == 64 ? (((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61))
+                                                : (desc_common | ((uint64_t)(16384 >> 4) << 16));
+        const uint64_t b_ks = (uint64_t)p.b_kstep16;
         const uint32_t a_slot16 = p.a_slot_bytes >> 4, b_stage16 = p.b_stage_bytes >> 4;
         const uint32_t a_base16 = (smem_base >> 4) & 0x3FFF, b_base16 = (b_base >> 4) & 0x3FFF;
         auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t flag) {
@@ -256,7 +269,7 @@ __global__ void __launch_bounds__(kWgradHThreads, 1) umma_wgradh_kernel(const __
                             mma(d_addr, a_desc0, b_desc0, acc_flag);
 #pragma unroll
                             for (int ks = 1; ks < 8; ++ks)   // K step = 16 pixels = 2048 B = 128 units
-                                mma(d_addr, a_desc0 + (uint64_t)(ks * 128), b_desc0 + (uint64_t)(ks * 128), 1u);
+                                mma(d_addr, a_desc0 + (uint64_t)(ks * 128), b_desc0 + ks * b_ks, 1u);
                         }
                     }
                     // last filter column: rows (2j, 2j+1) share one MMA (second atom = the next ring slot, or the mirror of slot 0 behind
@@ -270,7 +283,7 @@ __global__ void __launch_bounds__(kWgradHThreads, 1) umma_wgradh_kernel(const __
                         mma(d_addr, a_desc0, b_desc0, acc_flag);
 #pragma unroll
                         for (int ks = 1; ks < 8; ++ks)
-                            mma(d_addr, a_desc0 + (uint64_t)(ks * 128), b_desc0 + (uint64_t)(ks * 128), 1u);
+                            mma(d_addr, a_desc0 + (uint64_t)(ks * 128), b_desc0 + ks * b_ks, 1u);
                     }
                     commit(b_empty(bstage));
                     commit(a_empty(a_head));   // x row h + r0 - pr is not read by later output rows
@@ -310,7 +323,7 @@ __global__ void __launch_bounds__(kWgradHThreads, 1) umma_wgradh_kernel(const __
                     int rr, s;
                     if (qs < n_full) { rr = qs / p.SPf; s = 2 * (qs - rr * p.SPf) + (row >> 6); }      // taps (rr, 2sp) | (rr, 2sp+1)
                     else { rr = 2 * (qs - n_full) + (row >> 6); s = p.S - 1; }                         // taps (2j, S-1) | (2j+1, S-1)
-                    const bool valid = rr < it.rg;
+                    const bool valid = rr < it.rg && it.r0 + rr < p.R;
                     const int tap = (it.r0 + (valid ? rr : 0)) * p.S + s;
                     float* o = p.ws + ((long long)tap * p.Cin + it.cc * 64 + (row & 63)) * p.Cout + it.nt * p.BN;
                     const uint32_t t_addr = (uint32_t)(qs * p.BN) + ((uint32_t)(q * 32) << 16);
@@ -345,6 +358,7 @@ __global__ void __launch_bounds__(kWgradHThreads, 1) umma_wgradh_kernel(const __
 }
 
 int encode_map_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
+int encode_map_bf16_sw64(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
 
 bool conv_wgradh_eligible(int W, int Cin, int Cout, int R, int S, int dtype) {
     static int disabled = -1;
@@ -364,12 +378,30 @@ int conv_wgrad_wgradh(const void* x, const void* dy, float* ws, int N, int H, in
     // BN = 128 when possible (measured 5-40 % faster than 64 on the Cout >= 128 layers: fewer, longer MMAs per dy tile)
     { const char* e = getenv("STC_WGRADH_BN"); p.BN = (Cout % 128 == 0 && !(e && atoi(e) == 64)) ? 128 : 64; }
     p.SPf = S / 2;
-    // rows per group: as many as fit the 512 TMEM columns; a group of rg rows needs rg * (S/2) + ceil(rg / 2) accumulators of BN columns
+    p.cin_chunks = Cin / 64;
+    {   // CTA pairs (STC_WGRADH_CTA2=0 disables): over two ci chunks when there is an even number of them, else over two filter-row groups
+        static int en = -1;
+        if (en < 0) { const char* e = getenv("STC_WGRADH_CTA2"); en = (e && e[0] == '0') ? 0 : 1; }
+        p.cta2 = en ? 1 : 0;
+        p.pair_mode = (p.cin_chunks % 2 == 0) ? 0 : 1;
+        if (p.cta2 && p.pair_mode == 1 && R == 1) p.cta2 = 0;   // one filter row: nothing to pair
+    }
+    // rows per group: a group of rg rows needs rg * (S/2) + ceil(rg / 2) accumulators of BN columns in the 512 TMEM columns.  Single CTAs and
+    // ci-chunk pairs take as many rows as fit; group pairs take the row count with the fewest MMAs per pixel block over all pairs.
     p.RG = 0;
-    for (int rg = R; rg >= 1; --rg)
-        if ((rg * p.SPf + (rg + 1) / 2) * p.BN <= 512) { p.RG = rg; break; }
+    int best_cost = 1 << 30;
+    for (int rg = R; rg >= 1; --rg) {
+        const int nacc = rg * p.SPf + (rg + 1) / 2;
+        if (nacc * p.BN > 512) continue;
+        if (!(p.cta2 && p.pair_mode == 1)) { p.RG = rg; break; }
+        const int ng = (R + rg - 1) / rg, cost = ((ng + 1) / 2) * nacc;
+        if (cost < best_cost) { best_cost = cost; p.RG = rg; }
+    }
     STC_REQUIRE(p.RG >= 1, "conv_wgrad_wgradh: no plan");
     p.num_groups = (R + p.RG - 1) / p.RG;
+    if (p.cta2 && p.pair_mode == 1) p.num_groups = (p.num_groups + 1) / 2;   // pairs of groups
+    if (p.cta2 && p.pair_mode == 0) p.cin_chunks /= 2;                        // pairs of chunks
+    p.b_kstep16 = (p.cta2 && p.BN == 64) ? 64 : 128;
     const int bwh = 128 + S - 1;
     p.n_src = src ? src->n : 1;
     for (int j = 0, acc = 0; j < p.n_src; ++j) {
@@ -386,20 +418,12 @@ int conv_wgrad_wgradh(const void* x, const void* dy, float* ws, int N, int H, in
         uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)N};
         uint64_t str[4] = {2, (uint64_t)Cout * 2, (uint64_t)W * Cout * 2, (uint64_t)H * W * Cout * 2};
         uint32_t box[4] = {64, 128, 1, 1};
-        int rc = encode_map_bf16(&p.tmDY, dy, 4, dims, str, box);
+        int rc;
+        if (p.b_kstep16 == 64) { box[0] = 32; rc = encode_map_bf16_sw64(&p.tmDY, dy, 4, dims, str, box); }   // 32-channel half tiles, 64-byte swizzle
+        else rc = encode_map_bf16(&p.tmDY, dy, 4, dims, str, box);
         if (rc) return rc;
     }
     p.H = H; p.W = W; p.R = R; p.S = S; p.Cin = Cin; p.Cout = Cout;
-    p.cin_chunks = Cin / 64;
-    {   // CTA pairs over two consecutive ci chunks (STC_WGRADH_CTA2=0 disables)
-        static int en = -1;
-        if (en < 0) { const char* e = getenv("STC_WGRADH_CTA2"); en = (e && e[0] == '0') ? 0 : 1; }
-        bool ok = en && p.BN == 128 && p.cin_chunks % 2 == 0;
-        if (ok && src)   // a pair's two chunks may come from different sources, but every source must hold whole chunks (it does: c % 64 == 0)
-            ok = true;
-        p.cta2 = ok ? 1 : 0;
-        if (p.cta2) p.cin_chunks /= 2;
-    }
     p.num_n_tiles = Cout / p.BN;
     p.blocks_w = (W + 127) / 128;
     STC_REQUIRE(p.num_groups <= 8, "conv_wgrad_wgradh: too many filter-row groups");
@@ -411,7 +435,8 @@ int conv_wgrad_wgradh(const void* x, const void* dy, float* ws, int N, int H, in
     {   // CTAs per group in proportion to the group's cost per row; every group gets at least one, the counts sum to the grid
         int wgt[8], wsum = 0;
         for (int g = 0; g < p.num_groups; ++g) {
-            const int rg = (R - g * p.RG) < p.RG ? (R - g * p.RG) : p.RG;
+            const int gl = (p.cta2 && p.pair_mode == 1) ? 2 * g : g;   // the (leader) group whose row count the unit runs
+            const int rg = (R - gl * p.RG) < p.RG ? (R - gl * p.RG) : p.RG;
             wgt[g] = (rg * p.SPf + (rg + 1) / 2) * 8 + row_overhead;
             wsum += wgt[g];
         }
