@@ -25,6 +25,7 @@ class _Config:
     engine = _lib.ENGINE_AUTO       # dense engine selection passed to stc_conv_* / stc_gemm
     fold_linear_pairs = True        # bf16 + tcgen05: q/k/v + in_proj and fc1 + fc2 of TransformerLayer run as folded GEMMs
     ksa_lazy_df = True              # KSA branch gradients are consumed implicitly by the BN backward kernels (no df tensors)
+    chain_fanout_grads = True       # KSA: the input's four gradients are summed in the branch dgrads' epilogues (no add_n pass)
     fold_eval_bn = True             # inference: eval-mode BN folded into the conv weights, activation in the conv epilogue
     widen_narrow_convs = True       # bf16: 16 / 32-channel layers are zero-padded to the tcgen05 kernels' channel granularity
     # Inference with FROZEN weights (a deployed checkpoint): keep the folded / packed bf16 operands between forwards instead of rebuilding
@@ -435,15 +436,28 @@ def gemm(A, B, C, M, N, K, batch1, batch2, sA, sB, sC, alpha=1.0):
 # ---------------------------------------------------------------------------------------------
 # fan-out: explicit gradient summation with our add kernel (instead of autograd's implicit add)
 # ---------------------------------------------------------------------------------------------
+class _GradChain:
+    """Running sum of the gradients that flow into ONE fanned-out tensor from consumers whose backward can add into it for free (a conv
+    dgrad's residual input): each such consumer computes acc = its gradient + acc, returns None to autograd, and _Fanout.backward picks the sum
+    up.  Replaces an add_n pass over n full-size tensors (KernelSelectAttention: 3 branch dgrads + the residual path)."""
+    def __init__(self):
+        self.acc = None
+
+
 class _Fanout(Function):
     @staticmethod
     def forward(ctx, x, n):
         ctx.n = n
+        ctx.set_materialize_grads(False)   # consumers that chain their gradient (see _GradChain) return None, not a tensor of zeros
         return tuple(x.view_as(x) for _ in range(n))
 
     @staticmethod
     def backward(ctx, *grads):
         gs = [_chk(g) for g in grads if g is not None]
+        chain = getattr(ctx, "grad_chain", None)
+        if chain is not None and chain.acc is not None:
+            gs.append(chain.acc)
+            chain.acc = None
         if not gs:
             return None, None
         acc = gs[0]
@@ -653,7 +667,10 @@ class _ConvBnAct(Function):
         dx = None
         if ctx.needs_input_grad[0]:
             wpt = pack_weight(weight, dy.dtype, transpose_flip=True)
-            dx = conv_fprop(dy, wpt, None, None, weight.shape[1], R, S)
+            chain = getattr(ctx, "grad_chain", None)   # set by ksa_fuse: the input's other gradients are added in the dgrad epilogue
+            dx = conv_fprop(dy, wpt, None, chain.acc if chain is not None else None, weight.shape[1], R, S)
+            if chain is not None:
+                chain.acc, dx = dx, None
         return dx, dw, dbias, dgamma, dbeta, None, None, None
 
 
@@ -1078,8 +1095,9 @@ class _KSALazy:
 
 class _KSAFuse(Function):
     @staticmethod
-    def forward(ctx, x, f0, f1, f2, fc_w, fc_b, w0, b0, w1, b1, w2, b2, pobjs, lazy=None):
+    def forward(ctx, x, f0, f1, f2, fc_w, fc_b, w0, b0, w1, b1, w2, b2, pobjs, lazy=None, chain=None):
         ctx.lazy = lazy
+        ctx.chain = chain
         x, f0, f1, f2 = _chk(x), _chk(f0), _chk(f1), _chk(f2)
         N, H, W, C = x.shape
         HW = H * W
@@ -1132,10 +1150,13 @@ class _KSAFuse(Function):
             # the branch BN backward kernels read dout themselves (stc_bn_bwd_*_aff): no df tensors (4 x |x| of traffic less per level)
             lz = ctx.lazy
             lz.scale, lz.shift, lz.shift_scale, lz.rows, lz.ready = wts, dS, 1.0 / HW, HW, True
-            return (dout, dout, dout, dout, gfcW, gfcb, *grads, None, None)
+            dx = dout
+            if ctx.chain is not None:   # the residual path's gradient starts the chain the three branch dgrads add to (read, never written)
+                ctx.chain.acc, dx = dout, None
+            return (dx, dout, dout, dout, gfcW, gfcb, *grads, None, None, None)
         df0, df1, df2 = torch.empty_like(f0), torch.empty_like(f1), torch.empty_like(f2)
         lib.call("stc_ksa_df", dout, wts, dS, df0, df1, df2, N, HW, C, code, stream_ptr())
-        return (dout, df0, df1, df2, gfcW, gfcb, *grads, None, None)
+        return (dout, df0, df1, df2, gfcW, gfcb, *grads, None, None, None)
 
 
 def ksa_fuse(x, f0, f1, f2, fc, fcs):
@@ -1149,7 +1170,16 @@ def ksa_fuse(x, f0, f1, f2, fc, fcs):
         lazy = _KSALazy()
         for k, fn in enumerate(fns):
             fn.ksa_slot = (lazy, k)
-    return _KSAFuse.apply(x, f0, f1, f2, *ps, ps, lazy)
+    chain = None
+    fan = x.grad_fn
+    if (lazy is not None and config.chain_fanout_grads and fan is not None and type(fan).__name__ == "_FanoutBackward"
+            and all(fn.next_functions[0][0] is fan for fn in fns)):
+        # x and the three branch inputs are the four outputs of one fan-out: their gradients are summed inside the branch dgrads
+        chain = _GradChain()
+        fan.grad_chain = chain
+        for fn in fns:
+            fn.grad_chain = chain
+    return _KSAFuse.apply(x, f0, f1, f2, *ps, ps, lazy, chain)
 
 
 # ---------------------------------------------------------------------------------------------

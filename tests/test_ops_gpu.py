@@ -235,6 +235,33 @@ def test_ksa_block(S, dt, lazy):
     ops.config.ksa_lazy_df = True
 
 
+def test_ksa_input_gradient_chain_tcgen05(S):
+    """The KSA input's four gradients (residual path + three branch dgrads) summed inside the dgrad epilogues (ops._GradChain) against the
+    explicit add_n of four tensors: same sum up to the bf16 rounding of the partial sums, and no stc_add_n call on the chained path."""
+    from stc_unet_b200 import ops
+    torch.manual_seed(1)
+    C, N, H, W = 64, 2, 12, 128
+    ksa = S.KernelSelectAttention(channel=C).to(dev())
+    x = bf16_round(torch.randn(N, H, W, C, device=dev()))
+    go = bf16_round(torch.randn(N, H, W, C, device=dev())).to(torch.bfloat16)
+    grads, calls = {}, {}
+    for chain in (True, False):
+        ops.config.chain_fanout_grads = chain
+        ksa.zero_grad()
+        xo = x.to(torch.bfloat16).requires_grad_(True)
+        prof = ops.LaunchProfiler(time_all=True)
+        ops.set_profiler(prof)
+        try:
+            ksa.forward_residual(xo).backward(go)
+        finally:
+            ops.set_profiler(None)
+            ops.config.chain_fanout_grads = True
+        grads[chain] = xo.grad.float()
+        calls[chain] = sum(1 for r in prof.all_records if r[0] == "stc_add_n")
+    assert calls[True] == 0 and calls[False] >= 1
+    assert rel_l2(grads[True], grads[False]) < 8e-3
+
+
 @pytest.mark.parametrize("dt", DT)
 def test_transformer_block(S, dt):
     from oracle import stc_oracle as O
