@@ -429,6 +429,55 @@ torch.save({k_: t.cpu() for k_, t in out.items()}, sys.argv[1])
         assert torch.equal(res["0"][k], res["2"][k]), k
 
 
+def test_halo_kernels_on_cta_pairs_match_single_ctas(tc):
+    """umma_convh_kernel / umma_wgradh_kernel on CTA pairs (cta_group::2, M = 256: the pair shares one weight / dy tile, each CTA staging
+    half of it) against the single-CTA kernels (STC_CONVH_CTA2=0 STC_WGRADH_CTA2=0) on the same operands.  fprop / dgrad / split dgrad /
+    fused BN statistics inputs: bit-identical outputs (same K order).  wgrad: fp32 red.add order differs between the two partitions, so
+    1e-5 relative; covers the ci-chunk pairs (Cin % 128 == 0), the filter-row-group pairs (Cin = 64, incl. a group sticking out of the
+    filter) and the 32-channel dy half tiles in the 64-byte swizzle (Cout = 64)."""
+    import os
+    import subprocess, sys
+    code = r'''
+import os, sys, math, torch
+sys.path.insert(0, os.getcwd())
+import stc_unet_b200 as S
+from stc_unet_b200 import ops
+ops.config.engine = S._lib.ENGINE_TCGEN05
+BF = torch.bfloat16; dev = torch.device("cuda:0")
+g = torch.Generator(device="cuda").manual_seed(3)
+out = {}
+for (N, ci, co, H, W, k) in ((2, 64, 64, 16, 256, 3), (2, 64, 64, 12, 128, 7), (2, 128, 128, 8, 256, 5), (2, 256, 256, 6, 128, 3), (2, 128, 64, 10, 200, 3),
+                             (2, 64, 128, 9, 128, 5), (2, 192, 128, 4, 128, 3)):
+    x = torch.randn(N, H, W, ci, device=dev, generator=g).to(BF)
+    dy = torch.randn(N, H, W, co, device=dev, generator=g).to(BF)
+    w = torch.randn(co, ci, k, k, device=dev, generator=g) / math.sqrt(ci * k * k)
+    b = torch.randn(co, device=dev, generator=g)
+    res = torch.randn(N, H, W, co, device=dev, generator=g).to(BF)
+    tag = f"{ci}_{co}_{H}x{W}_k{k}"
+    out["f_" + tag] = ops.conv_fprop(x, ops.pack_weight(w, BF), b, res, co, k, k, act=1)
+    out["d_" + tag] = ops.conv_fprop(dy, ops.pack_weight(w, BF, transpose_flip=True), None, None, ci, k, k)
+    out["w_" + tag] = ops.conv_wgrad(x, dy, k, k)
+    if ci % 128 == 0:
+        a, c = ops.conv_dgrad_split(dy, ops.pack_weight(w, BF, transpose_flip=True), [ci // 2, ci // 2], k, k)
+        out["s0_" + tag], out["s1_" + tag] = a, c
+torch.save({k_: t.cpu() for k_, t in out.items()}, sys.argv[1])
+'''
+    import tempfile
+    res = {}
+    with tempfile.TemporaryDirectory() as d:
+        for mode in ("0", "1"):
+            path = os.path.join(d, f"o{mode}.pt")
+            r = subprocess.run([sys.executable, "-c", code, path], env=dict(os.environ, STC_CONVH_CTA2=mode, STC_WGRADH_CTA2=mode),
+                               capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), timeout=300)
+            assert r.returncode == 0, r.stderr[-2000:]
+            res[mode] = torch.load(path)
+    for k in res["0"]:
+        if k.startswith("w_"):
+            assert rel_l2(res["1"][k], res["0"][k]) < 1e-5, k
+        else:
+            assert torch.equal(res["0"][k], res["1"][k]), k
+
+
 def test_softmax_backward_in_the_dP_epilogue(tc):
     """stc_gemm_dsoftmax (opt-in, STC_DSOFTMAX_FUSED=1): dS = scale * P * (dO V^T - rowsum(dO * O)) out of the GEMM epilogue equals the
     separate product + softmax-backward pass up to bf16 rounding on well-conditioned inputs (no large common token component)."""

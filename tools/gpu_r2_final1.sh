@@ -3,7 +3,7 @@
 # ncu launch list with DRAM bytes of one eager step, ncu --set full of the dominant kernels
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-P=gpurun_out/r2f
+P=gpurun_out/r2p
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,power.limit --format=csv > ${P}_smi.csv 2>&1
 timeout 1500 python -m pytest tests -m gpu -q --timeout 900 -p no:cacheprovider > ${P}_pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -n 3 ${P}_pytest_gpu.log
 timeout 900 python bench.py --steps 20 --warmup 5 > ${P}_bench_n1.json 2> ${P}_bench_n1.err; echo "bench exit $?"
@@ -12,7 +12,7 @@ timeout 900 python bench.py --workload slide --steps 3 --warmup 2 > ${P}_bench_s
 timeout 900 python bench.py --model unetpp --steps 10 --warmup 3 > ${P}_bench_unetpp_n1.json 2> ${P}_bench_unetpp_n1.err; echo "unetpp exit $?"
 timeout 900 python bench.py --model unet --steps 10 --warmup 3 --no-gpu-eager > ${P}_bench_unet_n1.json 2> ${P}_bench_unet_n1.err; echo "unet exit $?"
 timeout 900 python bench.py --model unet_b --steps 10 --warmup 3 --no-gpu-eager > ${P}_bench_unet_b_n1.json 2> ${P}_bench_unet_b_n1.err; echo "unet_b exit $?"
-timeout 600 python tools/step_profile.py > ${P}_step_profile.txt 2>&1; echo "step_profile exit $?"
+timeout 600 python tools/step_profile.py --dense > ${P}_step_profile.txt 2>&1; echo "step_profile exit $?"
 timeout 600 python tools/conv_sweep.py > ${P}_conv_sweep.txt 2>&1; echo "sweep exit $?"
 timeout 900 python tools/ncu_step.py > ${P}_ncu_plain.log 2>&1 && \
 timeout 1500 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \

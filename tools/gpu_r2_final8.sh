@@ -3,7 +3,7 @@
 # the 2-rank parity tests and the peer-collective check
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-P=gpurun_out/r2f
+P=gpurun_out/r2p
 run() { n=$1; shift; python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29600 + n)) "$@"; }
 timeout 600 bash -c "$(declare -f run); run 8 bench.py --gpus 8 --steps 20 --warmup 5" > ${P}_bench_n8.json 2> ${P}_bench_n8.err; echo "n8 exit $?"
 timeout 600 bash -c "$(declare -f run); run 8 bench.py --gpus 8 --model unetpp --steps 10 --warmup 3" > ${P}_bench_unetpp_n8.json 2> ${P}_bench_unetpp_n8.err; echo "unetpp n8 exit $?"

@@ -33,4 +33,6 @@ for _ in range(2):
 for _ in range(2):
     ops.gemm(sc, v, o, L, hd, L, B, 1, (L * L, 0, L, 1), (L * hd, 0, hd, 1), (L * hd, 0, hd))
 conv(512, 512, 64, 3, wgrad=True)                                   # per-tap wgrad (W < 128), division-free producer
+# CTA-pair (cta_group::2) halo kernels, further shapes: 5x5 at level 1, BN = 256 at level 3, ci-chunk-pair wgrad at level 2, 3x3 wgrad at level 1
+conv(64, 64, 512, 5); conv(256, 256, 128, 3); conv(128, 128, 256, 7, wgrad=True); conv(64, 64, 512, 3, wgrad=True)
 torch.cuda.synchronize(); print("ok")
