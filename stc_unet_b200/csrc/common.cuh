@@ -98,6 +98,7 @@ struct ChanCat {
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 int num_sms();
+int max_cta_pairs(const void* func, int threads, size_t smem);
 
 // dtype dispatch: calls f(T{}) with T = float or bf16
 #define STC_DISPATCH_DTYPE(dtype, ...)                                  \

@@ -36,6 +36,31 @@ int num_sms() {
     return cached[dev];
 }
 
+// How many 2-CTA clusters of `func` (1 CTA per SM at this shared-memory size) the device can hold at once: the persistent pair kernels
+// launch exactly that many (a TPC with one SM fused off cannot host a pair; launching num_sms / 2 pairs would then run a second wave).
+int max_cta_pairs(const void* func, int threads, size_t smem) {
+    struct Entry { const void* f; size_t smem; int dev, n; };
+    static Entry cache[32];
+    static int used = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    for (int i = 0; i < used; ++i)
+        if (cache[i].f == func && cache[i].smem == smem && cache[i].dev == dev) return cache[i].n;
+    int n = num_sms() / 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(2 * n)); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int q = 0;
+    if (cudaOccupancyMaxActiveClusters(&q, func, &cfg) == cudaSuccess && q > 0 && q < n) n = q;
+    else cudaGetLastError();
+    if (used < 32) cache[used++] = Entry{func, smem, dev, n};
+    return n;
+}
+
 }  // namespace stc
 
 using namespace stc;

@@ -659,7 +659,7 @@ static int launch(UmmaParams& p, cudaStream_t st) {
             STC_CUDA(cudaFuncSetAttribute(umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             attr2[dev] = true;
         }
-        int pairs = num_sms() / 2;
+        int pairs = max_cta_pairs((const void*)umma2_kernel, kUmmaThreads, smem);
         if (p.num_tiles < pairs) pairs = p.num_tiles;
         if (pairs <= 0) return STC_OK;
         umma2_kernel<<<2 * pairs, kUmmaThreads, smem, st>>>(p);

@@ -667,7 +667,8 @@ int conv_fprop_convh(const void* x, const void* wp, const float* bias, const voi
     }
     int grid = p.num_strips < num_sms() ? p.num_strips : num_sms();
     if (cta2) {
-        int pairs = num_sms() / 2;
+        const void* fn = p.T == 4 ? (const void*)umma_convh_kernel<4, true> : p.T == 2 ? (const void*)umma_convh_kernel<2, true> : (const void*)umma_convh_kernel<1, true>;
+        int pairs = max_cta_pairs(fn, kConvHThreads, smem);
         if (p.num_strips < pairs) pairs = p.num_strips;
         grid = 2 * pairs;
     }

@@ -428,9 +428,26 @@ int conv_wgrad_wgradh(const void* x, const void* dy, float* ws, int N, int H, in
     p.blocks_w = (W + 127) / 128;
     STC_REQUIRE(p.num_groups <= 8, "conv_wgrad_wgradh: too many filter-row groups");
     p.rows_total = (long long)p.num_n_tiles * p.cin_chunks * p.blocks_w * N * H;
+    p.a_slot_bytes = 17408;
+    p.a_box_bytes = (uint32_t)bwh * 128;
+    p.b_stage_bytes = (uint32_t)(p.cta2 ? p.BN / 2 : p.BN) * 256;
+    p.a_slots = p.RG + 3;
+    p.b_stages = (p.BN == 64 || p.cta2) ? 4 : 3;
+    p.idesc = make_idesc_bf16(p.cta2 ? 256 : 128, p.BN, 1, 1);
+    p.ws = ws;
+    size_t smem = (size_t)(p.a_slots + 1) * p.a_slot_bytes + (size_t)p.b_stages * p.b_stage_bytes + (2 * p.a_slots + 2 * p.b_stages + 2) * 8 + 16 + 1024;
+    STC_REQUIRE(smem <= 227 * 1024, "conv_wgrad_wgradh: smem %zu", smem);
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        STC_CUDA(cudaFuncSetAttribute(umma_wgradh_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        STC_CUDA(cudaFuncSetAttribute(umma_wgradh_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set[dev] = true;
+    }
     static int row_overhead = -1;   // fixed per-row share (TMA issue, barrier round trips) in MMA units; STC_WGRADH_ROWCOST
     if (row_overhead < 0) { const char* e = getenv("STC_WGRADH_ROWCOST"); row_overhead = e ? atoi(e) : 16; }
-    const int units = p.cta2 ? num_sms() / 2 : num_sms();   // scheduling units: CTAs, or CTA pairs
+    const int units = p.cta2 ? max_cta_pairs((const void*)umma_wgradh_kernel<true>, kWgradHThreads, smem) : num_sms();   // scheduling units: CTAs, or CTA pairs
     int grid = p.rows_total * p.num_groups < units ? (int)(p.rows_total * p.num_groups) : units;
     {   // CTAs per group in proportion to the group's cost per row; every group gets at least one, the counts sum to the grid
         int wgt[8], wsum = 0;
@@ -452,23 +469,6 @@ int conv_wgrad_wgradh(const void* x, const void* dy, float* ws, int N, int H, in
             if (cnt[g] > 1) { --cnt[g]; --used; }
         p.grp_cta_begin[0] = 0;
         for (int g = 0; g < p.num_groups; ++g) p.grp_cta_begin[g + 1] = p.grp_cta_begin[g] + cnt[g];
-    }
-    p.a_slot_bytes = 17408;
-    p.a_box_bytes = (uint32_t)bwh * 128;
-    p.b_stage_bytes = (uint32_t)(p.cta2 ? p.BN / 2 : p.BN) * 256;
-    p.a_slots = p.RG + 3;
-    p.b_stages = (p.BN == 64 || p.cta2) ? 4 : 3;
-    p.idesc = make_idesc_bf16(p.cta2 ? 256 : 128, p.BN, 1, 1);
-    p.ws = ws;
-    size_t smem = (size_t)(p.a_slots + 1) * p.a_slot_bytes + (size_t)p.b_stages * p.b_stage_bytes + (2 * p.a_slots + 2 * p.b_stages + 2) * 8 + 16 + 1024;
-    STC_REQUIRE(smem <= 227 * 1024, "conv_wgrad_wgradh: smem %zu", smem);
-    static bool attr_set[64] = {false};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        STC_CUDA(cudaFuncSetAttribute(umma_wgradh_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        STC_CUDA(cudaFuncSetAttribute(umma_wgradh_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set[dev] = true;
     }
     if (p.cta2) {   // `grid` counted pairs: clusters of two CTAs (the two SMs of a TPC)
         cudaLaunchConfig_t cfg;
