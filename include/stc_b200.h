@@ -322,6 +322,17 @@ int stc_seg_loss_fwd(const float* logits, const int64_t* label, double* stats, f
 int stc_seg_loss_bwd(const float* logits, const int64_t* label, const double* stats, const float* g_ce, const float* g_dice,
                      float* dlogits, int N, long long HW, int C, int ignore_index, float smooth, void* stream);
 
+/* Row softmax of nn.MultiheadAttention (unet_backbone.py:202,207: softmax(q k^T / sqrt(hd)) and its backward) inside the score products,
+ * without the L x L score / dP tensors: a CTA owns a 128-row block over all its N tiles and visits them twice - sweep 0 keeps the row
+ * statistics (max and sum of exponentials; or sum(P dP) / sum(P)) in the epilogue thread that owns the row, sweep 1 recomputes the tiles
+ * and stores the final bf16 values.  P = softmax_rows(scale * bf16(A B^T));  dS = scale * P * (bf16(A B^T) - sum_j P dP / sum_j P) with
+ * P laid out like the output.  Arithmetic of stc_gemm + stc_softmax_rows_fwd / _bwd up to the order of the fp32 row sums.
+ * tcgen05 engine, bf16, M % 128 == 0, N a multiple of its tile (stc_gemm_softmax_ok; P may be NULL for the forward form). */
+int stc_gemm_softmax_ok(const stc_gemm_desc* d, const void* C, const void* P, int dtype, int engine);
+int stc_gemm_softmax(const void* A, const void* B, void* P, const stc_gemm_desc* d, float scale, int dtype, int engine, void* stream);
+int stc_gemm_softmax_bwd(const void* A, const void* B, const void* P, void* dS, const stc_gemm_desc* d, float scale, int dtype, int engine,
+                         void* stream);
+
 /* Softmax backward inside the dP product of nn.MultiheadAttention's backward (unet_backbone.py:202,207): C = alpha * P .* (A * B - D[row])
  * with A = dO, B = V^T, P = the stored probabilities (bf16, laid out like C) and D[b1, b2, m] = rowsum(dO * O) (fp32, stc_rowdot_heads):
  * dS = scale * P * (dP - D) leaves the GEMM's epilogue directly - the L x L dP tensor and the separate softmax-backward pass

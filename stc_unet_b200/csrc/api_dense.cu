@@ -21,7 +21,9 @@ int conv_wgrad_wgradh(const void*, const void*, float*, int, int, int, int, int,
 int conv_fprop_convh(const void*, const void*, const float*, const void*, void*, int, int, int, int, int, int, int, int, cudaStream_t, float* stats = nullptr,
                      int* stats_rows = nullptr, const ChanCat* src = nullptr, const ChanCat* dst = nullptr);
 bool conv_convh_stats_ok(int Cout, int R);
-int gemm_umma(const void*, const void*, void*, const stc_gemm_desc*, int, cudaStream_t, const void* mul_residual = nullptr, const float* rowvec = nullptr);
+int gemm_umma(const void*, const void*, void*, const stc_gemm_desc*, int, cudaStream_t, const void* mul_residual = nullptr, const float* rowvec = nullptr,
+              int row_mode = 0, float sm_scale = 0.f);
+bool gemm_umma_rowsoftmax_ok(const stc_gemm_desc* d, const void* C, const void* P);
 }  // namespace stc
 
 using namespace stc;
@@ -180,6 +182,27 @@ extern "C" int stc_gemm(const void* A, const void* B, void* C, const stc_gemm_de
     }
     g_last_engine = STC_ENGINE_SIMT;
     return gemm_simt(A, B, C, d, dtype, st);
+}
+
+/* Row softmax inside the score product (K4, nn.MultiheadAttention forward / backward), two sweeps over a 128-row block's N tiles with the row
+ * statistics kept in the epilogue threads (umma.cu, UmmaParams::epi_mode 2 / 3):
+ *   stc_gemm_softmax:       P  = softmax_rows(scale * bf16(A B^T))                          - the L x L scores are never written
+ *   stc_gemm_softmax_bwd:   dS = scale * P * (bf16(A B^T) - sum_j P dP / sum_j P)           - no dP tensor, no separate pass
+ * Same arithmetic as stc_gemm + stc_softmax_rows_fwd / _bwd (products rounded to bf16 first, __expf, division by the actual row sum), up to
+ * the order of the fp32 row sums.  tcgen05 engine, bf16, M % 128 == 0, N a multiple of its tile; stc_gemm_softmax_ok tells. */
+extern "C" int stc_gemm_softmax_ok(const stc_gemm_desc* d, const void* C, const void* P, int dtype, int engine) {
+    return (d && dtype == STC_BF16 && engine != STC_ENGINE_SIMT && gemm_umma_rowsoftmax_ok(d, C, P)) ? 1 : 0;
+}
+extern "C" int stc_gemm_softmax(const void* A, const void* B, void* P, const stc_gemm_desc* d, float scale, int dtype, int engine, void* stream) {
+    STC_REQUIRE(d && A && B && P && stc_gemm_softmax_ok(d, P, nullptr, dtype, engine), "gemm_softmax: not eligible (see stc_gemm_softmax_ok)");
+    g_last_engine = STC_ENGINE_TCGEN05;
+    return gemm_umma(A, B, P, d, dtype, (cudaStream_t)stream, nullptr, nullptr, 2, scale);
+}
+extern "C" int stc_gemm_softmax_bwd(const void* A, const void* B, const void* P, void* dS, const stc_gemm_desc* d, float scale, int dtype,
+                                    int engine, void* stream) {
+    STC_REQUIRE(d && A && B && P && dS && stc_gemm_softmax_ok(d, dS, P, dtype, engine), "gemm_softmax_bwd: not eligible (see stc_gemm_softmax_ok)");
+    g_last_engine = STC_ENGINE_TCGEN05;
+    return gemm_umma(A, B, dS, d, dtype, (cudaStream_t)stream, P, nullptr, 3, scale);
 }
 
 /* Softmax backward inside the dP product (K4): C = alpha * P .* (A * B - D[row]) with P laid out like C (bf16) and D fp32 indexed

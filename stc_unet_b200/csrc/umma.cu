@@ -55,7 +55,14 @@ struct alignas(64) UmmaParams {
     int store_tma;
     // epi_mode 1 (GEMM, bf16 out): out = alpha * residual * (acc - rowvec[row]) - the softmax backward dS = scale * P * (dP - D) applied in
     // the epilogue of the dP = dO V^T product (residual = P, rowvec = D = rowsum(dO * O)); rowvec index = b1 * rv_s1 + b2 * rv_s2 + m
+    // epi_mode 2 / 3 (GEMM, bf16 out, `sweeps` = 2): row softmax WITHOUT a score tensor.  A CTA owns a 128-row block over ALL its N tiles and
+    // runs them twice: sweep 0 only reads the accumulators and keeps per-row statistics in the epilogue thread that owns the row (TMEM lane
+    // = row, so no cross-thread reduction), sweep 1 recomputes the tiles and stores the final values.
+    //   2: P = softmax(sm_scale * bf16(A B^T)) - statistics = running row max / sum of exponentials (the scores S are never written)
+    //   3: dS = sm_scale * P * (bf16(A B^T) - D), D = sum(P * dP) / sum(P) over the row, P = `residual` (no dP tensor, no separate pass)
     int epi_mode;
+    int sweeps;
+    float sm_scale;
     const float* rowvec;
     long long rv_s1, rv_s2;
     // cta_group::2 variant (umma2_kernel): a CTA pair computes a 256 x BN tile; num_tiles counts PAIR tiles, b_* describe ONE CTA's half of B
@@ -146,7 +153,7 @@ __device__ __forceinline__ float epi_act(float v, int act) {
 constexpr int kUmmaThreads = 192;
 constexpr int kAccCols = 256;
 
-template <bool CTA2>
+template <bool CTA2, bool SWEEP2>
 __device__ __forceinline__ void umma_body(const UmmaParams& p) {
     extern __shared__ uint8_t smem_raw[];
     // 1024B alignment for the 128B swizzle atoms
@@ -163,6 +170,10 @@ __device__ __forceinline__ void umma_body(const UmmaParams& p) {
     const int rank = CTA2 ? (int)ptx::cluster_ctarank() : 0;                 // 0 = leader of the pair
     const int tile0 = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;        // persistent loop: pair (or CTA) index and stride
     const int tstep = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    // two-sweep row modes (epi_mode 2 / 3): the unit of the persistent loop is a row block over all its N tiles, visited twice
+    constexpr bool two_sweeps = SWEEP2;   // its own instantiation (umma_sweep_kernel): the plain kernels compile without the extra loop level
+    const int nsteps = two_sweeps ? 2 * p.num_n_tiles : 1;
+    const int nsup = two_sweeps ? p.num_tiles / p.num_n_tiles : p.num_tiles;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * p.stages + s); };
@@ -207,7 +218,8 @@ __device__ __forceinline__ void umma_body(const UmmaParams& p) {
             uint32_t phase = 0;
             const int bn_off = CTA2 ? rank * (p.BN / 2) : 0;   // cta2: this CTA stages its half of the N columns of B
             const int pw_end = p.tiles_w * p.BW, ph_end = p.tiles_h * p.BH;
-            for (int tile = tile0; tile < p.num_tiles; tile += tstep) {
+            for (int sup = tile0; sup < nsup; sup += tstep) for (int step = 0; step < nsteps; ++step) {
+                const int tile = two_sweeps ? sup * p.num_n_tiles + (step >= p.num_n_tiles ? step - p.num_n_tiles : step) : sup;
                 TileInfo t = decode_tile<CTA2>(p, tile, rank);
                 int cc = 0, r = 0, s = 0, tap = 0;            // CONV: k iteration = (tap = r * S + s, 64-channel chunk cc)
                 int pn = 0, ph0 = 0, pw0 = 0;                 // WGRAD: k iteration = pixel tile (image pn, origin ph0 / pw0)
@@ -301,7 +313,8 @@ __device__ __forceinline__ void umma_body(const UmmaParams& p) {
             uint32_t acc_phase[2] = {0, 0};
             long long w_te = 0, w_f = 0, n_t = 0;
             const long long t_begin = p.prof ? clock64() : 0;
-            for (int tile = tile0; tile < p.num_tiles; tile += tstep) {
+            for (int sup = tile0; sup < nsup; sup += tstep) for (int step = 0; step < nsteps; ++step) {
+                const int tile = two_sweeps ? sup * p.num_n_tiles + (step >= p.num_n_tiles ? step - p.num_n_tiles : step) : sup;
                 TileInfo t = decode_tile<CTA2>(p, tile, rank);
                 if (t.k1 <= t.k0) continue;
                 long long t0 = p.prof ? clock64() : 0;
@@ -352,11 +365,13 @@ __device__ __forceinline__ void umma_body(const UmmaParams& p) {
         uint32_t acc_phase[2] = {0, 0};
         const uint32_t tempty_leader0 = CTA2 ? ptx::mapa_shared(tempty_bar(0), 0) : 0u, tempty_leader1 = CTA2 ? ptx::mapa_shared(tempty_bar(1), 0) : 0u;
         long long w_tf = 0, t_work = 0;
+        float rs0 = 0.f, rs1 = 0.f;   // two-sweep row modes: this thread's row statistics (max / sum, or sum(P dP) / sum(P))
         auto release_acc = [&](int a) {
             if (CTA2) ptx::mbar_arrive_cluster(a ? tempty_leader1 : tempty_leader0);
             else ptx::mbar_arrive(tempty_bar(a));
         };
-        for (int tile = tile0; tile < p.num_tiles; tile += tstep) {
+        for (int sup = tile0; sup < nsup; sup += tstep) for (int step = 0; step < nsteps; ++step) {
+                const int tile = two_sweeps ? sup * p.num_n_tiles + (step >= p.num_n_tiles ? step - p.num_n_tiles : step) : sup;
             TileInfo t = decode_tile<CTA2>(p, tile, rank);
             if (t.k1 <= t.k0) continue;
             bool valid;
@@ -376,13 +391,106 @@ __device__ __forceinline__ void umma_body(const UmmaParams& p) {
                 off = ((long long)atom * 64 + (row & 63)) * p.Cout + (long long)t.nt * p.BN;
             }
             // epi_mode 1: alpha * D[row], subtracted from alpha * acc before the product with the residual (P)
-            const float dsub = (p.epi_mode && valid) ? p.alpha * __ldg(p.rowvec + t.b1 * p.rv_s1 + t.b2 * p.rv_s2 + (t.mt * 128 + row)) : 0.f;
+            const float dsub = (p.epi_mode == 1 && valid) ? p.alpha * __ldg(p.rowvec + t.b1 * p.rv_s1 + t.b2 * p.rv_s2 + (t.mt * 128 + row)) : 0.f;
             const long long pt0 = p.prof ? clock64() : 0;
             ptx::mbar_wait(tfull_bar(acc), acc_phase[acc]);
             const long long pt1 = p.prof ? clock64() : 0;
             w_tf += pt1 - pt0;
             ptx::tc_fence_after();
             const uint32_t t_addr = tmem_base + acc * kAccCols + ((uint32_t)(q * 32) << 16);
+            if (SWEEP2) {
+                // ---- two-sweep row softmax (see UmmaParams::epi_mode): this thread owns row `row` of the block for all N tiles and both sweeps ----
+                const bool fwd = p.epi_mode == 2;
+                const int sweep = step >= p.num_n_tiles ? 1 : 0;
+                if (step == 0) { rs0 = fwd ? -INFINITY : 0.f; rs1 = 0.f; }
+                if (step == p.num_n_tiles) {   // statistics complete: fwd 1 / sum of exponentials; bwd D = sum(P dP) / sum(P)
+                    if (fwd) rs1 = 1.f / rs1; else rs0 = rs0 / rs1;
+                }
+                const int c1 = t.mt * 128 + q * 32, c2 = t.b2, c3 = t.b1;
+                const uint32_t stg0 = smem_base + p.stages * stage_bytes + (uint32_t)q * 2u * kStageBufBytes;
+                for (int c = 0; c < p.BN; c += 64) {
+                    const uint32_t stg = stg0 + (uint32_t)stage_buf * kStageBufBytes;
+                    if (sweep) {
+                        if (lane == 0) ptx::bulk_wait_read<1>();
+                        __syncwarp();
+                    }
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        uint32_t v[32];
+                        ptx::tmem_ld_32x32(t_addr + c + half * 32, v);
+                        ptx::tmem_ld_wait();
+                        float f[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)   // the product rounded to bf16, exactly as the unfused path stores it
+                            f[j] = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[j]) * p.alpha));
+                        if (fwd) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] *= p.sm_scale;
+                            if (!sweep) {
+                                float cm = f[0];
+#pragma unroll
+                                for (int j = 1; j < 32; ++j) cm = fmaxf(cm, f[j]);
+                                const float m_new = fmaxf(rs0, cm);
+                                float add = 0.f;
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) add += __expf(f[j] - m_new);
+                                rs1 = rs1 * __expf(rs0 - m_new) + add;
+                                rs0 = m_new;
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) f[j] = __expf(f[j] - rs0) * rs1;
+                            }
+                        } else {
+                            const uint4* r = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.residual) + off + c + half * 32);
+                            float x[32];
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                uint4 rv = __ldg(r + g);
+                                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float2 xx = __bfloat1622float2(h[e]);
+                                    x[g * 8 + 2 * e] = xx.x;
+                                    x[g * 8 + 2 * e + 1] = xx.y;
+                                }
+                            }
+                            if (!sweep) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) { rs0 = fmaf(x[j], f[j], rs0); rs1 += x[j]; }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) f[j] = p.sm_scale * x[j] * (f[j] - rs0);
+                            }
+                        }
+                        if (sweep) {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                uint4 ov;
+                                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(f[g * 8 + 2 * e], f[g * 8 + 2 * e + 1]);
+                                ptx::st_shared_v4(stg + (uint32_t)lane * 128u + (uint32_t)(((half * 4 + g) ^ (lane & 7)) << 4), ov);
+                            }
+                        }
+                    }
+                    if (sweep) {
+                        ptx::fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) {
+                            ptx::tma_store_4d(&p.tmC, stg, t.nt * p.BN + c, c1, c2, c3);
+                            ptx::bulk_commit();
+                        }
+                        stage_buf ^= 1;
+                    }
+                }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) release_acc(acc);
+                acc_phase[acc] ^= 1;
+                acc ^= 1;
+                if (p.prof) t_work += clock64() - pt1;
+                continue;
+            }
             if (p.store_tma) {
                 // ---- staged epilogue: TMEM -> registers -> swizzled smem -> TMA store (bf16 out, CONV / GEMM modes) ----
                 int c1, c2, c3;   // box origin below the channel coordinate
@@ -428,7 +536,7 @@ __device__ __forceinline__ void umma_body(const UmmaParams& p) {
                                     x[g * 8 + 2 * e + 1] = xx.y;
                                 }
                             }
-                            if (p.epi_mode) {   // softmax backward: (alpha * acc - alpha * D[row]) * P
+                            if (p.epi_mode == 1) {   // softmax backward: (alpha * acc - alpha * D[row]) * P
 #pragma unroll
                                 for (int j = 0; j < 32; ++j) f[j] = (f[j] - dsub) * x[j];
                             } else {
@@ -567,9 +675,11 @@ __device__ __forceinline__ void umma_body(const UmmaParams& p) {
     }
 }
 
-__global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_constant__ UmmaParams p) { umma_body<false>(p); }
+__global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_constant__ UmmaParams p) { umma_body<false, false>(p); }
+// the two-sweep row-softmax GEMM (epi_mode 2 / 3)
+__global__ void __launch_bounds__(kUmmaThreads, 1) umma_sweep_kernel(const __grid_constant__ UmmaParams p) { umma_body<false, true>(p); }
 // the cta_group::2 variant: CTA pairs (cluster of 2 = the two SMs of a TPC) computing 256 x BN tiles
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1) umma2_kernel(const __grid_constant__ UmmaParams p) { umma_body<true>(p); }
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1) umma2_kernel(const __grid_constant__ UmmaParams p) { umma_body<true, false>(p); }
 
 // ------------------------------------------------------------------------------------------------
 // host side
@@ -667,6 +777,16 @@ static int launch(UmmaParams& p, cudaStream_t st) {
     }
     int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
     if (grid <= 0) return STC_OK;
+    if (p.sweeps == 2) {
+        static bool attr3[64] = {false};
+        if (dev >= 0 && dev < 64 && !attr3[dev]) {
+            STC_CUDA(cudaFuncSetAttribute(umma_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr3[dev] = true;
+        }
+        const int blocks = p.num_tiles / p.num_n_tiles;   // row blocks: the unit of the persistent loop
+        umma_sweep_kernel<<<blocks < grid ? blocks : grid, kUmmaThreads, smem, st>>>(p);
+        return check_launch("umma_sweep_kernel");
+    }
     umma_kernel<<<grid, kUmmaThreads, smem, st>>>(p);
     return check_launch("umma_kernel");
 }
@@ -880,11 +1000,25 @@ bool gemm_umma_eligible(const stc_gemm_desc* d, int dtype) {
     return true;
 }
 
+// row_mode 2 / 3: the two-sweep row softmax epilogues (UmmaParams::epi_mode); 3 takes P as `mul_residual` (no rowvec)
+bool gemm_umma_rowsoftmax_ok(const stc_gemm_desc* d, const void* C, const void* P) {
+    if (!gemm_umma_eligible(d, STC_BF16)) return false;
+    const int BN = pick_bn(d->N);
+    return BN % 64 == 0 && d->M % 128 == 0 && d->N % BN == 0 && ((uintptr_t)C & 15) == 0 && ((uintptr_t)P & 15) == 0 && d->sCm % 8 == 0 &&
+           !getenv_off("STC_TMA_STORE");
+}
+
 int gemm_umma(const void* A, const void* B, void* C, const stc_gemm_desc* d, int out_dtype, cudaStream_t st, const void* mul_residual,
-              const float* rowvec) {
+              const float* rowvec, int row_mode, float sm_scale) {
     STC_REQUIRE(gemm_umma_eligible(d, STC_BF16), "gemm_umma: descriptor not eligible");
-    STC_REQUIRE((mul_residual == nullptr) == (rowvec == nullptr) && (!mul_residual || (out_dtype == STC_BF16 && ((uintptr_t)mul_residual & 15) == 0)),
-                "gemm_umma: the softmax-backward epilogue needs P (bf16, 16-byte aligned, laid out like C) and D together");
+    if (row_mode) {
+        STC_REQUIRE((row_mode == 2 || row_mode == 3) && out_dtype == STC_BF16 && !rowvec && (row_mode == 3) == (mul_residual != nullptr) &&
+                        gemm_umma_rowsoftmax_ok(d, C, mul_residual),
+                    "gemm_umma: the two-sweep row softmax needs bf16 output, whole 128-row blocks and N tiles, and P for the backward form");
+    } else {
+        STC_REQUIRE((mul_residual == nullptr) == (rowvec == nullptr) && (!mul_residual || (out_dtype == STC_BF16 && ((uintptr_t)mul_residual & 15) == 0)),
+                    "gemm_umma: the softmax-backward epilogue needs P (bf16, 16-byte aligned, laid out like C) and D together");
+    }
     UmmaParams p;
     memset(&p, 0, sizeof(p));
     p.mode = MODE_GEMM;
@@ -892,7 +1026,7 @@ int gemm_umma(const void* A, const void* B, void* C, const stc_gemm_desc* d, int
     p.BN = pick_bn(d->N);
     p.a_mn_major = (d->sAk != 1);
     p.b_mn_major = (d->sBk != 1);
-    p.cta2 = (d->M % 128 == 0 && use_cta2(d->M / 128, p.BN, p.b_mn_major, (d->K + 63) / 64)) ? 1 : 0;
+    p.cta2 = (!row_mode && d->M % 128 == 0 && use_cta2(d->M / 128, p.BN, p.b_mn_major, (d->K + 63) / 64)) ? 1 : 0;
     const int bn_cta = p.cta2 ? p.BN / 2 : p.BN;          // columns of B staged by one CTA
     uint64_t b1 = (uint64_t)d->batch1, b2 = (uint64_t)d->batch2;
     {
@@ -945,7 +1079,14 @@ int gemm_umma(const void* A, const void* B, void* C, const stc_gemm_desc* d, int
     p.stages = pick_stages(p.a_stage_bytes + p.b_stage_bytes, p.store_tma);
     p.out = C; p.out_dtype = out_dtype; p.Cout = d->N;
     p.ldc = d->sCm; p.sC1 = d->sC1; p.sC2 = d->sC2; p.alpha = d->alpha;
-    if (mul_residual) {
+    p.sweeps = 1;
+    if (row_mode) {
+        STC_REQUIRE(p.store_tma, "gemm_umma: the two-sweep row softmax needs the staged (TMA store) epilogue");
+        p.epi_mode = row_mode;
+        p.sweeps = 2;
+        p.sm_scale = sm_scale;
+        p.residual = mul_residual;
+    } else if (mul_residual) {
         p.epi_mode = 1;
         p.residual = mul_residual;
         p.rowvec = rowvec;

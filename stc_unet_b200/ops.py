@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 from typing import Optional, Sequence
 
 import torch
@@ -26,6 +27,10 @@ class _Config:
     fold_linear_pairs = True        # bf16 + tcgen05: q/k/v + in_proj and fc1 + fc2 of TransformerLayer run as folded GEMMs
     ksa_lazy_df = True              # KSA branch gradients are consumed implicitly by the BN backward kernels (no df tensors)
     chain_fanout_grads = True       # KSA: the input's four gradients are summed in the branch dgrads' epilogues (no add_n pass)
+    # attention: softmax / its backward inside the QK^T / dO V^T products (stc_gemm_softmax*: two sweeps, no score tensor).  OPT-IN: correct to
+    # 3e-5, but measured SLOWER than product + separate pass (L = 4096: 0.77 -> 1.29 ms forward, 0.90 -> 2.03 ms backward): the second sweep
+    # doubles the MMA + accumulator read-out, which is what bounds a K = 256 product, and four epilogue warps do all the exponentials
+    fuse_attention_softmax = os.environ.get("STC_ATTN_FUSED", "0") == "1"
     fold_eval_bn = True             # inference: eval-mode BN folded into the conv weights, activation in the conv epilogue
     widen_narrow_convs = True       # bf16: 16 / 32-channel layers are zero-padded to the tcgen05 kernels' channel granularity
     # Inference with FROZEN weights (a deployed checkpoint): keep the folded / packed bf16 operands between forwards instead of rebuilding
@@ -1185,6 +1190,24 @@ def ksa_fuse(x, f0, f1, f2, fc, fcs):
 # ---------------------------------------------------------------------------------------------
 # Multi-head attention core: softmax(Q K^T / sqrt(hd)) V on (N, L, E) token tensors
 # ---------------------------------------------------------------------------------------------
+def _softmax_gemm(a, b, P, dS, L, hd, N, heads, sA, sB, sC, scale) -> bool:
+    """Row softmax inside the score product (stc_gemm_softmax / stc_gemm_softmax_bwd: two sweeps over a row block's N tiles, no L x L score
+    or dP tensor).  dS is None: P = softmax(scale * a b^T) is written into P.  Else: dS = scale * P * (a b^T - sum(P dP) / sum(P)).
+    False when the tcgen05 engine does not take the shape (the caller then runs the product and the softmax pass separately)."""
+    if not config.fuse_attention_softmax or a.dtype != torch.bfloat16:
+        return False
+    d = GemmDesc(L, L, hd, N, heads, sA[0], sA[1], sA[2], sA[3], sB[0], sB[1], sB[2], sB[3], sC[0], sC[1], sC[2], 1.0, 0.0)
+    out = P if dS is None else dS
+    if not lib.raw("stc_gemm_softmax_ok")(ctypes.byref(d), ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(P.data_ptr()), dtype_code(a.dtype), config.engine):
+        return False
+    flops = 2.0 * L * L * hd * N * heads   # algorithmic: ONE product (the second sweep's recomputation is this kernel's choice, not work)
+    if dS is None:
+        _dense("gemm", flops, lambda: lib.call("stc_gemm_softmax", a, b, P, d, float(scale), dtype_code(a.dtype), config.engine, stream_ptr()))
+    else:
+        _dense("gemm", flops, lambda: lib.call("stc_gemm_softmax_bwd", a, b, P, dS, d, float(scale), dtype_code(a.dtype), config.engine, stream_ptr()))
+    return True
+
+
 def _dsoftmax_gemm(do, v, P, o, dS, L, hd, N, heads, sA, sB, sC, scale) -> bool:
     """dS = scale * P * (dO V^T - rowsum(dO * O)) out of the dP product's epilogue (stc_gemm_dsoftmax); False when the tcgen05 engine
     does not take it (the caller then runs the product and the softmax-backward pass separately)."""
@@ -1218,9 +1241,10 @@ class _Attention(Function):
         tok = (L * E, hd)  # batch strides of a (N, L, E) tensor split into heads
         if q.dtype == torch.float32:   # exact-parity path: centred keys (same softmax, no common component in the fp32 scores)
             k = _center_tokens(k)
-        gemm(q, k, P, L, L, hd, N, heads, (*tok, E, 1), (*tok, 1, E), (heads * L * L, L * L, L))
         scale = 1.0 / math.sqrt(hd)
-        lib.call("stc_softmax_rows_fwd", P, P, N * heads * L, L, scale, dtype_code(q.dtype), stream_ptr())
+        if not _softmax_gemm(q, k, P, None, L, hd, N, heads, (*tok, E, 1), (*tok, 1, E), (heads * L * L, L * L, L), scale):
+            gemm(q, k, P, L, L, hd, N, heads, (*tok, E, 1), (*tok, 1, E), (heads * L * L, L * L, L))
+            lib.call("stc_softmax_rows_fwd", P, P, N * heads * L, L, scale, dtype_code(q.dtype), stream_ptr())
         o = torch.empty_like(q)
         gemm(P, v, o, L, hd, L, N, heads, (heads * L * L, L * L, L, 1), (*tok, E, 1), (L * E, hd, E))
         ctx.save_for_backward(q, k, v, P, o)
@@ -1241,7 +1265,9 @@ class _Attention(Function):
         gemm(P, do, dv, L, hd, L, N, heads, (*pb, 1, L), (*tok, E, 1), (L * E, hd, E))            # dV = P^T dO
         dP = torch.empty_like(P)
         vc = _center_tokens(v) if v.dtype == torch.float32 else v   # dS is invariant under a common shift of the values
-        if not _dsoftmax_gemm(do, vc, P, o, dP, L, hd, N, heads, (*tok, E, 1), (*tok, 1, E), (*pb, L), scale):   # dS from the dP epilogue
+        if _softmax_gemm(do, vc, P, dP, L, hd, N, heads, (*tok, E, 1), (*tok, 1, E), (*pb, L), scale):             # dS out of the dP product
+            pass
+        elif not _dsoftmax_gemm(do, vc, P, o, dP, L, hd, N, heads, (*tok, E, 1), (*tok, 1, E), (*pb, L), scale):   # opt-in variant with D = rowsum(dO * O)
             gemm(do, vc, dP, L, L, hd, N, heads, (*tok, E, 1), (*tok, 1, E), (*pb, L))              # dP = dO V^T
             lib.call("stc_softmax_rows_bwd", P, dP, dP, N * heads * L, L, scale, dtype_code(q.dtype), stream_ptr())
         dq = torch.empty_like(q)
@@ -1399,9 +1425,10 @@ class _AttentionPacked(Function):
         q, k, v = qkv[..., :E], qkv[..., E:2 * E], qkv[..., 2 * E:]
         P = torch.empty((N, heads, L, L), dtype=qkv.dtype, device=dev)
         pk = (L * E3, hd)   # batch strides of a packed (N, L, 3E) tensor split into heads
-        gemm(q, k, P, L, L, hd, N, heads, (*pk, E3, 1), (*pk, 1, E3), (heads * L * L, L * L, L))
         scale = 1.0 / math.sqrt(hd)
-        lib.call("stc_softmax_rows_fwd", P, P, N * heads * L, L, scale, dtype_code(qkv.dtype), stream_ptr())
+        if not _softmax_gemm(q, k, P, None, L, hd, N, heads, (*pk, E3, 1), (*pk, 1, E3), (heads * L * L, L * L, L), scale):
+            gemm(q, k, P, L, L, hd, N, heads, (*pk, E3, 1), (*pk, 1, E3), (heads * L * L, L * L, L))
+            lib.call("stc_softmax_rows_fwd", P, P, N * heads * L, L, scale, dtype_code(qkv.dtype), stream_ptr())
         o = torch.empty((N, L, E), dtype=qkv.dtype, device=dev)
         gemm(P, v, o, L, hd, L, N, heads, (heads * L * L, L * L, L, 1), (*pk, E3, 1), (L * E, hd, E))
         ctx.save_for_backward(qkv, P, o)
@@ -1425,7 +1452,9 @@ class _AttentionPacked(Function):
         dq, dk, dv = dqkv[..., :E], dqkv[..., E:2 * E], dqkv[..., 2 * E:]
         gemm(P, do, dv, L, hd, L, N, heads, (*pb, 1, L), (*tok, E, 1), (*pk, E3))                   # dV = P^T dO
         dP = torch.empty_like(P)
-        if not _dsoftmax_gemm(do, v, P, o, dP, L, hd, N, heads, (*tok, E, 1), (*pk, 1, E3), (*pb, L), scale):   # dS from the dP epilogue
+        if _softmax_gemm(do, v, P, dP, L, hd, N, heads, (*tok, E, 1), (*pk, 1, E3), (*pb, L), scale):              # dS out of the dP product
+            pass
+        elif not _dsoftmax_gemm(do, v, P, o, dP, L, hd, N, heads, (*tok, E, 1), (*pk, 1, E3), (*pb, L), scale):   # opt-in variant with D = rowsum(dO * O)
             gemm(do, v, dP, L, L, hd, N, heads, (*tok, E, 1), (*pk, 1, E3), (*pb, L))               # dP = dO V^T
             lib.call("stc_softmax_rows_bwd", P, dP, dP, N * heads * L, L, scale, dtype_code(qkv.dtype), stream_ptr())
         gemm(dP, k, dq, L, hd, L, N, heads, (*pb, L, 1), (*pk, E3, 1), (*pk, E3))                   # dQ = dS K

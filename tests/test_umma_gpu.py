@@ -93,6 +93,44 @@ def test_attention_tcgen05(tc, L, heads):
         assert rel_l2(a.grad.float(), b_.grad) < 3e-2
 
 
+@pytest.mark.parametrize("L", [256, 1024])
+def test_attention_softmax_inside_the_score_products(tc, L):
+    """stc_gemm_softmax / stc_gemm_softmax_bwd (two sweeps over a row block's N tiles, row statistics in the epilogue threads, no L x L
+    score / dP tensor) against the separate product + softmax passes: same arithmetic (products rounded to bf16, __expf, division by
+    the actual row sum) up to the order of the fp32 row sums, so outputs and gradients agree to bf16 rounding; the fused path makes no
+    stc_softmax_rows_* call; both agree with the fp32 reference."""
+    N, E, heads = 2, 512, 2
+    hd = E // heads
+    g = torch.Generator(device="cuda").manual_seed(14)
+    q, k, v = (bf16_round(torch.randn(N, L, E, device=dev(), generator=g) * 0.5) for _ in range(3))
+    go = bf16_round(torch.randn(N, L, E, device=dev(), generator=g))
+    qr, kr, vr = (t.clone().requires_grad_(True) for t in (q, k, v))
+    def hsplit(t): return t.view(N, L, heads, hd).transpose(1, 2)
+    att = torch.softmax(hsplit(qr) @ hsplit(kr).transpose(-1, -2) / math.sqrt(hd), -1)
+    ref = (att @ hsplit(vr)).transpose(1, 2).reshape(N, L, E)
+    ref.backward(go)
+    res, calls = {}, {}
+    for fused in (True, False):
+        tc.config.fuse_attention_softmax = fused
+        qo, ko, vo = (t.to(BF).requires_grad_(True) for t in (q, k, v))
+        prof = tc.LaunchProfiler(time_all=True)
+        tc.set_profiler(prof)
+        try:
+            out = tc.attention(qo, ko, vo, heads)
+            out.backward(go.to(BF))
+        finally:
+            tc.set_profiler(None)
+            tc.config.fuse_attention_softmax = False   # the shipped default (opt-in: measured slower, profiles/r2_attention_two_sweep.txt)
+        res[fused] = (out.float(), qo.grad.float(), ko.grad.float(), vo.grad.float())
+        calls[fused] = [r[0] for r in prof.all_records]
+    assert not any(c.startswith("stc_softmax_rows") for c in calls[True]) and "stc_gemm_softmax" in calls[True] and "stc_gemm_softmax_bwd" in calls[True]
+    assert sum(c.startswith("stc_softmax_rows") for c in calls[False]) == 2
+    for a, b_ in zip(res[True], res[False]):
+        assert rel_l2(a, b_) < 4e-3
+    for a, b_ in zip(res[True], (ref, qr.grad, kr.grad, vr.grad)):
+        assert rel_l2(a, b_) < 3e-2
+
+
 def test_linear_tokens_tcgen05(tc):
     g = torch.Generator(device="cuda").manual_seed(5)
     rows, E, O = 300, 512, 1536
