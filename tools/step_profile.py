@@ -26,7 +26,13 @@ def main():
     import stc_unet_b200 as S
     from stc_unet_b200 import ops
     from stc_unet_b200.train import Trainer
-    dev = torch.device("cuda", 0)
+    # under torchrun (WORLD_SIZE > 1) this profiles rank 0's step of the data-parallel run: SyncBN exchanges + gradient all-reduce included
+    world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
     bcfg, hcfg = bench.model_cfg(args.model, args.classes, args.dtype)
     seg = S.EncoderDecoder(bcfg, hcfg).to(dev)
@@ -46,6 +52,10 @@ def main():
     t1.record()
     torch.cuda.synchronize()
     ops.set_profiler(None)
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+        return
     agg = collections.OrderedDict()
     per = collections.defaultdict(list)
     for name, nbytes, s, e in prof.all_records:
@@ -76,3 +86,6 @@ def main():
 
 if __name__ == "__main__":
     main()
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and int(os.environ.get("RANK", "0")) == 0:
+        import torch.distributed as dist
+        dist.barrier()
