@@ -642,13 +642,19 @@ __device__ __forceinline__ void umma_body(const UmmaParams& p) {
                         const long long pix = (off - (long long)t.nt * p.BN) / p.Cout;
                         o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(j ? p.out2[j - 1] : p.out) + pix * ow + lc);
                     }
+                    uint4 ov[4];
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
-                        uint4 ov;
-                        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&ov);
+                        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&ov[g]);
 #pragma unroll
                         for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(f[g * 8 + 2 * e], f[g * 8 + 2 * e + 1]);
-                        o[g] = ov;
+                    }
+                    if ((reinterpret_cast<uintptr_t>(o) & 31) == 0) {   // two full 32-byte sectors per lane
+                        ptx::st_global_v8(o, ov[0], ov[1]);
+                        ptx::st_global_v8(o + 2, ov[2], ov[3]);
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) o[g] = ov[g];
                     }
                 } else {
                     float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off + c);
