@@ -63,7 +63,7 @@ __device__ __forceinline__ uint32_t tmem_ld_x<2>(uint32_t taddr) {
 struct Out { long long clk[32]; unsigned sink; };
 
 template <int X>
-__global__ void __launch_bounds__(160, 1) ld_probe(Out* out, int iters, int passes, int N, int slot) {
+__global__ void __launch_bounds__(160, 1) ld_probe(Out* out, int iters, int passes, int N, int slot, int M = 128) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 48 * 1024);
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(160, 1) ld_probe(Out* out, int iters, int pass
     const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
     const uint64_t a_desc0 = desc_hi | (uint64_t)((ptx::smem_u32(smem) >> 4) & 0x3FFF);
     const uint64_t b_desc0 = desc_hi | (uint64_t)((ptx::smem_u32(smem + 16 * 1024) >> 4) & 0x3FFF);
-    const uint32_t idesc = idesc_bf16(128, N);
+    const uint32_t idesc = idesc_bf16(M, N);
     uint32_t phase = 0, sink = 0;
     constexpr int COLS = X == 2 ? 64 : X;   // columns per call
     for (int mode = 1; mode <= 3; ++mode) {   // 1 = MMAs only, 2 = loads only, 3 = both
@@ -145,6 +145,16 @@ int main(int argc, char** argv) {
                    N, names[shape], c[1], c[1] / (4.0 * iters), c[2], bytes / c[2], c[3], (double)c[3] / (c[1] > c[2] ? c[1] : c[2]),
                    (double)c[3] / (c[1] + c[2]), c[4 + 3]);
         }
+    }
+    // M = 64 (weights-as-A formulations): clocks per MMA, MMAs alone
+    for (int N : {128, 256}) {
+        const int iters = 2000;
+        cudaMemset(d, 0, sizeof(Out));
+        ld_probe<32><<<sms, 160, smem>>>(d, iters, 1, N, 0, 64);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); return 1; }
+        Out h; cudaMemcpy(&h, d, sizeof(Out), cudaMemcpyDeviceToHost);
+        printf("M= 64 N=%3d  SS MMAs alone: %.1f clocks per MMA (%.0f flop/clk/SM of 8192)\n", N, h.clk[1] / (4.0 * iters), 2.0 * 64 * N * 16 / (h.clk[1] / (4.0 * iters)));
     }
     return 0;
 }
